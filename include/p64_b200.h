@@ -1,0 +1,212 @@
+/*
+ * p64_b200.h -- C ABI of the B200-native hot path for the PVRG-P64 H.261 encoder (maikmerten/p64).
+ *
+ * Plain C, pointers and sizes only.  Three groups of entry points:
+ *
+ *  (1) p64b_ctx_*   the device context: frame stores resident in HBM for N independent streams and the
+ *                   sm_100a kernels (motion estimation, MTYPE decision, prediction + loop filter,
+ *                   Chen DCT, quantise, inverse quantise, Chen IDCT, reconstruct).  This is what the
+ *                   reference's per-frame work in p64EncodeFrame()/p64EncodeGOB() binds to.
+ *  (2) p64b_bits_*  the sequential host side that stays on the CPU: H.261 picture/GOB/MB headers and the
+ *                   run-level VLC, consuming the per-macroblock records the device returns.
+ *  (3) p64b_enc_*   the sequence driver: (1)+(2)+ the reference's rate control for a batch of streams;
+ *                   what the `p64b` command line and the Python mirror call.
+ *
+ * All references "file:line" are into the reference tree (maikmerten/p64).
+ * Functions returning int return 0 on success and a negative P64B_E* code on failure;
+ * p64b_last_error() gives the message.  There is NO CPU fallback: without a CUDA device every
+ * p64b_ctx_ and p64b_enc_ call that needs one fails with P64B_ECUDA.
+ */
+#ifndef P64_B200_H
+#define P64_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define P64B_VERSION 1
+
+/* image types: globals.h IT_NTSC/IT_CIF/IT_QCIF, selected by -NTSC/-CIF/-QCIF (p64.c:281-292) */
+#define P64B_IT_NTSC 0 /* 352x240, 10 GOBs */
+#define P64B_IT_CIF  1 /* 352x288, 12 GOBs */
+#define P64B_IT_QCIF 2 /* 176x144,  3 GOBs */
+
+/* motion search: the stock three-step search (StepBME, me.c:255-330, called at me.c:352) or the
+ * exhaustive search (FastBME, me.c:187-246, the commented-out call at me.c:351) */
+#define P64B_ME_TSS  0
+#define P64B_ME_FULL 1
+
+#define P64B_EINVAL (-1)
+#define P64B_ECUDA  (-2)
+#define P64B_ENOMEM (-3)
+#define P64B_EIO    (-4)
+
+#define P64B_MDU_PER_GOB 33 /* NumberMDU, p64.c:1478 */
+
+/* One macroblock as the host VLC needs it (the globals WriteMBHeader()/WriteMDU() read:
+ * MType, CBP, MVDH, MVDV, UseQuant -- p64.c:85-98, marker.c:288-354).  8 bytes. */
+typedef struct p64b_mb {
+  uint8_t mtype;   /* final MType 0..9 after the CBP / type-4 / type-7 fallback (p64.c:887-908)       */
+  uint8_t cbp;     /* coded block pattern, bit (5-c) for block c; 0x3f for non-CBP types              */
+  int8_t  mvx;     /* MVDH as transmitted: the ME vector for MC types, 0 otherwise (marker.c:339-342) */
+  int8_t  mvy;     /* MVDV                                                                            */
+  uint8_t quant;   /* UseQuant (p64.c:832-837)                                                        */
+  uint8_t nzmask;  /* bit (5-c) set iff block c has any non-zero level (host fast path; not in ref)   */
+  uint16_t reserved;
+} p64b_mb;
+
+/* Zig-zag levels: int8 [6][64] per macroblock in transmission order (inputbuf[c][k], p64.c:167).
+ * AC levels are in [-127,127]; the DC level of an INTRA block is in [1,254] and is stored as uint8
+ * in the same byte. */
+#define P64B_LEVELS_PER_MB 384
+
+/* Motion-estimation record, the reference's MeX/MeY/MeVal/MeOVal/MeVAR/MeVAROR/MeMWOR (me.c:49-59). */
+typedef struct p64b_me {
+  int32_t mx, my, val, oval, var, varor, mwor, pad;
+} p64b_me;
+
+/* What one frame step needs besides pixels. */
+typedef struct p64b_step {
+  int32_t first_frame;  /* 1: CurrentFrame==StartFrame: no ME, every MB intra (p64.c:635, 770-771)       */
+  int32_t me_mode;      /* P64B_ME_TSS | P64B_ME_FULL                                                   */
+  int32_t search_limit; /* -i SearchLimit (p64.c:341-344); FULL searches [-limit/2, limit/2) (me.c:206)  */
+  int32_t force_intra;  /* stand-in for `-o < test.intra` ("0 sto MTYPE"): decision forced to type 0     */
+  int32_t gquant;       /* GQUANT for every GOB when `quant` is NULL (fixed-Q, -q)                      */
+  int32_t reserved[3];
+} p64b_step;
+
+const char *p64b_last_error(void);
+int p64b_version(void);
+
+/* geometry (SetCCITT, p64.c:1476-1514) */
+int p64b_width(int image_type);
+int p64b_height(int image_type);
+int p64b_frame_bytes(int image_type); /* planar Y,U,V 4:2:0, no padding (mem.h:37-42) */
+int p64b_num_gob(int image_type);
+int p64b_num_mb(int image_type);      /* NumberGOB*33 */
+
+/* ---------------------------------------------------------------------------------------------
+ * (1) device context
+ * ------------------------------------------------------------------------------------------- */
+typedef struct p64b_ctx p64b_ctx;
+
+/* Replaces MakeFstore/InitFS/ClearFS (p64.c:529-535): two zero-filled frame stores per stream, in HBM. */
+int p64b_ctx_create(p64b_ctx **out, int device, int image_type, int n_streams);
+void p64b_ctx_destroy(p64b_ctx *ctx);
+int p64b_ctx_streams(const p64b_ctx *ctx);
+/* Use an existing CUDA stream (cudaStream_t) for every kernel and copy; NULL = the context's own. */
+int p64b_ctx_set_cuda_stream(p64b_ctx *ctx, void *cuda_stream);
+/* Pinned host memory for source/record/level buffers (cudaHostAlloc); plain malloc'd buffers also work. */
+void *p64b_host_alloc(size_t bytes);
+void p64b_host_free(void *p);
+
+/* One frame step for every stream, host buffers in and out.  Replaces the body of p64EncodeFrame()
+ * between ReadIob() and SwapFS() (p64.c:633-661) in fixed-quantiser mode: GlobalMC/MotionEstimation
+ * (io.c:129, me.c:340), the MTYPE decision (p64.c:734-773), ReadCompressMDU (p64.c:823-913), the
+ * inverse half of WriteMDU (p64.c:952-957), DecodeSaveMDU (p64.c:971-1013) and SwapFS (p64.c:661).
+ *   src     [n_streams][frame_bytes]        current source frames (ReadIob, io.c:613-646)
+ *   mbs     [n_streams][num_mb]             GOB-major (transmission) order
+ *   levels  [n_streams][num_mb][6][64]
+ */
+int p64b_ctx_encode_frames(p64b_ctx *ctx, const p64b_step *step, const uint8_t *src, p64b_mb *mbs,
+                           int8_t *levels);
+/* Same with device pointers (inputs already resident in HBM, outputs left there). */
+int p64b_ctx_encode_frames_dev(p64b_ctx *ctx, const p64b_step *step, const uint8_t *src_dev,
+                               p64b_mb *mbs_dev, int8_t *levels_dev);
+
+/* Rate-control split (-r / -x): the quantiser of GOB g is chosen by the host from the bits written so
+ * far (ExecuteQuantization, p64.c:458-481, 697-702), so quantise..reconstruct runs per GOB.
+ *   begin : upload + motion estimation for the whole frame (quantiser independent)
+ *   gob   : decision..reconstruct for GOB `gob` of every stream with per-stream GQUANT quant[n_streams];
+ *           outputs cover that GOB only: mbs [n_streams][33], levels [n_streams][33][6][64]
+ *   end   : MBs the host overrode to "type 4, zero vector" on buffer overflow (p64.c:776-783) are
+ *           re-reconstructed as a copy and their LastIntra counter fixed; then SwapFS.
+ *           overflow [n_streams][num_mb] (non-zero = overridden) or NULL. */
+int p64b_ctx_frame_begin(p64b_ctx *ctx, const p64b_step *step, const uint8_t *src);
+int p64b_ctx_encode_gob(p64b_ctx *ctx, const p64b_step *step, int gob, const uint8_t *quant, p64b_mb *mbs,
+                        int8_t *levels);
+int p64b_ctx_frame_end(p64b_ctx *ctx, const uint8_t *overflow);
+
+/* Motion estimation alone on device-resident luma planes (config 4 microbenchmark):
+ * ref/cur [n_pairs][W*H], out [n_pairs][num_mb raster]. n_pairs may exceed the context's stream count. */
+int p64b_ctx_motion_estimation_dev(p64b_ctx *ctx, const uint8_t *ref_dev, const uint8_t *cur_dev, int n_pairs,
+                                   int me_mode, int search_limit, p64b_me *out_dev);
+
+/* The reference's ME arrays for one stream, raster MB order (for -o programs and tests; me.c:49-59). */
+int p64b_ctx_me_records(p64b_ctx *ctx, int stream, p64b_me *out);
+/* The current reference frame store (= last reconstructed frame, CFS after SwapFS), for -l statistics
+ * (stat.c:52) and closed-loop tests. */
+int p64b_ctx_download_recon(p64b_ctx *ctx, int stream, uint8_t *yuv);
+/* LastIntra counters [num_mb] GOB-major (p64.c:213). */
+int p64b_ctx_last_intra(p64b_ctx *ctx, int stream, uint8_t *out);
+/* number of kernel launches issued by this context so far */
+int64_t p64b_ctx_launches(const p64b_ctx *ctx);
+/* Measured issue peak of the packed 4-byte SAD instruction (VABSDIFF4.U8.ACC) on this device, in
+ * packed ops per second: the denominator of the ME roofline (no datasheet figure exists). */
+int p64b_measure_sad_peak(int device, double *ops_per_s, double *sm_clock_mhz);
+
+/* ---------------------------------------------------------------------------------------------
+ * (2) host bit stream: headers + VLC (marker.c, codec.c, huffman.c, stream.c)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct p64b_bits p64b_bits;
+
+p64b_bits *p64b_bits_create(int image_type);
+void p64b_bits_destroy(p64b_bits *b);
+/* WritePictureHeader, marker.c:103-137 (PSC, TR, PTYPE, PSPARE for NTSC: p64.c:408-423). */
+void p64b_bits_picture_header(p64b_bits *b, int temporal_reference);
+/* WriteGOBHeader, marker.c:182-209; gob is CurrentGOB (0-based); QCIF numbers GOBs 1,3,5 (p64.c:709-711). */
+void p64b_bits_gob_header(p64b_bits *b, int gob, int gquant);
+/* WriteMDU's write half: WriteMBHeader (marker.c:288-354) + EncodeDC/EncodeAC/CBPEncodeAC (codec.c:96-205,
+ * 346-355) for MB `mdu` (0..32) of the current GOB. */
+void p64b_bits_mb(p64b_bits *b, int mdu, const p64b_mb *rec, const int8_t *levels);
+/* mwtell, stream.c:233-238: bits written so far. */
+int64_t p64b_bits_tell(const p64b_bits *b);
+/* mwclose, stream.c:142-152: pad the last byte with 1-bits. Returns the byte count. */
+size_t p64b_bits_finish(p64b_bits *b);
+const uint8_t *p64b_bits_data(const p64b_bits *b, size_t *nbytes);
+/* per-category bit counters of the current frame (p64.c:1299-1332 statistics) */
+void p64b_bits_reset(p64b_bits *b);
+
+/* ---------------------------------------------------------------------------------------------
+ * (3) sequence driver: p64EncodeSequence / p64EncodeFrame / p64EncodeGOB (p64.c:524-786) for a batch
+ * ------------------------------------------------------------------------------------------- */
+typedef struct p64b_enc p64b_enc;
+
+typedef struct p64b_enc_params {
+  int32_t image_type;
+  int32_t n_streams;
+  int32_t device;
+  int32_t start_frame;     /* -a : only enters TemporalReference (p64.c:637)                       */
+  int32_t initial_quant;   /* -q ; 0 = default (8, or 10000000/Rate under -r: p64.c:574-590)       */
+  int32_t rate;            /* -r bits/s; 0 = fixed quantiser                                       */
+  int32_t frame_rate;      /* -f numerator (default 30000)                                         */
+  int32_t frame_rate_div;  /* -f denominator (default 1001)                                        */
+  int32_t frame_skip;      /* -k (default 1)                                                       */
+  int32_t me_mode;         /* P64B_ME_TSS (stock) | P64B_ME_FULL                                   */
+  int32_t search_limit;    /* -i (default 15)                                                      */
+  int32_t force_intra;     /* `-o < test.intra`                                                    */
+  int32_t vlc_threads;     /* host threads for the per-stream VLC (0 = one per core, capped)       */
+  int32_t reserved[3];
+} p64b_enc_params;
+
+void p64b_enc_default_params(p64b_enc_params *p);
+int p64b_enc_create(p64b_enc **out, const p64b_enc_params *p);
+void p64b_enc_destroy(p64b_enc *e);
+/* Encode the next frame of every stream: src [n_streams][frame_bytes] (host). */
+int p64b_enc_encode(p64b_enc *e, const uint8_t *src);
+/* Trailing picture header + padding (p64.c:600-605) for every stream. Call once after the last frame. */
+int p64b_enc_finish(p64b_enc *e);
+/* The stream's bytes so far (complete after p64b_enc_finish). */
+const uint8_t *p64b_enc_data(const p64b_enc *e, int stream, size_t *nbytes);
+p64b_ctx *p64b_enc_ctx(p64b_enc *e);
+/* Statistics the reference prints: buffer overflows (p64.c:779), bits of the first frame (p64.c:668). */
+int64_t p64b_enc_overflows(const p64b_enc *e, int stream);
+int64_t p64b_enc_first_frame_bits(const p64b_enc *e, int stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* P64_B200_H */

@@ -1,0 +1,328 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes access to the C oracle (oracle/p64_oracle.c), to the reference's
+own compiled objects (oracle/_ref/libp64ref.so) and to the reference binaries (oracle/_ref/p64_ref*).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+The product (p64_b200/) never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_DIR = os.path.join(HERE, "_ref")
+ME_TSS, ME_FULL = 0, 1
+IT_NTSC, IT_CIF, IT_QCIF = 0, 1, 2
+DIMS = {IT_NTSC: (352, 240), IT_CIF: (352, 288), IT_QCIF: (176, 144)}
+NGOB = {IT_NTSC: 10, IT_CIF: 12, IT_QCIF: 3}
+FLAG = {IT_NTSC: "-NTSC", IT_CIF: "-CIF", IT_QCIF: "-QCIF"}
+
+_u8p = C.POINTER(C.c_uint8)
+_i32p = C.POINTER(C.c_int32)
+
+
+def build() -> str:
+    """Compile the oracle (and, when /root/reference is present, the reference) -- `make -C oracle`."""
+    subprocess.run(["make", "-s", "-C", HERE], check=True, stdout=subprocess.DEVNULL)
+    return os.path.join(HERE, "libp64oracle.so")
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = os.path.join(HERE, "libp64oracle.so")
+        if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(os.path.join(HERE, "p64_oracle.c")):
+            build()
+        L = C.CDLL(path)
+        L.orc_create.restype = C.c_void_p
+        L.orc_create.argtypes = [C.c_int]
+        L.orc_destroy.argtypes = [C.c_void_p]
+        for n in ("orc_ref_plane", "orc_out_plane"):
+            getattr(L, n).restype = _u8p
+            getattr(L, n).argtypes = [C.c_void_p, C.c_int]
+        L.orc_me_records.restype = _i32p
+        L.orc_me_records.argtypes = [C.c_void_p]
+        L.orc_last_intra.restype = _u8p
+        L.orc_last_intra.argtypes = [C.c_void_p]
+        L.orc_swap.argtypes = [C.c_void_p]
+        L.orc_motion_estimation.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.orc_encode_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                       C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_encode_mb_auto.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_me_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.orc_sad_surface.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.orc_decide.restype = C.c_int
+        L.orc_decide.argtypes = [C.c_int] * 7
+        for n in ("orc_fdct", "orc_idct", "orc_zigzag", "orc_izigzag"):
+            getattr(L, n).argtypes = [C.c_void_p, C.c_void_p]
+        for n in ("orc_quant_intra", "orc_quant_inter", "orc_iquant_intra", "orc_iquant_inter"):
+            getattr(L, n).argtypes = [C.c_void_p, C.c_int]
+        L.orc_bound_dct.argtypes = [C.c_void_p]
+        L.orc_loop_filter.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _blk(a):
+    a = np.ascontiguousarray(a, dtype=np.int32).reshape(64)
+    return a
+
+
+def fdct(x):
+    x = _blk(x); y = np.empty(64, np.int32); lib().orc_fdct(_p(x), _p(y)); return y
+
+
+def idct(x):
+    x = _blk(x); y = np.empty(64, np.int32); lib().orc_idct(_p(x), _p(y)); return y
+
+
+def zigzag(x):
+    x = _blk(x); y = np.empty(64, np.int32); lib().orc_zigzag(_p(x), _p(y)); return y
+
+
+def izigzag(x):
+    x = _blk(x); y = np.empty(64, np.int32); lib().orc_izigzag(_p(x), _p(y)); return y
+
+
+def _inplace(name, x, q=None):
+    x = _blk(x).copy()
+    if q is None:
+        getattr(lib(), name)(_p(x))
+    else:
+        getattr(lib(), name)(_p(x), int(q))
+    return x
+
+
+def quant_intra(x, q): return _inplace("orc_quant_intra", x, q)
+def quant_inter(x, q): return _inplace("orc_quant_inter", x, q)
+def iquant_intra(x, q): return _inplace("orc_iquant_intra", x, q)
+def iquant_inter(x, q): return _inplace("orc_iquant_inter", x, q)
+def bound_dct(x): return _inplace("orc_bound_dct", x)
+
+
+def loop_filter(plane: np.ndarray, x: int, y: int):
+    plane = np.ascontiguousarray(plane, np.uint8)
+    out = np.empty(64, np.int32)
+    lib().orc_loop_filter(C.c_void_p(plane.ctypes.data + y * plane.shape[1] + x), plane.shape[1], _p(out))
+    return out
+
+
+def me_frame(ref: np.ndarray, cur: np.ndarray, mode: int, search_limit: int = 15) -> np.ndarray:
+    """-> int32 [nmb, 7] = MX,MY,MV,OMV,VAR,VAROR,MWOR in raster MB order."""
+    ref = np.ascontiguousarray(ref, np.uint8); cur = np.ascontiguousarray(cur, np.uint8)
+    h, w = ref.shape
+    out = np.empty(((h // 16) * (w // 16), 7), np.int32)
+    lib().orc_me_frame(_p(ref), _p(cur), w, h, mode, search_limit, _p(out))
+    return out
+
+
+def sad_surface(ref, cur, mbx, mby):
+    ref = np.ascontiguousarray(ref, np.uint8); cur = np.ascontiguousarray(cur, np.uint8)
+    h, w = ref.shape
+    out = np.empty((31, 31), np.int32)
+    lib().orc_sad_surface(_p(ref), _p(cur), w, h, mbx * 16, mby * 16, _p(out))
+    return out
+
+
+def decide(first, oval, val, var, varor, last_intra, force_intra=0):
+    return lib().orc_decide(int(first), int(oval), int(val), int(var), int(varor), int(last_intra), int(force_intra))
+
+
+class Encoder:
+    """Stateful oracle encoder for one stream (frame stores + LastIntra), hot path only."""
+
+    def __init__(self, image_type: int):
+        self.image_type = image_type
+        self.w, self.h = DIMS[image_type]
+        self.ngob = NGOB[image_type]
+        self.nmb = self.ngob * 33
+        self._h = lib().orc_create(image_type)
+        self.frame_index = 0
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_destroy(self._h)
+            self._h = None
+
+    def _planes(self, frame):
+        frame = np.ascontiguousarray(frame, np.uint8).reshape(-1)
+        n = self.w * self.h
+        return frame[:n], frame[n:n + n // 4], frame[n + n // 4:]
+
+    def encode_frame(self, frame, quant, me_mode=ME_TSS, search_limit=15, force_intra=False, swap=True):
+        """-> (recs int32 [nmb,5] = MType,CBP,MVDH,MVDV,UseQuant ; levels int32 [nmb,6,64]) GOB-major."""
+        y, u, v = self._planes(frame)
+        recs = np.zeros((self.nmb, 5), np.int32)
+        levels = np.zeros((self.nmb, 6, 64), np.int32)
+        lib().orc_encode_frame(self._h, _p(y), _p(u), _p(v), int(self.frame_index == 0), int(quant), me_mode,
+                               search_limit, int(force_intra), _p(recs), _p(levels))
+        if swap:
+            self.end_frame()
+        return recs, levels
+
+    # --- per-MB interface (rate-control tests drive the reference's MAIN LOOP from the host side) ---
+    def begin_frame(self, frame, me_mode=ME_TSS, search_limit=15):
+        self._cur = self._planes(frame)
+        self._src = (C.c_void_p * 3)(*[p.ctypes.data for p in self._cur])
+        if self.frame_index != 0:
+            lib().orc_motion_estimation(self._h, _p(self._cur[0]), me_mode, search_limit)
+
+    def encode_mb(self, g, m, quant, force_intra=False, overflow=False):
+        rec = np.zeros(5, np.int32)
+        lv = np.zeros((6, 64), np.int32)
+        lib().orc_encode_mb_auto(self._h, self._src, g, m, int(self.frame_index == 0), int(quant),
+                                 int(force_intra), int(overflow), _p(rec), _p(lv))
+        return rec, lv
+
+    def end_frame(self):
+        lib().orc_swap(self._h)
+        self.frame_index += 1
+
+    def me_records(self):
+        n = (self.w // 16) * (self.h // 16)
+        return np.ctypeslib.as_array(lib().orc_me_records(self._h), shape=(n, 7)).copy()
+
+    def last_intra(self):
+        return np.ctypeslib.as_array(lib().orc_last_intra(self._h), shape=(self.nmb,)).copy()
+
+    def recon(self):
+        """Reconstructed frame most recently completed (the current reference), planar uint8."""
+        n = self.w * self.h
+        parts = [np.ctypeslib.as_array(lib().orc_ref_plane(self._h, j), shape=(n if j == 0 else n // 4,))
+                 for j in range(3)]
+        return np.concatenate(parts).copy()
+
+
+# ------------------------------------------------------------------------------------------------
+# the compiled reference
+# ------------------------------------------------------------------------------------------------
+def have_ref() -> bool:
+    return os.path.exists(os.path.join(REF_DIR, "p64_ref")) and os.path.exists(os.path.join(REF_DIR, "libp64ref.so"))
+
+
+def ref_encode(y4m_path: str, out_path: str, image_type: int, n_frames: int, *, full_search=False, q=None,
+               rate=None, search_limit=None, intra_only=False, start=0, extra=()):
+    """Run the reference encoder binary (always -y4m: SURVEY F4). Returns its stdout."""
+    exe = os.path.join(REF_DIR, "p64_ref_fs" if full_search else "p64_ref")
+    prefix = y4m_path[:-4] if y4m_path.endswith(".y4m") else y4m_path
+    cmd = [exe, "-y4m", FLAG[image_type], "-a", str(start), "-b", str(start + n_frames - 1)]
+    if q is not None:
+        cmd += ["-q", str(q)]
+    if rate is not None:
+        cmd += ["-r", str(rate)]
+    if search_limit is not None:
+        cmd += ["-i", str(search_limit)]
+    if intra_only:
+        cmd += ["-o"]
+    cmd += list(extra) + [prefix, "-s", out_path]
+    stdin = open(os.path.join(REF_DIR, "test.intra"), "rb") if intra_only else subprocess.DEVNULL
+    try:
+        r = subprocess.run(cmd, stdin=stdin, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, check=True)
+    finally:
+        if intra_only:
+            stdin.close()
+    return r.stdout.decode(errors="replace")
+
+
+def ref_decode(p64_path: str, out_prefix: str):
+    """Decode with the reference into out_prefix.y4m (p64.c:1022-1126)."""
+    exe = os.path.join(REF_DIR, "p64_ref")
+    subprocess.run([exe, "-d", "-y4m", "-s", p64_path, out_prefix], stdout=subprocess.DEVNULL,
+                   stderr=subprocess.DEVNULL, check=True)
+    return out_prefix + ".y4m"
+
+
+class _MEM(C.Structure):
+    _fields_ = [("len", C.c_int), ("width", C.c_int), ("height", C.c_int), ("data", C.c_void_p)]
+
+
+class _IOBUF(C.Structure):
+    _fields_ = [("hpos", C.c_int), ("vpos", C.c_int), ("hor", C.c_int), ("ver", C.c_int), ("width", C.c_int),
+                ("height", C.c_int), ("flag", C.c_int), ("mem", C.POINTER(_MEM))]
+
+
+class RefLib:
+    """The reference's own me.o/chendct.o/transform.o/io.o, called through ctypes."""
+
+    def __init__(self):
+        self.L = C.CDLL(os.path.join(REF_DIR, "libp64ref.so"))
+        self.L.initmc()
+
+    def _mem(self, plane):
+        plane = np.ascontiguousarray(plane, np.uint8)
+        m = _MEM(plane.size, plane.shape[1], plane.shape[0], plane.ctypes.data)
+        return m, plane
+
+    def motion_estimation(self, ref, cur, full=False, search_limit=15):
+        rm, _r = self._mem(ref); cm, _c = self._mem(cur)
+        h, w = ref.shape
+        C.c_int.in_dll(self.L, "SearchLimit").value = search_limit
+        names = ["MeX", "MeY", "MeVal", "MeOVal", "MeVAR", "MeVAROR", "MeMWOR"]
+        n = (h // 16) * (w // 16)
+        out = np.zeros((n, 7), np.int32)
+        if not full:
+            self.L.MotionEstimation(C.byref(rm), C.byref(cm))
+            for k, nm in enumerate(names):
+                out[:, k] = np.ctypeslib.as_array((C.c_int * 1024).in_dll(self.L, nm))[:n]
+        else:
+            i = 0
+            for y in range(0, h, 16):
+                for x in range(0, w, 16):
+                    self.L.FastBME(x, y, C.byref(rm), x, y, C.byref(cm))
+                    out[i, 0] = C.c_int.in_dll(self.L, "MX").value
+                    out[i, 1] = C.c_int.in_dll(self.L, "MY").value
+                    out[i, 2] = C.c_int.in_dll(self.L, "MV").value
+                    out[i, 3] = C.c_int.in_dll(self.L, "OMV").value
+                    # VAR/VAROR/MWOR are file-static in me.c:44-46; recovered through the stock path below
+                    i += 1
+        return out
+
+    def _call2(self, name, x):
+        x = np.ascontiguousarray(x, np.int32).reshape(64).copy(); y = np.zeros(64, np.int32)
+        getattr(self.L, name)(_p(x), _p(y)); return y
+
+    def chen_dct(self, x): return self._call2("ChenDct", x)
+    def chen_idct(self, x): return self._call2("ChenIDct", x)
+    def zigzag(self, x): return self._call2("ZigzagMatrix", x)
+    def izigzag(self, x): return self._call2("IZigzagMatrix", x)
+
+    def _call1(self, name, x, *a):
+        x = np.ascontiguousarray(x, np.int32).reshape(64).copy()
+        getattr(self.L, name)(_p(x), *a); return x
+
+    def quant_intra(self, x, q): return self._call1("FlatBoundQuantizeMatrix", self._call1("CCITTFlatQuantize", x, 8, q))
+    def quant_inter(self, x, q): return self._call1("BoundQuantizeMatrix", self._call1("CCITTQuantize", x, q, q))
+    def iquant_intra(self, x, q): return self._call1("ICCITTFlatQuantize", x, 8, q)
+    def iquant_inter(self, x, q): return self._call1("ICCITTQuantize", x, q, q)
+    def bound_dct(self, x): return self._call1("BoundDctMatrix", x)
+
+    def loop_filter(self, plane, x, y):
+        m, plane = self._mem(plane)
+        iob = _IOBUF(0, 0, 1, 1, plane.shape[1], plane.shape[0], 0, C.pointer(m))
+        C.c_void_p.in_dll(self.L, "Iob").value = C.addressof(iob)
+        out = np.zeros(64, np.int32)
+        self.L.LoadFilterMatrix(C.c_void_p(plane.ctypes.data + y * plane.shape[1] + x), _p(out))
+        return out
+
+    def sub_compensate(self, plane, hpos, vpos, mvx, mvy, block, *, half=False, filt=False):
+        """Sub[F]Compensate / HalfSub[F]Compensate (io.c:200-496) on block (hpos,vpos) of `plane`."""
+        m, plane = self._mem(plane)
+        iob = _IOBUF(hpos, vpos, 1, 1, plane.shape[1], plane.shape[0], 0, C.pointer(m))
+        C.c_void_p.in_dll(self.L, "Iob").value = C.addressof(iob)
+        C.c_int.in_dll(self.L, "MVDH").value = mvx
+        C.c_int.in_dll(self.L, "MVDV").value = mvy
+        name = ("Half" if half else "") + "Sub" + ("F" if filt else "") + "Compensate"
+        x = np.ascontiguousarray(block, np.int32).reshape(64).copy()
+        getattr(self.L, name)(_p(x))
+        return x
