@@ -1,0 +1,104 @@
+"""ctypes binding of the C ABI (include/p64_b200.h).  Loading fails loudly: there is no fallback path."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libp64b200.so")
+
+
+class MB(C.Structure):
+    """p64b_mb"""
+    _fields_ = [("mtype", C.c_uint8), ("cbp", C.c_uint8), ("mvx", C.c_int8), ("mvy", C.c_int8),
+                ("quant", C.c_uint8), ("nzmask", C.c_uint8), ("reserved", C.c_uint16)]
+
+
+class ME(C.Structure):
+    """p64b_me"""
+    _fields_ = [(n, C.c_int32) for n in ("mx", "my", "val", "oval", "var", "varor", "mwor", "pad")]
+
+
+class Step(C.Structure):
+    """p64b_step"""
+    _fields_ = [("first_frame", C.c_int32), ("me_mode", C.c_int32), ("search_limit", C.c_int32),
+                ("force_intra", C.c_int32), ("gquant", C.c_int32), ("reserved", C.c_int32 * 3)]
+
+
+class EncParams(C.Structure):
+    """p64b_enc_params"""
+    _fields_ = [(n, C.c_int32) for n in ("image_type", "n_streams", "device", "start_frame", "initial_quant", "rate",
+                                         "frame_rate", "frame_rate_div", "frame_skip", "me_mode", "search_limit",
+                                         "force_intra", "vlc_threads")] + [("reserved", C.c_int32 * 3)]
+
+
+# name -> (restype, argtypes); every symbol include/p64_b200.h declares
+_vp, _i, _sz = C.c_void_p, C.c_int, C.c_size_t
+SIGNATURES = {
+    "p64b_last_error": (C.c_char_p, []),
+    "p64b_version": (_i, []),
+    "p64b_width": (_i, [_i]), "p64b_height": (_i, [_i]), "p64b_frame_bytes": (_i, [_i]),
+    "p64b_num_gob": (_i, [_i]), "p64b_num_mb": (_i, [_i]),
+    "p64b_ctx_create": (_i, [C.POINTER(_vp), _i, _i, _i]),
+    "p64b_ctx_destroy": (None, [_vp]),
+    "p64b_ctx_streams": (_i, [_vp]),
+    "p64b_ctx_set_cuda_stream": (_i, [_vp, _vp]),
+    "p64b_host_alloc": (_vp, [_sz]),
+    "p64b_host_free": (None, [_vp]),
+    "p64b_ctx_encode_frames": (_i, [_vp, C.POINTER(Step), _vp, _vp, _vp]),
+    "p64b_ctx_encode_frames_dev": (_i, [_vp, C.POINTER(Step), _vp, _vp, _vp]),
+    "p64b_ctx_frame_begin": (_i, [_vp, C.POINTER(Step), _vp]),
+    "p64b_ctx_encode_gob": (_i, [_vp, C.POINTER(Step), _i, _vp, _vp, _vp]),
+    "p64b_ctx_frame_end": (_i, [_vp, _vp]),
+    "p64b_ctx_motion_estimation_dev": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "p64b_ctx_sad_surface_dev": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
+    "p64b_ctx_me_records": (_i, [_vp, _i, _vp]),
+    "p64b_ctx_download_recon": (_i, [_vp, _i, _vp]),
+    "p64b_ctx_last_intra": (_i, [_vp, _i, _vp]),
+    "p64b_ctx_launches": (C.c_int64, [_vp]),
+    "p64b_measure_sad_peak": (_i, [_i, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "p64b_bits_create": (_vp, [_i]),
+    "p64b_bits_destroy": (None, [_vp]),
+    "p64b_bits_picture_header": (None, [_vp, _i]),
+    "p64b_bits_gob_header": (None, [_vp, _i, _i]),
+    "p64b_bits_mb": (None, [_vp, _i, _vp, _vp]),
+    "p64b_bits_tell": (C.c_int64, [_vp]),
+    "p64b_bits_finish": (_sz, [_vp]),
+    "p64b_bits_data": (C.POINTER(C.c_uint8), [_vp, C.POINTER(_sz)]),
+    "p64b_bits_reset": (None, [_vp]),
+    "p64b_enc_default_params": (None, [C.POINTER(EncParams)]),
+    "p64b_enc_create": (_i, [C.POINTER(_vp), C.POINTER(EncParams)]),
+    "p64b_enc_destroy": (None, [_vp]),
+    "p64b_enc_encode": (_i, [_vp, _vp]),
+    "p64b_enc_finish": (_i, [_vp]),
+    "p64b_enc_data": (C.POINTER(C.c_uint8), [_vp, _i, C.POINTER(_sz)]),
+    "p64b_enc_ctx": (_vp, [_vp]),
+    "p64b_enc_overflows": (C.c_int64, [_vp, _i]),
+    "p64b_enc_first_frame_bits": (C.c_int64, [_vp, _i]),
+}
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """The loaded C-ABI library. Raises if it has not been built (`python -m p64_b200.build`)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -m p64_b200.build` "
+                               "(p64_b200 has no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)          # AttributeError if the library does not export it
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+class P64Error(RuntimeError):
+    pass
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise P64Error(f"p64_b200 error {rc}: {lib().p64b_last_error().decode(errors='replace')}")

@@ -1,0 +1,335 @@
+// Device context and the p64b_ctx_* C ABI (include/p64_b200.h): frame stores resident in HBM for a batch
+// of independent streams, kernel launches, host<->device staging.  No CPU fallback: every entry point
+// fails with P64B_ECUDA when no CUDA device is usable.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "kernels.cuh"
+
+namespace p64b {
+
+static thread_local std::string g_err;
+void set_error(const std::string& s) { g_err = s; }
+
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      set_error(std::string(#call) + ": " + cudaGetErrorString(e_));                               \
+      return P64B_ECUDA;                                                                           \
+    }                                                                                              \
+  } while (0)
+
+static bool geom_for(int image_type, Geom* g) {
+  switch (image_type) {                      // SetCCITT, p64.c:1476-1514
+    case P64B_IT_NTSC: g->W = 352; g->H = 240; g->ngob = 10; g->qcif = 0; break;
+    case P64B_IT_CIF:  g->W = 352; g->H = 288; g->ngob = 12; g->qcif = 0; break;
+    case P64B_IT_QCIF: g->W = 176; g->H = 144; g->ngob = 3;  g->qcif = 1; break;
+    default: return false;
+  }
+  g->mbw = g->W / 16; g->mbh = g->H / 16; g->nmb = g->ngob * 33; g->frame_bytes = g->W * g->H * 3 / 2;
+  return true;
+}
+
+}  // namespace p64b
+
+using namespace p64b;
+
+struct p64b_ctx {
+  int device = 0, image_type = 0, S = 0;
+  Geom g{};
+  cudaStream_t own = nullptr, stream = nullptr;
+  uint8_t* d_src = nullptr;       // [S][frame_bytes]
+  uint8_t* d_fs[2] = {nullptr, nullptr};   // frame stores; d_fs[cur] = CFS (reference), d_fs[cur^1] = OFS
+  uint8_t* d_li[2] = {nullptr, nullptr};   // LastIntra, same double buffering
+  int cur = 0;
+  p64b_me* d_me = nullptr;        // [S][nmb]
+  p64b_mb* d_mbs = nullptr;       // [S][nmb]
+  int8_t* d_levels = nullptr;     // [S][nmb][384]
+  uint8_t* d_quant = nullptr;     // [S]
+  uint8_t* d_ovf = nullptr;       // [S][nmb]
+  const uint8_t* frame_src = nullptr;   // source of the frame in flight (frame_begin .. frame_end)
+  int64_t launches = 0;
+};
+
+static int use_device(const p64b_ctx* c) {
+  CU(cudaSetDevice(c->device));
+  return 0;
+}
+
+static int launch_me(p64b_ctx* c, const uint8_t* ref, const uint8_t* cur, size_t stride, int n_pairs, int me_mode,
+                     int search_limit, p64b_me* out, uint32_t* surface = nullptr) {
+  static bool attr_done = false;
+  const size_t smem = ME_SMEM_WORDS * sizeof(uint32_t);
+  if (!attr_done) {
+    CU(cudaFuncSetAttribute(me_surface_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  const int grid = n_pairs * c->g.mbw * c->g.mbh;
+  me_surface_kernel<<<grid, ME_THREADS, smem, c->stream>>>(ref, cur, stride, c->g, me_mode, search_limit, out, surface);
+  c->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+static int launch_mb(p64b_ctx* c, const p64b_step* st, const uint8_t* src, int gob_first, int gob_count,
+                     const uint8_t* d_quant, p64b_mb* mbs, int8_t* levels) {
+  MbArgs a;
+  a.g = c->g; a.src = src; a.ref = c->d_fs[c->cur]; a.out = c->d_fs[c->cur ^ 1];
+  a.me = c->d_me; a.li_prev = c->d_li[c->cur]; a.li_new = c->d_li[c->cur ^ 1];
+  a.quant = d_quant; a.mbs = mbs; a.levels = levels; a.n_streams = c->S;
+  a.gob_first = gob_first; a.gob_count = gob_count; a.out_mb_per_stream = gob_count * 33;
+  a.first_frame = st->first_frame; a.force_intra = st->force_intra; a.gquant = st->gquant;
+  const int n = c->S * gob_count * 33;
+  mb_encode_kernel<<<(n + MB_PER_CTA - 1) / MB_PER_CTA, MBK_THREADS, 0, c->stream>>>(a);
+  c->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+static int check_step(const p64b_step* st) {
+  if (!st) { set_error("step is NULL"); return P64B_EINVAL; }
+  if (st->me_mode != P64B_ME_TSS && st->me_mode != P64B_ME_FULL) { set_error("bad me_mode"); return P64B_EINVAL; }
+  if (st->search_limit < 1 || st->search_limit > 31) { set_error("search_limit out of [1,31]"); return P64B_EINVAL; }
+  return 0;
+}
+static int check_quant(int q) {
+  if (q < 1 || q > 31) { set_error("quantiser out of [1,31]"); return P64B_EINVAL; }
+  return 0;
+}
+
+extern "C" {
+
+const char* p64b_last_error(void) { return g_err.c_str(); }
+int p64b_version(void) { return P64B_VERSION; }
+
+int p64b_width(int t) { Geom g; return geom_for(t, &g) ? g.W : P64B_EINVAL; }
+int p64b_height(int t) { Geom g; return geom_for(t, &g) ? g.H : P64B_EINVAL; }
+int p64b_frame_bytes(int t) { Geom g; return geom_for(t, &g) ? g.frame_bytes : P64B_EINVAL; }
+int p64b_num_gob(int t) { Geom g; return geom_for(t, &g) ? g.ngob : P64B_EINVAL; }
+int p64b_num_mb(int t) { Geom g; return geom_for(t, &g) ? g.nmb : P64B_EINVAL; }
+
+int p64b_ctx_create(p64b_ctx** out, int device, int image_type, int n_streams) {
+  if (!out || n_streams < 1) { set_error("bad arguments"); return P64B_EINVAL; }
+  Geom g;
+  if (!geom_for(image_type, &g)) { set_error("unknown image type"); return P64B_EINVAL; }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    set_error(std::string("no CUDA device: ") + cudaGetErrorString(e) + " (p64_b200 has no CPU fallback)");
+    return P64B_ECUDA;
+  }
+  if (device < 0 || device >= ndev) { set_error("device index out of range"); return P64B_EINVAL; }
+  p64b_ctx* c = new p64b_ctx();
+  c->device = device; c->image_type = image_type; c->S = n_streams; c->g = g;
+  auto fail = [&](int rc) { p64b_ctx_destroy(c); return rc; };
+  if (use_device(c)) return fail(P64B_ECUDA);
+  const size_t fb = (size_t)n_streams * g.frame_bytes, slack = 64, nm = (size_t)n_streams * g.nmb;
+#define ALLOC(p, bytes)                                                                                  \
+  if (cudaMalloc((void**)&(p), (bytes)) != cudaSuccess) { set_error("cudaMalloc failed"); return fail(P64B_ENOMEM); } \
+  if (cudaMemset((p), 0, (bytes)) != cudaSuccess) { set_error("cudaMemset failed"); return fail(P64B_ECUDA); }
+  ALLOC(c->d_src, fb + slack);
+  ALLOC(c->d_fs[0], fb + slack);           // ClearFS: both stores start zero-filled (p64.c:532-535)
+  ALLOC(c->d_fs[1], fb + slack);
+  ALLOC(c->d_li[0], nm);                   // LastIntra zeroed (p64.c:1522-1528)
+  ALLOC(c->d_li[1], nm);
+  ALLOC(c->d_me, nm * sizeof(p64b_me));    // Me* arrays are zero on the first frame (me.c:49-59)
+  ALLOC(c->d_mbs, nm * sizeof(p64b_mb));
+  ALLOC(c->d_levels, nm * P64B_LEVELS_PER_MB);
+  ALLOC(c->d_quant, (size_t)n_streams);
+  ALLOC(c->d_ovf, nm);
+#undef ALLOC
+  if (cudaStreamCreateWithFlags(&c->own, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream create failed"); return fail(P64B_ECUDA); }
+  c->stream = c->own;
+  if (cudaDeviceSynchronize() != cudaSuccess) { set_error("sync failed"); return fail(P64B_ECUDA); }
+  *out = c;
+  return 0;
+}
+
+void p64b_ctx_destroy(p64b_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  cudaFree(c->d_src); cudaFree(c->d_fs[0]); cudaFree(c->d_fs[1]); cudaFree(c->d_li[0]); cudaFree(c->d_li[1]);
+  cudaFree(c->d_me); cudaFree(c->d_mbs); cudaFree(c->d_levels); cudaFree(c->d_quant); cudaFree(c->d_ovf);
+  if (c->own) cudaStreamDestroy(c->own);
+  delete c;
+}
+
+int p64b_ctx_streams(const p64b_ctx* c) { return c ? c->S : P64B_EINVAL; }
+
+int p64b_ctx_set_cuda_stream(p64b_ctx* c, void* s) {
+  if (!c) return P64B_EINVAL;
+  c->stream = s ? (cudaStream_t)s : c->own;
+  return 0;
+}
+
+void* p64b_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { set_error("cudaHostAlloc failed"); return nullptr; }
+  return p;
+}
+void p64b_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+static void swap_stores(p64b_ctx* c) { c->cur ^= 1; }    // SwapFS(CFS,OFS), p64.c:661
+
+int p64b_ctx_encode_frames_dev(p64b_ctx* c, const p64b_step* st, const uint8_t* src_dev, p64b_mb* mbs_dev,
+                               int8_t* levels_dev) {
+  if (!c || !src_dev || !mbs_dev || !levels_dev) { set_error("NULL argument"); return P64B_EINVAL; }
+  int rc;
+  if ((rc = check_step(st)) || (rc = check_quant(st->gquant)) || (rc = use_device(c))) return rc;
+  if (!st->first_frame) {
+    if ((rc = launch_me(c, c->d_fs[c->cur], src_dev, (size_t)c->g.frame_bytes, c->S, st->me_mode, st->search_limit, c->d_me))) return rc;
+  } else {
+    CU(cudaMemsetAsync(c->d_me, 0, (size_t)c->S * c->g.nmb * sizeof(p64b_me), c->stream));
+  }
+  if ((rc = launch_mb(c, st, src_dev, 0, c->g.ngob, nullptr, mbs_dev, levels_dev))) return rc;
+  swap_stores(c);
+  return 0;
+}
+
+int p64b_ctx_encode_frames(p64b_ctx* c, const p64b_step* st, const uint8_t* src, p64b_mb* mbs, int8_t* levels) {
+  if (!c || !src || !mbs || !levels) { set_error("NULL argument"); return P64B_EINVAL; }
+  int rc;
+  if ((rc = use_device(c))) return rc;
+  const size_t fb = (size_t)c->S * c->g.frame_bytes, nm = (size_t)c->S * c->g.nmb;
+  CU(cudaMemcpyAsync(c->d_src, src, fb, cudaMemcpyHostToDevice, c->stream));
+  if ((rc = p64b_ctx_encode_frames_dev(c, st, c->d_src, c->d_mbs, c->d_levels))) return rc;
+  CU(cudaMemcpyAsync(mbs, c->d_mbs, nm * sizeof(p64b_mb), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(levels, c->d_levels, nm * P64B_LEVELS_PER_MB, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int p64b_ctx_frame_begin(p64b_ctx* c, const p64b_step* st, const uint8_t* src) {
+  if (!c || !src) { set_error("NULL argument"); return P64B_EINVAL; }
+  int rc;
+  if ((rc = check_step(st)) || (rc = use_device(c))) return rc;
+  CU(cudaMemcpyAsync(c->d_src, src, (size_t)c->S * c->g.frame_bytes, cudaMemcpyHostToDevice, c->stream));
+  if (!st->first_frame) {
+    if ((rc = launch_me(c, c->d_fs[c->cur], c->d_src, (size_t)c->g.frame_bytes, c->S, st->me_mode, st->search_limit, c->d_me))) return rc;
+  } else {
+    CU(cudaMemsetAsync(c->d_me, 0, (size_t)c->S * c->g.nmb * sizeof(p64b_me), c->stream));
+  }
+  c->frame_src = c->d_src;
+  return 0;
+}
+
+int p64b_ctx_encode_gob(p64b_ctx* c, const p64b_step* st, int gob, const uint8_t* quant, p64b_mb* mbs, int8_t* levels) {
+  if (!c || !quant || !mbs || !levels) { set_error("NULL argument"); return P64B_EINVAL; }
+  if (!c->frame_src) { set_error("p64b_ctx_encode_gob outside frame_begin/frame_end"); return P64B_EINVAL; }
+  if (gob < 0 || gob >= c->g.ngob) { set_error("gob out of range"); return P64B_EINVAL; }
+  int rc;
+  if ((rc = check_step(st)) || (rc = use_device(c))) return rc;
+  for (int s = 0; s < c->S; s++) if ((rc = check_quant(quant[s]))) return rc;
+  CU(cudaMemcpyAsync(c->d_quant, quant, (size_t)c->S, cudaMemcpyHostToDevice, c->stream));
+  // outputs of one GOB are packed [S][33] at the head of the context's output buffers
+  if ((rc = launch_mb(c, st, c->frame_src, gob, 1, c->d_quant, c->d_mbs, c->d_levels))) return rc;
+  const size_t nm = (size_t)c->S * 33;
+  CU(cudaMemcpyAsync(mbs, c->d_mbs, nm * sizeof(p64b_mb), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(levels, c->d_levels, nm * P64B_LEVELS_PER_MB, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int p64b_ctx_frame_end(p64b_ctx* c, const uint8_t* overflow) {
+  if (!c) return P64B_EINVAL;
+  if (!c->frame_src) { set_error("p64b_ctx_frame_end without frame_begin"); return P64B_EINVAL; }
+  int rc;
+  if ((rc = use_device(c))) return rc;
+  if (overflow) {
+    const size_t nm = (size_t)c->S * c->g.nmb;
+    bool any = false;
+    for (size_t i = 0; i < nm && !any; i++) any = overflow[i] != 0;
+    if (any) {
+      CU(cudaMemcpyAsync(c->d_ovf, overflow, nm, cudaMemcpyHostToDevice, c->stream));
+      const int warps = (int)nm, threads = 256;
+      overflow_patch_kernel<<<(warps * 32 + threads - 1) / threads, threads, 0, c->stream>>>(
+          c->g, c->d_ovf, c->d_fs[c->cur], c->d_fs[c->cur ^ 1], c->d_li[c->cur], c->d_li[c->cur ^ 1], c->S);
+      c->launches++;
+      CU(cudaGetLastError());
+      CU(cudaStreamSynchronize(c->stream));   // `overflow` is caller memory
+    }
+  }
+  swap_stores(c);
+  c->frame_src = nullptr;
+  return 0;
+}
+
+int p64b_ctx_motion_estimation_dev(p64b_ctx* c, const uint8_t* ref_dev, const uint8_t* cur_dev, int n_pairs,
+                                   int me_mode, int search_limit, p64b_me* out_dev) {
+  if (!c || !ref_dev || !cur_dev || !out_dev || n_pairs < 1) { set_error("bad arguments"); return P64B_EINVAL; }
+  p64b_step st{}; st.me_mode = me_mode; st.search_limit = search_limit;
+  int rc;
+  if ((rc = check_step(&st)) || (rc = use_device(c))) return rc;
+  return launch_me(c, ref_dev, cur_dev, (size_t)c->g.W * c->g.H, n_pairs, me_mode, search_limit, out_dev);
+}
+
+int p64b_ctx_sad_surface_dev(p64b_ctx* c, const uint8_t* ref_dev, const uint8_t* cur_dev, int n_pairs, p64b_me* out_dev,
+                             uint32_t* surface_dev) {
+  if (!c || !ref_dev || !cur_dev || !out_dev || !surface_dev || n_pairs < 1) { set_error("bad arguments"); return P64B_EINVAL; }
+  int rc;
+  if ((rc = use_device(c))) return rc;
+  return launch_me(c, ref_dev, cur_dev, (size_t)c->g.W * c->g.H, n_pairs, P64B_ME_FULL, 31, out_dev, surface_dev);
+}
+
+int p64b_ctx_me_records(p64b_ctx* c, int stream, p64b_me* out) {
+  if (!c || !out || stream < 0 || stream >= c->S) { set_error("bad arguments"); return P64B_EINVAL; }
+  int rc;
+  if ((rc = use_device(c))) return rc;
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaMemcpy(out, c->d_me + (size_t)stream * c->g.nmb, (size_t)c->g.mbw * c->g.mbh * sizeof(p64b_me), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int p64b_ctx_download_recon(p64b_ctx* c, int stream, uint8_t* yuv) {
+  if (!c || !yuv || stream < 0 || stream >= c->S) { set_error("bad arguments"); return P64B_EINVAL; }
+  int rc;
+  if ((rc = use_device(c))) return rc;
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaMemcpy(yuv, c->d_fs[c->cur] + (size_t)stream * c->g.frame_bytes, c->g.frame_bytes, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int p64b_ctx_last_intra(p64b_ctx* c, int stream, uint8_t* out) {
+  if (!c || !out || stream < 0 || stream >= c->S) { set_error("bad arguments"); return P64B_EINVAL; }
+  int rc;
+  if ((rc = use_device(c))) return rc;
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaMemcpy(out, c->d_li[c->cur] + (size_t)stream * c->g.nmb, c->g.nmb, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int64_t p64b_ctx_launches(const p64b_ctx* c) { return c ? c->launches : 0; }
+
+int p64b_measure_sad_peak(int device, double* ops_per_s, double* sm_clock_mhz) {
+  if (!ops_per_s) return P64B_EINVAL;
+  CU(cudaSetDevice(device));
+  int sms = 0, khz = 0;
+  CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  CU(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device));
+  uint32_t* d = nullptr;
+  const int blocks = sms * 8, iters = 4000;
+  CU(cudaMalloc((void**)&d, sizeof(uint32_t) * blocks * 256));
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  sad_peak_kernel<<<blocks, 256>>>(d, 200, 1u);
+  CU(cudaDeviceSynchronize());
+  float best = 1e30f;
+  for (int r = 0; r < 5; r++) {
+    CU(cudaEventRecord(e0));
+    sad_peak_kernel<<<blocks, 256>>>(d, iters, (uint32_t)(r + 2));
+    CU(cudaEventRecord(e1));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0; CU(cudaEventElapsedTime(&ms, e0, e1));
+    if (ms < best) best = ms;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+  *ops_per_s = (double)blocks * 256.0 * iters * 64.0 / (best * 1e-3);
+  if (sm_clock_mhz) *sm_clock_mhz = khz / 1000.0;
+  return 0;
+}
+
+}  // extern "C"

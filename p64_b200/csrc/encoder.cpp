@@ -1,0 +1,223 @@
+// Sequence driver (p64b_enc_*): the reference's p64EncodeSequence / p64EncodeFrame / p64EncodeGOB host
+// control (p64.c:524-786) for a batch of independent streams.  Everything data-parallel is delegated to
+// the device context (p64b_ctx_*); what stays here is exactly what the north star keeps sequential:
+// headers + VLC (bits.cpp) and rate control (ExecuteQuantization p64.c:458-481, BufferContents p64.c:233-237,
+// the per-MB overflow test p64.c:776-783).
+#include <algorithm>
+#include <atomic>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/p64_b200.h"
+
+namespace p64b { void set_error(const std::string& s); }
+
+namespace {
+
+struct StreamState {
+  p64b_bits* bits = nullptr;
+  int gquant = 8;            // GQuant (p64.c:89)
+  int64_t buffer_offset = 0; // BufferOffset (p64.c:140)
+  int64_t total_bits = 0, first_frame_bits = 0, overflows = 0;
+};
+
+}  // namespace
+
+struct p64b_enc {
+  p64b_enc_params p{};
+  p64b_ctx* ctx = nullptr;
+  int S = 0, ngob = 0, nmb = 0, frame_bytes = 0;
+  int current_frame = 0;         // CurrentFrame (p64.c:121)
+  int frames_done = 0;
+  int qdfact = 1, qoffs = 1;     // QDFact, QOffs (p64.c:141-142)
+  bool finished = false;
+  std::vector<StreamState> st;
+  p64b_mb* h_mbs = nullptr;      // pinned [S][nmb]
+  int8_t* h_levels = nullptr;    // pinned [S][nmb][384]
+  uint8_t* h_src = nullptr;      // pinned staging [S][frame_bytes]
+  std::vector<uint8_t> quant, overflow;
+  int threads = 1;
+};
+
+namespace {
+
+template <class F>
+void parallel_streams(p64b_enc* e, F f) {
+  const int T = std::min(e->threads, e->S);
+  if (T <= 1) { for (int s = 0; s < e->S; s++) f(s); return; }
+  std::atomic<int> next{0};
+  std::vector<std::thread> th;
+  th.reserve(T);
+  for (int t = 0; t < T; t++)
+    th.emplace_back([&] { for (int s; (s = next.fetch_add(1)) < e->S;) f(s); });
+  for (auto& x : th) x.join();
+}
+
+// BufferContents(), p64.c:233-237, with CurrentGOB=g, CurrentMDU=m. int arithmetic as in the reference.
+inline int64_t buffer_contents(const p64b_enc* e, const StreamState& s, int g, int m) {
+  const int denom = e->ngob * 33 * e->p.frame_rate / e->p.frame_rate_div;
+  const int num = (int)((int64_t)(g * 33 + m) * e->p.rate * e->p.frame_skip);
+  return p64b_bits_tell(s.bits) + s.buffer_offset - (denom ? num / denom : 0);
+}
+inline int buffer_size(const p64b_enc* e) { return e->p.rate / 4; }   // BufferSize(), p64.c:237
+
+// ExecuteQuantization(), p64.c:458-481 (no interpreter): GQuant from the buffer fullness.
+inline int execute_quantization(const p64b_enc* e, const StreamState& s, int g, int m) {
+  int cur = (int)buffer_contents(e, s, g, m);
+  int q = cur / e->qdfact + e->qoffs;
+  return std::min(std::max(q, 1), 31);
+}
+
+}  // namespace
+
+extern "C" {
+
+void p64b_enc_default_params(p64b_enc_params* p) {
+  memset(p, 0, sizeof(*p));
+  p->image_type = P64B_IT_NTSC;       // the reference's default (p64.c:114)
+  p->n_streams = 1;
+  p->frame_rate = 30000; p->frame_rate_div = 1001;   // p64.c:128-129
+  p->frame_skip = 1;
+  p->me_mode = P64B_ME_TSS;           // the stock search (me.c:352)
+  p->search_limit = 15;               // me.c:62
+}
+
+int p64b_enc_create(p64b_enc** out, const p64b_enc_params* p) {
+  if (!out || !p) { p64b::set_error("NULL argument"); return P64B_EINVAL; }
+  if (p->n_streams < 1 || p->frame_rate < 1 || p->frame_rate_div < 1 || p->frame_skip < 1 ||
+      p->initial_quant < 0 || p->initial_quant > 31 || p->rate < 0 || (p->rate > 0 && p->rate < 320)) {
+    p64b::set_error("bad encoder parameters"); return P64B_EINVAL;
+  }
+  p64b_enc* e = new p64b_enc();
+  e->p = *p;
+  int rc = p64b_ctx_create(&e->ctx, p->device, p->image_type, p->n_streams);
+  if (rc) { delete e; return rc; }
+  e->S = p->n_streams; e->ngob = p64b_num_gob(p->image_type); e->nmb = p64b_num_mb(p->image_type);
+  e->frame_bytes = p64b_frame_bytes(p->image_type);
+  e->current_frame = p->start_frame;
+  int iq = p->initial_quant;                       // p64.c:574-590
+  if (p->rate) {
+    e->qdfact = p->rate / 320; e->qoffs = 1;
+    if (!iq) iq = std::min(std::max(10000000 / p->rate, 1), 31);
+  }
+  if (!iq) iq = 8;                                 // DEFAULT_QUANTIZATION
+  e->st.resize(e->S);
+  for (auto& s : e->st) { s.bits = p64b_bits_create(p->image_type); s.gquant = iq; }
+  e->h_mbs = (p64b_mb*)p64b_host_alloc((size_t)e->S * e->nmb * sizeof(p64b_mb));
+  e->h_levels = (int8_t*)p64b_host_alloc((size_t)e->S * e->nmb * P64B_LEVELS_PER_MB);
+  e->h_src = (uint8_t*)p64b_host_alloc((size_t)e->S * e->frame_bytes);
+  if (!e->h_mbs || !e->h_levels || !e->h_src) { p64b_enc_destroy(e); return P64B_ENOMEM; }
+  e->quant.assign(e->S, (uint8_t)iq);
+  e->overflow.assign((size_t)e->S * e->nmb, 0);
+  int hw = (int)std::thread::hardware_concurrency();
+  e->threads = p->vlc_threads > 0 ? p->vlc_threads : std::max(1, std::min(hw, 64));
+  *out = e;
+  return 0;
+}
+
+void p64b_enc_destroy(p64b_enc* e) {
+  if (!e) return;
+  for (auto& s : e->st) p64b_bits_destroy(s.bits);
+  p64b_host_free(e->h_mbs); p64b_host_free(e->h_levels); p64b_host_free(e->h_src);
+  p64b_ctx_destroy(e->ctx);
+  delete e;
+}
+
+int p64b_enc_encode(p64b_enc* e, const uint8_t* src) {
+  if (!e || !src) { p64b::set_error("NULL argument"); return P64B_EINVAL; }
+  if (e->finished) { p64b::set_error("encoder already finished"); return P64B_EINVAL; }
+  const bool first = e->frames_done == 0;          // CurrentFrame == StartFrame
+  p64b_step step{};
+  step.first_frame = first; step.me_mode = e->p.me_mode; step.search_limit = e->p.search_limit;
+  step.force_intra = e->p.force_intra;
+  const int tr = e->current_frame % 32;            // p64.c:637
+  memcpy(e->h_src, src, (size_t)e->S * e->frame_bytes);
+  int rc;
+  if (!e->p.rate) {
+    // fixed quantiser: one device step for the whole frame of every stream, then the VLC per stream
+    step.gquant = e->st[0].gquant;
+    if ((rc = p64b_ctx_encode_frames(e->ctx, &step, e->h_src, e->h_mbs, e->h_levels))) return rc;
+    parallel_streams(e, [&](int s) {
+      StreamState& ss = e->st[s];
+      p64b_bits_picture_header(ss.bits, tr);
+      const p64b_mb* mb = e->h_mbs + (size_t)s * e->nmb;
+      const int8_t* lv = e->h_levels + (size_t)s * e->nmb * P64B_LEVELS_PER_MB;
+      for (int g = 0; g < e->ngob; g++) {
+        p64b_bits_gob_header(ss.bits, g, ss.gquant);
+        for (int m = 0; m < 33; m++, mb++, lv += P64B_LEVELS_PER_MB) p64b_bits_mb(ss.bits, m, mb, lv);
+      }
+    });
+  } else {
+    // rate control: GQUANT of GOB g depends on the bits written for GOBs < g, so quantise..reconstruct runs
+    // per GOB (batched over streams); the overflow override is decided per MB during the VLC and patched
+    // into the reconstruction at frame end.
+    step.gquant = e->st[0].gquant;
+    if ((rc = p64b_ctx_frame_begin(e->ctx, &step, e->h_src))) return rc;
+    std::fill(e->overflow.begin(), e->overflow.end(), 0);
+    parallel_streams(e, [&](int s) { p64b_bits_picture_header(e->st[s].bits, tr); });
+    for (int g = 0; g < e->ngob; g++) {
+      for (int s = 0; s < e->S; s++) {
+        StreamState& ss = e->st[s];
+        if (!first) ss.gquant = execute_quantization(e, ss, g, 0);     // p64.c:697-702
+        e->quant[s] = (uint8_t)ss.gquant;
+      }
+      if ((rc = p64b_ctx_encode_gob(e->ctx, &step, g, e->quant.data(), e->h_mbs, e->h_levels))) return rc;
+      parallel_streams(e, [&](int s) {
+        StreamState& ss = e->st[s];
+        p64b_bits_gob_header(ss.bits, g, ss.gquant);
+        const p64b_mb* mb = e->h_mbs + (size_t)s * 33;
+        const int8_t* lv = e->h_levels + (size_t)s * 33 * P64B_LEVELS_PER_MB;
+        for (int m = 0; m < 33; m++, mb++, lv += P64B_LEVELS_PER_MB) {
+          if (buffer_contents(e, ss, g, m) > buffer_size(e)) {          // p64.c:776-783
+            p64b_mb o{}; o.mtype = 4; o.cbp = 0x3f; o.quant = (uint8_t)ss.gquant;
+            p64b_bits_mb(ss.bits, m, &o, lv);
+            e->overflow[(size_t)s * e->nmb + g * 33 + m] = 1;
+            ss.overflows++;
+          } else {
+            p64b_bits_mb(ss.bits, m, mb, lv);
+          }
+        }
+      });
+    }
+    if ((rc = p64b_ctx_frame_end(e->ctx, e->overflow.data()))) return rc;
+  }
+  for (auto& ss : e->st) {                          // p64.c:654-681
+    ss.total_bits = p64b_bits_tell(ss.bits);
+    if (first) ss.first_frame_bits = ss.total_bits;
+    if (e->p.rate) {
+      if (first) ss.buffer_offset = buffer_size(e) / 2 - buffer_contents(e, ss, e->ngob, 0);
+      ss.buffer_offset -= (int)((int64_t)e->p.rate * e->p.frame_skip * e->p.frame_rate_div / e->p.frame_rate);
+    }
+  }
+  e->frames_done++;
+  e->current_frame += e->p.frame_skip;
+  return 0;
+}
+
+int p64b_enc_finish(p64b_enc* e) {
+  if (!e) return P64B_EINVAL;
+  if (e->finished) return 0;
+  // p64.c:600-605: limit file growth, trailing picture header, pad with 1-bits
+  int last_plus_1 = e->p.start_frame + (e->frames_done ? (e->frames_done - 1) * e->p.frame_skip : 0) + 1;
+  int cf = e->frames_done ? std::min(e->current_frame, last_plus_1) : e->current_frame;
+  for (auto& ss : e->st) { p64b_bits_picture_header(ss.bits, cf % 32); p64b_bits_finish(ss.bits); }
+  e->finished = true;
+  return 0;
+}
+
+const uint8_t* p64b_enc_data(const p64b_enc* e, int stream, size_t* nbytes) {
+  if (!e || stream < 0 || stream >= e->S) { if (nbytes) *nbytes = 0; return nullptr; }
+  return p64b_bits_data(e->st[stream].bits, nbytes);
+}
+p64b_ctx* p64b_enc_ctx(p64b_enc* e) { return e ? e->ctx : nullptr; }
+int64_t p64b_enc_overflows(const p64b_enc* e, int stream) {
+  return (e && stream >= 0 && stream < e->S) ? e->st[stream].overflows : -1;
+}
+int64_t p64b_enc_first_frame_bits(const p64b_enc* e, int stream) {
+  return (e && stream >= 0 && stream < e->S) ? e->st[stream].first_frame_bits : -1;
+}
+
+}  // extern "C"

@@ -1,0 +1,614 @@
+// sm_100a kernels of the H.261 hot path.  All arithmetic is integer except the MTYPE decision (double),
+// exactly as in the reference; citations "file:line" are into maikmerten/p64.
+//
+//   me_surface_kernel   full 31x31 SAD surface per macroblock -> three-step walk or exhaustive argmin
+//                       + the VAR/VAROR/MWOR statistics                  (me.c:187-363)
+//   mb_encode_kernel    MTYPE decision, prediction (MC / half-vector chroma / loop filter), residual,
+//                       Chen DCT, quantise, zig-zag, CBP + type-4/7 fallback, inverse quantise,
+//                       Chen IDCT, reconstruct                        (p64.c:734-773, 823-913, 935-1013)
+//   overflow_patch_kernel  MBs the host overrode to "type 4, zero vector" (p64.c:776-783)
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/p64_b200.h"
+
+namespace p64b {
+
+struct Geom {
+  int W, H;        // luma size
+  int mbw, mbh;    // macroblocks per row / column
+  int ngob, nmb;   // GOBs, macroblocks per frame
+  int qcif;        // GOB layout selector (io.c:730-741)
+  int frame_bytes; // W*H*3/2
+};
+
+// ---------------------------------------------------------------------------------------------------
+// Motion estimation
+// ---------------------------------------------------------------------------------------------------
+constexpr int ME_THREADS = 128;        // 4 warps: warp w owns dy in [-15+8w, -15+8w+8); lane L owns dx = L-16
+constexpr int ME_WIN_ROWS = 47;        // window rows y0-15 .. y0+31
+constexpr int ME_ROW_WORDS = 12;       // 48 bytes: x0-16 .. x0+31
+constexpr int ME_COPY_WORDS = 584;     // >= 47*12, and == 8 (mod 32): lanes (k,q) hit 32 distinct banks
+constexpr int ME_SMEM_WORDS = 4 * ME_COPY_WORDS + 64 /*cur*/ + 31 * 31 /*surface*/ + 16 /*scratch*/;
+
+__device__ __forceinline__ uint32_t sad4(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));   // VABSDIFF4.U8.ACC
+  return d;
+}
+
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, bool valid) {
+  uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  int n = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(n));   // LDGSTS, zero fill
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+// One CTA per macroblock.  ref/cur: luma planes of `n_pairs` frames, `pair_stride` bytes apart.
+// out[pair][raster mb].
+__global__ void __launch_bounds__(ME_THREADS)
+me_surface_kernel(const uint8_t* __restrict__ ref, const uint8_t* __restrict__ cur, size_t pair_stride, Geom g,
+                  int me_mode, int search_limit, p64b_me* __restrict__ out, uint32_t* __restrict__ surface) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  uint32_t* win = smem;                              // [4][ME_COPY_WORDS]: copy k = window shifted left by k bytes
+  uint32_t* s_cur = smem + 4 * ME_COPY_WORDS;        // [16][4]
+  uint32_t* s_sad = s_cur + 64;                      // [31][31], index [dy+15][dx+15]
+  uint32_t* s_red = s_sad + 31 * 31;                 // [16]
+
+  const int nmb_r = g.mbw * g.mbh;
+  const int pair = blockIdx.x / nmb_r, mb = blockIdx.x % nmb_r;
+  const int x0 = (mb % g.mbw) * 16, y0 = (mb / g.mbw) * 16;
+  const uint8_t* rp = ref + (size_t)pair * pair_stride;
+  const uint8_t* cp = cur + (size_t)pair * pair_stride;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  // ---- stage the search window (47 rows x 48 B, out-of-frame chunks zero-filled) and the current block
+  for (int i = tid; i < ME_WIN_ROWS * 3; i += ME_THREADS) {
+    int r = i / 3, c = i % 3;
+    int gy = y0 - 15 + r, gx = x0 - 16 + 16 * c;
+    bool ok = gy >= 0 && gy < g.H && gx >= 0 && gx < g.W;
+    const uint8_t* src = ok ? rp + (size_t)gy * g.W + gx : rp;
+    cp_async16_zfill(win + r * ME_ROW_WORDS + 4 * c, src, ok);
+  }
+  if (tid < 16) cp_async16_zfill(s_cur + 4 * tid, cp + (size_t)(y0 + tid) * g.W + x0, true);
+  cp_async_wait_all();
+  __syncthreads();
+  // ---- byte-shifted copies 1..3 so that every packed SAD operand is an aligned word (no PRMT in the loop)
+  for (int i = tid; i < 3 * ME_WIN_ROWS * 11; i += ME_THREADS) {
+    int k = 1 + i / (ME_WIN_ROWS * 11), rem = i % (ME_WIN_ROWS * 11);
+    int idx = (rem / 11) * ME_ROW_WORDS + rem % 11;
+    win[k * ME_COPY_WORDS + idx] = __funnelshift_r(win[idx], win[idx + 1], 8 * k);
+  }
+  uint32_t c[16][4];
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    uint4 v = reinterpret_cast<const uint4*>(s_cur)[i];
+    c[i][0] = v.x; c[i][1] = v.y; c[i][2] = v.z; c[i][3] = v.w;
+  }
+  __syncthreads();
+
+  // ---- SAD surface: lane <-> dx = lane-16 (lane 0 idle), warp <-> 8 consecutive dy, sliding down 23 rows
+  {
+    const int o = lane, k = o & 3, q = o >> 2;
+    const uint32_t* base = win + k * ME_COPY_WORDS + q + (8 * warp) * ME_ROW_WORDS;
+    uint32_t acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[j] = 0;
+#pragma unroll
+    for (int t = 0; t < 23; t++) {
+      uint32_t r0 = base[t * ME_ROW_WORDS + 0], r1 = base[t * ME_ROW_WORDS + 1];
+      uint32_t r2 = base[t * ME_ROW_WORDS + 2], r3 = base[t * ME_ROW_WORDS + 3];
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const int i = t - j;
+        if (i >= 0 && i < 16) {
+          acc[j] = sad4(r0, c[i][0], acc[j]);
+          acc[j] = sad4(r1, c[i][1], acc[j]);
+          acc[j] = sad4(r2, c[i][2], acc[j]);
+          acc[j] = sad4(r3, c[i][3], acc[j]);
+        }
+      }
+    }
+    const int dx = o - 16, px = x0 + dx;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const int dyi = 8 * warp + j;                 // dy + 15
+      const int dy = dyi - 15, py = y0 + dy;
+      if (o >= 1 && dyi < 31) {
+        // legality: me.c:212-213, 292-293 (strict < on the far edge); (0,0) is always probed (me.c:203, 271)
+        bool legal = (px >= 0 && px < g.W - 16 && py >= 0 && py < g.H - 16) || (dx == 0 && dy == 0);
+        s_sad[dyi * 31 + (o - 1)] = legal ? acc[j] : 0xffffffffu;
+      }
+    }
+  }
+  __syncthreads();
+
+  if (surface)   // test hook: the whole surface, [dy+15][dx+15], 0xffffffff = illegal position
+    for (int i = tid; i < 31 * 31; i += ME_THREADS) surface[(size_t)blockIdx.x * 961 + i] = s_sad[i];
+
+  // ---- search over the surface
+  int mx = 0, my = 0;
+  uint32_t mv = s_sad[15 * 31 + 15];
+  const uint32_t omv = mv;
+  if (me_mode == P64B_ME_FULL) {
+    // FastBME (me.c:206-227): dx outer, dy inner over [-S/2, S/2), strict <, (0,0) first.
+    // key = SAD<<11 | scan order, (0,0) gets order 0.
+    const int lo = (-search_limit) / 2, hi = search_limit / 2;
+    uint32_t best = (omv << 11);
+    for (int i = tid; i < 31 * 31; i += ME_THREADS) {
+      int dxi = i / 31, dyi = i % 31;               // dx-major enumeration = scan order
+      int dx = dxi - 15, dy = dyi - 15;
+      uint32_t s = s_sad[dyi * 31 + dxi];
+      if (dx >= lo && dx < hi && dy >= lo && dy < hi && s != 0xffffffffu) {
+        uint32_t key = (s << 11) | (uint32_t)(1 + i);
+        best = min(best, key);
+      }
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, d));
+    if (lane == 0) s_red[warp] = best;
+    __syncthreads();
+    best = min(min(s_red[0], s_red[1]), min(s_red[2], s_red[3]));
+    mv = best >> 11;
+    int ord = best & 2047;
+    if (ord) { mx = (ord - 1) / 31 - 15; my = (ord - 1) % 31 - 15; }
+  } else {
+    // StepBME (me.c:273-311): steps 8,4,2,1; 8 neighbours in (diry outer, dirx inner) order; the centre
+    // moves once per step; strict < keeps the earlier candidate on ties.  Warp 0, lanes 0..7 probe in parallel.
+    if (warp == 0) {
+      for (int step = 8; step >= 1; step >>= 1) {
+        uint32_t key = (mv << 4);                     // current best, order 0
+        if (lane < 8) {
+          int n = lane < 4 ? lane : lane + 1;         // skip the centre (index 4)
+          int dx = mx + (n % 3 - 1) * step, dy = my + (n / 3 - 1) * step;
+          if (dx >= -15 && dx <= 15 && dy >= -15 && dy <= 15) {
+            uint32_t s = s_sad[(dy + 15) * 31 + dx + 15];
+            if (s != 0xffffffffu) key = min(key, (s << 4) | (uint32_t)(lane + 1));
+          }
+        }
+        uint32_t best = key;
+#pragma unroll
+        for (int d = 4; d >= 1; d >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, d));
+        best = __shfl_sync(0xffffffffu, best, 0);
+        int ord = best & 15;
+        if (ord) {
+          int n = ord - 1; n = n < 4 ? n : n + 1;
+          mx += (n % 3 - 1) * step; my += (n / 3 - 1) * step;
+          mv = best >> 4;
+        }
+      }
+      if (lane == 0) { s_red[0] = (uint32_t)mx; s_red[1] = (uint32_t)my; s_red[2] = mv; }
+    }
+    __syncthreads();
+    mx = (int)s_red[0]; my = (int)s_red[1]; mv = s_red[2];
+  }
+  __syncthreads();
+
+  // ---- statistics over the best-match reference block (me.c:230-245): 2 pixels per thread
+  {
+    const uint8_t* wb = reinterpret_cast<const uint8_t*>(win);
+    const uint8_t* cb = reinterpret_cast<const uint8_t*>(s_cur);
+    int i = tid >> 3, cx = (tid & 7) * 2;
+    int r0 = wb[(my + 15 + i) * 48 + mx + 16 + cx], r1 = wb[(my + 15 + i) * 48 + mx + 16 + cx + 1];
+    int c0 = cb[i * 16 + cx], c1 = cb[i * 16 + cx + 1];
+    int sv = (r0 - c0) * (r0 - c0) + (r1 - c1) * (r1 - c1);
+    int so = r0 * r0 + r1 * r1;
+    int sm = r0 + r1;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+      sv += __shfl_xor_sync(0xffffffffu, sv, d);
+      so += __shfl_xor_sync(0xffffffffu, so, d);
+      sm += __shfl_xor_sync(0xffffffffu, sm, d);
+    }
+    if (lane == 0) { s_red[4 + warp] = sv; s_red[8 + warp] = so; s_red[12 + warp] = sm; }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int var = s_red[4] + s_red[5] + s_red[6] + s_red[7];
+    int varor = s_red[8] + s_red[9] + s_red[10] + s_red[11];
+    int mwor = s_red[12] + s_red[13] + s_red[14] + s_red[15];
+    var /= 256;
+    varor = varor / 256 - (mwor / 256) * (mwor / 256);
+    int4* o = reinterpret_cast<int4*>(out + (size_t)pair * nmb_r + mb);
+    o[0] = make_int4(mx, my, (int)mv, (int)omv);
+    o[1] = make_int4(var, varor, mwor, 0);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Transform chain, one 8x8 block per thread, everything in registers
+// ---------------------------------------------------------------------------------------------------
+#define P64B_MS(e) ((e) >> 9)     // MSCALE: arithmetic shift = floor (chendct.c:46-53, NO_MULTIPLY)
+
+// Chen forward butterfly on 8 values (chendct.c:119-158 / 165-197). PRE: 1 = column pass (<<2), 0 = row pass (>>1)
+template <int PRE>
+__device__ __forceinline__ void fdct8(int& x0, int& x1, int& x2, int& x3, int& x4, int& x5, int& x6, int& x7) {
+  int a0, a1, a2, a3, b0, b1, b2, b3, c0, c1, c2, c3;
+  if (PRE) {
+    a0 = (x0 + x7) << 2; c3 = (x0 - x7) << 2; a1 = (x1 + x6) << 2; c2 = (x1 - x6) << 2;
+    a2 = (x2 + x5) << 2; c1 = (x2 - x5) << 2; a3 = (x3 + x4) << 2; c0 = (x3 - x4) << 2;
+  } else {
+    a0 = (x0 + x7) >> 1; c3 = (x0 - x7) >> 1; a1 = (x1 + x6) >> 1; c2 = (x1 - x6) >> 1;
+    a2 = (x2 + x5) >> 1; c1 = (x2 - x5) >> 1; a3 = (x3 + x4) >> 1; c0 = (x3 - x4) >> 1;
+  }
+  b0 = a0 + a3; b1 = a1 + a2; b2 = a1 - a2; b3 = a0 - a3;
+  x0 = P64B_MS(362 * (b0 + b1));
+  x4 = P64B_MS(362 * (b0 - b1));
+  x2 = P64B_MS(196 * b2 + 473 * b3);
+  x6 = P64B_MS(196 * b3 - 473 * b2);
+  b0 = P64B_MS(362 * (c2 - c1));
+  b1 = P64B_MS(362 * (c2 + c1));
+  a0 = c0 + b0; a1 = c0 - b0; a2 = c3 - b1; a3 = c3 + b1;
+  x1 = P64B_MS(100 * a0 + 502 * a3);
+  x3 = P64B_MS(426 * a2 - 284 * a1);
+  x5 = P64B_MS(426 * a1 + 284 * a2);
+  x7 = P64B_MS(100 * a3 - 502 * a0);
+}
+
+// Chen inverse butterfly (chendct.c:236-299 / 305-363). PRE: 1 = column pass (<<2)
+template <int PRE>
+__device__ __forceinline__ void idct8(int& x0, int& x1, int& x2, int& x3, int& x4, int& x5, int& x6, int& x7) {
+  const int sh = PRE ? 2 : 0;
+  int b0 = x0 << sh, a0 = x1 << sh, b2 = x2 << sh, a1 = x3 << sh;
+  int b1 = x4 << sh, a2 = x5 << sh, b3 = x6 << sh, a3 = x7 << sh;
+  int c0 = P64B_MS(100 * a0 - 502 * a3);
+  int c1 = P64B_MS(426 * a2 - 284 * a1);
+  int c2 = P64B_MS(426 * a1 + 284 * a2);
+  int c3 = P64B_MS(502 * a0 + 100 * a3);
+  a0 = P64B_MS(362 * (b0 + b1));
+  a1 = P64B_MS(362 * (b0 - b1));
+  a2 = P64B_MS(196 * b2 - 473 * b3);
+  a3 = P64B_MS(473 * b2 + 196 * b3);
+  b0 = a0 + a3; b1 = a1 + a2; b2 = a1 - a2; b3 = a0 - a3;
+  a0 = c0 + c1; a1 = c0 - c1; a2 = c3 - c2; a3 = c3 + c2;
+  c0 = a0; c1 = P64B_MS(362 * (a2 - a1)); c2 = P64B_MS(362 * (a2 + a1)); c3 = a3;
+  x0 = b0 + c3; x1 = b1 + c2; x2 = b2 + c1; x3 = b3 + c0;
+  x4 = b3 - c0; x5 = b2 - c1; x6 = b1 - c2; x7 = b0 - c3;
+}
+
+// ChenDct (chendct.c:97-206) on v[64] row-major, in place
+__device__ __forceinline__ void chen_fdct(int (&v)[64]) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) fdct8<1>(v[i], v[8 + i], v[16 + i], v[24 + i], v[32 + i], v[40 + i], v[48 + i], v[56 + i]);
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+    fdct8<0>(v[8 * i], v[8 * i + 1], v[8 * i + 2], v[8 * i + 3], v[8 * i + 4], v[8 * i + 5], v[8 * i + 6], v[8 * i + 7]);
+#pragma unroll
+  for (int i = 0; i < 64; i++) v[i] = (v[i] < 0 ? v[i] - 4 : v[i] + 4) / 8;
+}
+// ChenIDct (chendct.c:217-375)
+__device__ __forceinline__ void chen_idct(int (&v)[64]) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) idct8<1>(v[i], v[8 + i], v[16 + i], v[24 + i], v[32 + i], v[40 + i], v[48 + i], v[56 + i]);
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+    idct8<0>(v[8 * i], v[8 * i + 1], v[8 * i + 2], v[8 * i + 3], v[8 * i + 4], v[8 * i + 5], v[8 * i + 6], v[8 * i + 7]);
+#pragma unroll
+  for (int i = 0; i < 64; i++) v[i] = (v[i] < 0 ? v[i] - 8 : v[i] + 8) / 16;
+}
+
+// raster index of the coefficient that lands at zig-zag position k (inverse of transform.c:67-75)
+__host__ __device__ constexpr int izig(int k) {
+  constexpr int t[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+                         41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+                         30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+  return t[k];
+}
+
+// |v| / d for 0 <= a <= 4096, 2 <= d <= 62 by multiply-shift; rcp = floor(2^19/d)+1.
+// Exact: a*(rcp*d - 2^19) <= a*d < 2^19 (checked exhaustively in tests/test_host_logic.py).
+__device__ __forceinline__ int div_rcp(int a, int rcp) { return (a * rcp) >> 19; }
+
+// Quantise + bound (transform.c:271-350, 502-537).  Returns sum |level| (p64.c:892).
+__device__ __forceinline__ int quantise(int (&v)[64], int q, bool intra) {
+  const int d = 2 * q, rcp = (1 << 19) / d + 1, ev = (q & 1) ? 0 : 1;
+  int acc = 0;
+#pragma unroll
+  for (int i = 0; i < 64; i++) {
+    int x = v[i];
+    if (i == 0) {                                           // BoundDctMatrix: DC clamped from above only
+      x = min(x, 2047);
+      if (intra) {                                          // CCITTFlatQuantize DC + FlatBound
+        x = x > 0 ? (x + 4) / 8 : (x - 4) / 8;
+        x = min(max(x, 1), 254);
+        v[0] = x; acc += x;
+        continue;
+      }
+    } else {
+      x = min(max(x, -1023), 1023);
+    }
+    int a = abs(x) + ev;                                    // x==0, even q: (0-1)/(2q) = 0 = (0+1)/(2q)
+    int l = min(div_rcp(a, rcp), 127);
+    acc += l;
+    v[i] = x < 0 ? -l : l;
+  }
+  return acc;
+}
+
+// Inverse quantise (transform.c:359-451)
+__device__ __forceinline__ void dequantise(int (&v)[64], int q, bool intra) {
+  const int ev = (q & 1) ? 0 : 1;
+#pragma unroll
+  for (int i = 0; i < 64; i++) {
+    int l = v[i];
+    if (i == 0 && intra) { v[0] = l * 8; continue; }
+    int a = abs(l);
+    int r = (2 * a + 1) * q - ev;
+    v[i] = l == 0 ? 0 : (l < 0 ? -r : r);
+  }
+}
+
+// H.261 loop filter on one 8x8 block held in registers (LoadFilterMatrix, io.c:323-372).
+// The reference's two-stage rounding equals (S16+8)>>4 on the scale-16 sum (tests/test_oracle_vs_ref.py).
+__device__ __forceinline__ void loop_filter(int (&p)[64]) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    int a = p[8 * i], b;
+    p[8 * i] = a << 2;
+#pragma unroll
+    for (int j = 1; j < 7; j++) {
+      b = p[8 * i + j];
+      p[8 * i + j] = a + 2 * b + p[8 * i + j + 1];
+      a = b;
+    }
+    p[8 * i + 7] <<= 2;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    int a = p[j], b;
+    p[j] = (4 * a + 8) >> 4;
+#pragma unroll
+    for (int i = 1; i < 7; i++) {
+      b = p[8 * i + j];
+      p[8 * i + j] = (a + 2 * b + p[8 * i + 8 + j] + 8) >> 4;
+      a = b;
+    }
+    p[56 + j] = (4 * p[56 + j] + 8) >> 4;
+  }
+}
+
+__device__ __forceinline__ uint64_t ld8_unaligned(const uint8_t* p) {
+  // 8 bytes at any address from two aligned 8-byte loads (frame stores carry 16 bytes of slack at the end)
+  uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  const uint64_t* q = reinterpret_cast<const uint64_t*>(a & ~(uintptr_t)7);
+  int s = (int)(a & 7) * 8;
+  uint64_t lo = q[0];
+  if (s == 0) return lo;
+  uint64_t hi = q[1];
+  return (lo >> s) | (hi << (64 - s));
+}
+
+// MType property tables (p64.c:217-222) as bit masks over type 0..9
+constexpr uint32_t M_CBP = 0x36c, M_INTRA = 0x003, M_MF = 0x3f0, M_FILTER = 0x380, M_TCOEF = 0x36f;
+__device__ __forceinline__ bool mt_is(uint32_t mask, int mt) { return (mask >> mt) & 1u; }
+
+constexpr int MB_PER_CTA = 32;
+constexpr int MBK_THREADS = 6 * MB_PER_CTA;    // warp c <-> block c of 32 consecutive macroblocks
+
+struct MbArgs {
+  Geom g;
+  const uint8_t* src;      // [S][frame_bytes] source frames
+  const uint8_t* ref;      // [S][frame_bytes] previous reconstruction (CFS)
+  uint8_t* out;            // [S][frame_bytes] reconstruction being written (OFS)
+  const p64b_me* me;       // [S][nmb raster]
+  const uint8_t* li_prev;  // [S][nmb] LastIntra before this frame
+  uint8_t* li_new;         // [S][nmb]
+  const uint8_t* quant;    // [S] per-stream GQUANT or nullptr
+  p64b_mb* mbs;            // output records
+  int8_t* levels;          // output levels
+  int n_streams;
+  int gob_first, gob_count;   // task t -> stream t / gob_count, GOB gob_first + t % gob_count
+  int out_mb_per_stream;      // stride of the output arrays per stream, in MBs (nmb or 33)
+  int first_frame, force_intra, gquant;
+};
+
+// prediction for one block: SubOverlay / Sub[F]Compensate / HalfSub[F]Compensate (io.c:142-496)
+__device__ __forceinline__ void fetch_pred(const uint8_t* plane, int w, int bx, int by, int mt, int mvx, int mvy,
+                                           bool chroma, int (&p)[64]) {
+  int dx = 0, dy = 0;
+  if (mt_is(M_MF, mt)) { dx = chroma ? mvx / 2 : mvx; dy = chroma ? mvy / 2 : mvy; }   // C truncation (io.c:268-269)
+  const uint8_t* b = plane + (size_t)(by + dy) * w + bx + dx;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    uint64_t r = ld8_unaligned(b + (size_t)i * w);
+#pragma unroll
+    for (int j = 0; j < 8; j++) p[8 * i + j] = (int)((r >> (8 * j)) & 0xff);
+  }
+  if (mt_is(M_FILTER, mt)) loop_filter(p);
+}
+
+__global__ void __launch_bounds__(MBK_THREADS)
+mb_encode_kernel(MbArgs a) {
+  __shared__ int s_acc[6][MB_PER_CTA];
+  const Geom& g = a.g;
+  const int lane = threadIdx.x & 31, c = threadIdx.x >> 5;        // block index within the MB: p64.c:77-79
+  const int n = blockIdx.x * MB_PER_CTA + lane;
+  const int n_total = a.n_streams * a.gob_count * 33;
+  const bool active = n < n_total;
+  const int nn = active ? n : n_total - 1;
+  const int task = nn / 33, m = nn % 33;
+  const int s = task / a.gob_count, gob = a.gob_first + task % a.gob_count;
+  int col, row;                                                    // MoveTo, io.c:730-741
+  if (g.qcif) { col = m % 11; row = gob * 3 + m / 11; }
+  else { col = (gob & 1) * 11 + m % 11; row = (gob >> 1) * 3 + m / 11; }
+  const int mbi = gob * 33 + m;                                    // GOB-major index
+  const bool chroma = c >= 4;
+  const int w = chroma ? g.W / 2 : g.W;
+  const size_t poff = (size_t)s * g.frame_bytes + (c < 4 ? 0 : (c == 4 ? g.W * g.H : g.W * g.H * 5 / 4));
+  const int bx = chroma ? col * 8 : col * 16 + (c & 1) * 8;
+  const int by = chroma ? row * 8 : row * 16 + (c >> 1) * 8;
+
+  // ---- MTYPE decision (p64.c:734-773), double arithmetic exactly as written
+  int4 me0 = make_int4(0, 0, 0, 0), me1 = me0;
+  if (!a.first_frame) {
+    const int4* mp = reinterpret_cast<const int4*>(a.me + (size_t)s * g.mbw * g.mbh + row * g.mbw + col);
+    me0 = __ldg(mp); me1 = __ldg(mp + 1);
+  }
+  const int mvx = me0.x, mvy = me0.y;
+  const int li = a.li_prev[(size_t)s * g.nmb + mbi];
+  int mt = 0;
+  if (!a.first_frame) {
+    double x = (double)me0.w / 256.0, y = (double)me0.z / 256.0;
+    int var = me1.x, varor = me1.y;
+    if (var < 64 || varor > var) {
+      if (x < 1.0 || (x < 3.0 && y > x * 0.5) || y > __ddiv_rn(x, 1.1)) mt = 2;
+      else if (var < 6) mt = 5;
+      else mt = 8;
+    } else mt = 0;
+    if (a.force_intra) mt = 0;
+  }
+  if (li > 131) mt = 0;
+  const int q = a.quant ? a.quant[s] : a.gquant;
+
+  // ---- ReadCompressMDU (p64.c:823-886): source block, prediction, residual, DCT, quantise
+  int v[64], p[64];
+  {
+    const uint8_t* sp = a.src + poff + (size_t)by * w + bx;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      uint2 r = *reinterpret_cast<const uint2*>(sp + (size_t)i * w);
+#pragma unroll
+      for (int j = 0; j < 4; j++) { v[8 * i + j] = (r.x >> (8 * j)) & 0xff; v[8 * i + 4 + j] = (r.y >> (8 * j)) & 0xff; }
+    }
+  }
+  const bool intra = mt_is(M_INTRA, mt);
+  uint32_t pk[16];                                  // prediction kept as packed bytes until reconstruction
+#pragma unroll
+  for (int i = 0; i < 16; i++) pk[i] = 0;
+  if (!intra) {
+    fetch_pred(a.ref + poff, w, bx, by, mt, mvx, mvy, chroma, p);
+#pragma unroll
+    for (int i = 0; i < 64; i++) v[i] -= p[i];
+#pragma unroll
+    for (int i = 0; i < 16; i++)
+      pk[i] = (uint32_t)p[4 * i] | ((uint32_t)p[4 * i + 1] << 8) | ((uint32_t)p[4 * i + 2] << 16) | ((uint32_t)p[4 * i + 3] << 24);
+  }
+  chen_fdct(v);
+  const int acc = quantise(v, q, intra);
+
+  // ---- levels out, zig-zag order (transform.c:561-568): byte k = level at raster izig(k)
+  if (active) {
+    uint4* lp = reinterpret_cast<uint4*>(a.levels + ((size_t)s * a.out_mb_per_stream + (mbi - a.gob_first * 33)) * 384 + c * 64);
+#pragma unroll
+    for (int wd = 0; wd < 4; wd++) {
+      uint32_t u[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int b0 = 16 * wd + 4 * k;
+        u[k] = (uint32_t)(v[izig(b0)] & 0xff) | ((uint32_t)(v[izig(b0 + 1)] & 0xff) << 8) |
+               ((uint32_t)(v[izig(b0 + 2)] & 0xff) << 16) | ((uint32_t)(v[izig(b0 + 3)] & 0xff) << 24);
+      }
+      lp[wd] = make_uint4(u[0], u[1], u[2], u[3]);
+    }
+  }
+
+  // ---- CBP and the type-4 / type-7 fallback (p64.c:887-908)
+  s_acc[c][lane] = acc;
+  __syncthreads();
+  int cbp = 0x3f, nz = 0;
+  {
+    int pm = 0, cb = 0;
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+      int ak = s_acc[k][lane];
+      if (ak && !pm) pm = 1 << (5 - k);
+      if (ak > 1) cb |= 1 << (5 - k);
+      if (ak) nz |= 1 << (5 - k);
+    }
+    if (mt_is(M_CBP, mt)) {
+      cbp = cb ? cb : pm;
+      if (!cbp) { mt = mt_is(M_FILTER, mt) ? 7 : 4; cbp = 0x3f; }     // no coefficients at all: levels are already zero
+    }
+  }
+  const int mt_final = mt;
+
+  // ---- inverse half (p64.c:935-959) + DecodeSaveMDU (p64.c:971-1013)
+  const bool coded = ((cbp >> (5 - c)) & 1) && mt_is(M_TCOEF, mt_final);
+  if (coded) { dequantise(v, q, intra); chen_idct(v); }
+  else {
+#pragma unroll
+    for (int i = 0; i < 64; i++) v[i] = 0;
+  }
+  if (!intra) {
+    // a type-2 MB that fell back to type 4 predicts with the ME vector (p64.c:904, marker.c:339-342)
+    if (mt_final == 4 && (mvx | mvy)) {
+      fetch_pred(a.ref + poff, w, bx, by, mt_final, mvx, mvy, chroma, p);
+#pragma unroll
+      for (int i = 0; i < 64; i++) v[i] += p[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 64; i++) v[i] += (int)((pk[i >> 2] >> (8 * (i & 3))) & 0xff);
+    }
+  }
+  if (active) {
+    uint8_t* op = a.out + poff + (size_t)by * w + bx;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      uint32_t lo = 0, hi = 0;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        lo |= (uint32_t)min(max(v[8 * i + j], 0), 255) << (8 * j);          // BoundIDctMatrix
+        hi |= (uint32_t)min(max(v[8 * i + 4 + j], 0), 255) << (8 * j);
+      }
+      *reinterpret_cast<uint2*>(op + (size_t)i * w) = make_uint2(lo, hi);
+    }
+    if (c == 0) {
+      const bool mf = mt_is(M_MF, mt_final);
+      uint32_t r0 = (uint32_t)mt_final | ((uint32_t)cbp << 8) | ((uint32_t)((mf ? mvx : 0) & 0xff) << 16) |
+                    ((uint32_t)((mf ? mvy : 0) & 0xff) << 24);
+      uint32_t r1 = (uint32_t)q | ((uint32_t)nz << 8);
+      *reinterpret_cast<uint2*>(a.mbs + (size_t)s * a.out_mb_per_stream + (mbi - a.gob_first * 33)) = make_uint2(r0, r1);
+      a.li_new[(size_t)s * g.nmb + mbi] = mt_is(M_INTRA, mt_final) ? 0 : (uint8_t)(li + 1);   // p64.c:909-910
+    }
+  }
+}
+
+// MBs overridden by the host to MType 4 with a zero vector when the rate buffer overflowed (p64.c:776-783):
+// reconstruction = copy of the reference MB (AddCompensate at (0,0), TCoeffMType[4]=0), LastIntra++.
+// One warp per (stream, MB); exits immediately when the MB was not overridden.
+__global__ void overflow_patch_kernel(Geom g, const uint8_t* __restrict__ ovf, const uint8_t* __restrict__ ref,
+                                      uint8_t* __restrict__ out, const uint8_t* __restrict__ li_prev,
+                                      uint8_t* __restrict__ li_new, int n_streams) {
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (wid >= n_streams * g.nmb) return;
+  if (!ovf[wid]) return;
+  const int s = wid / g.nmb, mbi = wid % g.nmb, gob = mbi / 33, m = mbi % 33;
+  int col, row;
+  if (g.qcif) { col = m % 11; row = gob * 3 + m / 11; }
+  else { col = (gob & 1) * 11 + m % 11; row = (gob >> 1) * 3 + m / 11; }
+  const size_t fo = (size_t)s * g.frame_bytes;
+  {  // luma 16 rows x 16 B: lane -> (row = lane/2, half = lane%2)
+    size_t o = fo + (size_t)(row * 16 + lane / 2) * g.W + col * 16 + (lane & 1) * 8;
+    *reinterpret_cast<uint2*>(out + o) = *reinterpret_cast<const uint2*>(ref + o);
+  }
+  if (lane < 16) {  // chroma: 2 planes x 8 rows x 8 B
+    int pl = lane >> 3, r = lane & 7;
+    size_t o = fo + (size_t)g.W * g.H + (size_t)pl * (g.W * g.H / 4) + (size_t)(row * 8 + r) * (g.W / 2) + col * 8;
+    *reinterpret_cast<uint2*>(out + o) = *reinterpret_cast<const uint2*>(ref + o);
+  }
+  if (lane == 0) li_new[wid] = (uint8_t)(li_prev[wid] + 1);
+}
+
+// Register-only issue-rate probe for VABSDIFF4.U8.ACC (ME roofline denominator)
+__global__ void __launch_bounds__(256) sad_peak_kernel(uint32_t* out, int iters, uint32_t seed) {
+  uint32_t x[8], acc[8];
+  uint32_t b = seed * 2654435761u + threadIdx.x;
+#pragma unroll
+  for (int i = 0; i < 8; i++) { x[i] = b * (i + 3) + blockIdx.x; acc[i] = i; }
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int u = 0; u < 8; u++)
+#pragma unroll
+      for (int i = 0; i < 8; i++)
+        asm volatile("vabsdiff4.u32.u32.u32.add %0,%1,%2,%0;" : "+r"(acc[i]) : "r"(x[i]), "r"(b));
+  }
+  uint32_t r = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r += acc[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+
+}  // namespace p64b

@@ -1,0 +1,206 @@
+"""Python mirror of the C ABI objects: DeviceContext (p64b_ctx_*), BitWriter (p64b_bits_*), Encoder (p64b_enc_*).
+
+Names and argument meaning follow the reference: a context plays the role of the frame stores CFS/OFS
+(p64.c:69-72) plus the hot-path routines; BitWriter is marker.c/codec.c/stream.c; Encoder is
+p64EncodeSequence (p64.c:524-613).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import MB, ME, EncParams, Step, check
+
+MB_DTYPE = np.dtype([("mtype", "u1"), ("cbp", "u1"), ("mvx", "i1"), ("mvy", "i1"), ("quant", "u1"),
+                     ("nzmask", "u1"), ("reserved", "u2")])
+ME_DTYPE = np.dtype([(n, "i4") for n in ("mx", "my", "val", "oval", "var", "varor", "mwor", "pad")])
+
+
+def geometry(image_type: int):
+    L = _lib.lib()
+    return dict(width=L.p64b_width(image_type), height=L.p64b_height(image_type),
+                frame_bytes=L.p64b_frame_bytes(image_type), num_gob=L.p64b_num_gob(image_type),
+                num_mb=L.p64b_num_mb(image_type))
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return C.c_void_p(a.ctypes.data)
+
+
+def make_step(first_frame, gquant=8, me_mode=0, search_limit=15, force_intra=False) -> Step:
+    return Step(int(first_frame), int(me_mode), int(search_limit), int(force_intra), int(gquant))
+
+
+class DeviceContext:
+    def __init__(self, image_type: int, n_streams: int = 1, device: int = 0):
+        self.L = _lib.lib()
+        self.image_type, self.n_streams = image_type, n_streams
+        self.geom = geometry(image_type)
+        h = C.c_void_p()
+        check(self.L.p64b_ctx_create(C.byref(h), device, image_type, n_streams))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.p64b_ctx_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def set_cuda_stream(self, handle: int):
+        check(self.L.p64b_ctx_set_cuda_stream(self.h, C.c_void_p(handle)))
+
+    def _outputs(self, mb_per_stream):
+        mbs = np.zeros((self.n_streams, mb_per_stream), MB_DTYPE)
+        levels = np.zeros((self.n_streams, mb_per_stream, 6, 64), np.int8)
+        return mbs, levels
+
+    def encode_frames(self, step: Step, src: np.ndarray):
+        """src uint8 [n_streams, frame_bytes] (host) -> (mbs [S,nmb], levels int8 [S,nmb,6,64])."""
+        src = np.ascontiguousarray(src, np.uint8).reshape(self.n_streams, self.geom["frame_bytes"])
+        mbs, levels = self._outputs(self.geom["num_mb"])
+        check(self.L.p64b_ctx_encode_frames(self.h, C.byref(step), _ptr(src), _ptr(mbs), _ptr(levels)))
+        return mbs, levels
+
+    def encode_frames_dev(self, step: Step, src_dev: int, mbs_dev: int, levels_dev: int):
+        check(self.L.p64b_ctx_encode_frames_dev(self.h, C.byref(step), _ptr(src_dev), _ptr(mbs_dev), _ptr(levels_dev)))
+
+    def frame_begin(self, step: Step, src: np.ndarray):
+        src = np.ascontiguousarray(src, np.uint8).reshape(self.n_streams, self.geom["frame_bytes"])
+        self._src_keepalive = src
+        check(self.L.p64b_ctx_frame_begin(self.h, C.byref(step), _ptr(src)))
+
+    def encode_gob(self, step: Step, gob: int, quant):
+        quant = np.ascontiguousarray(quant, np.uint8).reshape(self.n_streams)
+        mbs, levels = self._outputs(33)
+        check(self.L.p64b_ctx_encode_gob(self.h, C.byref(step), gob, _ptr(quant), _ptr(mbs), _ptr(levels)))
+        return mbs, levels
+
+    def frame_end(self, overflow=None):
+        if overflow is not None:
+            overflow = np.ascontiguousarray(overflow, np.uint8).reshape(self.n_streams, self.geom["num_mb"])
+        check(self.L.p64b_ctx_frame_end(self.h, _ptr(overflow)))
+
+    def motion_estimation_dev(self, ref_dev: int, cur_dev: int, n_pairs: int, me_mode: int, search_limit: int,
+                              out_dev: int):
+        check(self.L.p64b_ctx_motion_estimation_dev(self.h, _ptr(ref_dev), _ptr(cur_dev), n_pairs, me_mode,
+                                                    search_limit, _ptr(out_dev)))
+
+    def me_records(self, stream: int = 0) -> np.ndarray:
+        out = np.zeros(self.geom["num_mb"], ME_DTYPE)
+        check(self.L.p64b_ctx_me_records(self.h, stream, _ptr(out)))
+        return out
+
+    def recon(self, stream: int = 0) -> np.ndarray:
+        out = np.zeros(self.geom["frame_bytes"], np.uint8)
+        check(self.L.p64b_ctx_download_recon(self.h, stream, _ptr(out)))
+        return out
+
+    def last_intra(self, stream: int = 0) -> np.ndarray:
+        out = np.zeros(self.geom["num_mb"], np.uint8)
+        check(self.L.p64b_ctx_last_intra(self.h, stream, _ptr(out)))
+        return out
+
+    @property
+    def launches(self) -> int:
+        return int(self.L.p64b_ctx_launches(self.h))
+
+
+class BitWriter:
+    def __init__(self, image_type: int):
+        self.L = _lib.lib()
+        self.h = C.c_void_p(self.L.p64b_bits_create(image_type))
+        if not self.h:
+            raise ValueError("bad image type")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.p64b_bits_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def picture_header(self, tr: int): self.L.p64b_bits_picture_header(self.h, tr)
+    def gob_header(self, gob: int, gquant: int): self.L.p64b_bits_gob_header(self.h, gob, gquant)
+
+    def mb(self, mdu: int, rec: np.ndarray, levels: np.ndarray):
+        """rec: MB_DTYPE scalar/0-d array; levels: int8 [6,64]"""
+        rec = np.ascontiguousarray(rec, MB_DTYPE)
+        levels = np.ascontiguousarray(levels, np.int8)
+        self.L.p64b_bits_mb(self.h, mdu, _ptr(rec), _ptr(levels))
+
+    def tell(self) -> int: return int(self.L.p64b_bits_tell(self.h))
+    def finish(self) -> int: return int(self.L.p64b_bits_finish(self.h))
+
+    def data(self) -> bytes:
+        n = C.c_size_t()
+        p = self.L.p64b_bits_data(self.h, C.byref(n))
+        return C.string_at(p, n.value)
+
+
+def default_params() -> EncParams:
+    p = EncParams()
+    _lib.lib().p64b_enc_default_params(C.byref(p))
+    return p
+
+
+class Encoder:
+    """Batch sequence encoder: `encode(frames)` once per frame time, then `finish()`; `data(s)` = stream bytes."""
+
+    def __init__(self, image_type: int, n_streams: int = 1, *, q: int = 0, rate: int = 0, me_mode: int = 0,
+                 search_limit: int = 15, force_intra: bool = False, start_frame: int = 0, device: int = 0,
+                 frame_rate=(30000, 1001), frame_skip: int = 1, vlc_threads: int = 0):
+        self.L = _lib.lib()
+        p = default_params()
+        p.image_type, p.n_streams, p.device, p.start_frame = image_type, n_streams, device, start_frame
+        p.initial_quant, p.rate, p.me_mode, p.search_limit = q, rate, me_mode, search_limit
+        p.force_intra, p.frame_rate, p.frame_rate_div, p.frame_skip = int(force_intra), frame_rate[0], frame_rate[1], frame_skip
+        p.vlc_threads = vlc_threads
+        self.n_streams = n_streams
+        self.geom = geometry(image_type)
+        h = C.c_void_p()
+        check(self.L.p64b_enc_create(C.byref(h), C.byref(p)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.p64b_enc_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def encode(self, frames: np.ndarray):
+        frames = np.ascontiguousarray(frames, np.uint8).reshape(self.n_streams, self.geom["frame_bytes"])
+        check(self.L.p64b_enc_encode(self.h, _ptr(frames)))
+
+    def finish(self):
+        check(self.L.p64b_enc_finish(self.h))
+
+    def data(self, stream: int = 0) -> bytes:
+        n = C.c_size_t()
+        p = self.L.p64b_enc_data(self.h, stream, C.byref(n))
+        return C.string_at(p, n.value)
+
+    def overflows(self, stream: int = 0) -> int: return int(self.L.p64b_enc_overflows(self.h, stream))
+    def first_frame_bits(self, stream: int = 0) -> int: return int(self.L.p64b_enc_first_frame_bits(self.h, stream))
+
+    def context_handle(self):
+        return C.c_void_p(self.L.p64b_enc_ctx(self.h))
+
+
+def encode_clip(image_type: int, clip: np.ndarray, **kw) -> bytes:
+    """One stream: clip uint8 [n_frames, frame_bytes] -> .p64 bytes."""
+    enc = Encoder(image_type, 1, **kw)
+    try:
+        for fr in clip:
+            enc.encode(fr[None])
+        enc.finish()
+        return enc.data(0)
+    finally:
+        enc.close()

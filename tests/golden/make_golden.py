@@ -1,0 +1,59 @@
+"""Generates tests/golden/streams.json: md5/size of the .p64 streams the UNMODIFIED reference encoder
+(oracle/_ref/p64_ref = stock three-step search, p64_ref_fs = FastBME toggled at me.c:351-352) writes for
+seeded synthetic clips, plus md5s of the frames its own decoder reconstructs from them (closed loop,
+p64.c:971-1013).  Run here (where /root/reference is mounted): `python tests/golden/make_golden.py`.
+The GPU box has no reference tree; tests compare against this committed file.
+"""
+import hashlib
+import json
+import os
+import sys
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import oracle as O  # noqa: E402
+from p64_b200 import y4m  # noqa: E402
+
+CASES = [
+    # name, image_type, n_frames, seed, kwargs for ref_encode
+    ("cif30_q8_tss", y4m.IT_CIF, 30, 1234, dict(q=8)),
+    ("cif30_q8_full31", y4m.IT_CIF, 30, 1234, dict(q=8, full_search=True, search_limit=31)),
+    ("cif8_q8_full15", y4m.IT_CIF, 8, 1234, dict(q=8, full_search=True)),
+    ("cif6_q3_tss", y4m.IT_CIF, 6, 99, dict(q=3)),
+    ("cif6_q31_full31", y4m.IT_CIF, 6, 99, dict(q=31, full_search=True, search_limit=31)),
+    ("qcif12_q8_intra", y4m.IT_QCIF, 12, 4321, dict(q=8, intra_only=True)),
+    ("qcif12_q8_tss", y4m.IT_QCIF, 12, 4321, dict(q=8)),
+    ("qcif140_q10_tss", y4m.IT_QCIF, 140, 7, dict(q=10)),          # forced-intra refresh fires (LastIntra > 131)
+    ("ntsc7_q8_tss", y4m.IT_NTSC, 7, 77, dict(q=8)),
+    ("ntsc7_q8_full31", y4m.IT_NTSC, 7, 77, dict(q=8, full_search=True, search_limit=31)),
+    ("cif30_r384000_tss", y4m.IT_CIF, 30, 1234, dict(rate=384000)),
+    ("cif30_r384000_full31", y4m.IT_CIF, 30, 1234, dict(rate=384000, full_search=True, search_limit=31)),
+    ("cif12_r128000_tss", y4m.IT_CIF, 12, 1234, dict(rate=128000)),  # buffer-overflow branch (p64.c:776-783)
+    ("cif12_r64000_full31", y4m.IT_CIF, 12, 1234, dict(rate=64000, full_search=True, search_limit=31)),
+    ("qcif20_r64000_tss", y4m.IT_QCIF, 20, 4321, dict(rate=64000)),
+]
+
+
+def main():
+    if not O.have_ref():
+        raise SystemExit("oracle/_ref missing: run `make -C oracle` where /root/reference is mounted")
+    out = {}
+    tmp = tempfile.mkdtemp()
+    for name, it, nf, seed, kw in CASES:
+        clip = y4m.synth_clip(it, nf, seed)
+        y4m.write_y4m(f"{tmp}/c.y4m", it, clip)
+        log = O.ref_encode(f"{tmp}/c.y4m", f"{tmp}/o.p64", it, nf, **kw)
+        data = open(f"{tmp}/o.p64", "rb").read()
+        O.ref_decode(f"{tmp}/o.p64", f"{tmp}/dec")
+        _, _, dec = y4m.read_y4m(f"{tmp}/dec.y4m")
+        out[name] = dict(image_type=it, n_frames=nf, seed=seed, args=kw, clip_md5=hashlib.md5(clip.tobytes()).hexdigest(),
+                         size=len(data), md5=hashlib.md5(data).hexdigest(), overflows=log.count("Buffer Overflow!"),
+                         decoded_frames=len(dec), last_recon_md5=hashlib.md5(dec[-1].tobytes()).hexdigest(),
+                         recon_md5=[hashlib.md5(f.tobytes()).hexdigest() for f in dec[:: max(1, len(dec) // 6)]])
+        print(name, len(data), out[name]["md5"], "ovf", out[name]["overflows"], "dec", len(dec))
+    json.dump(out, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "streams.json"), "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,86 @@
+"""Test-only helpers: the CPU oracle (oracle/) driven through the PRODUCT's host bit writer, restating the
+reference's sequence / rate control loop (p64.c:524-786) in Python so whole streams can be checked without a GPU."""
+import hashlib
+import json
+import os
+
+import numpy as np
+
+from oracle import oracle as O
+from p64_b200 import y4m
+from p64_b200.encoder import MB_DTYPE, BitWriter
+
+GOLDEN = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "streams.json")))
+
+
+def golden_clip(name):
+    g = GOLDEN[name]
+    clip = y4m.synth_clip(g["image_type"], g["n_frames"], g["seed"])
+    assert hashlib.md5(clip.tobytes()).hexdigest() == g["clip_md5"], "synthetic clip generator drifted"
+    return g, clip
+
+
+def golden_kwargs(g):
+    """reference CLI arguments of a golden case -> keyword arguments of p64_b200.encoder.Encoder"""
+    a = g["args"]
+    return dict(q=a.get("q", 0), rate=a.get("rate", 0), me_mode=1 if a.get("full_search") else 0,
+                search_limit=a.get("search_limit") or 15, force_intra=bool(a.get("intra_only")))
+
+
+def recs_to_mb(recs):
+    mb = np.zeros(len(recs), MB_DTYPE)
+    mb["mtype"], mb["cbp"], mb["mvx"], mb["mvy"], mb["quant"] = recs[:, 0], recs[:, 1], recs[:, 2], recs[:, 3], recs[:, 4]
+    return mb
+
+
+def levels_to_i8(levels):
+    """int32 oracle levels -> the ABI's int8 storage (intra DC 1..254 wraps into the same byte)."""
+    return levels.astype(np.uint8).view(np.int8)
+
+
+def oracle_encode_stream(image_type, clip, *, q=0, rate=0, me_mode=0, search_limit=15, force_intra=False,
+                         frame_rate=(30000, 1001), frame_skip=1, start_frame=0):
+    """Returns (.p64 bytes, per-frame recon list, overflow count)."""
+    enc = O.Encoder(image_type)
+    bw = BitWriter(image_type)
+    ngob = enc.ngob
+    qdfact, qoffs = 1, 1
+    iq = q
+    if rate:
+        qdfact = rate // 320
+        if not iq:
+            iq = min(max(10000000 // rate, 1), 31)
+    if not iq:
+        iq = 8
+    gquant, boff, ovfl = iq, 0, 0
+    denom = ngob * 33 * frame_rate[0] // frame_rate[1]
+
+    def contents(g, m):
+        return bw.tell() + boff - ((g * 33 + m) * rate * frame_skip) // denom
+
+    recons = []
+    cur = start_frame
+    for f, fr in enumerate(clip):
+        first = f == 0
+        bw.picture_header(cur % 32)
+        enc.begin_frame(fr, me_mode, search_limit)
+        for g in range(ngob):
+            if rate and not first:
+                c = contents(g, 0)
+                gquant = min(max(int(c / qdfact) + qoffs, 1), 31)      # C division truncates toward zero
+            bw.gob_header(g, gquant)
+            for m in range(33):
+                over = bool(rate) and contents(g, m) > rate // 4
+                ovfl += over
+                rec, lv = enc.encode_mb(g, m, gquant, force_intra, over)
+                bw.mb(m, recs_to_mb(rec[None])[0], levels_to_i8(lv))
+        enc.end_frame()
+        recons.append(enc.recon())
+        if rate:
+            if first:
+                boff = (rate // 4) // 2 - contents(ngob, 0)
+            boff -= rate * frame_skip * frame_rate[1] // frame_rate[0]
+        cur += frame_skip
+    bw.picture_header(cur % 32)
+    bw.finish()
+    return bw.data(), recons, ovfl
