@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""bench.py -- CIF frames/s through the H.261 hot path (ME + decision + prediction + Chen DCT + quantise + recon).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            this repo's CUDA path (one JSON line)
+    python bench.py --impl reference ...                           the UNMODIFIED reference CPU encoder, all host cores
+
+Workload (BASELINE.json configs[4], the per-GPU share): 256 independent synthetic CIF streams per GPU,
+fixed quantiser 8, exhaustive +-15 motion search (`-i 31`, FastBME), no rate control.  A step = one frame time
+of every stream (256 CIF frames per GPU): steady-state inter frames; the intra first frame falls in the warm-up.
+Multi-GPU: streams are partitioned across ranks, no collective on the data path (weak scaling).
+
+  value  device-resident: source frames already in HBM (a ring of distinct frame sets larger than L2), outputs left
+         in HBM; timed with CUDA events on the launching stream, max over ranks.
+  e2e    the reference-facing C-ABI call with HOST buffers: p64b_ctx_encode_frames(): H2D of the step's source frames
+         from pinned memory + kernels + D2H of every macroblock record and level, every step.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+STREAMS_PER_GPU = 256
+QUANT = 8
+SEARCH_LIMIT = 31
+RING = 6                      # distinct source frame sets resident in HBM (6 x 39 MB)
+CLIP_BANK = 8                 # distinct seeded clips; stream s plays clip s % 8 with a phase offset
+IT_CIF = 1
+# algorithmic work per unit (DESIGN.md "Measurement")
+SAD_OPS_PER_CIF_FRAME = 343473 * 64          # legal candidates (me.c:212-213) x 64 packed 4-byte SADs each
+MB_BYTES_INTER = 384 + 384 + 384 + 384 + 8   # source + prediction + reconstruction + int8 levels + record
+
+
+def _clocks_sampler(stop, out, gpu_index):
+    q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    while not stop.is_set():
+        try:
+            r = subprocess.run(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                               capture_output=True, text=True, timeout=5)
+            f = [x.strip() for x in r.stdout.strip().split(",")]
+            if len(f) >= 7:
+                out.append(f)
+        except Exception:
+            pass
+        stop.wait(0.1)
+
+
+def _summarise_clocks(samples):
+    if not samples:
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+    sm = sorted(int(float(s[0])) for s in samples)
+    reasons = []
+    for i, name in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
+        if any(s[3 + i].lower().startswith("active") for s in samples):
+            reasons.append(name)
+    return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(float(samples[0][1])), "reasons": reasons,
+            "samples": len(samples), "power_w_max": max(float(s[2]) for s in samples)}
+
+
+def make_sources(n_streams: int, n_sets: int, rank: int) -> np.ndarray:
+    """uint8 [n_sets, n_streams, frame_bytes]: set t holds frame (phase_s + t) of stream s's clip."""
+    from p64_b200 import y4m
+    bank = [y4m.synth_clip(IT_CIF, n_sets + CLIP_BANK, seed=1000 + 17 * rank + b, pan=((b % 5) - 2, (b % 3) - 1))
+            for b in range(CLIP_BANK)]
+    out = np.empty((n_sets, n_streams, bank[0].shape[1]), np.uint8)
+    for s in range(n_streams):
+        clip, phase = bank[s % CLIP_BANK], (s // CLIP_BANK) % CLIP_BANK
+        out[:, s] = clip[phase:phase + n_sets]
+    return out
+
+
+# --------------------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the unmodified reference encoder, one process per host core
+# --------------------------------------------------------------------------------------------------------------
+def run_reference_sample(frames_per_proc: int = 60, cores: int | None = None):
+    """-> (frames_per_s, cores, sample description). Uses oracle/_ref/p64_ref_fs (FastBME, -i 31) when built,
+    else reports kind 'port' from the C oracle."""
+    from oracle import oracle as O
+    from p64_b200 import y4m
+    cores = cores or os.cpu_count() or 1
+    tmp = tempfile.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        clip = y4m.synth_clip(IT_CIF, frames_per_proc, seed=1000)
+        if O.have_ref():
+            exe = os.path.join(O.REF_DIR, "p64_ref_fs")
+            for c in range(cores):
+                y4m.write_y4m(f"{tmp}/c{c}.y4m", IT_CIF, clip)
+            cmds = [[exe, "-y4m", "-CIF", "-a", "0", "-b", str(frames_per_proc - 1), "-q", str(QUANT), "-i", str(SEARCH_LIMIT),
+                     f"{tmp}/c{c}", "-s", f"{tmp}/o{c}.p64"] for c in range(cores)]
+            taskset = shutil.which("taskset")
+            t0 = time.perf_counter()
+            procs = [subprocess.Popen(([taskset, "-c", str(c)] if taskset else []) + cmd, stdout=subprocess.DEVNULL,
+                                      stderr=subprocess.DEVNULL) for c, cmd in enumerate(cmds)]
+            rcs = [p.wait() for p in procs]
+            dt = time.perf_counter() - t0
+            if any(rcs):
+                raise RuntimeError(f"reference encoder failed: {rcs}")
+            kind = "reference"
+            what = (f"{cores} pinned processes of the unmodified reference (oracle/_ref/p64_ref_fs: FastBME, -q {QUANT} -i {SEARCH_LIMIT}), "
+                    f"each encoding its own {frames_per_proc}-frame synthetic CIF Y4M from tmpfs, incl. its VLC and file I/O")
+            return cores * frames_per_proc / dt, cores, kind, what
+        # no compiled reference: time the C oracle port, single thread
+        enc = O.Encoder(IT_CIF)
+        n = min(frames_per_proc, 20)
+        t0 = time.perf_counter()
+        for f in range(n):
+            enc.encode_frame(clip[f], QUANT, O.ME_FULL, SEARCH_LIMIT)
+        dt = time.perf_counter() - t0
+        return n / dt, 1, "port", f"C oracle (oracle/p64_oracle.c), 1 thread, {n} synthetic CIF frames, hot path only (no VLC)"
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    vals = []
+    if args.warmup > 0:
+        run_reference_sample(20)
+    t_all = time.perf_counter()
+    for _ in range(args.steps):
+        fps, cores, kind, what = run_reference_sample(60)
+        vals.append(fps)
+    dt = time.perf_counter() - t_all
+    v = float(np.mean(vals))
+    line = {"impl": "reference", "metric": "CIF frames/sec encoded (ME+DCT+Q+recon)", "value": v, "unit": "frames/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 / max(1, args.steps),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "CIF 352x288 4:2:0 streams, fixed quantiser 8, full-search ME +-15 (-i 31), no rate control; "
+                                   "bounded sample: " + what},
+            "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": kind, "sample": what},
+            "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------------------------------------------
+# this repo's arm
+# --------------------------------------------------------------------------------------------------------------
+def main_cuda(args):
+    import torch
+    import torch.distributed as dist
+    from p64_b200 import _lib
+    from p64_b200.encoder import DeviceContext, make_step
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; p64_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    S, K, W = STREAMS_PER_GPU, args.steps, args.warmup
+    ctx = DeviceContext(IT_CIF, S, device=local)
+    g = ctx.geom
+    nmb, fb = g["num_mb"], g["frame_bytes"]
+    stream = torch.cuda.Stream()
+    ctx.set_cuda_stream(stream.cuda_stream)
+
+    n_sets = RING
+    host_sets = make_sources(S, n_sets, rank)
+    # pinned host ring for the e2e leg, device ring for the resident leg
+    L = _lib.lib()
+    pin = L.p64b_host_alloc(host_sets.nbytes)
+    pin_mbs = L.p64b_host_alloc(S * nmb * 8)
+    pin_lv = L.p64b_host_alloc(S * nmb * 384)
+    if not (pin and pin_mbs and pin_lv):
+        raise SystemExit("pinned allocation failed")
+    C.memmove(pin, host_sets.ctypes.data, host_sets.nbytes)
+    dev_sets = torch.from_numpy(host_sets).cuda()
+    d_mbs = torch.zeros(S * nmb * 8, dtype=torch.uint8, device="cuda")
+    d_lv = torch.zeros(S * nmb * 384, dtype=torch.int8, device="cuda")
+    set_bytes = S * fb
+
+    def ring(i):   # ping-pong through the ring so consecutive steps are consecutive frames of every clip
+        j = i % (2 * n_sets - 2)
+        return j if j < n_sets else 2 * n_sets - 2 - j
+
+    def step_dev(i, first=False):
+        ctx.encode_frames_dev(make_step(first, QUANT, 1, SEARCH_LIMIT), dev_sets.data_ptr() + ring(i) * set_bytes,
+                              d_mbs.data_ptr(), d_lv.data_ptr())
+
+    def step_host(i, first=False):
+        st = make_step(first, QUANT, 1, SEARCH_LIMIT)
+        _lib.check(L.p64b_ctx_encode_frames(ctx.h, C.byref(st), C.c_void_p(pin + ring(i) * set_bytes),
+                                            C.c_void_p(pin_mbs), C.c_void_p(pin_lv)))
+
+    # ---- device-resident leg -----------------------------------------------------------------------------
+    with torch.cuda.stream(stream):
+        for i in range(W):
+            step_dev(i, first=(i == 0))
+        barrier()
+        samples, stop = [], threading.Event()
+        th = threading.Thread(target=_clocks_sampler, args=(stop, samples, local), daemon=True)
+        th.start()
+        launches0 = ctx.launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(K):
+            step_dev(W + i)
+        e1.record(stream)
+        barrier()
+        launches = ctx.launches - launches0
+        ms = e0.elapsed_time(e1)
+        # per-kernel durations (CUDA events around every launch, on the launching stream), same K steps again
+        ctx.profile(True)
+        for i in range(K):
+            step_dev(W + K + i)
+        prof = ctx.profile_read()
+        ctx.profile(False)
+        # ---- e2e leg: host buffers through the C-ABI call --------------------------------------------------
+        for i in range(max(2, min(W, 3))):
+            step_host(W + 2 * K + i)
+        barrier()
+        t0 = time.perf_counter()
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0.record(stream)
+        for i in range(K):
+            step_host(W + 2 * K + 3 + i)
+        h1.record(stream)
+        barrier()
+        ms_e2e_wall = (time.perf_counter() - t0) * 1e3
+        ms_e2e = max(h0.elapsed_time(h1), ms_e2e_wall)   # the call is synchronous: host wall and device span agree
+        stop.set()
+        th.join(timeout=2)
+
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+
+    frames = world * S * K
+    value = frames / (ms * 1e-3)
+    e2e_value = frames / (ms_e2e * 1e-3)
+    line = None
+    if rank == 0:
+        peak_ops, clk = C.c_double(), C.c_double()
+        _lib.check(L.p64b_measure_sad_peak(local, C.byref(peak_ops), C.byref(clk)))
+        me_ms = prof["me"][0] / max(1, prof["me"][1])
+        mb_ms = prof["mb"][0] / max(1, prof["mb"][1])
+        me_ops = SAD_OPS_PER_CIF_FRAME * S
+        mb_bytes = MB_BYTES_INTER * nmb * S
+        hbm_peak, peak_src = 6650.0, "fallback"
+        try:
+            mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            hbm_peak, peak_src = float(mp["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+        me_roof = {"kernel": "me_surface_kernel", "bound": "int_issue", "achieved": me_ops / (me_ms * 1e-3) / 1e9,
+                   "peak": peak_ops.value / 1e9, "unit": "G packed-SAD ops/s", "frac": (me_ops / (me_ms * 1e-3)) / peak_ops.value,
+                   "traffic": None, "avg_launch_ms": me_ms, "launches_timed": prof["me"][1],
+                   "peak_source": "measured live: VABSDIFF4.U8.ACC issue-rate probe (p64b_measure_sad_peak)",
+                   "algorithmic": f"{SAD_OPS_PER_CIF_FRAME} packed SAD ops per CIF frame (343473 legal candidates x 64) x {S} frames per launch"}
+        mb_roof = {"kernel": "mb_encode_kernel", "bound": "hbm", "achieved": mb_bytes / (mb_ms * 1e-3) / 1e9, "peak": hbm_peak,
+                   "unit": "GB/s", "frac": (mb_bytes / (mb_ms * 1e-3) / 1e9) / hbm_peak, "traffic": None, "avg_launch_ms": mb_ms,
+                   "launches_timed": prof["mb"][1], "peak_source": peak_src,
+                   "algorithmic": f"{MB_BYTES_INTER} B per inter macroblock (384 source + 384 prediction + 384 reconstruction + 384 int8 levels + 8 record) x {nmb * S} macroblocks per launch"}
+        dominant = me_roof if me_ms >= mb_ms else mb_roof
+        cpu = None
+        if world == 1:
+            fps, cores, kind, what = run_reference_sample(60)
+            cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind, "sample": what}
+        line = {"metric": "CIF frames/sec encoded (ME+DCT+Q+recon)", "value": value, "unit": "frames/s", "n_gpus": world,
+                "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": {"workload": f"{S} independent synthetic CIF 352x288 4:2:0 streams per GPU (BASELINE configs[4] per-GPU share), "
+                                       f"one step = one inter frame of every stream, fixed quantiser {QUANT}, full-search ME +-15 (-i {SEARCH_LIMIT}), no rate control",
+                           "streams_per_gpu": S, "frames_per_step": world * S, "parallelism": f"streams partitioned over {world} GPU(s), no collective",
+                           "l2": f"inputs larger than L2: ring of {n_sets} source sets ({n_sets * set_bytes >> 20} MiB) + frame stores + outputs = {(n_sets + 3) * set_bytes >> 20} MiB per GPU"},
+                "roofline": dominant, "roofline_kernels": {"me_surface_kernel": me_roof, "mb_encode_kernel": mb_roof},
+                "kernel_share_of_step": {"me_surface_kernel": me_ms / (me_ms + mb_ms), "mb_encode_kernel": mb_ms / (me_ms + mb_ms)},
+                "cpu_baseline": cpu,
+                "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": S * fb, "d2h_bytes_per_step": S * nmb * (384 + 8),
+                        "ms_per_step": ms_e2e / K, "api": "p64b_ctx_encode_frames (host buffers, pinned)"},
+                "gpu_launches": int(launches), "clocks": _summarise_clocks(samples)}
+        print(json.dumps(line))
+    ctx.close()
+    L.p64b_host_free(pin); L.p64b_host_free(pin_mbs); L.p64b_host_free(pin_lv)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
+    return main_reference(args) if args.impl == "reference" else main_cuda(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -149,6 +149,11 @@ int p64b_ctx_download_recon(p64b_ctx *ctx, int stream, uint8_t *yuv);
 int p64b_ctx_last_intra(p64b_ctx *ctx, int stream, uint8_t *out);
 /* number of kernel launches issued by this context so far */
 int64_t p64b_ctx_launches(const p64b_ctx *ctx);
+/* Per-kernel device timing (CUDA events on the launching stream around every launch) for the roofline report.
+ * profile(ctx,1) clears and starts recording, profile(ctx,0) stops; profile_read sums the recorded launches:
+ * ms_total[2], count[2] -- index 0 = motion-estimation kernel, 1 = macroblock (DCT/quant/recon) kernel. */
+int p64b_ctx_profile(p64b_ctx *ctx, int enable);
+int p64b_ctx_profile_read(p64b_ctx *ctx, double *ms_total, int32_t *count);
 /* Measured issue peak of the packed 4-byte SAD instruction (VABSDIFF4.U8.ACC) on this device, in
  * packed ops per second: the denominator of the ME roofline (no datasheet figure exists). */
 int p64b_measure_sad_peak(int device, double *ops_per_s, double *sm_clock_mhz);

@@ -5,6 +5,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <utility>
+#include <vector>
 
 #include "kernels.cuh"
 
@@ -52,6 +54,21 @@ struct p64b_ctx {
   uint8_t* d_ovf = nullptr;       // [S][nmb]
   const uint8_t* frame_src = nullptr;   // source of the frame in flight (frame_begin .. frame_end)
   int64_t launches = 0;
+  // optional per-kernel timing with CUDA events on the launching stream (bench.py roofline)
+  bool prof = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_ev[2];   // 0 = ME kernel, 1 = MB kernel
+};
+
+struct ProfScope {   // records an event pair around one launch when profiling is on
+  p64b_ctx* c; int k; cudaEvent_t e1 = nullptr;
+  ProfScope(p64b_ctx* c_, int k_) : c(c_), k(k_) {
+    if (!c->prof) return;
+    cudaEvent_t e0;
+    if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) { e1 = nullptr; return; }
+    cudaEventRecord(e0, c->stream);
+    c->prof_ev[k].emplace_back(e0, e1);
+  }
+  ~ProfScope() { if (e1) cudaEventRecord(e1, c->stream); }
 };
 
 static int use_device(const p64b_ctx* c) {
@@ -68,6 +85,7 @@ static int launch_me(p64b_ctx* c, const uint8_t* ref, const uint8_t* cur, size_t
     attr_done = true;
   }
   const int grid = n_pairs * c->g.mbw * c->g.mbh;
+  ProfScope ps(c, 0);
   me_surface_kernel<<<grid, ME_THREADS, smem, c->stream>>>(ref, cur, stride, c->g, me_mode, search_limit, out, surface);
   c->launches++;
   CU(cudaGetLastError());
@@ -83,6 +101,7 @@ static int launch_mb(p64b_ctx* c, const p64b_step* st, const uint8_t* src, int g
   a.gob_first = gob_first; a.gob_count = gob_count; a.out_mb_per_stream = gob_count * 33;
   a.first_frame = st->first_frame; a.force_intra = st->force_intra; a.gquant = st->gquant;
   const int n = c->S * gob_count * 33;
+  ProfScope ps(c, 1);
   mb_encode_kernel<<<(n + MB_PER_CTA - 1) / MB_PER_CTA, MBK_THREADS, 0, c->stream>>>(a);
   c->launches++;
   CU(cudaGetLastError());
@@ -303,6 +322,29 @@ int p64b_ctx_last_intra(p64b_ctx* c, int stream, uint8_t* out) {
 }
 
 int64_t p64b_ctx_launches(const p64b_ctx* c) { return c ? c->launches : 0; }
+
+int p64b_ctx_profile(p64b_ctx* c, int enable) {
+  if (!c) return P64B_EINVAL;
+  int rc;
+  if ((rc = use_device(c))) return rc;
+  CU(cudaStreamSynchronize(c->stream));
+  for (auto& v : c->prof_ev) { for (auto& e : v) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); } v.clear(); }
+  c->prof = enable != 0;
+  return 0;
+}
+
+int p64b_ctx_profile_read(p64b_ctx* c, double* ms_total, int32_t* count) {
+  if (!c || !ms_total || !count) return P64B_EINVAL;
+  int rc;
+  if ((rc = use_device(c))) return rc;
+  CU(cudaStreamSynchronize(c->stream));
+  for (int k = 0; k < 2; k++) {
+    double t = 0;
+    for (auto& e : c->prof_ev[k]) { float ms = 0; CU(cudaEventElapsedTime(&ms, e.first, e.second)); t += ms; }
+    ms_total[k] = t; count[k] = (int32_t)c->prof_ev[k].size();
+  }
+  return 0;
+}
 
 int p64b_measure_sad_peak(int device, double* ops_per_s, double* sm_clock_mhz) {
   if (!ops_per_s) return P64B_EINVAL;

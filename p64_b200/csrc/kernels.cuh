@@ -30,7 +30,7 @@ constexpr int ME_THREADS = 128;        // 4 warps: warp w owns dy in [-15+8w, -1
 constexpr int ME_WIN_ROWS = 47;        // window rows y0-15 .. y0+31
 constexpr int ME_ROW_WORDS = 12;       // 48 bytes: x0-16 .. x0+31
 constexpr int ME_COPY_WORDS = 584;     // >= 47*12, and == 8 (mod 32): lanes (k,q) hit 32 distinct banks
-constexpr int ME_SMEM_WORDS = 4 * ME_COPY_WORDS + 64 /*cur*/ + 31 * 31 /*surface*/ + 16 /*scratch*/;
+constexpr int ME_SMEM_WORDS = 4 * ME_COPY_WORDS + 64 /*cur*/ + 31 * 31 /*surface*/ + 32 /*scratch*/;
 
 __device__ __forceinline__ uint32_t sad4(uint32_t a, uint32_t b, uint32_t c) {
   uint32_t d;
@@ -56,7 +56,7 @@ me_surface_kernel(const uint8_t* __restrict__ ref, const uint8_t* __restrict__ c
   uint32_t* win = smem;                              // [4][ME_COPY_WORDS]: copy k = window shifted left by k bytes
   uint32_t* s_cur = smem + 4 * ME_COPY_WORDS;        // [16][4]
   uint32_t* s_sad = s_cur + 64;                      // [31][31], index [dy+15][dx+15]
-  uint32_t* s_red = s_sad + 31 * 31;                 // [16]
+  uint32_t* s_red = s_sad + 31 * 31;                 // [32]
 
   const int nmb_r = g.mbw * g.mbh;
   const int pair = blockIdx.x / nmb_r, mb = blockIdx.x % nmb_r;
@@ -76,11 +76,14 @@ me_surface_kernel(const uint8_t* __restrict__ ref, const uint8_t* __restrict__ c
   if (tid < 16) cp_async16_zfill(s_cur + 4 * tid, cp + (size_t)(y0 + tid) * g.W + x0, true);
   cp_async_wait_all();
   __syncthreads();
-  // ---- byte-shifted copies 1..3 so that every packed SAD operand is an aligned word (no PRMT in the loop)
-  for (int i = tid; i < 3 * ME_WIN_ROWS * 11; i += ME_THREADS) {
-    int k = 1 + i / (ME_WIN_ROWS * 11), rem = i % (ME_WIN_ROWS * 11);
-    int idx = (rem / 11) * ME_ROW_WORDS + rem % 11;
-    win[k * ME_COPY_WORDS + idx] = __funnelshift_r(win[idx], win[idx + 1], 8 * k);
+  // ---- byte-shifted copies 1..3 so that every packed SAD operand is an aligned word (no PRMT in the loop):
+  // each (row, word) pair yields the three shifted words from the same two source words
+  for (int i = tid; i < ME_WIN_ROWS * 11; i += ME_THREADS) {
+    const int r = i / 11, idx = i + r;              // r*12 + (i - 11 r)
+    const uint32_t lo = win[idx], hi = win[idx + 1];
+    win[1 * ME_COPY_WORDS + idx] = __funnelshift_r(lo, hi, 8);
+    win[2 * ME_COPY_WORDS + idx] = __funnelshift_r(lo, hi, 16);
+    win[3 * ME_COPY_WORDS + idx] = __funnelshift_r(lo, hi, 24);
   }
   uint32_t c[16][4];
 #pragma unroll
@@ -113,15 +116,29 @@ me_surface_kernel(const uint8_t* __restrict__ ref, const uint8_t* __restrict__ c
       }
     }
     const int dx = o - 16, px = x0 + dx;
+    const bool need_surface = (me_mode != P64B_ME_FULL) || (surface != nullptr);
+    // FastBME (me.c:206-227): dx outer, dy inner over [-S/2, S/2), strict <, (0,0) probed first:
+    // winner = min over key = SAD<<11 | scan order, where (0,0) has order 0 and the rest 1 + (dx+15)*31 + (dy+15).
+    const int lo = (-search_limit) / 2, hi = search_limit / 2;
+    uint32_t best = 0xffffffffu;
 #pragma unroll
     for (int j = 0; j < 8; j++) {
       const int dyi = 8 * warp + j;                 // dy + 15
       const int dy = dyi - 15, py = y0 + dy;
       if (o >= 1 && dyi < 31) {
         // legality: me.c:212-213, 292-293 (strict < on the far edge); (0,0) is always probed (me.c:203, 271)
-        bool legal = (px >= 0 && px < g.W - 16 && py >= 0 && py < g.H - 16) || (dx == 0 && dy == 0);
-        s_sad[dyi * 31 + (o - 1)] = legal ? acc[j] : 0xffffffffu;
+        const bool centre = (dx == 0 && dy == 0);
+        const bool legal = (px >= 0 && px < g.W - 16 && py >= 0 && py < g.H - 16) || centre;
+        if (need_surface) s_sad[dyi * 31 + (o - 1)] = legal ? acc[j] : 0xffffffffu;
+        if (centre) { s_red[3] = acc[j]; best = min(best, acc[j] << 11); }
+        else if (legal && dx >= lo && dx < hi && dy >= lo && dy < hi)
+          best = min(best, (acc[j] << 11) | (uint32_t)(1 + (o - 1) * 31 + dyi));
       }
+    }
+    if (me_mode == P64B_ME_FULL) {
+#pragma unroll
+      for (int d = 16; d >= 1; d >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, d));
+      if (lane == 0) s_red[4 + warp] = best;
     }
   }
   __syncthreads();
@@ -129,31 +146,14 @@ me_surface_kernel(const uint8_t* __restrict__ ref, const uint8_t* __restrict__ c
   if (surface)   // test hook: the whole surface, [dy+15][dx+15], 0xffffffff = illegal position
     for (int i = tid; i < 31 * 31; i += ME_THREADS) surface[(size_t)blockIdx.x * 961 + i] = s_sad[i];
 
-  // ---- search over the surface
+  // ---- search result
   int mx = 0, my = 0;
-  uint32_t mv = s_sad[15 * 31 + 15];
+  uint32_t mv = s_red[3];
   const uint32_t omv = mv;
   if (me_mode == P64B_ME_FULL) {
-    // FastBME (me.c:206-227): dx outer, dy inner over [-S/2, S/2), strict <, (0,0) first.
-    // key = SAD<<11 | scan order, (0,0) gets order 0.
-    const int lo = (-search_limit) / 2, hi = search_limit / 2;
-    uint32_t best = (omv << 11);
-    for (int i = tid; i < 31 * 31; i += ME_THREADS) {
-      int dxi = i / 31, dyi = i % 31;               // dx-major enumeration = scan order
-      int dx = dxi - 15, dy = dyi - 15;
-      uint32_t s = s_sad[dyi * 31 + dxi];
-      if (dx >= lo && dx < hi && dy >= lo && dy < hi && s != 0xffffffffu) {
-        uint32_t key = (s << 11) | (uint32_t)(1 + i);
-        best = min(best, key);
-      }
-    }
-#pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, d));
-    if (lane == 0) s_red[warp] = best;
-    __syncthreads();
-    best = min(min(s_red[0], s_red[1]), min(s_red[2], s_red[3]));
+    const uint32_t best = min(min(s_red[4], s_red[5]), min(s_red[6], s_red[7]));
     mv = best >> 11;
-    int ord = best & 2047;
+    const int ord = best & 2047;
     if (ord) { mx = (ord - 1) / 31 - 15; my = (ord - 1) % 31 - 15; }
   } else {
     // StepBME (me.c:273-311): steps 8,4,2,1; 8 neighbours in (diry outer, dirx inner) order; the centre
@@ -185,7 +185,6 @@ me_surface_kernel(const uint8_t* __restrict__ ref, const uint8_t* __restrict__ c
     __syncthreads();
     mx = (int)s_red[0]; my = (int)s_red[1]; mv = s_red[2];
   }
-  __syncthreads();
 
   // ---- statistics over the best-match reference block (me.c:230-245): 2 pixels per thread
   {
@@ -203,13 +202,13 @@ me_surface_kernel(const uint8_t* __restrict__ ref, const uint8_t* __restrict__ c
       so += __shfl_xor_sync(0xffffffffu, so, d);
       sm += __shfl_xor_sync(0xffffffffu, sm, d);
     }
-    if (lane == 0) { s_red[4 + warp] = sv; s_red[8 + warp] = so; s_red[12 + warp] = sm; }
+    if (lane == 0) { s_red[8 + warp] = sv; s_red[12 + warp] = so; s_red[16 + warp] = sm; }
   }
   __syncthreads();
   if (tid == 0) {
-    int var = s_red[4] + s_red[5] + s_red[6] + s_red[7];
-    int varor = s_red[8] + s_red[9] + s_red[10] + s_red[11];
-    int mwor = s_red[12] + s_red[13] + s_red[14] + s_red[15];
+    int var = s_red[8] + s_red[9] + s_red[10] + s_red[11];
+    int varor = s_red[12] + s_red[13] + s_red[14] + s_red[15];
+    int mwor = s_red[16] + s_red[17] + s_red[18] + s_red[19];
     var /= 256;
     varor = varor / 256 - (mwor / 256) * (mwor / 256);
     int4* o = reinterpret_cast<int4*>(out + (size_t)pair * nmb_r + mb);

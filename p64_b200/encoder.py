@@ -107,6 +107,16 @@ class DeviceContext:
         check(self.L.p64b_ctx_last_intra(self.h, stream, _ptr(out)))
         return out
 
+    def profile(self, enable: bool):
+        check(self.L.p64b_ctx_profile(self.h, int(enable)))
+
+    def profile_read(self):
+        """-> {"me": (ms_total, launches), "mb": (ms_total, launches)}"""
+        ms = (C.c_double * 2)()
+        n = (C.c_int32 * 2)()
+        check(self.L.p64b_ctx_profile_read(self.h, ms, n))
+        return {"me": (ms[0], n[0]), "mb": (ms[1], n[1])}
+
     @property
     def launches(self) -> int:
         return int(self.L.p64b_ctx_launches(self.h))
