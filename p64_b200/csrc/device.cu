@@ -1,6 +1,7 @@
 // Device context and the p64b_ctx_* C ABI (include/p64_b200.h): frame stores resident in HBM for a batch
 // of independent streams, kernel launches, host<->device staging.  No CPU fallback: every entry point
 // fails with P64B_ECUDA when no CUDA device is usable.
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -76,19 +77,62 @@ static int use_device(const p64b_ctx* c) {
   return 0;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult st;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &st) == cudaSuccess && st == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// u8 tensor {W, H, n_pairs} over luma planes `stride` bytes apart; box {bw, bh, 1}; out-of-bounds -> 0
+static int make_plane_map(CUtensorMap* tm, const uint8_t* base, int W, int H, size_t stride, int n_pairs, int bw, int bh) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return P64B_ECUDA; }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (stride & 15)) { set_error("luma planes must be 16-byte aligned"); return P64B_EINVAL; }
+  cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_pairs};
+  cuuint64_t strides[2] = {(cuuint64_t)W, (cuuint64_t)stride};
+  cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)bh, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(base), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed: " + std::to_string((int)r)); return P64B_ECUDA; }
+  return 0;
+}
+
 static int launch_me(p64b_ctx* c, const uint8_t* ref, const uint8_t* cur, size_t stride, int n_pairs, int me_mode,
                      int search_limit, p64b_me* out, uint32_t* surface = nullptr) {
   static bool attr_done = false;
-  const size_t smem = ME_SMEM_WORDS * sizeof(uint32_t);
   if (!attr_done) {
-    CU(cudaFuncSetAttribute(me_surface_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaFuncSetAttribute(me_surface_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ME_SMEM_BYTES));
     attr_done = true;
   }
-  const int grid = n_pairs * c->g.mbw * c->g.mbh;
+  int rc;
+  CUtensorMap tm_ref, tm_cur;
+  if ((rc = make_plane_map(&tm_ref, ref, c->g.W, c->g.H, stride, n_pairs, 48, ME_WIN_ROWS))) return rc;
+  if ((rc = make_plane_map(&tm_cur, cur, c->g.W, c->g.H, stride, n_pairs, 16, 16))) return rc;
   ProfScope ps(c, 0);
-  me_surface_kernel<<<grid, ME_THREADS, smem, c->stream>>>(ref, cur, stride, c->g, me_mode, search_limit, out, surface);
-  c->launches++;
-  CU(cudaGetLastError());
+  for (int z0 = 0; z0 < n_pairs; z0 += 65535) {      // gridDim.z limit
+    const int nz = std::min(65535, n_pairs - z0);
+    if (z0) {
+      if ((rc = make_plane_map(&tm_ref, ref + (size_t)z0 * stride, c->g.W, c->g.H, stride, nz, 48, ME_WIN_ROWS))) return rc;
+      if ((rc = make_plane_map(&tm_cur, cur + (size_t)z0 * stride, c->g.W, c->g.H, stride, nz, 16, 16))) return rc;
+    }
+    dim3 grid(c->g.mbw, c->g.mbh, nz);
+    me_surface_kernel<<<grid, ME_THREADS, ME_SMEM_BYTES, c->stream>>>(
+        tm_ref, tm_cur, c->g, me_mode, search_limit, out + (size_t)z0 * c->g.mbw * c->g.mbh,
+        surface ? surface + (size_t)z0 * c->g.mbw * c->g.mbh * 961 : nullptr);
+    c->launches++;
+    CU(cudaGetLastError());
+  }
   return 0;
 }
 

@@ -9,6 +9,7 @@
 //   overflow_patch_kernel  MBs the host overrode to "type 4, zero vector" (p64.c:776-783)
 #pragma once
 #include <cstdint>
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include "../../include/p64_b200.h"
@@ -26,57 +27,74 @@ struct Geom {
 // ---------------------------------------------------------------------------------------------------
 // Motion estimation
 // ---------------------------------------------------------------------------------------------------
-constexpr int ME_THREADS = 128;        // 4 warps: warp w owns dy in [-15+8w, -15+8w+8); lane L owns dx = L-16
+// One CTA (4 warps) per macroblock.  The 47x48-byte search window is staged by one TMA tile load (out-of-frame
+// samples zero-filled by the TMA unit) and replicated shifted by 1..3 bytes, so that every packed-SAD operand in
+// the hot loop is an aligned 32-bit shared-memory word (no PRMT/funnel shifts in the loop).  warp <-> byte shift k,
+// lane <-> (word offset q, dy group gq): candidate dx = 4q+k-16, dy in {2gq + {0,1,8,9,16,17,24,25}} - 15.
+// Each thread keeps the whole current block in 64 registers and slides down 41 window rows, feeding 8
+// independent VABSDIFF4.U8.ACC accumulators (512 packed SADs per thread, 164 LDS.32).
+constexpr int ME_THREADS = 128;
 constexpr int ME_WIN_ROWS = 47;        // window rows y0-15 .. y0+31
-constexpr int ME_ROW_WORDS = 12;       // 48 bytes: x0-16 .. x0+31
-constexpr int ME_COPY_WORDS = 584;     // >= 47*12, and == 8 (mod 32): lanes (k,q) hit 32 distinct banks
-constexpr int ME_SMEM_WORDS = 4 * ME_COPY_WORDS + 64 /*cur*/ + 31 * 31 /*surface*/ + 32 /*scratch*/;
+constexpr int ME_ROW_WORDS = 12;       // 48 bytes: x0-16+k .. x0+31+k
+constexpr int ME_COPY_WORDS = 576;     // 47*48 = 2256 B rounded up to 2304 (TMA destinations are 128-B aligned)
+constexpr int ME_WIN_BYTES = ME_WIN_ROWS * 48;
+constexpr int ME_SMEM_BYTES = 128 /*align*/ + 4 * ME_COPY_WORDS * 4 + 256 /*cur*/ + 31 * 31 * 4 /*surface*/ + 32 * 4 + 16;
 
 __device__ __forceinline__ uint32_t sad4(uint32_t a, uint32_t b, uint32_t c) {
   uint32_t d;
   asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));   // VABSDIFF4.U8.ACC
   return d;
 }
-
-__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, bool valid) {
-  uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-  int n = valid ? 16 : 0;
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(n));   // LDGSTS, zero fill
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-__device__ __forceinline__ void cp_async_wait_all() {
-  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// TMA: 3-D tiled bulk tensor load global -> shared, completion on an mbarrier (UTMALDG in SASS)
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, int x, int y, int z, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(smem_u32(dst)), "l"(tm), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
 }
 
-// One CTA per macroblock.  ref/cur: luma planes of `n_pairs` frames, `pair_stride` bytes apart.
-// out[pair][raster mb].
+// tm_ref / tm_cur: u8 tensors {W, H, n_pairs}; boxes {48,47,1} and {16,16,1}.  grid = (mbw, mbh, n_pairs).
 __global__ void __launch_bounds__(ME_THREADS)
-me_surface_kernel(const uint8_t* __restrict__ ref, const uint8_t* __restrict__ cur, size_t pair_stride, Geom g,
+me_surface_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constant__ CUtensorMap tm_cur, Geom g,
                   int me_mode, int search_limit, p64b_me* __restrict__ out, uint32_t* __restrict__ surface) {
-  extern __shared__ __align__(16) uint32_t smem[];
-  uint32_t* win = smem;                              // [4][ME_COPY_WORDS]: copy k = window shifted left by k bytes
-  uint32_t* s_cur = smem + 4 * ME_COPY_WORDS;        // [16][4]
-  uint32_t* s_sad = s_cur + 64;                      // [31][31], index [dy+15][dx+15]
-  uint32_t* s_red = s_sad + 31 * 31;                 // [32]
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sbase = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);   // TMA destinations: 128-B aligned
+  uint32_t* win = reinterpret_cast<uint32_t*>(sbase);                   // [4][ME_COPY_WORDS]
+  uint32_t* s_cur = win + 4 * ME_COPY_WORDS;                            // [16][4]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(s_cur + 64);             // mbarrier (8-B aligned)
+  uint32_t* s_red = s_cur + 64 + 4;                                     // [32]
+  uint32_t* s_sad = s_red + 32;                                         // [31][31], index [dy+15][dx+15]
 
-  const int nmb_r = g.mbw * g.mbh;
-  const int pair = blockIdx.x / nmb_r, mb = blockIdx.x % nmb_r;
-  const int x0 = (mb % g.mbw) * 16, y0 = (mb / g.mbw) * 16;
-  const uint8_t* rp = ref + (size_t)pair * pair_stride;
-  const uint8_t* cp = cur + (size_t)pair * pair_stride;
+  const int x0 = blockIdx.x * 16, y0 = blockIdx.y * 16, pair = blockIdx.z;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  // ---- stage the search window (47 rows x 48 B, out-of-frame chunks zero-filled) and the current block
-  for (int i = tid; i < ME_WIN_ROWS * 3; i += ME_THREADS) {
-    int r = i / 3, c = i % 3;
-    int gy = y0 - 15 + r, gx = x0 - 16 + 16 * c;
-    bool ok = gy >= 0 && gy < g.H && gx >= 0 && gx < g.W;
-    const uint8_t* src = ok ? rp + (size_t)gy * g.W + gx : rp;
-    cp_async16_zfill(win + r * ME_ROW_WORDS + 4 * c, src, ok);
-  }
-  if (tid < 16) cp_async16_zfill(s_cur + 4 * tid, cp + (size_t)(y0 + tid) * g.W + x0, true);
-  cp_async_wait_all();
+  if (tid == 0) mbar_init(bar, 1);
   __syncthreads();
-  // ---- byte-shifted copies 1..3 so that every packed SAD operand is an aligned word (no PRMT in the loop):
+  if (tid == 0) {
+    mbar_expect_tx(bar, ME_WIN_BYTES + 256);
+    tma_load_3d(win, &tm_ref, x0 - 16, y0 - 15, pair, bar);      // out-of-frame samples arrive as zeros
+    tma_load_3d(s_cur, &tm_cur, x0, y0, pair, bar);
+  }
+  mbar_wait(bar, 0);
+  // byte-shifted copies 1..3 (TMA needs a 16-byte aligned innermost start, so only copy 0 comes from the TMA unit):
   // each (row, word) pair yields the three shifted words from the same two source words
   for (int i = tid; i < ME_WIN_ROWS * 11; i += ME_THREADS) {
     const int r = i / 11, idx = i + r;              // r*12 + (i - 11 r)
@@ -85,28 +103,31 @@ me_surface_kernel(const uint8_t* __restrict__ ref, const uint8_t* __restrict__ c
     win[2 * ME_COPY_WORDS + idx] = __funnelshift_r(lo, hi, 16);
     win[3 * ME_COPY_WORDS + idx] = __funnelshift_r(lo, hi, 24);
   }
+
   uint32_t c[16][4];
 #pragma unroll
   for (int i = 0; i < 16; i++) {
     uint4 v = reinterpret_cast<const uint4*>(s_cur)[i];
     c[i][0] = v.x; c[i][1] = v.y; c[i][2] = v.z; c[i][3] = v.w;
   }
+
   __syncthreads();
 
-  // ---- SAD surface: lane <-> dx = lane-16 (lane 0 idle), warp <-> 8 consecutive dy, sliding down 23 rows
+  // ---- SAD surface
+  const int k = warp, q = lane & 7, gq = lane >> 3;
+  const int o = 4 * q + k;                                  // dx + 16
   {
-    const int o = lane, k = o & 3, q = o >> 2;
-    const uint32_t* base = win + k * ME_COPY_WORDS + q + (8 * warp) * ME_ROW_WORDS;
+    const uint32_t* base = win + k * ME_COPY_WORDS + (2 * gq) * ME_ROW_WORDS + q;
     uint32_t acc[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) acc[j] = 0;
 #pragma unroll
-    for (int t = 0; t < 23; t++) {
-      uint32_t r0 = base[t * ME_ROW_WORDS + 0], r1 = base[t * ME_ROW_WORDS + 1];
-      uint32_t r2 = base[t * ME_ROW_WORDS + 2], r3 = base[t * ME_ROW_WORDS + 3];
+    for (int t = 0; t < 41; t++) {
+      const uint32_t r0 = base[t * ME_ROW_WORDS + 0], r1 = base[t * ME_ROW_WORDS + 1];
+      const uint32_t r2 = base[t * ME_ROW_WORDS + 2], r3 = base[t * ME_ROW_WORDS + 3];
 #pragma unroll
       for (int j = 0; j < 8; j++) {
-        const int i = t - j;
+        const int i = t - (8 * (j >> 1) + (j & 1));
         if (i >= 0 && i < 16) {
           acc[j] = sad4(r0, c[i][0], acc[j]);
           acc[j] = sad4(r1, c[i][1], acc[j]);
@@ -115,27 +136,31 @@ me_surface_kernel(const uint8_t* __restrict__ ref, const uint8_t* __restrict__ c
         }
       }
     }
+    // legality: me.c:212-213, 292-293 (strict < on the far edge).  FastBME (me.c:206-227) scans dx outer, dy inner
+    // over [-S/2, S/2) with strict <, after probing (0,0): winner = min key = SAD<<11 | (1 + (dx+15)*31 + (dy+15)),
+    // and (0,0) re-enters after the reduction with order 0 so that it wins ties.
     const int dx = o - 16, px = x0 + dx;
-    const bool need_surface = (me_mode != P64B_ME_FULL) || (surface != nullptr);
-    // FastBME (me.c:206-227): dx outer, dy inner over [-S/2, S/2), strict <, (0,0) probed first:
-    // winner = min over key = SAD<<11 | scan order, where (0,0) has order 0 and the rest 1 + (dx+15)*31 + (dy+15).
-    const int lo = (-search_limit) / 2, hi = search_limit / 2;
+    const bool full = me_mode == P64B_ME_FULL;
+    const int lo = full ? (-search_limit) / 2 : -15, hi = full ? search_limit / 2 : 16;
+    const bool xok = o >= 1 && px >= 0 && px < g.W - 16;
+    const bool xin = xok && dx >= lo && dx < hi;
+    const int dyi_lo = max(15 - y0, 0), dyi_hi = min(g.H - 17 - y0 + 15, 30);        // legal rows of the surface
+    const int dyi_rlo = max(dyi_lo, 15 + lo), dyi_rhi = min(dyi_hi, 14 + hi);        // ... inside the search range
+    const bool need_surface = !full || surface != nullptr;
     uint32_t best = 0xffffffffu;
+    const uint32_t ord0 = 1 + (o - 1) * 31 + 2 * gq;
 #pragma unroll
     for (int j = 0; j < 8; j++) {
-      const int dyi = 8 * warp + j;                 // dy + 15
-      const int dy = dyi - 15, py = y0 + dy;
-      if (o >= 1 && dyi < 31) {
-        // legality: me.c:212-213, 292-293 (strict < on the far edge); (0,0) is always probed (me.c:203, 271)
-        const bool centre = (dx == 0 && dy == 0);
-        const bool legal = (px >= 0 && px < g.W - 16 && py >= 0 && py < g.H - 16) || centre;
-        if (need_surface) s_sad[dyi * 31 + (o - 1)] = legal ? acc[j] : 0xffffffffu;
-        if (centre) { s_red[3] = acc[j]; best = min(best, acc[j] << 11); }
-        else if (legal && dx >= lo && dx < hi && dy >= lo && dy < hi)
-          best = min(best, (acc[j] << 11) | (uint32_t)(1 + (o - 1) * 31 + dyi));
-      }
+      const int dj = 8 * (j >> 1) + (j & 1);
+      const int dyi = 2 * gq + dj;                          // dy + 15
+      if (xin && dyi >= dyi_rlo && dyi <= dyi_rhi) best = min(best, (acc[j] << 11) | (ord0 + dj));
+      if (need_surface && o >= 1 && dyi < 31) s_sad[dyi * 31 + (o - 1)] = (xok && dyi >= dyi_lo && dyi <= dyi_hi) ? acc[j] : 0xffffffffu;
     }
-    if (me_mode == P64B_ME_FULL) {
+    if (o == 16 && gq == 3) {                               // the (0,0) probe (me.c:203, 271): dyi = 6 + 9 -> j = 3
+      s_red[3] = acc[3];
+      if (need_surface) s_sad[15 * 31 + 15] = acc[3];
+    }
+    if (full) {
 #pragma unroll
       for (int d = 16; d >= 1; d >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, d));
       if (lane == 0) s_red[4 + warp] = best;
@@ -144,14 +169,15 @@ me_surface_kernel(const uint8_t* __restrict__ ref, const uint8_t* __restrict__ c
   __syncthreads();
 
   if (surface)   // test hook: the whole surface, [dy+15][dx+15], 0xffffffff = illegal position
-    for (int i = tid; i < 31 * 31; i += ME_THREADS) surface[(size_t)blockIdx.x * 961 + i] = s_sad[i];
+    for (int i = tid; i < 31 * 31; i += ME_THREADS)
+      surface[((size_t)(pair * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 961 + i] = s_sad[i];
 
   // ---- search result
   int mx = 0, my = 0;
   uint32_t mv = s_red[3];
   const uint32_t omv = mv;
   if (me_mode == P64B_ME_FULL) {
-    const uint32_t best = min(min(s_red[4], s_red[5]), min(s_red[6], s_red[7]));
+    const uint32_t best = min(min(min(s_red[4], s_red[5]), min(s_red[6], s_red[7])), omv << 11);
     mv = best >> 11;
     const int ord = best & 2047;
     if (ord) { mx = (ord - 1) / 31 - 15; my = (ord - 1) % 31 - 15; }
@@ -186,16 +212,15 @@ me_surface_kernel(const uint8_t* __restrict__ ref, const uint8_t* __restrict__ c
     mx = (int)s_red[0]; my = (int)s_red[1]; mv = s_red[2];
   }
 
-  // ---- statistics over the best-match reference block (me.c:230-245): 2 pixels per thread
-  {
-    const uint8_t* wb = reinterpret_cast<const uint8_t*>(win);
-    const uint8_t* cb = reinterpret_cast<const uint8_t*>(s_cur);
-    int i = tid >> 3, cx = (tid & 7) * 2;
-    int r0 = wb[(my + 15 + i) * 48 + mx + 16 + cx], r1 = wb[(my + 15 + i) * 48 + mx + 16 + cx + 1];
-    int c0 = cb[i * 16 + cx], c1 = cb[i * 16 + cx + 1];
-    int sv = (r0 - c0) * (r0 - c0) + (r1 - c1) * (r1 - c1);
-    int so = r0 * r0 + r1 * r1;
-    int sm = r0 + r1;
+  // ---- statistics over the best-match reference block (me.c:230-245), on packed words:
+  // sum r = SAD(r,0); sum r^2 = dp4a(r,r); sum (r-c)^2 = dp4a(r,r) - 2 dp4a(r,c) + dp4a(c,c)
+  if (tid < 64) {
+    const int i = tid >> 2, wc = tid & 3, oo = mx + 16;
+    const uint32_t r = win[(oo & 3) * ME_COPY_WORDS + (my + 15 + i) * ME_ROW_WORDS + (oo >> 2) + wc];
+    const uint32_t cw = s_cur[i * 4 + wc];
+    uint32_t sm = sad4(r, 0u, 0u);
+    uint32_t so = __dp4a(r, r, 0u);
+    uint32_t sv = so + __dp4a(cw, cw, 0u) - 2u * __dp4a(r, cw, 0u);
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) {
       sv += __shfl_xor_sync(0xffffffffu, sv, d);
@@ -206,14 +231,14 @@ me_surface_kernel(const uint8_t* __restrict__ ref, const uint8_t* __restrict__ c
   }
   __syncthreads();
   if (tid == 0) {
-    int var = s_red[8] + s_red[9] + s_red[10] + s_red[11];
-    int varor = s_red[12] + s_red[13] + s_red[14] + s_red[15];
-    int mwor = s_red[16] + s_red[17] + s_red[18] + s_red[19];
+    int var = (int)(s_red[8] + s_red[9]);
+    int varor = (int)(s_red[12] + s_red[13]);
+    int mwor = (int)(s_red[16] + s_red[17]);
     var /= 256;
     varor = varor / 256 - (mwor / 256) * (mwor / 256);
-    int4* o = reinterpret_cast<int4*>(out + (size_t)pair * nmb_r + mb);
-    o[0] = make_int4(mx, my, (int)mv, (int)omv);
-    o[1] = make_int4(var, varor, mwor, 0);
+    int4* op = reinterpret_cast<int4*>(out + ((size_t)pair * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x);
+    op[0] = make_int4(mx, my, (int)mv, (int)omv);
+    op[1] = make_int4(var, varor, mwor, 0);
   }
 }
 
