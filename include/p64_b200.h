@@ -113,6 +113,14 @@ void p64b_host_free(void *p);
  */
 int p64b_ctx_encode_frames(p64b_ctx *ctx, const p64b_step *step, const uint8_t *src, p64b_mb *mbs,
                            int8_t *levels);
+/* The same step, pipelined: submit() returns as soon as the work is enqueued (upload on a copy stream, kernels on
+ * the context's stream, download on a second copy stream) so that consecutive steps overlap their PCIe traffic with
+ * each other's kernels; wait(ticket) blocks until that step's mbs/levels are complete in the caller's buffers.
+ * src/mbs/levels must stay valid (and src unmodified) until wait() returns; use pinned memory (p64b_host_alloc).
+ * At most 3 steps may be in flight; p64b_ctx_encode_frames() == submit + wait. */
+int p64b_ctx_submit(p64b_ctx *ctx, const p64b_step *step, const uint8_t *src, p64b_mb *mbs, int8_t *levels,
+                    int64_t *ticket);
+int p64b_ctx_wait(p64b_ctx *ctx, int64_t ticket);
 /* Same with device pointers (inputs already resident in HBM, outputs left there). */
 int p64b_ctx_encode_frames_dev(p64b_ctx *ctx, const p64b_step *step, const uint8_t *src_dev,
                                p64b_mb *mbs_dev, int8_t *levels_dev);

@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libp64b200.so")
+LIB_PATH = os.environ.get("P64B_LIB") or os.path.join(HERE, "libp64b200.so")   # P64B_LIB: experiments only
 
 
 class MB(C.Structure):
@@ -46,6 +46,8 @@ SIGNATURES = {
     "p64b_host_alloc": (_vp, [_sz]),
     "p64b_host_free": (None, [_vp]),
     "p64b_ctx_encode_frames": (_i, [_vp, C.POINTER(Step), _vp, _vp, _vp]),
+    "p64b_ctx_submit": (_i, [_vp, C.POINTER(Step), _vp, _vp, _vp, C.POINTER(C.c_int64)]),
+    "p64b_ctx_wait": (_i, [_vp, C.c_int64]),
     "p64b_ctx_encode_frames_dev": (_i, [_vp, C.POINTER(Step), _vp, _vp, _vp]),
     "p64b_ctx_frame_begin": (_i, [_vp, C.POINTER(Step), _vp]),
     "p64b_ctx_encode_gob": (_i, [_vp, C.POINTER(Step), _i, _vp, _vp, _vp]),

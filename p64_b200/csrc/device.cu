@@ -44,7 +44,16 @@ struct p64b_ctx {
   int device = 0, image_type = 0, S = 0;
   Geom g{};
   cudaStream_t own = nullptr, stream = nullptr;
-  uint8_t* d_src = nullptr;       // [S][frame_bytes]
+  uint8_t* d_src = nullptr;       // [S][frame_bytes]   (= slot 0 of the pipelined path)
+  // pipelined host path (submit / wait): NSLOT sets of device staging buffers, separate copy streams
+  static constexpr int NSLOT = 3;
+  uint8_t* p_src[NSLOT] = {};
+  p64b_mb* p_mbs[NSLOT] = {};
+  int8_t* p_levels[NSLOT] = {};
+  cudaEvent_t ev_h2d[NSLOT] = {}, ev_comp[NSLOT] = {}, ev_d2h[NSLOT] = {};
+  bool slot_used[NSLOT] = {};
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  int64_t submitted = 0;
   uint8_t* d_fs[2] = {nullptr, nullptr};   // frame stores; d_fs[cur] = CFS (reference), d_fs[cur^1] = OFS
   uint8_t* d_li[2] = {nullptr, nullptr};   // LastIntra, same double buffering
   int cur = 0;
@@ -112,7 +121,8 @@ static int launch_me(p64b_ctx* c, const uint8_t* ref, const uint8_t* cur, size_t
                      int search_limit, p64b_me* out, uint32_t* surface = nullptr) {
   static bool attr_done = false;
   if (!attr_done) {
-    CU(cudaFuncSetAttribute(me_surface_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ME_SMEM_BYTES));
+    CU(cudaFuncSetAttribute(me_surface_kernel<ME_V_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, ME_SMEM_BYTES));
+    CU(cudaFuncSetAttribute(me_surface_kernel<ME_V_SURF>, cudaFuncAttributeMaxDynamicSharedMemorySize, ME_SMEM_BYTES));
     attr_done = true;
   }
   int rc;
@@ -127,9 +137,12 @@ static int launch_me(p64b_ctx* c, const uint8_t* ref, const uint8_t* cur, size_t
       if ((rc = make_plane_map(&tm_cur, cur + (size_t)z0 * stride, c->g.W, c->g.H, stride, nz, 16, 16))) return rc;
     }
     dim3 grid(c->g.mbw, c->g.mbh, nz);
-    me_surface_kernel<<<grid, ME_THREADS, ME_SMEM_BYTES, c->stream>>>(
-        tm_ref, tm_cur, c->g, me_mode, search_limit, out + (size_t)z0 * c->g.mbw * c->g.mbh,
-        surface ? surface + (size_t)z0 * c->g.mbw * c->g.mbh * 961 : nullptr);
+    p64b_me* o = out + (size_t)z0 * c->g.mbw * c->g.mbh;
+    uint32_t* sf = surface ? surface + (size_t)z0 * c->g.mbw * c->g.mbh * 961 : nullptr;
+    if (me_mode == P64B_ME_FULL && !surface)
+      me_surface_kernel<ME_V_FULL><<<grid, ME_THREADS, ME_SMEM_BYTES, c->stream>>>(tm_ref, tm_cur, c->g, me_mode, search_limit, o, sf);
+    else
+      me_surface_kernel<ME_V_SURF><<<grid, ME_THREADS, ME_SMEM_BYTES, c->stream>>>(tm_ref, tm_cur, c->g, me_mode, search_limit, o, sf);
     c->launches++;
     CU(cudaGetLastError());
   }
@@ -203,9 +216,21 @@ int p64b_ctx_create(p64b_ctx** out, int device, int image_type, int n_streams) {
   ALLOC(c->d_levels, nm * P64B_LEVELS_PER_MB);
   ALLOC(c->d_quant, (size_t)n_streams);
   ALLOC(c->d_ovf, nm);
-#undef ALLOC
-  if (cudaStreamCreateWithFlags(&c->own, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream create failed"); return fail(P64B_ECUDA); }
+  c->p_src[0] = c->d_src; c->p_mbs[0] = c->d_mbs; c->p_levels[0] = c->d_levels;
+  for (int i = 1; i < p64b_ctx::NSLOT; i++) {
+    ALLOC(c->p_src[i], fb + slack);
+    ALLOC(c->p_mbs[i], nm * sizeof(p64b_mb));
+    ALLOC(c->p_levels[i], nm * P64B_LEVELS_PER_MB);
+  }
+  for (int i = 0; i < p64b_ctx::NSLOT; i++)
+    if (cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_comp[i], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_d2h[i], cudaEventDisableTiming) != cudaSuccess) { set_error("event create failed"); return fail(P64B_ECUDA); }
+  if (cudaStreamCreateWithFlags(&c->own, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream create failed"); return fail(P64B_ECUDA); }
   c->stream = c->own;
+#undef ALLOC
   if (cudaDeviceSynchronize() != cudaSuccess) { set_error("sync failed"); return fail(P64B_ECUDA); }
   *out = c;
   return 0;
@@ -217,6 +242,16 @@ void p64b_ctx_destroy(p64b_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   cudaFree(c->d_src); cudaFree(c->d_fs[0]); cudaFree(c->d_fs[1]); cudaFree(c->d_li[0]); cudaFree(c->d_li[1]);
   cudaFree(c->d_me); cudaFree(c->d_mbs); cudaFree(c->d_levels); cudaFree(c->d_quant); cudaFree(c->d_ovf);
+  if (c->s_h2d) cudaStreamSynchronize(c->s_h2d);
+  if (c->s_d2h) cudaStreamSynchronize(c->s_d2h);
+  for (int i = 0; i < p64b_ctx::NSLOT; i++) {
+    if (i) { cudaFree(c->p_src[i]); cudaFree(c->p_mbs[i]); cudaFree(c->p_levels[i]); }
+    if (c->ev_h2d[i]) cudaEventDestroy(c->ev_h2d[i]);
+    if (c->ev_comp[i]) cudaEventDestroy(c->ev_comp[i]);
+    if (c->ev_d2h[i]) cudaEventDestroy(c->ev_d2h[i]);
+  }
+  if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
+  if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
   if (c->own) cudaStreamDestroy(c->own);
   delete c;
 }
@@ -253,23 +288,57 @@ int p64b_ctx_encode_frames_dev(p64b_ctx* c, const p64b_step* st, const uint8_t* 
   return 0;
 }
 
-int p64b_ctx_encode_frames(p64b_ctx* c, const p64b_step* st, const uint8_t* src, p64b_mb* mbs, int8_t* levels) {
-  if (!c || !src || !mbs || !levels) { set_error("NULL argument"); return P64B_EINVAL; }
+// Pipelined host path.  submit(n) enqueues, without blocking the host:
+//   copy stream  : H2D of the step's source frames into staging slot n % NSLOT
+//   compute stream (the context's stream): ME + MB kernels (ordered after the H2D; frame stores chain the steps)
+//   copy-back stream : D2H of records + levels into the caller's buffers
+// so that step n+1's upload and step n-1's download overlap step n's kernels.  wait(ticket) blocks until the
+// caller's output buffers of that step are complete.  Host buffers should be pinned (p64b_host_alloc).
+int p64b_ctx_submit(p64b_ctx* c, const p64b_step* st, const uint8_t* src, p64b_mb* mbs, int8_t* levels, int64_t* ticket) {
+  if (!c || !src || !mbs || !levels || !ticket) { set_error("NULL argument"); return P64B_EINVAL; }
+  if (c->frame_src) { set_error("p64b_ctx_submit inside frame_begin/frame_end"); return P64B_EINVAL; }
+  int rc;
+  if ((rc = check_step(st)) || (rc = check_quant(st->gquant)) || (rc = use_device(c))) return rc;
+  const int slot = (int)(c->submitted % p64b_ctx::NSLOT);
+  const size_t fb = (size_t)c->S * c->g.frame_bytes, nm = (size_t)c->S * c->g.nmb;
+  if (c->slot_used[slot]) {
+    CU(cudaStreamWaitEvent(c->s_h2d, c->ev_comp[slot], 0));    // the slot's source was consumed by its last kernels
+    CU(cudaStreamWaitEvent(c->stream, c->ev_d2h[slot], 0));    // its outputs were downloaded
+  }
+  CU(cudaMemcpyAsync(c->p_src[slot], src, fb, cudaMemcpyHostToDevice, c->s_h2d));
+  CU(cudaEventRecord(c->ev_h2d[slot], c->s_h2d));
+  CU(cudaStreamWaitEvent(c->stream, c->ev_h2d[slot], 0));
+  if ((rc = p64b_ctx_encode_frames_dev(c, st, c->p_src[slot], c->p_mbs[slot], c->p_levels[slot]))) return rc;
+  CU(cudaEventRecord(c->ev_comp[slot], c->stream));
+  CU(cudaStreamWaitEvent(c->s_d2h, c->ev_comp[slot], 0));
+  CU(cudaMemcpyAsync(mbs, c->p_mbs[slot], nm * sizeof(p64b_mb), cudaMemcpyDeviceToHost, c->s_d2h));
+  CU(cudaMemcpyAsync(levels, c->p_levels[slot], nm * P64B_LEVELS_PER_MB, cudaMemcpyDeviceToHost, c->s_d2h));
+  CU(cudaEventRecord(c->ev_d2h[slot], c->s_d2h));
+  c->slot_used[slot] = true;
+  *ticket = c->submitted++;
+  return 0;
+}
+
+int p64b_ctx_wait(p64b_ctx* c, int64_t ticket) {
+  if (!c || ticket < 0 || ticket >= c->submitted) { set_error("bad ticket"); return P64B_EINVAL; }
   int rc;
   if ((rc = use_device(c))) return rc;
-  const size_t fb = (size_t)c->S * c->g.frame_bytes, nm = (size_t)c->S * c->g.nmb;
-  CU(cudaMemcpyAsync(c->d_src, src, fb, cudaMemcpyHostToDevice, c->stream));
-  if ((rc = p64b_ctx_encode_frames_dev(c, st, c->d_src, c->d_mbs, c->d_levels))) return rc;
-  CU(cudaMemcpyAsync(mbs, c->d_mbs, nm * sizeof(p64b_mb), cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaMemcpyAsync(levels, c->d_levels, nm * P64B_LEVELS_PER_MB, cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaEventSynchronize(c->ev_d2h[ticket % p64b_ctx::NSLOT]));
   return 0;
+}
+
+int p64b_ctx_encode_frames(p64b_ctx* c, const p64b_step* st, const uint8_t* src, p64b_mb* mbs, int8_t* levels) {
+  int64_t t;
+  int rc = p64b_ctx_submit(c, st, src, mbs, levels, &t);
+  return rc ? rc : p64b_ctx_wait(c, t);
 }
 
 int p64b_ctx_frame_begin(p64b_ctx* c, const p64b_step* st, const uint8_t* src) {
   if (!c || !src) { set_error("NULL argument"); return P64B_EINVAL; }
   int rc;
   if ((rc = check_step(st)) || (rc = use_device(c))) return rc;
+  CU(cudaStreamSynchronize(c->s_h2d));      // drain any pipelined steps still in flight (they share staging slot 0)
+  CU(cudaStreamSynchronize(c->s_d2h));
   CU(cudaMemcpyAsync(c->d_src, src, (size_t)c->S * c->g.frame_bytes, cudaMemcpyHostToDevice, c->stream));
   if (!st->first_frame) {
     if ((rc = launch_me(c, c->d_fs[c->cur], c->d_src, (size_t)c->g.frame_bytes, c->S, st->me_mode, st->search_limit, c->d_me))) return rc;

@@ -72,6 +72,10 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, in
 }
 
 // tm_ref / tm_cur: u8 tensors {W, H, n_pairs}; boxes {48,47,1} and {16,16,1}.  grid = (mbw, mbh, n_pairs).
+// VARIANT: ME_V_FULL exhaustive argmin straight from registers; ME_V_SURF stages the 31x31 surface in shared
+// memory for the three-step walk (me_mode == TSS) and/or the test hook (surface != nullptr).
+constexpr int ME_V_FULL = 0, ME_V_SURF = 1;
+template <int VARIANT>
 __global__ void __launch_bounds__(ME_THREADS)
 me_surface_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constant__ CUtensorMap tm_cur, Geom g,
                   int me_mode, int search_limit, p64b_me* __restrict__ out, uint32_t* __restrict__ surface) {
@@ -143,32 +147,36 @@ me_surface_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_const
     const bool full = me_mode == P64B_ME_FULL;
     const int lo = full ? (-search_limit) / 2 : -15, hi = full ? search_limit / 2 : 16;
     const bool xok = o >= 1 && px >= 0 && px < g.W - 16;
-    const bool xin = xok && dx >= lo && dx < hi;
     const int dyi_lo = max(15 - y0, 0), dyi_hi = min(g.H - 17 - y0 + 15, 30);        // legal rows of the surface
-    const int dyi_rlo = max(dyi_lo, 15 + lo), dyi_rhi = min(dyi_hi, 14 + hi);        // ... inside the search range
-    const bool need_surface = !full || surface != nullptr;
-    uint32_t best = 0xffffffffu;
-    const uint32_t ord0 = 1 + (o - 1) * 31 + 2 * gq;
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-      const int dj = 8 * (j >> 1) + (j & 1);
-      const int dyi = 2 * gq + dj;                          // dy + 15
-      if (xin && dyi >= dyi_rlo && dyi <= dyi_rhi) best = min(best, (acc[j] << 11) | (ord0 + dj));
-      if (need_surface && o >= 1 && dyi < 31) s_sad[dyi * 31 + (o - 1)] = (xok && dyi >= dyi_lo && dyi <= dyi_hi) ? acc[j] : 0xffffffffu;
-    }
-    if (o == 16 && gq == 3) {                               // the (0,0) probe (me.c:203, 271): dyi = 6 + 9 -> j = 3
-      s_red[3] = acc[3];
-      if (need_surface) s_sad[15 * 31 + 15] = acc[3];
-    }
+    if (o == 16 && gq == 3) s_red[3] = acc[3];               // the (0,0) probe (me.c:203, 271): dyi = 6 + 9 -> j = 3
     if (full) {
+      // rows inside the search range as a bit mask over dyi (CTA-uniform), then this thread's 8 rows
+      const int rlo = max(dyi_lo, 15 + lo), rhi = min(dyi_hi, 14 + hi);
+      uint32_t rows = rhi >= rlo ? ((2u << rhi) - 1u) & ~((1u << rlo) - 1u) : 0u;
+      rows = (xok && dx >= lo && dx < hi) ? rows >> (2 * gq) : 0u;
+      uint32_t best = 0xffffffffu;
 #pragma unroll
-      for (int d = 16; d >= 1; d >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, d));
+      for (int j = 0; j < 8; j++) {
+        const int dj = 8 * (j >> 1) + (j & 1);
+        const uint32_t key = acc[j] * 2048u + (uint32_t)dj;
+        if (rows & (1u << dj)) best = min(best, key);
+      }
+      if (best != 0xffffffffu) best += 1 + (o - 1) * 31 + 2 * gq;
+      best = __reduce_min_sync(0xffffffffu, best);
       if (lane == 0) s_red[4 + warp] = best;
+    }
+    if (VARIANT == ME_V_SURF) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const int dyi = 2 * gq + 8 * (j >> 1) + (j & 1);    // dy + 15
+        if (o >= 1 && dyi < 31) s_sad[dyi * 31 + (o - 1)] = (xok && dyi >= dyi_lo && dyi <= dyi_hi) ? acc[j] : 0xffffffffu;
+      }
+      if (o == 16 && gq == 3) s_sad[15 * 31 + 15] = acc[3];
     }
   }
   __syncthreads();
 
-  if (surface)   // test hook: the whole surface, [dy+15][dx+15], 0xffffffff = illegal position
+  if (VARIANT == ME_V_SURF && surface)   // test hook: the whole surface, [dy+15][dx+15], 0xffffffff = illegal position
     for (int i = tid; i < 31 * 31; i += ME_THREADS)
       surface[((size_t)(pair * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 961 + i] = s_sad[i];
 
@@ -181,7 +189,7 @@ me_surface_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_const
     mv = best >> 11;
     const int ord = best & 2047;
     if (ord) { mx = (ord - 1) / 31 - 15; my = (ord - 1) % 31 - 15; }
-  } else {
+  } else if (VARIANT == ME_V_SURF) {
     // StepBME (me.c:273-311): steps 8,4,2,1; 8 neighbours in (diry outer, dirx inner) order; the centre
     // moves once per step; strict < keeps the earlier candidate on ties.  Warp 0, lanes 0..7 probe in parallel.
     if (warp == 0) {
@@ -221,12 +229,9 @@ me_surface_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_const
     uint32_t sm = sad4(r, 0u, 0u);
     uint32_t so = __dp4a(r, r, 0u);
     uint32_t sv = so + __dp4a(cw, cw, 0u) - 2u * __dp4a(r, cw, 0u);
-#pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) {
-      sv += __shfl_xor_sync(0xffffffffu, sv, d);
-      so += __shfl_xor_sync(0xffffffffu, so, d);
-      sm += __shfl_xor_sync(0xffffffffu, sm, d);
-    }
+    sv = __reduce_add_sync(0xffffffffu, sv);
+    so = __reduce_add_sync(0xffffffffu, so);
+    sm = __reduce_add_sync(0xffffffffu, sm);
     if (lane == 0) { s_red[8 + warp] = sv; s_red[12 + warp] = so; s_red[16 + warp] = sm; }
   }
   __syncthreads();
@@ -444,7 +449,10 @@ __device__ __forceinline__ void fetch_pred(const uint8_t* plane, int w, int bx, 
   if (mt_is(M_FILTER, mt)) loop_filter(p);
 }
 
-__global__ void __launch_bounds__(MBK_THREADS)
+#ifndef MBK_MINB
+#define MBK_MINB 1
+#endif
+__global__ void __launch_bounds__(MBK_THREADS, MBK_MINB)
 mb_encode_kernel(MbArgs a) {
   __shared__ int s_acc[6][MB_PER_CTA];
   const Geom& g = a.g;

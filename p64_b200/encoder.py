@@ -68,6 +68,15 @@ class DeviceContext:
         check(self.L.p64b_ctx_encode_frames(self.h, C.byref(step), _ptr(src), _ptr(mbs), _ptr(levels)))
         return mbs, levels
 
+    def submit(self, step: Step, src_ptr: int, mbs_ptr: int, levels_ptr: int) -> int:
+        """Pipelined host path (raw pinned host pointers); returns a ticket for wait()."""
+        t = C.c_int64()
+        check(self.L.p64b_ctx_submit(self.h, C.byref(step), _ptr(src_ptr), _ptr(mbs_ptr), _ptr(levels_ptr), C.byref(t)))
+        return t.value
+
+    def wait(self, ticket: int):
+        check(self.L.p64b_ctx_wait(self.h, ticket))
+
     def encode_frames_dev(self, step: Step, src_dev: int, mbs_dev: int, levels_dev: int):
         check(self.L.p64b_ctx_encode_frames_dev(self.h, C.byref(step), _ptr(src_dev), _ptr(mbs_dev), _ptr(levels_dev)))
 
