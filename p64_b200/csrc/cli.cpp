@@ -1,0 +1,132 @@
+// p64b -- command line with the reference encoder's flags (p64.c:262-449, Help() p64.c:1537-1568) on top of the
+// B200 hot path.  Encoder only (the decoder is out of scope); input is Y4M (the reference's raw-component path
+// crashes at end of sequence).  Extra flags that the reference lacks are spelled with two dashes:
+//   --me tss|full   the stock three-step search (me.c:352) or the exhaustive FastBME (me.c:351)   [default tss]
+//   --intra-only    stand-in for `-o < test.intra` (every macroblock intra)
+//   --device N      CUDA device
+// Same stdout markers as the reference (START>SEQUENCE, START>Frame: n, END>Frame: n, END>SEQUENCE, and the
+// "Bits for first frame" line, p64.c:595-611, 627, 665).
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/p64_b200.h"
+
+static void help() {
+  printf("p64b -a StartFrame -b LastFrame [-NTSC] [-CIF] [-QCIF] [-y4m]\n"
+         "     [-f FrameRate[/Div]] [-i SearchLimit] [-k FrameSkip] [-q Quantization] [-r Rate] [-x FileSizeBits]\n"
+         "     [-s StreamFile] [--me tss|full] [--intra-only] [--device N] Y4MFilePrefix\n"
+         "Encodes PrefixYUV4MPEG2 file `Prefix.y4m` (or `-` for stdin) into an H.261 stream; the data-parallel hot path\n"
+         "(motion estimation, DCT, quantisation, reconstruction) runs on the GPU. There is no CPU fallback.\n");
+}
+
+struct Y4m {
+  FILE* f = nullptr;
+  int w = 0, h = 0;
+  bool open(const char* path) {
+    f = strcmp(path, "-") ? fopen(path, "rb") : stdin;
+    if (!f) return false;
+    char hdr[256];
+    if (!fgets(hdr, sizeof hdr, f) || strncmp(hdr, "YUV4MPEG2", 9)) return false;
+    for (char* t = strtok(hdr + 9, " \n"); t; t = strtok(nullptr, " \n")) {
+      if (t[0] == 'W') w = atoi(t + 1);
+      else if (t[0] == 'H') h = atoi(t + 1);
+      else if (t[0] == 'C' && strcmp(t, "C420jpeg") && strcmp(t, "C420")) {
+        fprintf(stderr, "p64b: chroma format %s needs the reference's re-siting filters (y4m_input.c:195-545), not supported\n", t);
+        return false;
+      }
+    }
+    return w > 0 && h > 0;
+  }
+  bool frame(uint8_t* dst) {
+    char line[128];
+    if (!fgets(line, sizeof line, f) || strncmp(line, "FRAME", 5)) return false;
+    size_t n = (size_t)w * h * 3 / 2;
+    return fread(dst, 1, n, f) == n;
+  }
+};
+
+int main(int argc, char** argv) {
+  p64b_enc_params p;
+  p64b_enc_default_params(&p);
+  int start = 0, last = 0, file_size_bits = 0;
+  std::string prefix, stream_file;
+  if (argc == 1) { help(); return -1; }
+  for (int i = 1; i < argc; i++) {
+    std::string a = argv[i];
+    auto next = [&]() -> const char* { if (i + 1 >= argc) { help(); exit(1); } return argv[++i]; };
+    if (a == "-NTSC") p.image_type = P64B_IT_NTSC;
+    else if (a == "-CIF") p.image_type = P64B_IT_CIF;
+    else if (a == "-QCIF") p.image_type = P64B_IT_QCIF;
+    else if (a == "-y4m") {}
+    else if (a == "--me") { std::string m = next(); p.me_mode = m == "full" ? P64B_ME_FULL : P64B_ME_TSS; }
+    else if (a == "--intra-only" || a == "-o") p.force_intra = 1;
+    else if (a == "--device") p.device = atoi(next());
+    else if (a == "-a") start = atoi(next());
+    else if (a == "-b") last = atoi(next());
+    else if (a == "-f") {                                  // p64.c:316-340
+      const char* v = next();
+      p.frame_rate = atoi(v); p.frame_rate_div = 1;
+      if (const char* s = strpbrk(v, "/:")) p.frame_rate_div = atoi(s + 1) > 0 ? atoi(s + 1) : 1;
+      else if (const char* d = strchr(v, '.')) {
+        for (size_t k = strlen(d + 1); k > 0; --k) p.frame_rate_div *= 10;
+        p.frame_rate = p.frame_rate * p.frame_rate_div + atoi(d + 1);
+      }
+    }
+    else if (a == "-i") p.search_limit = atoi(next());
+    else if (a == "-k") p.frame_skip = atoi(next());
+    else if (a == "-q") p.initial_quant = atoi(next());
+    else if (a == "-r") p.rate = atoi(next());
+    else if (a == "-x") file_size_bits = atoi(next());
+    else if (a == "-s") stream_file = next();
+    else if (a == "-l" || a == "-z") next();               // accepted, ignored (statistics / suffixes)
+    else if (a == "-v" || a == "-c" || a == "-p") {}
+    else if (a == "-") prefix = "-";
+    else if (a[0] == '-') { printf("Illegal Option %s\n", a.c_str()); return 3; }
+    else prefix = a;
+  }
+  if (prefix.empty()) { printf("A file prefix should be specified.\n"); return 3; }
+  if (start > last) { printf("Need positive number of frames.\n"); return 3; }
+  if (p.search_limit < 1 || p.search_limit > 31 || p.initial_quant < 0 || p.initial_quant > 31) { printf("Parameter out of bounds.\n"); return 3; }
+  if (file_size_bits)                                       // p64.c:572-573
+    p.rate = (int)((long long)file_size_bits * p.frame_rate / p.frame_rate_div / (p.frame_skip * (last - start + 1)));
+  p.start_frame = start;
+  if (stream_file.empty()) stream_file = prefix + ".p64";
+
+  Y4m in;
+  std::string path = prefix == "-" ? "-" : prefix + ".y4m";
+  if (!in.open(path.c_str())) { fprintf(stderr, "Unable to open '%s'.\n", path.c_str()); return -1; }
+  if (in.w != p64b_width(p.image_type) || in.h != p64b_height(p.image_type)) {
+    fprintf(stderr, "p64b: %dx%d input does not match the selected image type (%dx%d)\n", in.w, in.h,
+            p64b_width(p.image_type), p64b_height(p.image_type));
+    return 3;
+  }
+  p64b_enc* enc = nullptr;
+  if (p64b_enc_create(&enc, &p)) { fprintf(stderr, "p64b: %s\n", p64b_last_error()); return 2; }
+  std::vector<uint8_t> frame(p64b_frame_bytes(p.image_type));
+  for (int i = start; i > 0; --i)                           // seek to StartFrame (p64.c:562-565)
+    if (!in.frame(frame.data())) return 3;
+  if (p.rate) {
+    printf("Rate: %d   QDFact: %d  QOffs: %d\n", p.rate, p.rate / 320, 1);
+  }
+  printf("START>SEQUENCE\n");
+  for (int cf = start; cf <= last; cf += p.frame_skip) {
+    printf("START>Frame: %d\n", cf);
+    if (!in.frame(frame.data())) { p64b_enc_destroy(enc); return 3; }
+    if (p64b_enc_encode(enc, frame.data())) { fprintf(stderr, "p64b: %s\n", p64b_last_error()); return 2; }
+    printf("END>Frame: %d\n", cf);
+  }
+  p64b_enc_finish(enc);
+  size_t n = 0;
+  const uint8_t* data = p64b_enc_data(enc, 0, &n);
+  FILE* out = fopen(stream_file.c_str(), "wb");
+  if (!out || fwrite(data, 1, n, out) != n) { printf("Cannot Open Output File\n"); return 1; }
+  fclose(out);
+  printf("END>SEQUENCE\n");
+  printf("Bits for first frame: %lld   Number of buffer overflows: %lld\n", (long long)p64b_enc_first_frame_bits(enc, 0),
+         (long long)p64b_enc_overflows(enc, 0));
+  p64b_enc_destroy(enc);
+  return 0;
+}

@@ -1,0 +1,187 @@
+"""CPU-only checks: the C-ABI library loads without a GPU and exports every symbol include/p64_b200.h declares;
+host-side logic (VLC tables, bit writer, multiply-shift divider, geometry, Y4M, CLI) behaves as specified."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("P64_REFERENCE", "/root/reference")
+
+
+@pytest.fixture(scope="module")
+def L():
+    from p64_b200 import build, _lib
+    build.build_lib()
+    return _lib.lib()
+
+
+def test_library_exports_every_declared_symbol(L):
+    hdr = open(os.path.join(ROOT, "include", "p64_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(p64b_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 40
+    from p64_b200 import _lib
+    raw = C.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(raw, name), f"{name} declared in include/p64_b200.h but not exported"
+    assert declared == set(_lib.SIGNATURES), "ctypes signature table out of sync with the header"
+
+
+def test_geometry(L):
+    assert [L.p64b_width(t) for t in range(3)] == [352, 352, 176]
+    assert [L.p64b_height(t) for t in range(3)] == [240, 288, 144]
+    assert [L.p64b_num_gob(t) for t in range(3)] == [10, 12, 3]
+    assert [L.p64b_num_mb(t) for t in range(3)] == [330, 396, 99]
+    assert [L.p64b_frame_bytes(t) for t in range(3)] == [126720, 152064, 38016]
+    assert L.p64b_width(9) < 0
+
+
+def test_fails_loudly_without_gpu(L):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    h = C.c_void_p()
+    rc = L.p64b_ctx_create(C.byref(h), 0, 1, 1)
+    assert rc == -2 and b"no CPU fallback" in L.p64b_last_error()
+    from p64_b200.encoder import Encoder
+    from p64_b200._lib import P64Error
+    with pytest.raises(P64Error):
+        Encoder(1, 1, q=8)
+
+
+def test_vlc_tables_match_reference_ctables(L):
+    """every (value,length,code) of ctables.h:28-317 must come out of the product's bit writer"""
+    path = os.path.join(REF, "ctables.h")
+    if not os.path.exists(path):
+        pytest.skip("reference tree not present")
+    src = re.sub(r"/\*.*?\*/", "", open(path).read(), flags=re.S)
+
+    def tab(name):
+        nums = [int(x) for x in re.findall(r"-?\d+", re.search(name + r"\[\] = \{(.*?)\};", src, re.S).group(1))]
+        return [(nums[i], nums[i + 1], nums[i + 2]) for i in range(0, len(nums) - 2, 3) if nums[i] >= 0]
+
+    from p64_b200.encoder import MB_DTYPE, BitWriter
+
+    def mb_bits(rec, levels, prev=None):
+        bw = BitWriter(1)
+        if prev is not None:
+            bw.mb(0, prev[0], prev[1])
+        n0 = bw.tell()
+        bw.mb(1 if prev is not None else 0, rec, levels)
+        n1 = bw.tell()
+        bw.finish()
+        bits = "".join(f"{b:08b}" for b in bw.data())
+        return bits[n0:n1]
+
+    z = np.zeros((6, 64), np.int8)
+    # MTYPE + MBA=1: an intra MB with all DC=1 -> "1" + mtype code + 6x(DC 8 bits + EOB "10")
+    mt = {v: format(c, f"0{l}b") for v, l, c in tab("MTypeCoeff")}
+    rec = np.zeros((), MB_DTYPE); rec["mtype"] = 0; rec["cbp"] = 0x3f
+    lv = z.copy(); lv[:, 0] = 1
+    assert mb_bits(rec, lv) == "1" + mt[0] + ("00000001" + "10") * 6
+    # CBP table: type 2 MB, block pattern from cbp, single level +1 at position 0 in each coded block -> "1"+"0" then EOB
+    cb = {v: format(c, f"0{l}b") for v, l, c in tab("CBPCoeff")}
+    for cbp in range(1, 64):
+        rec["mtype"], rec["cbp"] = 2, cbp
+        lv = z.copy()
+        for c in range(6):
+            if cbp & (1 << (5 - c)):
+                lv[c, 0] = 1
+        assert mb_bits(rec, lv) == "1" + mt[2] + cb[cbp] + ("1" + "0" + "10") * bin(cbp).count("1")
+    # MVD table: type 4 MB (MC, no coefficients) as first MB of a GOB -> absolute vector components
+    mvd = {v: format(c, f"0{l}b") for v, l, c in tab("MVDCoeff")}
+    for mv in range(-15, 16):
+        rec["mtype"], rec["cbp"], rec["mvx"], rec["mvy"] = 4, 0x3f, mv, -mv
+        assert mb_bits(rec, z) == "1" + mt[4] + mvd[mv & 31] + mvd[(-mv) & 31]
+    # differential coding with wrap (marker.c:325-331) for the second MB of a row
+    prev = np.zeros((), MB_DTYPE); prev["mtype"], prev["cbp"], prev["mvx"], prev["mvy"] = 4, 0x3f, 15, -15
+    rec["mtype"], rec["mvx"], rec["mvy"] = 4, -15, 15            # difference -30 -> +2, +30 -> -2
+    assert mb_bits(rec, z, prev=(prev, z)) == "1" + mt[4] + mvd[2] + mvd[(-2) & 31]
+    # TCOEFF: second coefficient of an intra block (table 1), every (run, level) incl. escapes
+    t1 = {v: format(c, f"0{l}b") for v, l, c in tab("TCoeff1")}
+    rec = np.zeros((), MB_DTYPE); rec["mtype"], rec["cbp"] = 0, 0x3f
+    for run in range(0, 63):
+        for level in (1, 2, 3, 5, 15, 16, 127, -1, -4, -127):
+            lv = z.copy(); lv[:, 0] = 1; lv[0, 1 + run] = level
+            code = abs(level) | (run << 8)
+            if code in t1 and code != 0x1b01:
+                want = t1[code] + ("1" if level < 0 else "0")
+            else:
+                want = t1[0x1b01] + format(run, "06b") + format(level & 0xff, "08b")
+            bits = mb_bits(rec, lv)
+            assert bits == "1" + mt[0] + "00000001" + want + "10" + ("00000001" + "10") * 5, (run, level)
+    # MBA table through a skipped-address gap
+    mba = {v: format(c, f"0{l}b") for v, l, c in tab("MBACoeff")}
+    for gap in range(1, 33):
+        bw = BitWriter(1); bw.gob_header(0, 8); n0 = bw.tell()
+        lv = z.copy(); lv[:, 0] = 1
+        bw.mb(gap - 1, rec, lv); n1 = bw.tell(); bw.finish()
+        bits = "".join(f"{b:08b}" for b in bw.data())[n0:n1]
+        assert bits.startswith(mba[gap] + mt[0])
+
+
+def test_headers_and_padding(L):
+    from p64_b200.encoder import BitWriter
+    for it, ptype, spare in [(0, 4, True), (1, 4, False), (2, 0, False)]:
+        bw = BitWriter(it)
+        bw.picture_header(21)
+        n = bw.tell()
+        want = format(0x10, "020b") + format(21, "05b") + format(ptype, "06b") + ("1" + format(0x8c, "08b") if spare else "") + "0"
+        assert n == len(want)
+        bw.gob_header(2, 17)
+        want += format(1, "016b") + format((4 if it == 2 else 2) + 1, "04b") + format(17, "05b") + "0"
+        assert bw.tell() == len(want)
+        nbytes = bw.finish()
+        want += "1" * (-len(want) % 8)                      # mwclose pads with ones (stream.c:142-152)
+        assert nbytes * 8 == len(want)
+        assert "".join(f"{b:08b}" for b in bw.data()) == want
+
+
+def test_dc_coding_rules(L):
+    """EncodeDC, codec.c:346-355: clamp to [1,254], 128 is sent as 255"""
+    from p64_b200.encoder import MB_DTYPE, BitWriter
+    rec = np.zeros((), MB_DTYPE); rec["cbp"] = 0x3f
+    for dc, sent in [(1, 1), (254, 254), (128, 255), (127, 127), (200, 200)]:
+        lv = np.zeros((6, 64), np.uint8); lv[:, 0] = dc
+        bw = BitWriter(1); bw.mb(0, rec, lv.view(np.int8)); bw.finish()
+        bits = "".join(f"{b:08b}" for b in bw.data())
+        assert bits[5:13] == format(sent, "08b")            # after MBA "1" + MTYPE "0001"
+
+
+def test_multiply_shift_dividers_are_exact():
+    """the kernels replace x/(2Q) by (x*rcp)>>19 with rcp = floor(2^19/d)+1 (kernels.cuh div_rcp): exact on the whole
+    input range the path can produce (|coef| <= 2048 after BoundDctMatrix, +1 for even Q)."""
+    a = np.arange(0, 4097, dtype=np.int64)
+    for q in range(1, 32):
+        d = 2 * q
+        rcp = (1 << 19) // d + 1
+        assert np.array_equal((a * rcp) >> 19, a // d), q
+        assert int(a.max() * rcp) < 2 ** 31
+
+
+def test_y4m_roundtrip(tmp_path):
+    from p64_b200 import y4m
+    clip = y4m.synth_clip(y4m.IT_QCIF, 3, seed=9)
+    y4m.write_y4m(str(tmp_path / "a.y4m"), y4m.IT_QCIF, clip)
+    w, h, back = y4m.read_y4m(str(tmp_path / "a.y4m"))
+    assert (w, h) == (176, 144) and np.array_equal(back, clip)
+    assert np.array_equal(y4m.synth_clip(y4m.IT_QCIF, 3, seed=9), clip)     # deterministic
+
+
+def test_cli_builds_and_reports_missing_gpu(tmp_path):
+    import torch
+    from p64_b200 import build, y4m
+    cli = build.build_cli()
+    assert os.path.exists(cli)
+    r = subprocess.run([cli], capture_output=True, text=True)
+    assert r.returncode != 0 and "StartFrame" in r.stdout
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by the gpu tests")
+    y4m.write_y4m(str(tmp_path / "c.y4m"), y4m.IT_QCIF, y4m.synth_clip(y4m.IT_QCIF, 1, 1))
+    r = subprocess.run([cli, "-y4m", "-QCIF", "-a", "0", "-b", "0", "-q", "8", str(tmp_path / "c"), "-s", str(tmp_path / "o.p64")],
+                       capture_output=True, text=True)
+    assert r.returncode == 2 and "no CPU fallback" in r.stderr

@@ -204,3 +204,51 @@ def test_full_size_batch_properties():
         assert np.array_equal(ctx.recon(0), orc.recon())
     finally:
         ctx.close()
+
+
+def test_cli_matches_reference_golden(tmp_path):
+    """the p64b command line (reference flags) writes the reference's bytes"""
+    import subprocess
+    from p64_b200 import build
+    cli = build.build_cli()
+    for name, extra in [("cif8_q8_full15", ["--me", "full"]), ("qcif12_q8_tss", []), ("qcif12_q8_intra", ["--intra-only"]),
+                        ("cif12_r128000_tss", [])]:
+        g, clip = golden_clip(name)
+        y4m.write_y4m(str(tmp_path / "c.y4m"), g["image_type"], clip)
+        a = g["args"]
+        cmd = [cli, "-y4m", y4m.FLAG[g["image_type"]], "-a", "0", "-b", str(g["n_frames"] - 1)]
+        cmd += (["-q", str(a["q"])] if "q" in a else []) + (["-r", str(a["rate"])] if "rate" in a else [])
+        cmd += (["-i", str(a["search_limit"])] if a.get("search_limit") else []) + extra
+        cmd += [str(tmp_path / "c"), "-s", str(tmp_path / "o.p64")]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        data = open(tmp_path / "o.p64", "rb").read()
+        assert hashlib.md5(data).hexdigest() == g["md5"], name
+        assert f"Number of buffer overflows: {g['overflows']}" in r.stdout
+
+
+def test_pipelined_submit_wait_equals_synchronous():
+    import ctypes as C
+    from p64_b200 import _lib
+    it = y4m.IT_QCIF
+    S, nf = 3, 7
+    clips = [y4m.synth_clip(it, nf, seed=300 + s) for s in range(S)]
+    sync = DeviceContext(it, S); pipe = DeviceContext(it, S)
+    try:
+        L = _lib.lib()
+        fb, nmb = sync.geom["frame_bytes"], sync.geom["num_mb"]
+        want = [sync.encode_frames(make_step(f == 0, 8, 1, 31), np.stack([c[f] for c in clips])) for f in range(nf)]
+        src = [np.stack([c[f] for c in clips]).copy() for f in range(nf)]
+        outs = [(np.zeros((S, nmb), want[0][0].dtype), np.zeros((S, nmb, 6, 64), np.int8)) for _ in range(nf)]
+        tickets = [pipe.submit(make_step(f == 0, 8, 1, 31), src[f].ctypes.data, outs[f][0].ctypes.data, outs[f][1].ctypes.data)
+                   for f in range(3)]
+        for f in range(3, nf):
+            pipe.wait(tickets[f - 3])
+            tickets.append(pipe.submit(make_step(False, 8, 1, 31), src[f].ctypes.data, outs[f][0].ctypes.data, outs[f][1].ctypes.data))
+        for t in tickets:
+            pipe.wait(t)
+        for f in range(nf):
+            assert np.array_equal(outs[f][0], want[f][0]) and np.array_equal(outs[f][1], want[f][1]), f
+        assert np.array_equal(pipe.recon(S - 1), sync.recon(S - 1))
+    finally:
+        sync.close(); pipe.close()
