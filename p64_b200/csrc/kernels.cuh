@@ -298,26 +298,26 @@ __device__ __forceinline__ void idct8(int& x0, int& x1, int& x2, int& x3, int& x
   x4 = b3 - c0; x5 = b2 - c1; x6 = b1 - c2; x7 = b0 - c3;
 }
 
-// ChenDct (chendct.c:97-206) on v[64] row-major, in place
-__device__ __forceinline__ void chen_fdct(int (&v)[64]) {
+// ChenDct (chendct.c:97-206) on v[64] row-major, in place, WITHOUT the final "/8 with rounding" (chendct.c:204-205):
+// that step is folded into the quantiser below.
+__device__ __forceinline__ void chen_fdct_raw(int (&v)[64]) {
 #pragma unroll
   for (int i = 0; i < 8; i++) fdct8<1>(v[i], v[8 + i], v[16 + i], v[24 + i], v[32 + i], v[40 + i], v[48 + i], v[56 + i]);
 #pragma unroll
   for (int i = 0; i < 8; i++)
     fdct8<0>(v[8 * i], v[8 * i + 1], v[8 * i + 2], v[8 * i + 3], v[8 * i + 4], v[8 * i + 5], v[8 * i + 6], v[8 * i + 7]);
-#pragma unroll
-  for (int i = 0; i < 64; i++) v[i] = (v[i] < 0 ? v[i] - 4 : v[i] + 4) / 8;
 }
-// ChenIDct (chendct.c:217-375)
-__device__ __forceinline__ void chen_idct(int (&v)[64]) {
+// ChenIDct (chendct.c:217-375) without the final "/16 with rounding" (chendct.c:373-374), folded into the reconstruction.
+__device__ __forceinline__ void chen_idct_raw(int (&v)[64]) {
 #pragma unroll
   for (int i = 0; i < 8; i++) idct8<1>(v[i], v[8 + i], v[16 + i], v[24 + i], v[32 + i], v[40 + i], v[48 + i], v[56 + i]);
 #pragma unroll
   for (int i = 0; i < 8; i++)
     idct8<0>(v[8 * i], v[8 * i + 1], v[8 * i + 2], v[8 * i + 3], v[8 * i + 4], v[8 * i + 5], v[8 * i + 6], v[8 * i + 7]);
-#pragma unroll
-  for (int i = 0; i < 64; i++) v[i] = (v[i] < 0 ? v[i] - 8 : v[i] + 8) / 16;
 }
+// trunc((v<0 ? v-h : v+h) / 2h) for h = 4, 8 (chendct.c:205, 374) == (v + h + (v>>31)) >> log2(2h)   [arithmetic shifts]
+__device__ __forceinline__ int round_div8(int v) { return (v + 4 + (v >> 31)) >> 3; }
+__device__ __forceinline__ int round_div16(int v) { return (v + 8 + (v >> 31)) >> 4; }
 
 // raster index of the coefficient that lands at zig-zag position k (inverse of transform.c:67-75)
 __host__ __device__ constexpr int izig(int k) {
@@ -327,47 +327,56 @@ __host__ __device__ constexpr int izig(int k) {
   return t[k];
 }
 
-// |v| / d for 0 <= a <= 4096, 2 <= d <= 62 by multiply-shift; rcp = floor(2^19/d)+1.
-// Exact: a*(rcp*d - 2^19) <= a*d < 2^19 (checked exhaustively in tests/test_host_logic.py).
-__device__ __forceinline__ int div_rcp(int a, int rcp) { return (a * rcp) >> 19; }
-
-// Quantise + bound (transform.c:271-350, 502-537).  Returns sum |level| (p64.c:892).
-__device__ __forceinline__ int quantise(int (&v)[64], int q, bool intra) {
-  const int d = 2 * q, rcp = (1 << 19) / d + 1, ev = (q & 1) ? 0 : 1;
+// ChenDct's final rounding + BoundDctMatrix + CCITT[Flat]Quantize + [Flat]BoundQuantizeMatrix
+// (chendct.c:204-205, transform.c:271-350, 460-537) in sign-magnitude form on the RAW transform output v:
+//   |x| = (|v|+4)>>3 clamped to 1023  ==  (min(|v|,8187)+4)>>3
+//   |level| = floor((|x| + ev) / 2Q) = floor((min(|v|,8187) + 4 + 8ev) / 16Q)          (ev = 1 for even Q; nested floors)
+//           = ((a*M + K) >> 22) with M = floor(2^22/16Q)+1, K = (4+8ev)*M   -- exact because (a+12)*16Q < 2^22
+// (tests/test_abi_and_host.py checks the identity exhaustively).  The DC term keeps the reference's two steps
+// (it is clamped from above only, transform.c:464-466).  Returns sum |level| (p64.c:892); v[] := signed levels.
+__device__ __forceinline__ int quantise_raw(int (&v)[64], int q, bool intra) {
+  const uint32_t ev = (q & 1) ? 0u : 1u;
+  const uint32_t M = (1u << 22) / (16u * q) + 1u, K = (4u + 8u * ev) * M;
   int acc = 0;
-#pragma unroll
-  for (int i = 0; i < 64; i++) {
-    int x = v[i];
-    if (i == 0) {                                           // BoundDctMatrix: DC clamped from above only
-      x = min(x, 2047);
-      if (intra) {                                          // CCITTFlatQuantize DC + FlatBound
-        x = x > 0 ? (x + 4) / 8 : (x - 4) / 8;
-        x = min(max(x, 1), 254);
-        v[0] = x; acc += x;
-        continue;
-      }
+  {
+    int x = min(round_div8(v[0]), 2047);
+    if (intra) {
+      x = min(max((x + 4) >> 3, 1), 254);                    // (x-4)/8 <= 0 for x <= 0 and is clamped to 1 anyway
+      v[0] = x; acc = x;
     } else {
-      x = min(max(x, -1023), 1023);
+      const int rcp = (1 << 19) / (2 * q) + 1;
+      int l = min(((abs(x) + (int)ev) * rcp) >> 19, 127);
+      acc = l;
+      v[0] = x < 0 ? -l : l;
     }
-    int a = abs(x) + ev;                                    // x==0, even q: (0-1)/(2q) = 0 = (0+1)/(2q)
-    int l = min(div_rcp(a, rcp), 127);
+  }
+#pragma unroll
+  for (int i = 1; i < 64; i++) {
+    const int x = v[i], sg = x >> 31;
+    const uint32_t a = (uint32_t)min(abs(x), 8187);
+    const int l = min((int)((a * M + K) >> 22), 127);
     acc += l;
-    v[i] = x < 0 ? -l : l;
+    v[i] = (l ^ sg) - sg;
   }
   return acc;
 }
 
-// Inverse quantise (transform.c:359-451)
+// Inverse quantise (transform.c:359-451): (2|l|+1)Q - ev with the sign of l, 0 stays 0; intra DC = 8 l
 __device__ __forceinline__ void dequantise(int (&v)[64], int q, bool intra) {
-  const int ev = (q & 1) ? 0 : 1;
+  const int ev = (q & 1) ? 0 : 1, q2 = 2 * q, qo = q - ev;
 #pragma unroll
   for (int i = 0; i < 64; i++) {
-    int l = v[i];
+    const int l = v[i];
     if (i == 0 && intra) { v[0] = l * 8; continue; }
-    int a = abs(l);
-    int r = (2 * a + 1) * q - ev;
-    v[i] = l == 0 ? 0 : (l < 0 ? -r : r);
+    const int sg = l >> 31, a = abs(l);
+    const int r = a ? a * q2 + qo : 0;
+    v[i] = (r ^ sg) - sg;
   }
+}
+
+__device__ __forceinline__ int ubyte(uint32_t w, int k) { return (int)__byte_perm(w, 0, 0x4440 + k); }   // PRMT, zero-extended byte k
+__device__ __forceinline__ uint32_t pack4(int a, int b, int c, int d) {                                   // low bytes of a,b,c,d
+  return __byte_perm(__byte_perm((uint32_t)a, (uint32_t)b, 0x0040), __byte_perm((uint32_t)c, (uint32_t)d, 0x0040), 0x5410);
 }
 
 // H.261 loop filter on one 8x8 block held in registers (LoadFilterMatrix, io.c:323-372).
@@ -399,17 +408,6 @@ __device__ __forceinline__ void loop_filter(int (&p)[64]) {
   }
 }
 
-__device__ __forceinline__ uint64_t ld8_unaligned(const uint8_t* p) {
-  // 8 bytes at any address from two aligned 8-byte loads (frame stores carry 16 bytes of slack at the end)
-  uintptr_t a = reinterpret_cast<uintptr_t>(p);
-  const uint64_t* q = reinterpret_cast<const uint64_t*>(a & ~(uintptr_t)7);
-  int s = (int)(a & 7) * 8;
-  uint64_t lo = q[0];
-  if (s == 0) return lo;
-  uint64_t hi = q[1];
-  return (lo >> s) | (hi << (64 - s));
-}
-
 // MType property tables (p64.c:217-222) as bit masks over type 0..9
 constexpr uint32_t M_CBP = 0x36c, M_INTRA = 0x003, M_MF = 0x3f0, M_FILTER = 0x380, M_TCOEF = 0x36f;
 __device__ __forceinline__ bool mt_is(uint32_t mask, int mt) { return (mask >> mt) & 1u; }
@@ -434,23 +432,35 @@ struct MbArgs {
   int first_frame, force_intra, gquant;
 };
 
-// prediction for one block: SubOverlay / Sub[F]Compensate / HalfSub[F]Compensate (io.c:142-496)
-__device__ __forceinline__ void fetch_pred(const uint8_t* plane, int w, int bx, int by, int mt, int mvx, int mvy,
-                                           bool chroma, int (&p)[64]) {
+// Prediction for one block as 16 packed words (8 rows x 8 bytes): SubOverlay / SubCompensate / HalfSubCompensate
+// addressing (io.c:142-313).  Rows are fetched with two aligned 8-byte loads and a funnel shift (frame stores carry
+// slack at the end).  Chroma vector = MV/2 with C truncation (io.c:268-269).
+__device__ __forceinline__ void fetch_pred_packed(const uint8_t* plane, int w, int bx, int by, bool mc, int mvx, int mvy,
+                                                  bool chroma, uint32_t (&pk)[16]) {
   int dx = 0, dy = 0;
-  if (mt_is(M_MF, mt)) { dx = chroma ? mvx / 2 : mvx; dy = chroma ? mvy / 2 : mvy; }   // C truncation (io.c:268-269)
+  if (mc) { dx = chroma ? mvx / 2 : mvx; dy = chroma ? mvy / 2 : mvy; }
   const uint8_t* b = plane + (size_t)(by + dy) * w + bx + dx;
+  const uintptr_t ad = reinterpret_cast<uintptr_t>(b);
+  const uint2* qp = reinterpret_cast<const uint2*>(ad & ~(uintptr_t)7);
+  const int sh = (int)(ad & 7) * 8;
+  const int wq = w >> 3;                                  // row pitch in 8-byte units
+  if (sh == 0) {
 #pragma unroll
-  for (int i = 0; i < 8; i++) {
-    uint64_t r = ld8_unaligned(b + (size_t)i * w);
+    for (int i = 0; i < 8; i++) { const uint2 r = __ldg(qp + i * wq); pk[2 * i] = r.x; pk[2 * i + 1] = r.y; }
+  } else {
 #pragma unroll
-    for (int j = 0; j < 8; j++) p[8 * i + j] = (int)((r >> (8 * j)) & 0xff);
+    for (int i = 0; i < 8; i++) {
+      const uint2 r0 = __ldg(qp + i * wq), r1 = __ldg(qp + i * wq + 1);
+      uint32_t w0 = r0.x, w1 = r0.y, w2 = r1.x;
+      if (sh & 32) { w0 = r0.y; w1 = r1.x; w2 = r1.y; }
+      pk[2 * i] = __funnelshift_r(w0, w1, sh);
+      pk[2 * i + 1] = __funnelshift_r(w1, w2, sh);
+    }
   }
-  if (mt_is(M_FILTER, mt)) loop_filter(p);
 }
 
 #ifndef MBK_MINB
-#define MBK_MINB 1
+#define MBK_MINB 2
 #endif
 __global__ void __launch_bounds__(MBK_THREADS, MBK_MINB)
 mb_encode_kernel(MbArgs a) {
@@ -472,6 +482,15 @@ mb_encode_kernel(MbArgs a) {
   const size_t poff = (size_t)s * g.frame_bytes + (c < 4 ? 0 : (c == 4 ? g.W * g.H : g.W * g.H * 5 / 4));
   const int bx = chroma ? col * 8 : col * 16 + (c & 1) * 8;
   const int by = chroma ? row * 8 : row * 16 + (c >> 1) * 8;
+
+  // ---- source block (ReadBlock, io.c:793-820): issued first, it does not depend on the decision
+  uint2 srow[8];
+  {
+    const uint2* sp = reinterpret_cast<const uint2*>(a.src + poff + (size_t)by * w + bx);
+    const int wq = w >> 3;
+#pragma unroll
+    for (int i = 0; i < 8; i++) srow[i] = __ldg(sp + i * wq);
+  }
 
   // ---- MTYPE decision (p64.c:734-773), double arithmetic exactly as written
   int4 me0 = make_int4(0, 0, 0, 0), me1 = me0;
@@ -495,31 +514,32 @@ mb_encode_kernel(MbArgs a) {
   if (li > 131) mt = 0;
   const int q = a.quant ? a.quant[s] : a.gquant;
 
-  // ---- ReadCompressMDU (p64.c:823-886): source block, prediction, residual, DCT, quantise
-  int v[64], p[64];
-  {
-    const uint8_t* sp = a.src + poff + (size_t)by * w + bx;
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-      uint2 r = *reinterpret_cast<const uint2*>(sp + (size_t)i * w);
-#pragma unroll
-      for (int j = 0; j < 4; j++) { v[8 * i + j] = (r.x >> (8 * j)) & 0xff; v[8 * i + 4 + j] = (r.y >> (8 * j)) & 0xff; }
-    }
-  }
+  // ---- ReadCompressMDU (p64.c:823-886): prediction, residual, DCT, quantise
   const bool intra = mt_is(M_INTRA, mt);
-  uint32_t pk[16];                                  // prediction kept as packed bytes until reconstruction
+  uint32_t pk[16];                                  // prediction as packed bytes
 #pragma unroll
   for (int i = 0; i < 16; i++) pk[i] = 0;
+  int v[64];
   if (!intra) {
-    fetch_pred(a.ref + poff, w, bx, by, mt, mvx, mvy, chroma, p);
+    fetch_pred_packed(a.ref + poff, w, bx, by, mt_is(M_MF, mt), mvx, mvy, chroma, pk);
+    if (mt_is(M_FILTER, mt)) {                      // LoadFilterMatrix, io.c:323-372
 #pragma unroll
-    for (int i = 0; i < 64; i++) v[i] -= p[i];
+      for (int i = 0; i < 64; i++) v[i] = ubyte(pk[i >> 2], i & 3);
+      loop_filter(v);
 #pragma unroll
-    for (int i = 0; i < 16; i++)
-      pk[i] = (uint32_t)p[4 * i] | ((uint32_t)p[4 * i + 1] << 8) | ((uint32_t)p[4 * i + 2] << 16) | ((uint32_t)p[4 * i + 3] << 24);
+      for (int i = 0; i < 16; i++) pk[i] = pack4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    }
   }
-  chen_fdct(v);
-  const int acc = quantise(v, q, intra);
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      v[8 * i + j] = ubyte(srow[i].x, j) - ubyte(pk[2 * i], j);
+      v[8 * i + 4 + j] = ubyte(srow[i].y, j) - ubyte(pk[2 * i + 1], j);
+    }
+  }
+  chen_fdct_raw(v);
+  const int acc = quantise_raw(v, q, intra);
 
   // ---- levels out, zig-zag order (transform.c:561-568): byte k = level at raster izig(k)
   if (active) {
@@ -530,8 +550,7 @@ mb_encode_kernel(MbArgs a) {
 #pragma unroll
       for (int k = 0; k < 4; k++) {
         const int b0 = 16 * wd + 4 * k;
-        u[k] = (uint32_t)(v[izig(b0)] & 0xff) | ((uint32_t)(v[izig(b0 + 1)] & 0xff) << 8) |
-               ((uint32_t)(v[izig(b0 + 2)] & 0xff) << 16) | ((uint32_t)(v[izig(b0 + 3)] & 0xff) << 24);
+        u[k] = pack4(v[izig(b0)], v[izig(b0 + 1)], v[izig(b0 + 2)], v[izig(b0 + 3)]);
       }
       lp[wd] = make_uint4(u[0], u[1], u[2], u[3]);
     }
@@ -559,34 +578,24 @@ mb_encode_kernel(MbArgs a) {
 
   // ---- inverse half (p64.c:935-959) + DecodeSaveMDU (p64.c:971-1013)
   const bool coded = ((cbp >> (5 - c)) & 1) && mt_is(M_TCOEF, mt_final);
-  if (coded) { dequantise(v, q, intra); chen_idct(v); }
-  else {
+  // a type-2 MB that fell back to type 4 predicts with the ME vector (p64.c:904, marker.c:339-342)
+  if (!intra && mt_final == 4 && (mvx | mvy)) fetch_pred_packed(a.ref + poff, w, bx, by, true, mvx, mvy, chroma, pk);
+  if (coded) {
+    dequantise(v, q, intra);
+    chen_idct_raw(v);
 #pragma unroll
-    for (int i = 0; i < 64; i++) v[i] = 0;
-  }
-  if (!intra) {
-    // a type-2 MB that fell back to type 4 predicts with the ME vector (p64.c:904, marker.c:339-342)
-    if (mt_final == 4 && (mvx | mvy)) {
-      fetch_pred(a.ref + poff, w, bx, by, mt_final, mvx, mvy, chroma, p);
+    for (int i = 0; i < 16; i++) {                  // ChenIDct rounding + Add*Compensate + BoundIDctMatrix
+      int o[4];
 #pragma unroll
-      for (int i = 0; i < 64; i++) v[i] += p[i];
-    } else {
-#pragma unroll
-      for (int i = 0; i < 64; i++) v[i] += (int)((pk[i >> 2] >> (8 * (i & 3))) & 0xff);
+      for (int j = 0; j < 4; j++) o[j] = min(max(round_div16(v[4 * i + j]) + ubyte(pk[i], j), 0), 255);
+      pk[i] = pack4(o[0], o[1], o[2], o[3]);
     }
   }
   if (active) {
-    uint8_t* op = a.out + poff + (size_t)by * w + bx;
+    uint2* op = reinterpret_cast<uint2*>(a.out + poff + (size_t)by * w + bx);
+    const int wq = w >> 3;
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-      uint32_t lo = 0, hi = 0;
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        lo |= (uint32_t)min(max(v[8 * i + j], 0), 255) << (8 * j);          // BoundIDctMatrix
-        hi |= (uint32_t)min(max(v[8 * i + 4 + j], 0), 255) << (8 * j);
-      }
-      *reinterpret_cast<uint2*>(op + (size_t)i * w) = make_uint2(lo, hi);
-    }
+    for (int i = 0; i < 8; i++) op[i * wq] = make_uint2(pk[2 * i], pk[2 * i + 1]);   // uncoded: reconstruction = prediction
     if (c == 0) {
       const bool mf = mt_is(M_MF, mt_final);
       uint32_t r0 = (uint32_t)mt_final | ((uint32_t)cbp << 8) | ((uint32_t)((mf ? mvx : 0) & 0xff) << 16) |

@@ -152,15 +152,42 @@ def test_dc_coding_rules(L):
         assert bits[5:13] == format(sent, "08b")            # after MBA "1" + MTYPE "0001"
 
 
-def test_multiply_shift_dividers_are_exact():
-    """the kernels replace x/(2Q) by (x*rcp)>>19 with rcp = floor(2^19/d)+1 (kernels.cuh div_rcp): exact on the whole
-    input range the path can produce (|coef| <= 2048 after BoundDctMatrix, +1 for even Q)."""
-    a = np.arange(0, 4097, dtype=np.int64)
+def test_multiply_shift_dividers_are_exact(orc):
+    """kernels.cuh quantise_raw folds ChenDct's final rounding, the +-1023 bound and the quantiser into one
+    multiply-shift on |v|: |level| = ((min(|v|,8187)*M + K) >> 22), M = floor(2^22/16Q)+1, K = (4+8ev)*M.
+    Checked against the oracle's step-by-step arithmetic for every raw value the transform can produce and every Q."""
+    v = np.arange(-20000, 20001, dtype=np.int64)
+    x = np.where(v < 0, -((-v + 4) // 8), (v + 4) // 8)                 # (v<0 ? v-4 : v+4)/8, C truncation
+    x = np.clip(x, -1023, 1023)
+    a = np.minimum(np.abs(v), 8187).astype(np.uint64)
     for q in range(1, 32):
-        d = 2 * q
-        rcp = (1 << 19) // d + 1
-        assert np.array_equal((a * rcp) >> 19, a // d), q
-        assert int(a.max() * rcp) < 2 ** 31
+        ev = 0 if q & 1 else 1
+        want = np.minimum((np.abs(x) + ev) // (2 * q), 127) * np.sign(v)  # (x>0 ? x+ev : x-ev)/(2Q), then +-127
+        M = (1 << 22) // (16 * q) + 1
+        K = (4 + 8 * ev) * M
+        prod = a * np.uint64(M) + np.uint64(K)
+        assert int(prod.max()) < 2 ** 32                                 # fits the uint32 arithmetic used on device
+        got = np.minimum((prod >> np.uint64(22)).astype(np.int64), 127) * np.sign(v)
+        assert np.array_equal(got, want), q
+        # the DC path keeps (x*rcp)>>19
+        aa = np.arange(0, 4097, dtype=np.int64)
+        rcp = (1 << 19) // (2 * q) + 1
+        assert np.array_equal((aa * rcp) >> 19, aa // (2 * q))
+    # and against the oracle's own functions on a sample
+    blk = np.zeros(64, np.int32)
+    for q in (1, 2, 7, 8, 31):
+        for val in (-9000, -8188, -8187, -1024 * 8, -12, -5, -4, 0, 3, 4, 11, 12, 8187, 8188, 16000):
+            xx = int(np.clip((val + 4) // 8 if val >= 0 else -((-val + 4) // 8), -1023, 1023))
+            blk[:] = 0; blk[5] = xx
+            want = int(orc.quant_inter(blk, q)[5])
+            ev = 0 if q & 1 else 1
+            M = (1 << 22) // (16 * q) + 1
+            got = min(((min(abs(val), 8187) * M + (4 + 8 * ev) * M) & 0xffffffff) >> 22, 127) * (1 if val > 0 else -1 if val < 0 else 0)
+            assert got == want, (q, val)
+    # rounding identities (chendct.c:205, 374)
+    w = np.arange(-5000, 5001, dtype=np.int64)
+    assert np.array_equal((w + 4 + (w >> 63)) >> 3, np.where(w < 0, -((-w + 4) // 8), (w + 4) // 8))
+    assert np.array_equal((w + 8 + (w >> 63)) >> 4, np.where(w < 0, -((-w + 8) // 16), (w + 8) // 16))
 
 
 def test_y4m_roundtrip(tmp_path):
