@@ -143,8 +143,9 @@ int p64b_ctx_frame_end(p64b_ctx *ctx, const uint8_t *overflow);
 int p64b_ctx_motion_estimation_dev(p64b_ctx *ctx, const uint8_t *ref_dev, const uint8_t *cur_dev, int n_pairs,
                                    int me_mode, int search_limit, p64b_me *out_dev);
 
-/* Test hook: additionally writes every macroblock's 31x31 SAD surface, surface_dev uint32 [n_pairs][num_mb][31][31]
- * indexed [dy+15][dx+15]; 0xffffffff marks positions the reference's legality rule excludes (me.c:212-213). */
+/* Test hook: the three-step search (out_dev = its records) that additionally writes every macroblock's 31x31 SAD
+ * surface, surface_dev uint32 [n_pairs][num_mb][31][31] indexed [dy+15][dx+15]; 0xffffffff marks positions the
+ * reference's legality rule excludes (me.c:292-293); [15][15] always holds SAD(0,0) (me.c:262-271). */
 int p64b_ctx_sad_surface_dev(p64b_ctx *ctx, const uint8_t *ref_dev, const uint8_t *cur_dev, int n_pairs,
                              p64b_me *out_dev, uint32_t *surface_dev);
 

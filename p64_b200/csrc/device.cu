@@ -64,6 +64,7 @@ struct p64b_ctx {
   uint8_t* d_ovf = nullptr;       // [S][nmb]
   const uint8_t* frame_src = nullptr;   // source of the frame in flight (frame_begin .. frame_end)
   int64_t launches = 0;
+  bool me_attr_done = false;
   // optional per-kernel timing with CUDA events on the launching stream (bench.py roofline)
   bool prof = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_ev[2];   // 0 = ME kernel, 1 = MB kernel
@@ -117,18 +118,38 @@ static int make_plane_map(CUtensorMap* tm, const uint8_t* base, int W, int H, si
   return 0;
 }
 
+// Legal surface positions (d+15) per macroblock column / row class, first | interior | last: inside the frame with the
+// reference's strict < on the far edge (me.c:212-213, 292-293) and inside the search range -- FastBME scans
+// [-S/2, S/2) (me.c:206-208), StepBME reaches [-15,15] (me.c:294).  Interior macroblocks see the whole range
+// (16 > 15).  One byte per class; hi is stored +1 so that 0 means "empty".
+static MeRanges me_ranges(const Geom& g, int me_mode, int search_limit) {
+  const bool full = me_mode == P64B_ME_FULL;
+  const int rlo = full ? 15 - search_limit / 2 : 0, rhi = full ? 14 + search_limit / 2 : 30;
+  MeRanges r{0, 0, 0, 0};
+  for (int cls = 0; cls < 3; cls++) {
+    const int x0 = cls == 0 ? 0 : (cls == 1 ? 16 : g.W - 16), y0 = cls == 0 ? 0 : (cls == 1 ? 16 : g.H - 16);
+    int xlo = std::max(rlo, 15 - x0), xhi = std::min(rhi, g.W - 2 - x0);
+    int ylo = std::max(rlo, 15 - y0), yhi = std::min(rhi, g.H - 2 - y0);
+    if (xhi < xlo) { xlo = 15; xhi = -1; }
+    if (yhi < ylo) { ylo = 15; yhi = -1; }
+    r.xlo |= (uint32_t)xlo << (8 * cls); r.xhi |= (uint32_t)(xhi + 1) << (8 * cls);
+    r.ylo |= (uint32_t)ylo << (8 * cls); r.yhi |= (uint32_t)(yhi + 1) << (8 * cls);
+  }
+  return r;
+}
+
 static int launch_me(p64b_ctx* c, const uint8_t* ref, const uint8_t* cur, size_t stride, int n_pairs, int me_mode,
                      int search_limit, p64b_me* out, uint32_t* surface = nullptr) {
-  static bool attr_done = false;
-  if (!attr_done) {
-    CU(cudaFuncSetAttribute(me_surface_kernel<ME_V_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, ME_SMEM_BYTES));
-    CU(cudaFuncSetAttribute(me_surface_kernel<ME_V_SURF>, cudaFuncAttributeMaxDynamicSharedMemorySize, ME_SMEM_BYTES));
-    attr_done = true;
-  }
   int rc;
+  if (!c->me_attr_done) {   // many small CTAs per SM: ask for the large shared-memory carveout
+    CU(cudaFuncSetAttribute(me_surface_kernel<ME_V_FULL>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(me_surface_kernel<ME_V_SURF>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    c->me_attr_done = true;
+  }
   CUtensorMap tm_ref, tm_cur;
   if ((rc = make_plane_map(&tm_ref, ref, c->g.W, c->g.H, stride, n_pairs, 48, ME_WIN_ROWS))) return rc;
   if ((rc = make_plane_map(&tm_cur, cur, c->g.W, c->g.H, stride, n_pairs, 16, 16))) return rc;
+  const MeRanges rg = me_ranges(c->g, me_mode, search_limit);
   ProfScope ps(c, 0);
   for (int z0 = 0; z0 < n_pairs; z0 += 65535) {      // gridDim.z limit
     const int nz = std::min(65535, n_pairs - z0);
@@ -140,9 +161,9 @@ static int launch_me(p64b_ctx* c, const uint8_t* ref, const uint8_t* cur, size_t
     p64b_me* o = out + (size_t)z0 * c->g.mbw * c->g.mbh;
     uint32_t* sf = surface ? surface + (size_t)z0 * c->g.mbw * c->g.mbh * 961 : nullptr;
     if (me_mode == P64B_ME_FULL && !surface)
-      me_surface_kernel<ME_V_FULL><<<grid, ME_THREADS, ME_SMEM_BYTES, c->stream>>>(tm_ref, tm_cur, c->g, me_mode, search_limit, o, sf);
+      me_surface_kernel<ME_V_FULL><<<grid, ME_THREADS, ME_SMEM_FULL, c->stream>>>(tm_ref, tm_cur, rg, me_mode, o, sf);
     else
-      me_surface_kernel<ME_V_SURF><<<grid, ME_THREADS, ME_SMEM_BYTES, c->stream>>>(tm_ref, tm_cur, c->g, me_mode, search_limit, o, sf);
+      me_surface_kernel<ME_V_SURF><<<grid, ME_THREADS, ME_SMEM_SURF, c->stream>>>(tm_ref, tm_cur, rg, me_mode, o, sf);
     c->launches++;
     CU(cudaGetLastError());
   }
@@ -404,7 +425,7 @@ int p64b_ctx_sad_surface_dev(p64b_ctx* c, const uint8_t* ref_dev, const uint8_t*
   if (!c || !ref_dev || !cur_dev || !out_dev || !surface_dev || n_pairs < 1) { set_error("bad arguments"); return P64B_EINVAL; }
   int rc;
   if ((rc = use_device(c))) return rc;
-  return launch_me(c, ref_dev, cur_dev, (size_t)c->g.W * c->g.H, n_pairs, P64B_ME_FULL, 31, out_dev, surface_dev);
+  return launch_me(c, ref_dev, cur_dev, (size_t)c->g.W * c->g.H, n_pairs, P64B_ME_TSS, 31, out_dev, surface_dev);
 }
 
 int p64b_ctx_me_records(p64b_ctx* c, int stream, p64b_me* out) {

@@ -27,18 +27,36 @@ struct Geom {
 // ---------------------------------------------------------------------------------------------------
 // Motion estimation
 // ---------------------------------------------------------------------------------------------------
-// One CTA (4 warps) per macroblock.  The 47x48-byte search window is staged by one TMA tile load (out-of-frame
+// One CTA (3 warps) per macroblock.  The 47x48-byte search window is staged by one TMA tile load (out-of-frame
 // samples zero-filled by the TMA unit) and replicated shifted by 1..3 bytes, so that every packed-SAD operand in
-// the hot loop is an aligned 32-bit shared-memory word (no PRMT/funnel shifts in the loop).  warp <-> byte shift k,
-// lane <-> (word offset q, dy group gq): candidate dx = 4q+k-16, dy in {2gq + {0,1,8,9,16,17,24,25}} - 15.
-// Each thread keeps the whole current block in 64 registers and slides down 41 window rows, feeding 8
-// independent VABSDIFF4.U8.ACC accumulators (512 packed SADs per thread, 164 LDS.32).
-constexpr int ME_THREADS = 128;
+// the hot loop is an aligned 32-bit shared-memory word (no PRMT/funnel shifts in the loop).
+//
+// Work mapping.  Only the part of the 31x31 surface that the reference can ever look at is evaluated: the legal
+// positions (me.c:212-213, 292-293) inside the search range -- a rectangle of ndx x ndy positions: 30x30 for
+// FastBME -i 31 inside the frame ([-15,14], me.c:206-208), 31x31 for StepBME, 15 or 16 wide/high for macroblocks
+// on a frame edge, smaller for a short -i range.  SAD(0,0), which both searches probe first whatever the
+// legality (me.c:203, 271), is computed separately by 64 threads.
+//   ndx > 16 : lane = dx position, warp = group of NC consecutive dy positions            (3 groups)
+//   ndx <= 16: lane = (dx position, lane>>4 = second dy group): a warp covers 16 dx x 2 groups (6 groups)
+// with NC = 10/5/3 (exhaustive search: 30 or 15 rows) or 11/6/3 (three-step search: 31 or 16 rows) candidates per
+// thread, so edge macroblocks cost 1/2 and corner macroblocks about 1/4 of an interior one and no dy row is
+// wasted for the north-star configuration.  A thread keeps the whole current block in 64 registers and slides
+// down 15+NC window rows (4 LDS.32 per row), feeding NC independent VABSDIFF4.U8.ACC chains.
+// Shared-memory banks: word address = k*584 + row*12 + q with (k,q) = ((dx+16)&3, (dx+16)>>2) -> bank 8k+q+const:
+// conflict-free for the 31 dx of a warp; for the 16x2 mapping the second group is NC rows = 12*NC words further:
+// +28 (NC=5) or +4 (NC=3) banks -> the complementary 16 banks.
+constexpr int ME_THREADS = 96;
 constexpr int ME_WIN_ROWS = 47;        // window rows y0-15 .. y0+31
 constexpr int ME_ROW_WORDS = 12;       // 48 bytes: x0-16+k .. x0+31+k
-constexpr int ME_COPY_WORDS = 576;     // 47*48 = 2256 B rounded up to 2304 (TMA destinations are 128-B aligned)
+constexpr int ME_COPY_WORDS = 584;     // 47*12 = 564 words + pad; == 8 (mod 32): see the bank formula above
 constexpr int ME_WIN_BYTES = ME_WIN_ROWS * 48;
-constexpr int ME_SMEM_BYTES = 128 /*align*/ + 4 * ME_COPY_WORDS * 4 + 256 /*cur*/ + 31 * 31 * 4 /*surface*/ + 32 * 4 + 16;
+constexpr int ME_SMEM_FULL = 128 /*align*/ + 4 * ME_COPY_WORDS * 4 + 256 /*cur*/ + 16 /*mbarrier*/ + 32 * 4 /*red*/ + 32 * 4 /*pen*/;
+constexpr int ME_SMEM_SURF = ME_SMEM_FULL + 31 * 31 * 4;
+constexpr uint32_t ME_ILLEGAL = 0x10000u;   // start value of an illegal candidate's accumulator: above any SAD (<= 65280)
+
+// CTA-uniform legal ranges in surface positions d+15, per macroblock-column / row class
+// (0 = first, 1 = interior, 2 = last), computed on the host: one byte per class.
+struct MeRanges { uint32_t xlo, xhi, ylo, yhi; };
 
 __device__ __forceinline__ uint32_t sad4(uint32_t a, uint32_t b, uint32_t c) {
   uint32_t d;
@@ -71,21 +89,69 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, in
       ::"r"(smem_u32(dst)), "l"(tm), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
 }
 
-// tm_ref / tm_cur: u8 tensors {W, H, n_pairs}; boxes {48,47,1} and {16,16,1}.  grid = (mbw, mbh, n_pairs).
-// VARIANT: ME_V_FULL exhaustive argmin straight from registers; ME_V_SURF stages the 31x31 surface in shared
-// memory for the three-step walk (me_mode == TSS) and/or the test hook (surface != nullptr).
 constexpr int ME_V_FULL = 0, ME_V_SURF = 1;
+
+// One thread's NC candidates at dy positions yb .. yb+NC-1 (accumulators start at 0 or ME_ILLEGAL), then either the
+// exhaustive-search key (FastBME, me.c:206-227: dx outer, dy inner, strict <, after probing (0,0): winner = min of
+// SAD<<11 | (1 + (dx+15)*32 + (dy+15)); (0,0) re-enters after the reduction with order 0 so that it wins ties)
+// and/or the surface entries for the three-step walk.
+template <int VARIANT, int NC>
+__device__ __forceinline__ void sweep_pick(const uint32_t* __restrict__ base, const uint32_t (&c)[16][4],
+                                           const uint32_t* s_pen, uint32_t* s_sad, int xi, int yb, bool xok, bool full,
+                                           uint32_t* s_best) {
+  constexpr int P = NC >= 5 ? 1 : 2;          // partial chains per candidate: at least 5 independent chains
+  uint32_t a[NC][P];
+#pragma unroll
+  for (int j = 0; j < NC; j++) {
+    a[j][0] = s_pen[yb + j];
+    if (P == 2) a[j][P - 1] = 0;
+  }
+#pragma unroll
+  for (int t = 0; t < 15 + NC; t++) {
+    const uint32_t r0 = base[t * ME_ROW_WORDS + 0], r1 = base[t * ME_ROW_WORDS + 1];
+    const uint32_t r2 = base[t * ME_ROW_WORDS + 2], r3 = base[t * ME_ROW_WORDS + 3];
+#pragma unroll
+    for (int j = 0; j < NC; j++) {
+      const int i = t - j;
+      if (i >= 0 && i < 16) {
+        a[j][0] = sad4(r0, c[i][0], a[j][0]); a[j][P - 1] = sad4(r1, c[i][1], a[j][P - 1]);
+        a[j][0] = sad4(r2, c[i][2], a[j][0]); a[j][P - 1] = sad4(r3, c[i][3], a[j][P - 1]);
+      }
+    }
+  }
+  uint32_t acc[NC];
+#pragma unroll
+  for (int j = 0; j < NC; j++) acc[j] = P == 2 ? a[j][0] + a[j][P - 1] : a[j][0];
+  if (full) {
+    uint32_t best = 0xffffffffu;
+#pragma unroll
+    for (int j = 0; j < NC; j++) best = min(best, acc[j] * 2048u + (uint32_t)j);
+    best = xok ? best + (uint32_t)(1 + xi * 32 + yb) : 0xffffffffu;
+    best = __reduce_min_sync(0xffffffffu, best);
+    if ((threadIdx.x & 31) == 0) *s_best = best;
+  }
+  if (VARIANT == ME_V_SURF) {
+#pragma unroll
+    for (int j = 0; j < NC; j++)
+      if (xok && acc[j] < ME_ILLEGAL) s_sad[(yb + j) * 31 + xi] = acc[j];     // the rest keeps the 0xffffffff prefill
+  }
+}
+
+// tm_ref / tm_cur: u8 tensors {W, H, n_pairs}; boxes {48,47,1} and {16,16,1}.  grid = (mbw, mbh, n_pairs).
+// VARIANT: ME_V_FULL exhaustive argmin straight from registers; ME_V_SURF additionally stages the 31x31 surface in
+// shared memory for the three-step walk (me_mode == TSS) and the test hook (surface != nullptr).
 template <int VARIANT>
 __global__ void __launch_bounds__(ME_THREADS)
-me_surface_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constant__ CUtensorMap tm_cur, Geom g,
-                  int me_mode, int search_limit, p64b_me* __restrict__ out, uint32_t* __restrict__ surface) {
+me_surface_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constant__ CUtensorMap tm_cur, MeRanges rg,
+                  int me_mode, p64b_me* __restrict__ out, uint32_t* __restrict__ surface) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sbase = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);   // TMA destinations: 128-B aligned
   uint32_t* win = reinterpret_cast<uint32_t*>(sbase);                   // [4][ME_COPY_WORDS]
   uint32_t* s_cur = win + 4 * ME_COPY_WORDS;                            // [16][4]
   uint64_t* bar = reinterpret_cast<uint64_t*>(s_cur + 64);             // mbarrier (8-B aligned)
   uint32_t* s_red = s_cur + 64 + 4;                                     // [32]
-  uint32_t* s_sad = s_red + 32;                                         // [31][31], index [dy+15][dx+15]
+  uint32_t* s_pen = s_red + 32;                                         // [32] per dy position: 0 or ME_ILLEGAL
+  uint32_t* s_sad = s_pen + 32;                                         // [31][31], index [dy+15][dx+15] (ME_V_SURF)
 
   const int x0 = blockIdx.x * 16, y0 = blockIdx.y * 16, pair = blockIdx.z;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -97,15 +163,39 @@ me_surface_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_const
     tma_load_3d(win, &tm_ref, x0 - 16, y0 - 15, pair, bar);      // out-of-frame samples arrive as zeros
     tma_load_3d(s_cur, &tm_cur, x0, y0, pair, bar);
   }
+
+  // ---- search geometry while the TMA loads are in flight (CTA-uniform part from the host table)
+  const bool full = me_mode == P64B_ME_FULL;
+  const int cx = 8 * (blockIdx.x == 0 ? 0 : (blockIdx.x == gridDim.x - 1 ? 2 : 1));
+  const int cy = 8 * (blockIdx.y == 0 ? 0 : (blockIdx.y == gridDim.y - 1 ? 2 : 1));
+  const int lxlo = (rg.xlo >> cx) & 0xff, lxhi = (int)((rg.xhi >> cx) & 0xff) - 1;   // hi stored +1 (0 = empty range)
+  const int lylo = (rg.ylo >> cy) & 0xff, lyhi = (int)((rg.yhi >> cy) & 0xff) - 1;
+  const int ndy = lyhi - lylo + 1;
+  const bool xr = lxhi - lxlo < 16;
+  constexpr int NCB = VARIANT == ME_V_FULL ? 10 : 11, NCS = VARIANT == ME_V_FULL ? 5 : 6, NCT = 3;
+  const int nc = xr ? (ndy > 6 * NCT ? NCS : NCT) : (ndy > 3 * NCS ? NCB : NCS);
+  int xi = lxlo + (xr ? (lane & 15) : lane);
+  const bool xok = xi <= lxhi;
+  xi = min(xi, 30);                                              // surplus lanes: any in-window column
+  const int yb = min(lylo + nc * (xr ? 2 * warp + (lane >> 4) : warp), 32 - nc);
+  if (tid < 32) s_pen[tid] = (tid >= lylo && tid <= lyhi) ? 0u : ME_ILLEGAL;
+  if (VARIANT == ME_V_SURF)
+    for (int i = tid; i < 31 * 31; i += ME_THREADS) s_sad[i] = 0xffffffffu;
+
   mbar_wait(bar, 0);
   // byte-shifted copies 1..3 (TMA needs a 16-byte aligned innermost start, so only copy 0 comes from the TMA unit):
-  // each (row, word) pair yields the three shifted words from the same two source words
-  for (int i = tid; i < ME_WIN_ROWS * 11; i += ME_THREADS) {
-    const int r = i / 11, idx = i + r;              // r*12 + (i - 11 r)
-    const uint32_t lo = win[idx], hi = win[idx + 1];
-    win[1 * ME_COPY_WORDS + idx] = __funnelshift_r(lo, hi, 8);
-    win[2 * ME_COPY_WORDS + idx] = __funnelshift_r(lo, hi, 16);
-    win[3 * ME_COPY_WORDS + idx] = __funnelshift_r(lo, hi, 24);
+  // each 16-byte quad + the following word yields the three shifted quads
+  for (int u = tid; u < ME_WIN_ROWS * 3; u += ME_THREADS) {
+    const int idx = 4 * u;                          // row (u/3) * 12 + 4 * (u%3)
+    const uint4 a = *reinterpret_cast<const uint4*>(win + idx);
+    const uint32_t nx = win[idx + 4];
+#pragma unroll
+    for (int k = 1; k < 4; k++) {
+      uint4 o;
+      o.x = __funnelshift_r(a.x, a.y, 8 * k); o.y = __funnelshift_r(a.y, a.z, 8 * k);
+      o.z = __funnelshift_r(a.z, a.w, 8 * k); o.w = __funnelshift_r(a.w, nx, 8 * k);
+      *reinterpret_cast<uint4*>(win + k * ME_COPY_WORDS + idx) = o;
+    }
   }
 
   uint32_t c[16][4];
@@ -114,136 +204,88 @@ me_surface_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_const
     uint4 v = reinterpret_cast<const uint4*>(s_cur)[i];
     c[i][0] = v.x; c[i][1] = v.y; c[i][2] = v.z; c[i][3] = v.w;
   }
+  // SAD(0,0) = OMV (me.c:203, 271), needed whatever the search does: 64 threads, one packed SAD each
+  if (tid < 64) {
+    const int i = tid >> 2, wc = tid & 3;
+    uint32_t s0 = sad4(win[(15 + i) * ME_ROW_WORDS + 4 + wc], s_cur[tid], 0u);
+    s0 = __reduce_add_sync(0xffffffffu, s0);
+    if (lane == 0) s_red[20 + warp] = s0;
+  }
 
   __syncthreads();
 
   // ---- SAD surface
-  const int k = warp, q = lane & 7, gq = lane >> 3;
-  const int o = 4 * q + k;                                  // dx + 16
   {
-    const uint32_t* base = win + k * ME_COPY_WORDS + (2 * gq) * ME_ROW_WORDS + q;
-    uint32_t acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; j++) acc[j] = 0;
-#pragma unroll
-    for (int t = 0; t < 41; t++) {
-      const uint32_t r0 = base[t * ME_ROW_WORDS + 0], r1 = base[t * ME_ROW_WORDS + 1];
-      const uint32_t r2 = base[t * ME_ROW_WORDS + 2], r3 = base[t * ME_ROW_WORDS + 3];
-#pragma unroll
-      for (int j = 0; j < 8; j++) {
-        const int i = t - (8 * (j >> 1) + (j & 1));
-        if (i >= 0 && i < 16) {
-          acc[j] = sad4(r0, c[i][0], acc[j]);
-          acc[j] = sad4(r1, c[i][1], acc[j]);
-          acc[j] = sad4(r2, c[i][2], acc[j]);
-          acc[j] = sad4(r3, c[i][3], acc[j]);
-        }
-      }
-    }
-    // legality: me.c:212-213, 292-293 (strict < on the far edge).  FastBME (me.c:206-227) scans dx outer, dy inner
-    // over [-S/2, S/2) with strict <, after probing (0,0): winner = min key = SAD<<11 | (1 + (dx+15)*31 + (dy+15)),
-    // and (0,0) re-enters after the reduction with order 0 so that it wins ties.
-    const int dx = o - 16, px = x0 + dx;
-    const bool full = me_mode == P64B_ME_FULL;
-    const int lo = full ? (-search_limit) / 2 : -15, hi = full ? search_limit / 2 : 16;
-    const bool xok = o >= 1 && px >= 0 && px < g.W - 16;
-    const int dyi_lo = max(15 - y0, 0), dyi_hi = min(g.H - 17 - y0 + 15, 30);        // legal rows of the surface
-    if (o == 16 && gq == 3) s_red[3] = acc[3];               // the (0,0) probe (me.c:203, 271): dyi = 6 + 9 -> j = 3
-    if (full) {
-      // rows inside the search range as a bit mask over dyi (CTA-uniform), then this thread's 8 rows
-      const int rlo = max(dyi_lo, 15 + lo), rhi = min(dyi_hi, 14 + hi);
-      uint32_t rows = rhi >= rlo ? ((2u << rhi) - 1u) & ~((1u << rlo) - 1u) : 0u;
-      rows = (xok && dx >= lo && dx < hi) ? rows >> (2 * gq) : 0u;
-      uint32_t best = 0xffffffffu;
-#pragma unroll
-      for (int j = 0; j < 8; j++) {
-        const int dj = 8 * (j >> 1) + (j & 1);
-        const uint32_t key = acc[j] * 2048u + (uint32_t)dj;
-        if (rows & (1u << dj)) best = min(best, key);
-      }
-      if (best != 0xffffffffu) best += 1 + (o - 1) * 31 + 2 * gq;
-      best = __reduce_min_sync(0xffffffffu, best);
-      if (lane == 0) s_red[4 + warp] = best;
-    }
-    if (VARIANT == ME_V_SURF) {
-#pragma unroll
-      for (int j = 0; j < 8; j++) {
-        const int dyi = 2 * gq + 8 * (j >> 1) + (j & 1);    // dy + 15
-        if (o >= 1 && dyi < 31) s_sad[dyi * 31 + (o - 1)] = (xok && dyi >= dyi_lo && dyi <= dyi_hi) ? acc[j] : 0xffffffffu;
-      }
-      if (o == 16 && gq == 3) s_sad[15 * 31 + 15] = acc[3];
-    }
+    const int o = xi + 1;                                       // dx + 16
+    const uint32_t* base = win + (o & 3) * ME_COPY_WORDS + yb * ME_ROW_WORDS + (o >> 2);
+    uint32_t* s_best = s_red + 4 + warp;
+    if (nc == NCB)      sweep_pick<VARIANT, NCB>(base, c, s_pen, s_sad, xi, yb, xok, full, s_best);
+    else if (nc == NCS) sweep_pick<VARIANT, NCS>(base, c, s_pen, s_sad, xi, yb, xok, full, s_best);
+    else                sweep_pick<VARIANT, NCT>(base, c, s_pen, s_sad, xi, yb, xok, full, s_best);
   }
   __syncthreads();
+  if (warp) return;                       // the search result and the statistics are one warp's work
 
-  if (VARIANT == ME_V_SURF && surface)   // test hook: the whole surface, [dy+15][dx+15], 0xffffffff = illegal position
-    for (int i = tid; i < 31 * 31; i += ME_THREADS)
-      surface[((size_t)(pair * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 961 + i] = s_sad[i];
+  const uint32_t omv = s_red[20] + s_red[21];
+  const size_t mb_index = ((size_t)pair * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  if (VARIANT == ME_V_SURF) {
+    if (lane == 0) s_sad[15 * 31 + 15] = omv;     // (0,0) is in the surface even where a later probe of it would be illegal
+    __syncwarp();
+    if (surface)   // test hook: the whole surface, [dy+15][dx+15], 0xffffffff = illegal position
+      for (int i = lane; i < 31 * 31; i += 32) surface[mb_index * 961 + i] = s_sad[i];
+  }
 
   // ---- search result
   int mx = 0, my = 0;
-  uint32_t mv = s_red[3];
-  const uint32_t omv = mv;
-  if (me_mode == P64B_ME_FULL) {
-    const uint32_t best = min(min(min(s_red[4], s_red[5]), min(s_red[6], s_red[7])), omv << 11);
+  uint32_t mv = omv;
+  if (full) {
+    const uint32_t best = min(min(s_red[4], s_red[5]), min(s_red[6], omv << 11));
     mv = best >> 11;
     const int ord = best & 2047;
-    if (ord) { mx = (ord - 1) / 31 - 15; my = (ord - 1) % 31 - 15; }
+    if (ord) { mx = ((ord - 1) >> 5) - 15; my = ((ord - 1) & 31) - 15; }
   } else if (VARIANT == ME_V_SURF) {
     // StepBME (me.c:273-311): steps 8,4,2,1; 8 neighbours in (diry outer, dirx inner) order; the centre
-    // moves once per step; strict < keeps the earlier candidate on ties.  Warp 0, lanes 0..7 probe in parallel.
-    if (warp == 0) {
-      for (int step = 8; step >= 1; step >>= 1) {
-        uint32_t key = (mv << 4);                     // current best, order 0
-        if (lane < 8) {
-          int n = lane < 4 ? lane : lane + 1;         // skip the centre (index 4)
-          int dx = mx + (n % 3 - 1) * step, dy = my + (n / 3 - 1) * step;
-          if (dx >= -15 && dx <= 15 && dy >= -15 && dy <= 15) {
-            uint32_t s = s_sad[(dy + 15) * 31 + dx + 15];
-            if (s != 0xffffffffu) key = min(key, (s << 4) | (uint32_t)(lane + 1));
-          }
-        }
-        uint32_t best = key;
-#pragma unroll
-        for (int d = 4; d >= 1; d >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, d));
-        best = __shfl_sync(0xffffffffu, best, 0);
-        int ord = best & 15;
-        if (ord) {
-          int n = ord - 1; n = n < 4 ? n : n + 1;
-          mx += (n % 3 - 1) * step; my += (n / 3 - 1) * step;
-          mv = best >> 4;
+    // moves once per step; strict < keeps the earlier candidate on ties.  Lanes 0..7 probe in parallel.
+    for (int step = 8; step >= 1; step >>= 1) {
+      uint32_t key = (mv << 4);                     // current best, order 0
+      if (lane < 8) {
+        int n = lane < 4 ? lane : lane + 1;         // skip the centre (index 4)
+        int dx = mx + (n % 3 - 1) * step, dy = my + (n / 3 - 1) * step;
+        if (dx >= -15 && dx <= 15 && dy >= -15 && dy <= 15) {
+          uint32_t s = s_sad[(dy + 15) * 31 + dx + 15];
+          if (s != 0xffffffffu) key = min(key, (s << 4) | (uint32_t)(lane + 1));
         }
       }
-      if (lane == 0) { s_red[0] = (uint32_t)mx; s_red[1] = (uint32_t)my; s_red[2] = mv; }
+      const uint32_t best = __reduce_min_sync(0xffffffffu, key);
+      int ord = best & 15;
+      if (ord) {
+        int n = ord - 1; n = n < 4 ? n : n + 1;
+        mx += (n % 3 - 1) * step; my += (n / 3 - 1) * step;
+        mv = best >> 4;
+      }
     }
-    __syncthreads();
-    mx = (int)s_red[0]; my = (int)s_red[1]; mv = s_red[2];
   }
 
-  // ---- statistics over the best-match reference block (me.c:230-245), on packed words:
+  // ---- statistics over the best-match reference block (me.c:230-245), on packed words, two per lane:
   // sum r = SAD(r,0); sum r^2 = dp4a(r,r); sum (r-c)^2 = dp4a(r,r) - 2 dp4a(r,c) + dp4a(c,c)
-  if (tid < 64) {
-    const int i = tid >> 2, wc = tid & 3, oo = mx + 16;
-    const uint32_t r = win[(oo & 3) * ME_COPY_WORDS + (my + 15 + i) * ME_ROW_WORDS + (oo >> 2) + wc];
-    const uint32_t cw = s_cur[i * 4 + wc];
-    uint32_t sm = sad4(r, 0u, 0u);
-    uint32_t so = __dp4a(r, r, 0u);
-    uint32_t sv = so + __dp4a(cw, cw, 0u) - 2u * __dp4a(r, cw, 0u);
+  {
+    const int i = lane >> 1, wc = (lane & 1) * 2, oo = mx + 16;
+    const uint32_t* rp = win + (oo & 3) * ME_COPY_WORDS + (my + 15 + i) * ME_ROW_WORDS + (oo >> 2) + wc;
+    const uint32_t ra = rp[0], rb = rp[1];
+    const uint2 cw = *reinterpret_cast<const uint2*>(s_cur + i * 4 + wc);
+    uint32_t sm = sad4(rb, 0u, sad4(ra, 0u, 0u));
+    uint32_t so = __dp4a(rb, rb, __dp4a(ra, ra, 0u));
+    uint32_t sv = so + __dp4a(cw.y, cw.y, __dp4a(cw.x, cw.x, 0u)) - 2u * __dp4a(rb, cw.y, __dp4a(ra, cw.x, 0u));
     sv = __reduce_add_sync(0xffffffffu, sv);
     so = __reduce_add_sync(0xffffffffu, so);
     sm = __reduce_add_sync(0xffffffffu, sm);
-    if (lane == 0) { s_red[8 + warp] = sv; s_red[12 + warp] = so; s_red[16 + warp] = sm; }
-  }
-  __syncthreads();
-  if (tid == 0) {
-    int var = (int)(s_red[8] + s_red[9]);
-    int varor = (int)(s_red[12] + s_red[13]);
-    int mwor = (int)(s_red[16] + s_red[17]);
-    var /= 256;
-    varor = varor / 256 - (mwor / 256) * (mwor / 256);
-    int4* op = reinterpret_cast<int4*>(out + ((size_t)pair * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x);
-    op[0] = make_int4(mx, my, (int)mv, (int)omv);
-    op[1] = make_int4(var, varor, mwor, 0);
+    if (lane == 0) {
+      const int var = (int)sv / 256, mwor = (int)sm;
+      const int varor = (int)so / 256 - (mwor / 256) * (mwor / 256);
+      int4* op = reinterpret_cast<int4*>(out + mb_index);
+      op[0] = make_int4(mx, my, (int)mv, (int)omv);
+      op[1] = make_int4(var, varor, mwor, 0);
+    }
   }
 }
 

@@ -58,6 +58,34 @@ def test_me_matches_oracle(it, mode, limit):
         assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("it", [y4m.IT_QCIF, y4m.IT_CIF])
+def test_sad_surface_matches_oracle(it):
+    """every legal position of every macroblock's 31x31 SAD surface (me.c:92-176, legality me.c:292-293)"""
+    import ctypes as C
+    import torch
+    from p64_b200 import _lib
+    w, h = y4m.DIMS[it]
+    rng = np.random.default_rng(3)
+    ref = rng.integers(0, 256, (h, w)).astype(np.uint8)
+    cur = np.roll(ref, (2, -7), axis=(0, 1)) ^ (rng.integers(0, 8, (h, w)).astype(np.uint8))
+    ctx = DeviceContext(it, 1)
+    try:
+        nmb = (w // 16) * (h // 16)
+        r = torch.from_numpy(ref).cuda(); c = torch.from_numpy(cur).cuda()
+        out = torch.zeros(nmb * 8, dtype=torch.int32, device="cuda")
+        surf = torch.zeros(nmb * 961, dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
+        _lib.check(ctx.L.p64b_ctx_sad_surface_dev(ctx.h, C.c_void_p(r.data_ptr()), C.c_void_p(c.data_ptr()), 1,
+                                                  C.c_void_p(out.data_ptr()), C.c_void_p(surf.data_ptr())))
+        torch.cuda.synchronize()
+        sf = surf.cpu().numpy().reshape(nmb, 31, 31)
+        for mb in range(nmb):
+            assert np.array_equal(sf[mb], O.sad_surface(ref, cur, mb % (w // 16), mb // (w // 16))), mb
+        assert np.array_equal(out.cpu().numpy().reshape(nmb, 8)[:, :7], O.me_frame(ref, cur, 0, 15))
+    finally:
+        ctx.close()
+
+
 @pytest.mark.parametrize("it,nf,seed", [(y4m.IT_QCIF, 6, 4321), (y4m.IT_CIF, 5, 1234), (y4m.IT_NTSC, 4, 77)])
 @pytest.mark.parametrize("mode,limit,q,intra", [(0, 15, 8, False), (1, 31, 8, False), (1, 15, 3, False),
                                                 (0, 15, 31, False), (0, 15, 1, False), (0, 15, 5, True),
