@@ -285,7 +285,7 @@ def main_cuda(args):
             hbm_peak, peak_src = float(mp["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
         except Exception:
             pass
-        me_roof = {"kernel": "me_surface_kernel", "bound": "int_issue", "achieved": me_ops / (me_ms * 1e-3) / 1e9,
+        me_roof = {"kernel": "me_search_kernel", "bound": "int_issue", "achieved": me_ops / (me_ms * 1e-3) / 1e9,
                    "peak": peak_ops.value / 1e9, "unit": "G packed-SAD ops/s", "frac": (me_ops / (me_ms * 1e-3)) / peak_ops.value,
                    "traffic": None, "avg_launch_ms": me_ms, "launches_timed": prof["me"][1],
                    "peak_source": "measured live: VABSDIFF4.U8.ACC issue-rate probe (p64b_measure_sad_peak)",
@@ -306,8 +306,8 @@ def main_cuda(args):
                                        f"one step = one inter frame of every stream, fixed quantiser {QUANT}, full-search ME +-15 (-i {SEARCH_LIMIT}), no rate control",
                            "streams_per_gpu": S, "frames_per_step": world * S, "parallelism": f"streams partitioned over {world} GPU(s), no collective",
                            "l2": f"inputs larger than L2: ring of {n_sets} source sets ({n_sets * set_bytes >> 20} MiB) + frame stores + outputs = {(n_sets + 3) * set_bytes >> 20} MiB per GPU"},
-                "roofline": dominant, "roofline_kernels": {"me_surface_kernel": me_roof, "mb_encode_kernel": mb_roof},
-                "kernel_share_of_step": {"me_surface_kernel": me_ms / (me_ms + mb_ms), "mb_encode_kernel": mb_ms / (me_ms + mb_ms)},
+                "roofline": dominant, "roofline_kernels": {"me_search_kernel": me_roof, "mb_encode_kernel": mb_roof},
+                "kernel_share_of_step": {"me_search_kernel": me_ms / (me_ms + mb_ms), "mb_encode_kernel": mb_ms / (me_ms + mb_ms)},
                 "cpu_baseline": cpu,
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": S * fb, "d2h_bytes_per_step": S * nmb * (384 + 8),
                         "ms_per_step": ms_e2e / K, "api": "p64b_ctx_submit/p64b_ctx_wait (host buffers, pinned; 3 steps in flight)"},

@@ -65,6 +65,7 @@ struct p64b_ctx {
   const uint8_t* frame_src = nullptr;   // source of the frame in flight (frame_begin .. frame_end)
   int64_t launches = 0;
   bool me_attr_done = false;
+  int n_sm = 0;
   // optional per-kernel timing with CUDA events on the launching stream (bench.py roofline)
   bool prof = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_ev[2];   // 0 = ME kernel, 1 = MB kernel
@@ -141,32 +142,30 @@ static MeRanges me_ranges(const Geom& g, int me_mode, int search_limit) {
 static int launch_me(p64b_ctx* c, const uint8_t* ref, const uint8_t* cur, size_t stride, int n_pairs, int me_mode,
                      int search_limit, p64b_me* out, uint32_t* surface = nullptr) {
   int rc;
-  if (!c->me_attr_done) {   // many small CTAs per SM: ask for the large shared-memory carveout
-    CU(cudaFuncSetAttribute(me_surface_kernel<ME_V_FULL>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CU(cudaFuncSetAttribute(me_surface_kernel<ME_V_SURF>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  if (!c->me_attr_done) {
+    CU(cudaFuncSetAttribute(me_search_kernel<ME_V_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, ME_SMEM_FULL));
+    CU(cudaFuncSetAttribute(me_search_kernel<ME_V_SURF>, cudaFuncAttributeMaxDynamicSharedMemorySize, ME_SMEM_SURF));
+    CU(cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, c->device));
     c->me_attr_done = true;
   }
   CUtensorMap tm_ref, tm_cur;
   if ((rc = make_plane_map(&tm_ref, ref, c->g.W, c->g.H, stride, n_pairs, 48, ME_WIN_ROWS))) return rc;
   if ((rc = make_plane_map(&tm_cur, cur, c->g.W, c->g.H, stride, n_pairs, 16, 16))) return rc;
-  const MeRanges rg = me_ranges(c->g, me_mode, search_limit);
+  const bool surf = !(me_mode == P64B_ME_FULL && !surface);
+  MeArgs a;
+  a.rg = me_ranges(c->g, me_mode, search_limit);
+  a.me_mode = me_mode; a.mbw = c->g.mbw; a.mbh = c->g.mbh; a.n_pairs = n_pairs; a.out = out; a.surface = surface;
+  // persistent worker warps: as many CTAs as stay resident (4 per SM; 3 with the surface in shared memory)
+  const long long total = (long long)n_pairs * a.mbw * a.mbh;
+  if (total > 0x7fffffffLL) { set_error("too many macroblocks in one motion-estimation call"); return P64B_EINVAL; }
+  const int grid = (int)std::min<long long>((long long)c->n_sm * (surf ? 3 : 4), (total + ME_WARPS - 1) / ME_WARPS);
+  const int wstride = grid * ME_WARPS, per_pair = a.mbw * a.mbh;
+  a.sp = wstride / per_pair; a.sy = (wstride % per_pair) / a.mbw; a.sx = wstride % a.mbw;
   ProfScope ps(c, 0);
-  for (int z0 = 0; z0 < n_pairs; z0 += 65535) {      // gridDim.z limit
-    const int nz = std::min(65535, n_pairs - z0);
-    if (z0) {
-      if ((rc = make_plane_map(&tm_ref, ref + (size_t)z0 * stride, c->g.W, c->g.H, stride, nz, 48, ME_WIN_ROWS))) return rc;
-      if ((rc = make_plane_map(&tm_cur, cur + (size_t)z0 * stride, c->g.W, c->g.H, stride, nz, 16, 16))) return rc;
-    }
-    dim3 grid(c->g.mbw, c->g.mbh, nz);
-    p64b_me* o = out + (size_t)z0 * c->g.mbw * c->g.mbh;
-    uint32_t* sf = surface ? surface + (size_t)z0 * c->g.mbw * c->g.mbh * 961 : nullptr;
-    if (me_mode == P64B_ME_FULL && !surface)
-      me_surface_kernel<ME_V_FULL><<<grid, ME_THREADS, ME_SMEM_FULL, c->stream>>>(tm_ref, tm_cur, rg, me_mode, o, sf);
-    else
-      me_surface_kernel<ME_V_SURF><<<grid, ME_THREADS, ME_SMEM_SURF, c->stream>>>(tm_ref, tm_cur, rg, me_mode, o, sf);
-    c->launches++;
-    CU(cudaGetLastError());
-  }
+  if (!surf) me_search_kernel<ME_V_FULL><<<grid, ME_THREADS, ME_SMEM_FULL, c->stream>>>(tm_ref, tm_cur, a);
+  else       me_search_kernel<ME_V_SURF><<<grid, ME_THREADS, ME_SMEM_SURF, c->stream>>>(tm_ref, tm_cur, a);
+  c->launches++;
+  CU(cudaGetLastError());
   return 0;
 }
 

@@ -27,36 +27,53 @@ struct Geom {
 // ---------------------------------------------------------------------------------------------------
 // Motion estimation
 // ---------------------------------------------------------------------------------------------------
-// One CTA (3 warps) per macroblock.  The 47x48-byte search window is staged by one TMA tile load (out-of-frame
-// samples zero-filled by the TMA unit) and replicated shifted by 1..3 bytes, so that every packed-SAD operand in
-// the hot loop is an aligned 32-bit shared-memory word (no PRMT/funnel shifts in the loop).
-//
-// Work mapping.  Only the part of the 31x31 surface that the reference can ever look at is evaluated: the legal
-// positions (me.c:212-213, 292-293) inside the search range -- a rectangle of ndx x ndy positions: 30x30 for
-// FastBME -i 31 inside the frame ([-15,14], me.c:206-208), 31x31 for StepBME, 15 or 16 wide/high for macroblocks
-// on a frame edge, smaller for a short -i range.  SAD(0,0), which both searches probe first whatever the
-// legality (me.c:203, 271), is computed separately by 64 threads.
-//   ndx > 16 : lane = dx position, warp = group of NC consecutive dy positions            (3 groups)
-//   ndx <= 16: lane = (dx position, lane>>4 = second dy group): a warp covers 16 dx x 2 groups (6 groups)
-// with NC = 10/5/3 (exhaustive search: 30 or 15 rows) or 11/6/3 (three-step search: 31 or 16 rows) candidates per
-// thread, so edge macroblocks cost 1/2 and corner macroblocks about 1/4 of an interior one and no dy row is
-// wasted for the north-star configuration.  A thread keeps the whole current block in 64 registers and slides
-// down 15+NC window rows (4 LDS.32 per row), feeding NC independent VABSDIFF4.U8.ACC chains.
-// Shared-memory banks: word address = k*584 + row*12 + q with (k,q) = ((dx+16)&3, (dx+16)>>2) -> bank 8k+q+const:
-// conflict-free for the 31 dx of a warp; for the 16x2 mapping the second group is NC rows = 12*NC words further:
-// +28 (NC=5) or +4 (NC=3) banks -> the complementary 16 banks.
-constexpr int ME_THREADS = 96;
+// Persistent kernel, ONE WARP PER MACROBLOCK: every warp owns a slice of shared memory and walks its own list of
+// macroblocks with no CTA-wide synchronisation at all.  Per macroblock:
+//   * the 47x48-byte search window and the 16x16 current block arrive by TMA tile loads (out-of-frame samples
+//     zero-filled by the TMA unit) into a double buffer: the loads for the warp's NEXT macroblock are issued before
+//     the current one is processed, so the TMA latency is never exposed;
+//   * the window is replicated shifted by 1..3 bytes (TMA needs a 16-byte aligned innermost start), so that every
+//     packed-SAD operand in the hot loop is an aligned 32-bit shared-memory word (no PRMT/funnel shift in the loop);
+//   * lane = dx position; the warp sweeps the legal dy positions in passes of 10 (or 5) candidates per thread: a
+//     thread keeps the whole current block in 64 registers and slides down 15+NC window rows (4 LDS.32 per row),
+//     feeding NC independent VABSDIFF4.U8.ACC chains.
+// Only the part of the 31x31 surface that the reference can ever look at is evaluated: the legal positions
+// (me.c:212-213, 292-293) inside the search range -- 30x30 for FastBME -i 31 inside the frame ([-15,14],
+// me.c:206-208), 31x31 for StepBME, 15 or 16 wide/high for macroblocks on a frame edge.  With <= 16 legal dx the
+// two half-warps take the two halves of the dy range, so edge macroblocks cost 1/2 and corner macroblocks about 1/3
+// of an interior one.  SAD(0,0), which both searches probe first whatever the legality (me.c:203, 271), is computed
+// separately (two packed SADs per lane).
+// Shared-memory banks: the word of copy k = (dx+16)&3 at word offset q = (dx+16)>>2 lies in bank 8k+q+const
+// (copy 0 starts 128-byte aligned, copy k at 584(k-1)+8 words from an aligned base): conflict-free for the 31 dx of a
+// warp; in the two-half mapping the second half is 15 rows = 180 words further: +20 banks -> the complementary banks.
+constexpr int ME_WARPS = 4;            // warps per CTA (independent workers)
+constexpr int ME_THREADS = 32 * ME_WARPS;
 constexpr int ME_WIN_ROWS = 47;        // window rows y0-15 .. y0+31
 constexpr int ME_ROW_WORDS = 12;       // 48 bytes: x0-16+k .. x0+31+k
-constexpr int ME_COPY_WORDS = 584;     // 47*12 = 564 words + pad; == 8 (mod 32): see the bank formula above
 constexpr int ME_WIN_BYTES = ME_WIN_ROWS * 48;
-constexpr int ME_SMEM_FULL = 128 /*align*/ + 4 * ME_COPY_WORDS * 4 + 256 /*cur*/ + 16 /*mbarrier*/ + 32 * 4 /*red*/ + 32 * 4 /*pen*/;
-constexpr int ME_SMEM_SURF = ME_SMEM_FULL + 31 * 31 * 4;
+// per-warp shared memory, in 32-bit words
+constexpr int ME_BUF_WORDS = 608 + 64;                 // TMA window (564 used, padded to 128-byte multiple) + current block
+constexpr int ME_SHIFT_OFF = 2 * ME_BUF_WORDS;         // byte-shifted copies 1..3: copy k at ME_SHIFT_OFF + 8 + 584 (k-1)
+constexpr int ME_COPY_WORDS = 584;
+constexpr int ME_SAD_OFF = ME_SHIFT_OFF + 8 + 3 * ME_COPY_WORDS + 8;      // [31][31] surface (ME_V_SURF only)
+constexpr int ME_WARP_WORDS_FULL = (ME_SAD_OFF + 31) / 32 * 32;
+constexpr int ME_WARP_WORDS_SURF = (ME_SAD_OFF + 31 * 31 + 31) / 32 * 32;
+constexpr int ME_CTA_WORDS = 3 * 32 /*pen tables*/ + 2 * 2 * ME_WARPS /*mbarriers*/ + 16;
+constexpr int ME_SMEM_FULL = 128 + 4 * (ME_WARPS * ME_WARP_WORDS_FULL + ME_CTA_WORDS);
+constexpr int ME_SMEM_SURF = 128 + 4 * (ME_WARPS * ME_WARP_WORDS_SURF + ME_CTA_WORDS);
 constexpr uint32_t ME_ILLEGAL = 0x10000u;   // start value of an illegal candidate's accumulator: above any SAD (<= 65280)
 
 // CTA-uniform legal ranges in surface positions d+15, per macroblock-column / row class
-// (0 = first, 1 = interior, 2 = last), computed on the host: one byte per class.
+// (0 = first, 1 = interior, 2 = last), computed on the host: one byte per class (hi stored +1, 0 = empty).
 struct MeRanges { uint32_t xlo, xhi, ylo, yhi; };
+struct MeArgs {
+  MeRanges rg;
+  int me_mode;
+  int mbw, mbh, n_pairs;
+  int sx, sy, sp;          // (total worker warps) decomposed as sp * mbw*mbh + sy * mbw + sx: the walk's stride
+  p64b_me* out;
+  uint32_t* surface;
+};
 
 __device__ __forceinline__ uint32_t sad4(uint32_t a, uint32_t b, uint32_t c) {
   uint32_t d;
@@ -91,21 +108,16 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, in
 
 constexpr int ME_V_FULL = 0, ME_V_SURF = 1;
 
-// One thread's NC candidates at dy positions yb .. yb+NC-1 (accumulators start at 0 or ME_ILLEGAL), then either the
-// exhaustive-search key (FastBME, me.c:206-227: dx outer, dy inner, strict <, after probing (0,0): winner = min of
-// SAD<<11 | (1 + (dx+15)*32 + (dy+15)); (0,0) re-enters after the reduction with order 0 so that it wins ties)
-// and/or the surface entries for the three-step walk.
+// One pass: this thread's NC candidates at dy positions yb .. yb+NC-1 (accumulators start at 0 or ME_ILLEGAL from the
+// row table).  Returns min_j (SAD_j << 11 | yb + j): the dy part of the exhaustive-search key.  ME_V_SURF also
+// stores the legal entries into the surface.
 template <int VARIANT, int NC>
-__device__ __forceinline__ void sweep_pick(const uint32_t* __restrict__ base, const uint32_t (&c)[16][4],
-                                           const uint32_t* s_pen, uint32_t* s_sad, int xi, int yb, bool xok, bool full,
-                                           uint32_t* s_best) {
-  constexpr int P = NC >= 5 ? 1 : 2;          // partial chains per candidate: at least 5 independent chains
-  uint32_t a[NC][P];
+__device__ __forceinline__ uint32_t sweep_pass(const uint32_t* __restrict__ colbase, const uint32_t (&c)[16][4],
+                                               const uint32_t* pen, uint32_t* s_sad, int xi, int yb, bool xok) {
+  const uint32_t* base = colbase + yb * ME_ROW_WORDS;
+  uint32_t a[NC];
 #pragma unroll
-  for (int j = 0; j < NC; j++) {
-    a[j][0] = s_pen[yb + j];
-    if (P == 2) a[j][P - 1] = 0;
-  }
+  for (int j = 0; j < NC; j++) a[j] = pen[yb + j];
 #pragma unroll
   for (int t = 0; t < 15 + NC; t++) {
     const uint32_t r0 = base[t * ME_ROW_WORDS + 0], r1 = base[t * ME_ROW_WORDS + 1];
@@ -114,178 +126,197 @@ __device__ __forceinline__ void sweep_pick(const uint32_t* __restrict__ base, co
     for (int j = 0; j < NC; j++) {
       const int i = t - j;
       if (i >= 0 && i < 16) {
-        a[j][0] = sad4(r0, c[i][0], a[j][0]); a[j][P - 1] = sad4(r1, c[i][1], a[j][P - 1]);
-        a[j][0] = sad4(r2, c[i][2], a[j][0]); a[j][P - 1] = sad4(r3, c[i][3], a[j][P - 1]);
+        a[j] = sad4(r0, c[i][0], a[j]); a[j] = sad4(r1, c[i][1], a[j]);
+        a[j] = sad4(r2, c[i][2], a[j]); a[j] = sad4(r3, c[i][3], a[j]);
       }
     }
-  }
-  uint32_t acc[NC];
-#pragma unroll
-  for (int j = 0; j < NC; j++) acc[j] = P == 2 ? a[j][0] + a[j][P - 1] : a[j][0];
-  if (full) {
-    uint32_t best = 0xffffffffu;
-#pragma unroll
-    for (int j = 0; j < NC; j++) best = min(best, acc[j] * 2048u + (uint32_t)j);
-    best = xok ? best + (uint32_t)(1 + xi * 32 + yb) : 0xffffffffu;
-    best = __reduce_min_sync(0xffffffffu, best);
-    if ((threadIdx.x & 31) == 0) *s_best = best;
   }
   if (VARIANT == ME_V_SURF) {
 #pragma unroll
     for (int j = 0; j < NC; j++)
-      if (xok && acc[j] < ME_ILLEGAL) s_sad[(yb + j) * 31 + xi] = acc[j];     // the rest keeps the 0xffffffff prefill
+      if (xok && a[j] < ME_ILLEGAL) s_sad[(yb + j) * 31 + xi] = a[j];     // the rest keeps the 0xffffffff prefill
   }
+  uint32_t best = 0xffffffffu;
+#pragma unroll
+  for (int j = 0; j < NC; j++) best = min(best, a[j] * 2048u + (uint32_t)j);
+  return best + (uint32_t)yb;
 }
 
-// tm_ref / tm_cur: u8 tensors {W, H, n_pairs}; boxes {48,47,1} and {16,16,1}.  grid = (mbw, mbh, n_pairs).
+// tm_ref / tm_cur: u8 tensors {W, H, n_pairs}; boxes {48,47,1} and {16,16,1}.  grid = worker CTAs (persistent).
 // VARIANT: ME_V_FULL exhaustive argmin straight from registers; ME_V_SURF additionally stages the 31x31 surface in
 // shared memory for the three-step walk (me_mode == TSS) and the test hook (surface != nullptr).
 template <int VARIANT>
-__global__ void __launch_bounds__(ME_THREADS)
-me_surface_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constant__ CUtensorMap tm_cur, MeRanges rg,
-                  int me_mode, p64b_me* __restrict__ out, uint32_t* __restrict__ surface) {
+__global__ void __launch_bounds__(ME_THREADS, 4)
+me_search_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constant__ CUtensorMap tm_cur,
+                 const __grid_constant__ MeArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* sbase = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);   // TMA destinations: 128-B aligned
-  uint32_t* win = reinterpret_cast<uint32_t*>(sbase);                   // [4][ME_COPY_WORDS]
-  uint32_t* s_cur = win + 4 * ME_COPY_WORDS;                            // [16][4]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(s_cur + 64);             // mbarrier (8-B aligned)
-  uint32_t* s_red = s_cur + 64 + 4;                                     // [32]
-  uint32_t* s_pen = s_red + 32;                                         // [32] per dy position: 0 or ME_ILLEGAL
-  uint32_t* s_sad = s_pen + 32;                                         // [31][31], index [dy+15][dx+15] (ME_V_SURF)
+  constexpr int WARP_WORDS = VARIANT == ME_V_FULL ? ME_WARP_WORDS_FULL : ME_WARP_WORDS_SURF;
+  uint32_t* sm = reinterpret_cast<uint32_t*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
+  const int lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);      // warp-uniform for the compiler
+  uint32_t* wsm = sm + warp * WARP_WORDS;                                // this warp's slice (128-byte aligned)
+  uint32_t* s_pen = sm + ME_WARPS * WARP_WORDS;                          // [3][32] per row class: 0 or ME_ILLEGAL
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_pen + 96) + 2 * warp;   // one mbarrier per buffer
+  uint32_t* s_sad = wsm + ME_SAD_OFF;
 
-  const int x0 = blockIdx.x * 16, y0 = blockIdx.y * 16, pair = blockIdx.z;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-  if (tid == 0) mbar_init(bar, 1);
+  if (threadIdx.x < 96) {
+    const int cls = threadIdx.x >> 5, r = threadIdx.x & 31;
+    const int lo = (a.rg.ylo >> (8 * cls)) & 0xff, hi = (int)((a.rg.yhi >> (8 * cls)) & 0xff) - 1;
+    s_pen[threadIdx.x] = (r >= lo && r <= hi) ? 0u : ME_ILLEGAL;
+  }
+  if (lane == 0) { mbar_init(bars, 1); mbar_init(bars + 1, 1); }
   __syncthreads();
-  if (tid == 0) {
-    mbar_expect_tx(bar, ME_WIN_BYTES + 256);
-    tma_load_3d(win, &tm_ref, x0 - 16, y0 - 15, pair, bar);      // out-of-frame samples arrive as zeros
-    tma_load_3d(s_cur, &tm_cur, x0, y0, pair, bar);
+
+  const bool full = a.me_mode == P64B_ME_FULL;
+  const int per_pair = a.mbw * a.mbh, total = per_pair * a.n_pairs;
+  int n = blockIdx.x * ME_WARPS + warp;
+  const int stride = gridDim.x * ME_WARPS;
+  int pair = n / per_pair, by = (n - pair * per_pair) / a.mbw, bx = n - pair * per_pair - by * a.mbw;
+
+  if (n < total && lane == 0) {
+    mbar_expect_tx(bars, ME_WIN_BYTES + 256);
+    tma_load_3d(wsm, &tm_ref, bx * 16 - 16, by * 16 - 15, pair, bars);      // out-of-frame samples arrive as zeros
+    tma_load_3d(wsm + 608, &tm_cur, bx * 16, by * 16, pair, bars);
   }
 
-  // ---- search geometry while the TMA loads are in flight (CTA-uniform part from the host table)
-  const bool full = me_mode == P64B_ME_FULL;
-  const int cx = 8 * (blockIdx.x == 0 ? 0 : (blockIdx.x == gridDim.x - 1 ? 2 : 1));
-  const int cy = 8 * (blockIdx.y == 0 ? 0 : (blockIdx.y == gridDim.y - 1 ? 2 : 1));
-  const int lxlo = (rg.xlo >> cx) & 0xff, lxhi = (int)((rg.xhi >> cx) & 0xff) - 1;   // hi stored +1 (0 = empty range)
-  const int lylo = (rg.ylo >> cy) & 0xff, lyhi = (int)((rg.yhi >> cy) & 0xff) - 1;
-  const int ndy = lyhi - lylo + 1;
-  const bool xr = lxhi - lxlo < 16;
-  constexpr int NCB = VARIANT == ME_V_FULL ? 10 : 11, NCS = VARIANT == ME_V_FULL ? 5 : 6, NCT = 3;
-  const int nc = xr ? (ndy > 6 * NCT ? NCS : NCT) : (ndy > 3 * NCS ? NCB : NCS);
-  int xi = lxlo + (xr ? (lane & 15) : lane);
-  const bool xok = xi <= lxhi;
-  xi = min(xi, 30);                                              // surplus lanes: any in-window column
-  const int yb = min(lylo + nc * (xr ? 2 * warp + (lane >> 4) : warp), 32 - nc);
-  if (tid < 32) s_pen[tid] = (tid >= lylo && tid <= lyhi) ? 0u : ME_ILLEGAL;
-  if (VARIANT == ME_V_SURF)
-    for (int i = tid; i < 31 * 31; i += ME_THREADS) s_sad[i] = 0xffffffffu;
-
-  mbar_wait(bar, 0);
-  // byte-shifted copies 1..3 (TMA needs a 16-byte aligned innermost start, so only copy 0 comes from the TMA unit):
-  // each 16-byte quad + the following word yields the three shifted quads
-  for (int u = tid; u < ME_WIN_ROWS * 3; u += ME_THREADS) {
-    const int idx = 4 * u;                          // row (u/3) * 12 + 4 * (u%3)
-    const uint4 a = *reinterpret_cast<const uint4*>(win + idx);
-    const uint32_t nx = win[idx + 4];
-#pragma unroll
-    for (int k = 1; k < 4; k++) {
-      uint4 o;
-      o.x = __funnelshift_r(a.x, a.y, 8 * k); o.y = __funnelshift_r(a.y, a.z, 8 * k);
-      o.z = __funnelshift_r(a.z, a.w, 8 * k); o.w = __funnelshift_r(a.w, nx, 8 * k);
-      *reinterpret_cast<uint4*>(win + k * ME_COPY_WORDS + idx) = o;
+  for (int it = 0; n < total; it++) {
+    // ---- the warp's next macroblock: start its loads into the other buffer
+    int nbx = bx + a.sx, nby = by + a.sy, npair = pair + a.sp;
+    if (nbx >= a.mbw) { nbx -= a.mbw; nby++; }
+    if (nby >= a.mbh) { nby -= a.mbh; npair++; }
+    const int b = it & 1;
+    if (n + stride < total && lane == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the buffer's earlier generic-proxy reads are done
+      uint32_t* nb = wsm + (b ^ 1) * ME_BUF_WORDS;
+      mbar_expect_tx(bars + (b ^ 1), ME_WIN_BYTES + 256);
+      tma_load_3d(nb, &tm_ref, nbx * 16 - 16, nby * 16 - 15, npair, bars + (b ^ 1));
+      tma_load_3d(nb + 608, &tm_cur, nbx * 16, nby * 16, npair, bars + (b ^ 1));
     }
-  }
 
-  uint32_t c[16][4];
+    // ---- search geometry of this macroblock (warp-uniform, from the host table)
+    const int cx = 8 * (bx == 0 ? 0 : (bx == a.mbw - 1 ? 2 : 1)), cyi = by == 0 ? 0 : (by == a.mbh - 1 ? 2 : 1);
+    const int lxlo = (a.rg.xlo >> cx) & 0xff, lxhi = (int)((a.rg.xhi >> cx) & 0xff) - 1;
+    const int lylo = (a.rg.ylo >> (8 * cyi)) & 0xff, lyhi = (int)((a.rg.yhi >> (8 * cyi)) & 0xff) - 1;
+    const bool xr = lxhi - lxlo < 16;
+    const int ndy = max(lyhi - lylo + 1, 0);
+    const int rpg = xr ? (ndy + 1) >> 1 : ndy;                        // dy rows per lane group
+    int xi = lxlo + (xr ? (lane & 15) : lane);
+    const bool xok = xi <= lxhi;
+    xi = min(xi, 30);                                                 // surplus lanes: any in-window column
+    const int ystart = lylo + ((xr && lane >= 16) ? rpg : 0);
+    const uint32_t* pen = s_pen + 32 * cyi;
+    uint32_t* win = wsm + b * ME_BUF_WORDS;                           // copy 0 (TMA), [47][12]
+    const uint32_t* s_cur = win + 608;                                // [16][4]
+    uint32_t* shifted = wsm + ME_SHIFT_OFF + 8;                       // copy k at shifted + 584 (k-1)
+    if (VARIANT == ME_V_SURF)
+      for (int i = lane; i < 31 * 31; i += 32) s_sad[i] = 0xffffffffu;
+
+    mbar_wait(bars + b, (it >> 1) & 1);
+    // byte-shifted copies 1..3: each 16-byte quad + the following word yields the three shifted quads
+#pragma unroll 1
+    for (int u = lane; u < ME_WIN_ROWS * 3; u += 32) {
+      const int idx = 4 * u;                          // row (u/3) * 12 + 4 * (u%3)
+      const uint4 v = *reinterpret_cast<const uint4*>(win + idx);
+      const uint32_t nx = win[idx + 4];
 #pragma unroll
-  for (int i = 0; i < 16; i++) {
-    uint4 v = reinterpret_cast<const uint4*>(s_cur)[i];
-    c[i][0] = v.x; c[i][1] = v.y; c[i][2] = v.z; c[i][3] = v.w;
-  }
-  // SAD(0,0) = OMV (me.c:203, 271), needed whatever the search does: 64 threads, one packed SAD each
-  if (tid < 64) {
-    const int i = tid >> 2, wc = tid & 3;
-    uint32_t s0 = sad4(win[(15 + i) * ME_ROW_WORDS + 4 + wc], s_cur[tid], 0u);
-    s0 = __reduce_add_sync(0xffffffffu, s0);
-    if (lane == 0) s_red[20 + warp] = s0;
-  }
-
-  __syncthreads();
-
-  // ---- SAD surface
-  {
-    const int o = xi + 1;                                       // dx + 16
-    const uint32_t* base = win + (o & 3) * ME_COPY_WORDS + yb * ME_ROW_WORDS + (o >> 2);
-    uint32_t* s_best = s_red + 4 + warp;
-    if (nc == NCB)      sweep_pick<VARIANT, NCB>(base, c, s_pen, s_sad, xi, yb, xok, full, s_best);
-    else if (nc == NCS) sweep_pick<VARIANT, NCS>(base, c, s_pen, s_sad, xi, yb, xok, full, s_best);
-    else                sweep_pick<VARIANT, NCT>(base, c, s_pen, s_sad, xi, yb, xok, full, s_best);
-  }
-  __syncthreads();
-  if (warp) return;                       // the search result and the statistics are one warp's work
-
-  const uint32_t omv = s_red[20] + s_red[21];
-  const size_t mb_index = ((size_t)pair * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-  if (VARIANT == ME_V_SURF) {
-    if (lane == 0) s_sad[15 * 31 + 15] = omv;     // (0,0) is in the surface even where a later probe of it would be illegal
+      for (int k = 1; k < 4; k++) {
+        uint4 o;
+        o.x = __funnelshift_r(v.x, v.y, 8 * k); o.y = __funnelshift_r(v.y, v.z, 8 * k);
+        o.z = __funnelshift_r(v.z, v.w, 8 * k); o.w = __funnelshift_r(v.w, nx, 8 * k);
+        *reinterpret_cast<uint4*>(shifted + (k - 1) * ME_COPY_WORDS + idx) = o;
+      }
+    }
+    uint32_t c[16][4];
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+      const uint4 v = reinterpret_cast<const uint4*>(s_cur)[i];
+      c[i][0] = v.x; c[i][1] = v.y; c[i][2] = v.z; c[i][3] = v.w;
+    }
+    // SAD(0,0) = OMV (me.c:203, 271): two packed SADs per lane
+    uint32_t omv;
+    {
+      const int i = lane >> 1, wc = (lane & 1) * 2;
+      const uint2 r = *reinterpret_cast<const uint2*>(win + (15 + i) * ME_ROW_WORDS + 4 + wc);
+      const uint2 cw = *reinterpret_cast<const uint2*>(s_cur + i * 4 + wc);
+      omv = __reduce_add_sync(0xffffffffu, sad4(r.y, cw.y, sad4(r.x, cw.x, 0u)));
+    }
     __syncwarp();
-    if (surface)   // test hook: the whole surface, [dy+15][dx+15], 0xffffffff = illegal position
-      for (int i = lane; i < 31 * 31; i += 32) surface[mb_index * 961 + i] = s_sad[i];
-  }
 
-  // ---- search result
-  int mx = 0, my = 0;
-  uint32_t mv = omv;
-  if (full) {
-    const uint32_t best = min(min(s_red[4], s_red[5]), min(s_red[6], omv << 11));
-    mv = best >> 11;
-    const int ord = best & 2047;
-    if (ord) { mx = ((ord - 1) >> 5) - 15; my = ((ord - 1) & 31) - 15; }
-  } else if (VARIANT == ME_V_SURF) {
-    // StepBME (me.c:273-311): steps 8,4,2,1; 8 neighbours in (diry outer, dirx inner) order; the centre
-    // moves once per step; strict < keeps the earlier candidate on ties.  Lanes 0..7 probe in parallel.
-    for (int step = 8; step >= 1; step >>= 1) {
-      uint32_t key = (mv << 4);                     // current best, order 0
-      if (lane < 8) {
-        int n = lane < 4 ? lane : lane + 1;         // skip the centre (index 4)
-        int dx = mx + (n % 3 - 1) * step, dy = my + (n / 3 - 1) * step;
-        if (dx >= -15 && dx <= 15 && dy >= -15 && dy <= 15) {
-          uint32_t s = s_sad[(dy + 15) * 31 + dx + 15];
-          if (s != 0xffffffffu) key = min(key, (s << 4) | (uint32_t)(lane + 1));
+    // ---- SAD sweep over the legal rectangle
+    const int o = xi + 1, k = o & 3;                             // o = dx + 16
+    const uint32_t* colbase = (k ? shifted + (k - 1) * ME_COPY_WORDS : win) + (o >> 2);
+    uint32_t best = 0xffffffffu;
+    for (int done = 0; done < rpg;) {
+      if (rpg - done > 5) { best = min(best, sweep_pass<VARIANT, 10>(colbase, c, pen, s_sad, xi, min(ystart + done, 22), xok)); done += 10; }
+      else                { best = min(best, sweep_pass<VARIANT, 5>(colbase, c, pen, s_sad, xi, min(ystart + done, 27), xok)); done += 5; }
+    }
+
+    const size_t mb_index = ((size_t)pair * a.mbh + by) * a.mbw + bx;
+    if (VARIANT == ME_V_SURF) {
+      __syncwarp();
+      if (lane == 0) s_sad[15 * 31 + 15] = omv;     // (0,0) is in the surface even where a later probe of it would be illegal
+      __syncwarp();
+      if (a.surface)   // test hook: the whole surface, [dy+15][dx+15], 0xffffffff = illegal position
+        for (int i = lane; i < 31 * 31; i += 32) a.surface[mb_index * 961 + i] = s_sad[i];
+    }
+
+    // ---- search result
+    int mx = 0, my = 0;
+    uint32_t mv = omv;
+    if (full) {
+      // FastBME (me.c:206-227) scans dx outer, dy inner with strict <, after probing (0,0): winner = min of
+      // SAD<<11 | (1 + (dx+15)*32 + (dy+15)); (0,0) enters with order 0 so that it wins ties
+      best = xok ? best + (uint32_t)(1 + xi * 32) : 0xffffffffu;
+      best = min(__reduce_min_sync(0xffffffffu, best), omv << 11);
+      mv = best >> 11;
+      const int ord = best & 2047;
+      if (ord) { mx = ((ord - 1) >> 5) - 15; my = ((ord - 1) & 31) - 15; }
+    } else if (VARIANT == ME_V_SURF) {
+      // StepBME (me.c:273-311): steps 8,4,2,1; 8 neighbours in (diry outer, dirx inner) order; the centre
+      // moves once per step; strict < keeps the earlier candidate on ties.  Lanes 0..7 probe in parallel.
+      for (int step = 8; step >= 1; step >>= 1) {
+        uint32_t key = (mv << 4);                     // current best, order 0
+        if (lane < 8) {
+          int nn = lane < 4 ? lane : lane + 1;        // skip the centre (index 4)
+          int dx = mx + (nn % 3 - 1) * step, dy = my + (nn / 3 - 1) * step;
+          if (dx >= -15 && dx <= 15 && dy >= -15 && dy <= 15) {
+            uint32_t sv = s_sad[(dy + 15) * 31 + dx + 15];
+            if (sv != 0xffffffffu) key = min(key, (sv << 4) | (uint32_t)(lane + 1));
+          }
+        }
+        const uint32_t bk = __reduce_min_sync(0xffffffffu, key);
+        int ord = bk & 15;
+        if (ord) {
+          int nn = ord - 1; nn = nn < 4 ? nn : nn + 1;
+          mx += (nn % 3 - 1) * step; my += (nn / 3 - 1) * step;
+          mv = bk >> 4;
         }
       }
-      const uint32_t best = __reduce_min_sync(0xffffffffu, key);
-      int ord = best & 15;
-      if (ord) {
-        int n = ord - 1; n = n < 4 ? n : n + 1;
-        mx += (n % 3 - 1) * step; my += (n / 3 - 1) * step;
-        mv = best >> 4;
+    }
+
+    // ---- statistics over the best-match reference block (me.c:230-245), on packed words, two per lane:
+    // sum r = SAD(r,0); sum r^2 = dp4a(r,r); sum (r-c)^2 = dp4a(r,r) - 2 dp4a(r,c) + dp4a(c,c)
+    {
+      const int i = lane >> 1, wc = (lane & 1) * 2, oo = mx + 16, kk = oo & 3;
+      const uint32_t* rp = (kk ? shifted + (kk - 1) * ME_COPY_WORDS : win) + (my + 15 + i) * ME_ROW_WORDS + (oo >> 2) + wc;
+      const uint32_t ra = rp[0], rb = rp[1];
+      const uint2 cw = *reinterpret_cast<const uint2*>(s_cur + i * 4 + wc);
+      uint32_t smm = sad4(rb, 0u, sad4(ra, 0u, 0u));
+      uint32_t so = __dp4a(rb, rb, __dp4a(ra, ra, 0u));
+      uint32_t sv = so + __dp4a(cw.y, cw.y, __dp4a(cw.x, cw.x, 0u)) - 2u * __dp4a(rb, cw.y, __dp4a(ra, cw.x, 0u));
+      sv = __reduce_add_sync(0xffffffffu, sv);
+      so = __reduce_add_sync(0xffffffffu, so);
+      smm = __reduce_add_sync(0xffffffffu, smm);
+      if (lane == 0) {
+        const int var = (int)sv / 256, mwor = (int)smm;
+        const int varor = (int)so / 256 - (mwor / 256) * (mwor / 256);
+        int4* op = reinterpret_cast<int4*>(a.out + mb_index);
+        op[0] = make_int4(mx, my, (int)mv, (int)omv);
+        op[1] = make_int4(var, varor, mwor, 0);
       }
     }
-  }
-
-  // ---- statistics over the best-match reference block (me.c:230-245), on packed words, two per lane:
-  // sum r = SAD(r,0); sum r^2 = dp4a(r,r); sum (r-c)^2 = dp4a(r,r) - 2 dp4a(r,c) + dp4a(c,c)
-  {
-    const int i = lane >> 1, wc = (lane & 1) * 2, oo = mx + 16;
-    const uint32_t* rp = win + (oo & 3) * ME_COPY_WORDS + (my + 15 + i) * ME_ROW_WORDS + (oo >> 2) + wc;
-    const uint32_t ra = rp[0], rb = rp[1];
-    const uint2 cw = *reinterpret_cast<const uint2*>(s_cur + i * 4 + wc);
-    uint32_t sm = sad4(rb, 0u, sad4(ra, 0u, 0u));
-    uint32_t so = __dp4a(rb, rb, __dp4a(ra, ra, 0u));
-    uint32_t sv = so + __dp4a(cw.y, cw.y, __dp4a(cw.x, cw.x, 0u)) - 2u * __dp4a(rb, cw.y, __dp4a(ra, cw.x, 0u));
-    sv = __reduce_add_sync(0xffffffffu, sv);
-    so = __reduce_add_sync(0xffffffffu, so);
-    sm = __reduce_add_sync(0xffffffffu, sm);
-    if (lane == 0) {
-      const int var = (int)sv / 256, mwor = (int)sm;
-      const int varor = (int)so / 256 - (mwor / 256) * (mwor / 256);
-      int4* op = reinterpret_cast<int4*>(out + mb_index);
-      op[0] = make_int4(mx, my, (int)mv, (int)omv);
-      op[1] = make_int4(var, varor, mwor, 0);
-    }
+    __syncwarp();          // every lane is done with this buffer and the shifted copies
+    n += stride; bx = nbx; by = nby; pair = npair;
   }
 }
 
