@@ -66,6 +66,8 @@ struct p64b_ctx {
   int64_t launches = 0;
   bool me_attr_done = false;
   int n_sm = 0;
+  uint32_t* d_me_queue = nullptr;   // [2] work counters of the persistent ME kernel (alternating per launch)
+  int64_t me_launches = 0;
   // optional per-kernel timing with CUDA events on the launching stream (bench.py roofline)
   bool prof = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_ev[2];   // 0 = ME kernel, 1 = MB kernel
@@ -159,8 +161,15 @@ static int launch_me(p64b_ctx* c, const uint8_t* ref, const uint8_t* cur, size_t
   const long long total = (long long)n_pairs * a.mbw * a.mbh;
   if (total > 0x7fffffffLL) { set_error("too many macroblocks in one motion-estimation call"); return P64B_EINVAL; }
   const int grid = (int)std::min<long long>((long long)c->n_sm * (surf ? 3 : 4), (total + ME_WARPS - 1) / ME_WARPS);
-  const int wstride = grid * ME_WARPS, per_pair = a.mbw * a.mbh;
-  a.sp = wstride / per_pair; a.sy = (wstride % per_pair) / a.mbw; a.sx = wstride % a.mbw;
+  // n / per_pair by multiply-high (exact for n < 2^31: the magic's excess e < per_pair and n * e < 2^(32+shift))
+  const uint32_t per_pair = (uint32_t)(a.mbw * a.mbh);
+  uint32_t sh = 0;
+  while ((2u << sh) < per_pair) sh++;                       // 2^sh < per_pair <= 2^(sh+1): the magic fits 32 bits
+  a.shift_pp = sh;
+  a.magic_pp = (uint32_t)(((1ull << (32 + sh)) + per_pair - 1) / per_pair);
+  a.magic_w = 65536u / (uint32_t)a.mbw + 1u;               // r / mbw for r < per_pair <= 1024
+  a.queue = c->d_me_queue; a.parity = (int)(c->me_launches++ & 1);
+  a.m8 = 1u << 8; a.m16 = 1u << 16; a.m24 = 1u << 24; a.m2048 = 2048u;
   ProfScope ps(c, 0);
   if (!surf) me_search_kernel<ME_V_FULL><<<grid, ME_THREADS, ME_SMEM_FULL, c->stream>>>(tm_ref, tm_cur, a);
   else       me_search_kernel<ME_V_SURF><<<grid, ME_THREADS, ME_SMEM_SURF, c->stream>>>(tm_ref, tm_cur, a);
@@ -236,6 +245,7 @@ int p64b_ctx_create(p64b_ctx** out, int device, int image_type, int n_streams) {
   ALLOC(c->d_levels, nm * P64B_LEVELS_PER_MB);
   ALLOC(c->d_quant, (size_t)n_streams);
   ALLOC(c->d_ovf, nm);
+  ALLOC(c->d_me_queue, 2 * sizeof(uint32_t));
   c->p_src[0] = c->d_src; c->p_mbs[0] = c->d_mbs; c->p_levels[0] = c->d_levels;
   for (int i = 1; i < p64b_ctx::NSLOT; i++) {
     ALLOC(c->p_src[i], fb + slack);
@@ -261,7 +271,7 @@ void p64b_ctx_destroy(p64b_ctx* c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   cudaFree(c->d_src); cudaFree(c->d_fs[0]); cudaFree(c->d_fs[1]); cudaFree(c->d_li[0]); cudaFree(c->d_li[1]);
-  cudaFree(c->d_me); cudaFree(c->d_mbs); cudaFree(c->d_levels); cudaFree(c->d_quant); cudaFree(c->d_ovf);
+  cudaFree(c->d_me); cudaFree(c->d_mbs); cudaFree(c->d_levels); cudaFree(c->d_quant); cudaFree(c->d_ovf); cudaFree(c->d_me_queue);
   if (c->s_h2d) cudaStreamSynchronize(c->s_h2d);
   if (c->s_d2h) cudaStreamSynchronize(c->s_d2h);
   for (int i = 0; i < p64b_ctx::NSLOT; i++) {

@@ -27,8 +27,9 @@ struct Geom {
 // ---------------------------------------------------------------------------------------------------
 // Motion estimation
 // ---------------------------------------------------------------------------------------------------
-// Persistent kernel, ONE WARP PER MACROBLOCK: every warp owns a slice of shared memory and walks its own list of
-// macroblocks with no CTA-wide synchronisation at all.  Per macroblock:
+// Persistent kernel, ONE WARP PER MACROBLOCK: every warp owns a slice of shared memory and pulls macroblocks from a
+// global work queue (an atomic counter; the index of the macroblock after next is requested one macroblock ahead,
+// so its latency is hidden) with no CTA-wide synchronisation at all.  Per macroblock:
 //   * the 47x48-byte search window and the 16x16 current block arrive by TMA tile loads (out-of-frame samples
 //     zero-filled by the TMA unit) into a double buffer: the loads for the warp's NEXT macroblock are issued before
 //     the current one is processed, so the TMA latency is never exposed;
@@ -70,7 +71,10 @@ struct MeArgs {
   MeRanges rg;
   int me_mode;
   int mbw, mbh, n_pairs;
-  int sx, sy, sp;          // (total worker warps) decomposed as sp * mbw*mbh + sy * mbw + sx: the walk's stride
+  uint32_t magic_pp, shift_pp, magic_w;   // n / (mbw*mbh) = umulhi(n, magic_pp) >> shift_pp;  r / mbw = r * magic_w >> 16
+  uint32_t* queue;         // [2] work counters: this launch takes macroblocks from queue[parity] and zeroes the other
+  int parity;
+  uint32_t m8, m16, m24, m2048;   // 1<<8, 1<<16, 1<<24, 2048 in registers: keeps those multiplies on the FMA pipe
   p64b_me* out;
   uint32_t* surface;
 };
@@ -113,7 +117,8 @@ constexpr int ME_V_FULL = 0, ME_V_SURF = 1;
 // stores the legal entries into the surface.
 template <int VARIANT, int NC>
 __device__ __forceinline__ uint32_t sweep_pass(const uint32_t* __restrict__ colbase, const uint32_t (&c)[16][4],
-                                               const uint32_t* pen, uint32_t* s_sad, int xi, int yb, bool xok) {
+                                               const uint32_t* pen, uint32_t* s_sad, int xi, int yb, bool xok,
+                                               uint32_t m2048) {
   const uint32_t* base = colbase + yb * ME_ROW_WORDS;
   uint32_t a[NC];
 #pragma unroll
@@ -138,7 +143,7 @@ __device__ __forceinline__ uint32_t sweep_pass(const uint32_t* __restrict__ colb
   }
   uint32_t best = 0xffffffffu;
 #pragma unroll
-  for (int j = 0; j < NC; j++) best = min(best, a[j] * 2048u + (uint32_t)j);
+  for (int j = 0; j < NC; j++) best = min(best, a[j] * m2048 + (uint32_t)j);      // IMAD (FMA pipe), not LEA (ALU pipe)
   return best + (uint32_t)yb;
 }
 
@@ -169,29 +174,35 @@ me_search_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_consta
 
   const bool full = a.me_mode == P64B_ME_FULL;
   const int per_pair = a.mbw * a.mbh, total = per_pair * a.n_pairs;
-  int n = blockIdx.x * ME_WARPS + warp;
-  const int stride = gridDim.x * ME_WARPS;
-  int pair = n / per_pair, by = (n - pair * per_pair) / a.mbw, bx = n - pair * per_pair - by * a.mbw;
-
-  if (n < total && lane == 0) {
-    mbar_expect_tx(bars, ME_WIN_BYTES + 256);
-    tma_load_3d(wsm, &tm_ref, bx * 16 - 16, by * 16 - 15, pair, bars);      // out-of-frame samples arrive as zeros
-    tma_load_3d(wsm + 608, &tm_cur, bx * 16, by * 16, pair, bars);
+  const int n_workers = gridDim.x * ME_WARPS;
+  if (blockIdx.x == 0 && threadIdx.x == 0) a.queue[a.parity ^ 1] = 0;      // the next launch's counter
+  // macroblock n -> (pair, by, bx); n is also the raster index of its output record
+  auto issue_loads = [&](int n, int buf) {
+    const int pair = (int)(__umulhi((uint32_t)n, a.magic_pp) >> a.shift_pp), r = n - pair * per_pair;
+    const int by = (int)(((uint32_t)r * a.magic_w) >> 16), bx = r - by * a.mbw;
+    uint32_t* nb = wsm + buf * ME_BUF_WORDS;
+    mbar_expect_tx(bars + buf, ME_WIN_BYTES + 256);
+    tma_load_3d(nb, &tm_ref, bx * 16 - 16, by * 16 - 15, pair, bars + buf);      // out-of-frame samples arrive as zeros
+    tma_load_3d(nb + 608, &tm_cur, bx * 16, by * 16, pair, bars + buf);
+  };
+  int n = blockIdx.x * ME_WARPS + warp;           // first macroblock: static; the rest come from the queue
+  uint32_t ticket = 0;                            // lane 0: queue position of the warp's NEXT macroblock
+  if (lane == 0) {
+    if (n < total) issue_loads(n, 0);
+    ticket = atomicAdd(a.queue + a.parity, 1u);
   }
 
   for (int it = 0; n < total; it++) {
-    // ---- the warp's next macroblock: start its loads into the other buffer
-    int nbx = bx + a.sx, nby = by + a.sy, npair = pair + a.sp;
-    if (nbx >= a.mbw) { nbx -= a.mbw; nby++; }
-    if (nby >= a.mbh) { nby -= a.mbh; npair++; }
+    // ---- the warp's next macroblock: start its loads into the other buffer, request the one after it
     const int b = it & 1;
-    if (n + stride < total && lane == 0) {
+    const int n_next = n_workers + (int)__shfl_sync(0xffffffffu, ticket, 0);
+    if (lane == 0 && n_next < total) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the buffer's earlier generic-proxy reads are done
-      uint32_t* nb = wsm + (b ^ 1) * ME_BUF_WORDS;
-      mbar_expect_tx(bars + (b ^ 1), ME_WIN_BYTES + 256);
-      tma_load_3d(nb, &tm_ref, nbx * 16 - 16, nby * 16 - 15, npair, bars + (b ^ 1));
-      tma_load_3d(nb + 608, &tm_cur, nbx * 16, nby * 16, npair, bars + (b ^ 1));
+      issue_loads(n_next, b ^ 1);
+      ticket = atomicAdd(a.queue + a.parity, 1u);
     }
+    const int r_ = n - (int)(__umulhi((uint32_t)n, a.magic_pp) >> a.shift_pp) * per_pair;
+    const int by = (int)(((uint32_t)r_ * a.magic_w) >> 16), bx = r_ - by * a.mbw;
 
     // ---- search geometry of this macroblock (warp-uniform, from the host table)
     const int cx = 8 * (bx == 0 ? 0 : (bx == a.mbw - 1 ? 2 : 1)), cyi = by == 0 ? 0 : (by == a.mbh - 1 ? 2 : 1);
@@ -218,11 +229,14 @@ me_search_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_consta
       const int idx = 4 * u;                          // row (u/3) * 12 + 4 * (u%3)
       const uint4 v = *reinterpret_cast<const uint4*>(win + idx);
       const uint32_t nx = win[idx + 4];
+      // funnel shift right by 8k as hi32(lo * 2^(32-8k)) + hi * 2^(32-8k): IMAD.HI + IMAD on the otherwise idle FMA pipe
+      // (SHF would compete with VABSDIFF4 for the ALU pipe); the multipliers come in registers so they stay multiplies
 #pragma unroll
       for (int k = 1; k < 4; k++) {
+        const uint32_t m = k == 1 ? a.m24 : (k == 2 ? a.m16 : a.m8);
         uint4 o;
-        o.x = __funnelshift_r(v.x, v.y, 8 * k); o.y = __funnelshift_r(v.y, v.z, 8 * k);
-        o.z = __funnelshift_r(v.z, v.w, 8 * k); o.w = __funnelshift_r(v.w, nx, 8 * k);
+        o.x = __umulhi(v.x, m) + v.y * m; o.y = __umulhi(v.y, m) + v.z * m;
+        o.z = __umulhi(v.z, m) + v.w * m; o.w = __umulhi(v.w, m) + nx * m;
         *reinterpret_cast<uint4*>(shifted + (k - 1) * ME_COPY_WORDS + idx) = o;
       }
     }
@@ -247,11 +261,11 @@ me_search_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_consta
     const uint32_t* colbase = (k ? shifted + (k - 1) * ME_COPY_WORDS : win) + (o >> 2);
     uint32_t best = 0xffffffffu;
     for (int done = 0; done < rpg;) {
-      if (rpg - done > 5) { best = min(best, sweep_pass<VARIANT, 10>(colbase, c, pen, s_sad, xi, min(ystart + done, 22), xok)); done += 10; }
-      else                { best = min(best, sweep_pass<VARIANT, 5>(colbase, c, pen, s_sad, xi, min(ystart + done, 27), xok)); done += 5; }
+      if (rpg - done > 5) { best = min(best, sweep_pass<VARIANT, 10>(colbase, c, pen, s_sad, xi, min(ystart + done, 22), xok, a.m2048)); done += 10; }
+      else                { best = min(best, sweep_pass<VARIANT, 5>(colbase, c, pen, s_sad, xi, min(ystart + done, 27), xok, a.m2048)); done += 5; }
     }
 
-    const size_t mb_index = ((size_t)pair * a.mbh + by) * a.mbw + bx;
+    const size_t mb_index = (size_t)n;
     if (VARIANT == ME_V_SURF) {
       __syncwarp();
       if (lane == 0) s_sad[15 * 31 + 15] = omv;     // (0,0) is in the surface even where a later probe of it would be illegal
@@ -316,7 +330,7 @@ me_search_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_consta
       }
     }
     __syncwarp();          // every lane is done with this buffer and the shifted copies
-    n += stride; bx = nbx; by = nby; pair = npair;
+    n = n_next;
   }
 }
 
