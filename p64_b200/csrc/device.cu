@@ -187,6 +187,12 @@ static int launch_mb(p64b_ctx* c, const p64b_step* st, const uint8_t* src, int g
   a.gob_first = gob_first; a.gob_count = gob_count; a.out_mb_per_stream = gob_count * 33;
   a.first_frame = st->first_frame; a.force_intra = st->force_intra; a.gquant = st->gquant;
   const int n = c->S * gob_count * 33;
+  {   // n / mps by multiply-high, exact for n < 2^31 (same construction as in launch_me)
+    const uint32_t mps = (uint32_t)gob_count * 33u;
+    uint32_t sh = 0;
+    while ((2u << sh) < mps) sh++;
+    a.mps_shift = sh; a.mps_magic = (uint32_t)(((1ull << (32 + sh)) + mps - 1) / mps);
+  }
   ProfScope ps(c, 1);
   mb_encode_kernel<<<(n + MB_PER_CTA - 1) / MB_PER_CTA, MBK_THREADS, 0, c->stream>>>(a);
   c->launches++;

@@ -385,23 +385,6 @@ __device__ __forceinline__ void idct8(int& x0, int& x1, int& x2, int& x3, int& x
   x4 = b3 - c0; x5 = b2 - c1; x6 = b1 - c2; x7 = b0 - c3;
 }
 
-// ChenDct (chendct.c:97-206) on v[64] row-major, in place, WITHOUT the final "/8 with rounding" (chendct.c:204-205):
-// that step is folded into the quantiser below.
-__device__ __forceinline__ void chen_fdct_raw(int (&v)[64]) {
-#pragma unroll
-  for (int i = 0; i < 8; i++) fdct8<1>(v[i], v[8 + i], v[16 + i], v[24 + i], v[32 + i], v[40 + i], v[48 + i], v[56 + i]);
-#pragma unroll
-  for (int i = 0; i < 8; i++)
-    fdct8<0>(v[8 * i], v[8 * i + 1], v[8 * i + 2], v[8 * i + 3], v[8 * i + 4], v[8 * i + 5], v[8 * i + 6], v[8 * i + 7]);
-}
-// ChenIDct (chendct.c:217-375) without the final "/16 with rounding" (chendct.c:373-374), folded into the reconstruction.
-__device__ __forceinline__ void chen_idct_raw(int (&v)[64]) {
-#pragma unroll
-  for (int i = 0; i < 8; i++) idct8<1>(v[i], v[8 + i], v[16 + i], v[24 + i], v[32 + i], v[40 + i], v[48 + i], v[56 + i]);
-#pragma unroll
-  for (int i = 0; i < 8; i++)
-    idct8<0>(v[8 * i], v[8 * i + 1], v[8 * i + 2], v[8 * i + 3], v[8 * i + 4], v[8 * i + 5], v[8 * i + 6], v[8 * i + 7]);
-}
 // trunc((v<0 ? v-h : v+h) / 2h) for h = 4, 8 (chendct.c:205, 374) == (v + h + (v>>31)) >> log2(2h)   [arithmetic shifts]
 __device__ __forceinline__ int round_div8(int v) { return (v + 4 + (v >> 31)) >> 3; }
 __device__ __forceinline__ int round_div16(int v) { return (v + 8 + (v >> 31)) >> 4; }
@@ -413,94 +396,23 @@ __host__ __device__ constexpr int izig(int k) {
                          30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
   return t[k];
 }
-
-// ChenDct's final rounding + BoundDctMatrix + CCITT[Flat]Quantize + [Flat]BoundQuantizeMatrix
-// (chendct.c:204-205, transform.c:271-350, 460-537) in sign-magnitude form on the RAW transform output v:
-//   |x| = (|v|+4)>>3 clamped to 1023  ==  (min(|v|,8187)+4)>>3
-//   |level| = floor((|x| + ev) / 2Q) = floor((min(|v|,8187) + 4 + 8ev) / 16Q)          (ev = 1 for even Q; nested floors)
-//           = ((a*M + K) >> 22) with M = floor(2^22/16Q)+1, K = (4+8ev)*M   -- exact because (a+12)*16Q < 2^22
-// (tests/test_abi_and_host.py checks the identity exhaustively).  The DC term keeps the reference's two steps
-// (it is clamped from above only, transform.c:464-466).  Returns sum |level| (p64.c:892); v[] := signed levels.
-__device__ __forceinline__ int quantise_raw(int (&v)[64], int q, bool intra) {
-  const uint32_t ev = (q & 1) ? 0u : 1u;
-  const uint32_t M = (1u << 22) / (16u * q) + 1u, K = (4u + 8u * ev) * M;
-  int acc = 0;
-  {
-    int x = min(round_div8(v[0]), 2047);
-    if (intra) {
-      x = min(max((x + 4) >> 3, 1), 254);                    // (x-4)/8 <= 0 for x <= 0 and is clamped to 1 anyway
-      v[0] = x; acc = x;
-    } else {
-      const int rcp = (1 << 19) / (2 * q) + 1;
-      int l = min(((abs(x) + (int)ev) * rcp) >> 19, 127);
-      acc = l;
-      v[0] = x < 0 ? -l : l;
-    }
-  }
-#pragma unroll
-  for (int i = 1; i < 64; i++) {
-    const int x = v[i], sg = x >> 31;
-    const uint32_t a = (uint32_t)min(abs(x), 8187);
-    const int l = min((int)((a * M + K) >> 22), 127);
-    acc += l;
-    v[i] = (l ^ sg) - sg;
-  }
-  return acc;
+// transmission position of raster coefficient i: ZigzagMatrix is the scatter out[zz[i]] = in[i] (transform.c:561-568)
+struct ZigTable { uint8_t pos[64]; };
+__host__ __device__ constexpr ZigTable make_zig() {
+  ZigTable z{};
+  for (int k = 0; k < 64; k++) z.pos[izig(k)] = (uint8_t)k;
+  return z;
 }
-
-// Inverse quantise (transform.c:359-451): (2|l|+1)Q - ev with the sign of l, 0 stays 0; intra DC = 8 l
-__device__ __forceinline__ void dequantise(int (&v)[64], int q, bool intra) {
-  const int ev = (q & 1) ? 0 : 1, q2 = 2 * q, qo = q - ev;
-#pragma unroll
-  for (int i = 0; i < 64; i++) {
-    const int l = v[i];
-    if (i == 0 && intra) { v[0] = l * 8; continue; }
-    const int sg = l >> 31, a = abs(l);
-    const int r = a ? a * q2 + qo : 0;
-    v[i] = (r ^ sg) - sg;
-  }
-}
+__constant__ ZigTable c_zig = make_zig();
 
 __device__ __forceinline__ int ubyte(uint32_t w, int k) { return (int)__byte_perm(w, 0, 0x4440 + k); }   // PRMT, zero-extended byte k
 __device__ __forceinline__ uint32_t pack4(int a, int b, int c, int d) {                                   // low bytes of a,b,c,d
   return __byte_perm(__byte_perm((uint32_t)a, (uint32_t)b, 0x0040), __byte_perm((uint32_t)c, (uint32_t)d, 0x0040), 0x5410);
 }
 
-// H.261 loop filter on one 8x8 block held in registers (LoadFilterMatrix, io.c:323-372).
-// The reference's two-stage rounding equals (S16+8)>>4 on the scale-16 sum (tests/test_oracle_vs_ref.py).
-__device__ __forceinline__ void loop_filter(int (&p)[64]) {
-#pragma unroll
-  for (int i = 0; i < 8; i++) {
-    int a = p[8 * i], b;
-    p[8 * i] = a << 2;
-#pragma unroll
-    for (int j = 1; j < 7; j++) {
-      b = p[8 * i + j];
-      p[8 * i + j] = a + 2 * b + p[8 * i + j + 1];
-      a = b;
-    }
-    p[8 * i + 7] <<= 2;
-  }
-#pragma unroll
-  for (int j = 0; j < 8; j++) {
-    int a = p[j], b;
-    p[j] = (4 * a + 8) >> 4;
-#pragma unroll
-    for (int i = 1; i < 7; i++) {
-      b = p[8 * i + j];
-      p[8 * i + j] = (a + 2 * b + p[8 * i + 8 + j] + 8) >> 4;
-      a = b;
-    }
-    p[56 + j] = (4 * p[56 + j] + 8) >> 4;
-  }
-}
-
 // MType property tables (p64.c:217-222) as bit masks over type 0..9
 constexpr uint32_t M_CBP = 0x36c, M_INTRA = 0x003, M_MF = 0x3f0, M_FILTER = 0x380, M_TCOEF = 0x36f;
 __device__ __forceinline__ bool mt_is(uint32_t mask, int mt) { return (mask >> mt) & 1u; }
-
-constexpr int MB_PER_CTA = 32;
-constexpr int MBK_THREADS = 6 * MB_PER_CTA;    // warp c <-> block c of 32 consecutive macroblocks
 
 struct MbArgs {
   Geom g;
@@ -517,67 +429,116 @@ struct MbArgs {
   int gob_first, gob_count;   // task t -> stream t / gob_count, GOB gob_first + t % gob_count
   int out_mb_per_stream;      // stride of the output arrays per stream, in MBs (nmb or 33)
   int first_frame, force_intra, gquant;
+  uint32_t mps_magic, mps_shift;  // n / (gob_count*33) = umulhi(n, mps_magic) >> mps_shift
 };
 
-// Prediction for one block as 16 packed words (8 rows x 8 bytes): SubOverlay / SubCompensate / HalfSubCompensate
-// addressing (io.c:142-313).  Rows are fetched with two aligned 8-byte loads and a funnel shift (frame stores carry
-// slack at the end).  Chroma vector = MV/2 with C truncation (io.c:268-269).
-__device__ __forceinline__ void fetch_pred_packed(const uint8_t* plane, int w, int bx, int by, bool mc, int mvx, int mvy,
-                                                  bool chroma, uint32_t (&pk)[16]) {
-  int dx = 0, dy = 0;
-  if (mc) { dx = chroma ? mvx / 2 : mvx; dy = chroma ? mvy / 2 : mvy; }
-  const uint8_t* b = plane + (size_t)(by + dy) * w + bx + dx;
-  const uintptr_t ad = reinterpret_cast<uintptr_t>(b);
+// ---------------------------------------------------------------------------------------------------
+// Transform chain: 8 lanes per 8x8 block (lane = row), a warp = two macroblocks = 12 blocks in three rounds of four:
+//   round 0: Y(0,0) Y(1,0) of both macroblocks   (32 contiguous bytes per pixel row when the two are neighbours)
+//   round 1: Y(0,1) Y(1,1)                       round 2: U, V
+// Each Chen pass works on the 8 values a lane holds; the column passes (which the reference runs FIRST, chendct.c:
+// 119-158 / 236-299 -- the >>9 floors make the order matter) are reached by transposing the block through a padded
+// shared-memory tile (8 STS.32 + 2 LDS.128, conflict-free).  Nothing is synchronised wider than the 8 lanes of a block.
+// ---------------------------------------------------------------------------------------------------
+constexpr int MBK_WARPS = 8;
+constexpr int MBK_THREADS = 32 * MBK_WARPS;
+constexpr int MB_PER_CTA = 2 * MBK_WARPS;
+constexpr int MBK_TILE = 104;     // [8][12] words + 8: the four lane groups of a warp start 8 banks apart
+
+// lane r of the group holds v[c] = element (r, c)  ->  v[i] = element (i, r)
+__device__ __forceinline__ void transpose8(uint32_t* tile, int r, int (&v)[8], uint32_t gmask) {
+#pragma unroll
+  for (int c = 0; c < 8; c++) tile[c * 12 + r] = (uint32_t)v[c];
+  __syncwarp(gmask);
+  const uint4 lo = *reinterpret_cast<const uint4*>(tile + r * 12), hi = *reinterpret_cast<const uint4*>(tile + r * 12 + 4);
+  v[0] = (int)lo.x; v[1] = (int)lo.y; v[2] = (int)lo.z; v[3] = (int)lo.w;
+  v[4] = (int)hi.x; v[5] = (int)hi.y; v[6] = (int)hi.z; v[7] = (int)hi.w;
+}
+
+// One 8-byte row of the prediction at any byte alignment: aligned 8-byte loads + funnel shift
+// (frame stores carry slack at the end).
+__device__ __forceinline__ uint2 fetch_row8(const uint8_t* p) {
+  const uintptr_t ad = reinterpret_cast<uintptr_t>(p);
   const uint2* qp = reinterpret_cast<const uint2*>(ad & ~(uintptr_t)7);
   const int sh = (int)(ad & 7) * 8;
-  const int wq = w >> 3;                                  // row pitch in 8-byte units
-  if (sh == 0) {
+  const uint2 r0 = __ldg(qp);
+  if (sh == 0) return r0;
+  const uint2 r1 = __ldg(qp + 1);
+  uint32_t w0 = r0.x, w1 = r0.y, w2 = r1.x;
+  if (sh & 32) { w0 = r0.y; w1 = r1.x; w2 = r1.y; }
+  return make_uint2(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh));
+}
+
+// H.261 loop filter (LoadFilterMatrix, io.c:323-372) for row r of a block whose rows live in the 8 lanes of a group.
+// Separable 1-2-1 with the block's edge rows / columns passed through in that dimension; the reference's two-stage
+// rounding equals (S16+8)>>4 on the scale-16 sum (tests/test_oracle_vs_ref.py), so the vertical pass can run first:
+// on the neighbours' packed bytes widened to 16-bit pairs.
+__device__ __forceinline__ uint2 loop_filter_row(uint2 pk, int r, uint32_t gmask) {
+  uint2 up, dn;
+  up.x = __shfl_up_sync(gmask, pk.x, 1, 8); up.y = __shfl_up_sync(gmask, pk.y, 1, 8);
+  dn.x = __shfl_down_sync(gmask, pk.x, 1, 8); dn.y = __shfl_down_sync(gmask, pk.y, 1, 8);
+  if (r == 0 || r == 7) { up = pk; dn = pk; }             // edge rows: 4 * own sample
+  int V[8];
 #pragma unroll
-    for (int i = 0; i < 8; i++) { const uint2 r = __ldg(qp + i * wq); pk[2 * i] = r.x; pk[2 * i + 1] = r.y; }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-      const uint2 r0 = __ldg(qp + i * wq), r1 = __ldg(qp + i * wq + 1);
-      uint32_t w0 = r0.x, w1 = r0.y, w2 = r1.x;
-      if (sh & 32) { w0 = r0.y; w1 = r1.x; w2 = r1.y; }
-      pk[2 * i] = __funnelshift_r(w0, w1, sh);
-      pk[2 * i + 1] = __funnelshift_r(w1, w2, sh);
-    }
+  for (int h = 0; h < 2; h++) {
+    const uint32_t cw = h ? pk.y : pk.x, uw = h ? up.y : up.x, dw = h ? dn.y : dn.x;
+    const uint32_t lo = __byte_perm(uw, 0, 0x4140) + 2u * __byte_perm(cw, 0, 0x4140) + __byte_perm(dw, 0, 0x4140);
+    const uint32_t hi = __byte_perm(uw, 0, 0x4342) + 2u * __byte_perm(cw, 0, 0x4342) + __byte_perm(dw, 0, 0x4342);
+    V[4 * h] = (int)(lo & 0xffffu); V[4 * h + 1] = (int)(lo >> 16);
+    V[4 * h + 2] = (int)(hi & 0xffffu); V[4 * h + 3] = (int)(hi >> 16);
   }
+  int o[8];
+  o[0] = (4 * V[0] + 8) >> 4; o[7] = (4 * V[7] + 8) >> 4;
+#pragma unroll
+  for (int j = 1; j < 7; j++) o[j] = (V[j - 1] + 2 * V[j] + V[j + 1] + 8) >> 4;
+  return make_uint2(pack4(o[0], o[1], o[2], o[3]), pack4(o[4], o[5], o[6], o[7]));
 }
 
 #ifndef MBK_MINB
-#define MBK_MINB 2
+#define MBK_MINB 3
 #endif
 __global__ void __launch_bounds__(MBK_THREADS, MBK_MINB)
-mb_encode_kernel(MbArgs a) {
-  __shared__ int s_acc[6][MB_PER_CTA];
+mb_encode_kernel(const __grid_constant__ MbArgs a) {
+  __shared__ __align__(16) uint32_t s_tile[MBK_WARPS][4][2][MBK_TILE];
+  __shared__ __align__(8) uint8_t s_lev[MBK_WARPS][4][64];
+  __shared__ uint32_t s_qm[32];
   const Geom& g = a.g;
-  const int lane = threadIdx.x & 31, c = threadIdx.x >> 5;        // block index within the MB: p64.c:77-79
-  const int n = blockIdx.x * MB_PER_CTA + lane;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int grp = lane >> 3, r = lane & 7, half = lane >> 4, g1 = grp & 1;
+  const uint32_t gmask = 0xffu << (8 * grp);
+  // multiply-shift quantiser constant per quantiser value: M = floor(2^22 / 16Q) + 1 = floor(2^18 / Q) + 1 (see quantise below)
+  if (threadIdx.x < 32) s_qm[threadIdx.x] = threadIdx.x ? (1u << 18) / threadIdx.x + 1u : 0u;
+  __syncthreads();
+
   const int n_total = a.n_streams * a.gob_count * 33;
+  const int n = (blockIdx.x * MBK_WARPS + warp) * 2 + half;
   const bool active = n < n_total;
   const int nn = active ? n : n_total - 1;
-  const int task = nn / 33, m = nn % 33;
-  const int s = task / a.gob_count, gob = a.gob_first + task % a.gob_count;
+  const int mps = a.gob_count * 33;                               // macroblocks per stream in this launch
+  const int s = (int)(__umulhi((uint32_t)nn, a.mps_magic) >> a.mps_shift), rem = nn - s * mps;
+  const int gob = a.gob_first + rem / 33, m = rem % 33;
   int col, row;                                                    // MoveTo, io.c:730-741
   if (g.qcif) { col = m % 11; row = gob * 3 + m / 11; }
   else { col = (gob & 1) * 11 + m % 11; row = (gob >> 1) * 3 + m / 11; }
   const int mbi = gob * 33 + m;                                    // GOB-major index
-  const bool chroma = c >= 4;
-  const int w = chroma ? g.W / 2 : g.W;
-  const size_t poff = (size_t)s * g.frame_bytes + (c < 4 ? 0 : (c == 4 ? g.W * g.H : g.W * g.H * 5 / 4));
-  const int bx = chroma ? col * 8 : col * 16 + (c & 1) * 8;
-  const int by = chroma ? row * 8 : row * 16 + (c >> 1) * 8;
+  const size_t fo = (size_t)s * g.frame_bytes;
+  uint32_t* t0 = s_tile[warp][grp][0];
+  uint32_t* t1 = s_tile[warp][grp][1];
+  uint8_t* levp = s_lev[warp][grp];
+  const uint2 zz = reinterpret_cast<const uint2*>(c_zig.pos)[r];     // transmission positions of raster 8r .. 8r+7
 
-  // ---- source block (ReadBlock, io.c:793-820): issued first, it does not depend on the decision
-  uint2 srow[8];
-  {
-    const uint2* sp = reinterpret_cast<const uint2*>(a.src + poff + (size_t)by * w + bx);
-    const int wq = w >> 3;
+  // per round: plane geometry of this lane's block (p64.c:77-79: blocks 0..3 = Y(h,v), 4 = U, 5 = V)
+  int w_[3], off_[3];                                               // row pitch; byte offset of the row's first pixel in the frame
 #pragma unroll
-    for (int i = 0; i < 8; i++) srow[i] = __ldg(sp + i * wq);
+  for (int rd = 0; rd < 3; rd++) {
+    if (rd < 2) { w_[rd] = g.W; off_[rd] = (row * 16 + rd * 8 + r) * g.W + col * 16 + g1 * 8; }
+    else { w_[rd] = g.W >> 1; off_[rd] = g.W * g.H + g1 * (g.W * g.H >> 2) + (row * 8 + r) * (g.W >> 1) + col * 8; }
   }
+
+  // ---- source rows (ReadBlock, io.c:793-820): issued first, they do not depend on the decision
+  uint2 sv[3];
+#pragma unroll
+  for (int rd = 0; rd < 3; rd++) sv[rd] = __ldg(reinterpret_cast<const uint2*>(a.src + fo + off_[rd]));
 
   // ---- MTYPE decision (p64.c:734-773), double arithmetic exactly as written
   int4 me0 = make_int4(0, 0, 0, 0), me1 = me0;
@@ -600,61 +561,93 @@ mb_encode_kernel(MbArgs a) {
   }
   if (li > 131) mt = 0;
   const int q = a.quant ? a.quant[s] : a.gquant;
-
-  // ---- ReadCompressMDU (p64.c:823-886): prediction, residual, DCT, quantise
   const bool intra = mt_is(M_INTRA, mt);
-  uint32_t pk[16];                                  // prediction as packed bytes
+
+  // ---- prediction rows: SubOverlay / SubCompensate / HalfSubCompensate addressing (io.c:142-313); chroma vector =
+  // MV/2 with C truncation (io.c:268-269); loop filter for the filter types
+  auto fetch_pred = [&](int rd, bool mc) -> uint2 {
+    int dx = 0, dy = 0;
+    if (mc) { dx = rd == 2 ? mvx / 2 : mvx; dy = rd == 2 ? mvy / 2 : mvy; }
+    return fetch_row8(a.ref + fo + off_[rd] + dy * w_[rd] + dx);
+  };
+  uint2 pk[3];
 #pragma unroll
-  for (int i = 0; i < 16; i++) pk[i] = 0;
-  int v[64];
-  if (!intra) {
-    fetch_pred_packed(a.ref + poff, w, bx, by, mt_is(M_MF, mt), mvx, mvy, chroma, pk);
-    if (mt_is(M_FILTER, mt)) {                      // LoadFilterMatrix, io.c:323-372
-#pragma unroll
-      for (int i = 0; i < 64; i++) v[i] = ubyte(pk[i >> 2], i & 3);
-      loop_filter(v);
-#pragma unroll
-      for (int i = 0; i < 16; i++) pk[i] = pack4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  for (int rd = 0; rd < 3; rd++) {
+    pk[rd] = make_uint2(0u, 0u);
+    if (!intra) {
+      pk[rd] = fetch_pred(rd, mt_is(M_MF, mt));
+      if (mt_is(M_FILTER, mt)) pk[rd] = loop_filter_row(pk[rd], r, gmask);
     }
   }
+
+  // ---- ReadCompressMDU (p64.c:823-886): residual, Chen DCT, bound, quantise, zig-zag.
+  // ChenDct's final rounding + BoundDctMatrix + CCITT[Flat]Quantize + [Flat]BoundQuantizeMatrix (chendct.c:204-205,
+  // transform.c:271-350, 460-537) in sign-magnitude form on the RAW transform output v:
+  //   |x| = (|v|+4)>>3 clamped to 1023  ==  (min(|v|,8187)+4)>>3
+  //   |level| = floor((|x| + ev) / 2Q) = floor((min(|v|,8187) + 4 + 8ev) / 16Q)          (ev = 1 for even Q; nested floors)
+  //           = ((a*M + K) >> 22) with M = floor(2^22/16Q)+1, K = (4+8ev)*M   -- exact because (a+12)*16Q < 2^22
+  // (tests/test_abi_and_host.py checks the identity exhaustively).  The DC term keeps the reference's two steps
+  // (it is clamped from above only, transform.c:464-466).
+  const uint32_t ev = (q & 1) ? 0u : 1u, M = s_qm[q], K = (4u + 8u * ev) * M;
+  int lv[3][8], acc[3];
+  const size_t mb_out = (size_t)s * a.out_mb_per_stream + (mbi - a.gob_first * 33);
 #pragma unroll
-  for (int i = 0; i < 8; i++) {
+  for (int rd = 0; rd < 3; rd++) {
+    int v[8];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-      v[8 * i + j] = ubyte(srow[i].x, j) - ubyte(pk[2 * i], j);
-      v[8 * i + 4 + j] = ubyte(srow[i].y, j) - ubyte(pk[2 * i + 1], j);
+      v[j] = ubyte(sv[rd].x, j) - ubyte(pk[rd].x, j);
+      v[4 + j] = ubyte(sv[rd].y, j) - ubyte(pk[rd].y, j);
     }
-  }
-  chen_fdct_raw(v);
-  const int acc = quantise_raw(v, q, intra);
-
-  // ---- levels out, zig-zag order (transform.c:561-568): byte k = level at raster izig(k)
-  if (active) {
-    uint4* lp = reinterpret_cast<uint4*>(a.levels + ((size_t)s * a.out_mb_per_stream + (mbi - a.gob_first * 33)) * 384 + c * 64);
+    transpose8(t0, r, v, gmask);
+    fdct8<1>(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+    transpose8(t1, r, v, gmask);
+    fdct8<0>(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+    int sum = 0;
 #pragma unroll
-    for (int wd = 0; wd < 4; wd++) {
-      uint32_t u[4];
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const int b0 = 16 * wd + 4 * k;
-        u[k] = pack4(v[izig(b0)], v[izig(b0 + 1)], v[izig(b0 + 2)], v[izig(b0 + 3)]);
-      }
-      lp[wd] = make_uint4(u[0], u[1], u[2], u[3]);
+    for (int j = 0; j < 8; j++) {
+      const int x = v[j], sg = x >> 31;
+      const uint32_t aa = (uint32_t)min(abs(x), 8187);
+      const int l = min((int)((aa * M + K) >> 22), 127);
+      sum += l;
+      lv[rd][j] = (l ^ sg) - sg;
     }
+    if (r == 0) {                                             // the DC term of the block
+      sum -= abs(lv[rd][0]);
+      int x = min(round_div8(v[0]), 2047), l;
+      if (intra) l = min(max((x + 4) >> 3, 1), 254);          // (x-4)/8 <= 0 for x <= 0 and is clamped to 1 anyway
+      else { l = min((int)(((uint32_t)(abs(x) + (int)ev) * M) >> 19), 127); l = x < 0 ? -l : l; }
+      lv[rd][0] = l;
+      sum += abs(l);
+    }
+#pragma unroll
+    for (int d = 1; d < 8; d <<= 1) sum += __shfl_xor_sync(gmask, sum, d);
+    acc[rd] = sum;                                            // sum |level| of the block (p64.c:892), in all its lanes
+    // levels out in transmission order (transform.c:561-568), int8 (intra DC as uint8)
+#pragma unroll
+    for (int j = 0; j < 8; j++) levp[((j < 4 ? zz.x : zz.y) >> (8 * (j & 3))) & 0xff] = (uint8_t)lv[rd][j];
+    __syncwarp(gmask);
+    const uint2 lw = *reinterpret_cast<const uint2*>(levp + 8 * r);
+    const int c = rd < 2 ? 2 * rd + g1 : 4 + g1;
+    if (active) *reinterpret_cast<uint2*>(a.levels + mb_out * 384 + c * 64 + 8 * r) = lw;
   }
 
-  // ---- CBP and the type-4 / type-7 fallback (p64.c:887-908)
-  s_acc[c][lane] = acc;
-  __syncthreads();
+  // ---- CBP and the type-4 / type-7 fallback (p64.c:887-908): block c of the macroblock sits in round c/2 (4,5: round 2)
+  // of lane group c&1
   int cbp = 0x3f, nz = 0;
   {
     int pm = 0, cb = 0;
 #pragma unroll
-    for (int k = 0; k < 6; k++) {
-      int ak = s_acc[k][lane];
-      if (ak && !pm) pm = 1 << (5 - k);
-      if (ak > 1) cb |= 1 << (5 - k);
-      if (ak) nz |= 1 << (5 - k);
+    for (int rd = 0; rd < 3; rd++) {
+      const int other = __shfl_xor_sync(0xffffffffu, acc[rd], 8);
+      const int a0 = g1 ? other : acc[rd], a1 = g1 ? acc[rd] : other;      // blocks 2rd, 2rd+1
+      const int b0 = 1 << (5 - 2 * rd), b1 = b0 >> 1;
+      if (a0 && !pm) pm = b0;
+      if (a0 > 1) cb |= b0;
+      if (a0) nz |= b0;
+      if (a1 && !pm) pm = b1;
+      if (a1 > 1) cb |= b1;
+      if (a1) nz |= b1;
     }
     if (mt_is(M_CBP, mt)) {
       cbp = cb ? cb : pm;
@@ -664,33 +657,48 @@ mb_encode_kernel(MbArgs a) {
   const int mt_final = mt;
 
   // ---- inverse half (p64.c:935-959) + DecodeSaveMDU (p64.c:971-1013)
-  const bool coded = ((cbp >> (5 - c)) & 1) && mt_is(M_TCOEF, mt_final);
   // a type-2 MB that fell back to type 4 predicts with the ME vector (p64.c:904, marker.c:339-342)
-  if (!intra && mt_final == 4 && (mvx | mvy)) fetch_pred_packed(a.ref + poff, w, bx, by, true, mvx, mvy, chroma, pk);
-  if (coded) {
-    dequantise(v, q, intra);
-    chen_idct_raw(v);
+  if (!intra && mt_final == 4 && (mvx | mvy)) {
 #pragma unroll
-    for (int i = 0; i < 16; i++) {                  // ChenIDct rounding + Add*Compensate + BoundIDctMatrix
-      int o[4];
-#pragma unroll
-      for (int j = 0; j < 4; j++) o[j] = min(max(round_div16(v[4 * i + j]) + ubyte(pk[i], j), 0), 255);
-      pk[i] = pack4(o[0], o[1], o[2], o[3]);
-    }
+    for (int rd = 0; rd < 3; rd++) pk[rd] = fetch_pred(rd, true);
   }
-  if (active) {
-    uint2* op = reinterpret_cast<uint2*>(a.out + poff + (size_t)by * w + bx);
-    const int wq = w >> 3;
+  const int q2 = 2 * q, qo = q - (int)ev;
 #pragma unroll
-    for (int i = 0; i < 8; i++) op[i * wq] = make_uint2(pk[2 * i], pk[2 * i + 1]);   // uncoded: reconstruction = prediction
-    if (c == 0) {
-      const bool mf = mt_is(M_MF, mt_final);
-      uint32_t r0 = (uint32_t)mt_final | ((uint32_t)cbp << 8) | ((uint32_t)((mf ? mvx : 0) & 0xff) << 16) |
-                    ((uint32_t)((mf ? mvy : 0) & 0xff) << 24);
-      uint32_t r1 = (uint32_t)q | ((uint32_t)nz << 8);
-      *reinterpret_cast<uint2*>(a.mbs + (size_t)s * a.out_mb_per_stream + (mbi - a.gob_first * 33)) = make_uint2(r0, r1);
-      a.li_new[(size_t)s * g.nmb + mbi] = mt_is(M_INTRA, mt_final) ? 0 : (uint8_t)(li + 1);   // p64.c:909-910
+  for (int rd = 0; rd < 3; rd++) {
+    const int c = rd < 2 ? 2 * rd + g1 : 4 + g1;
+    const bool coded = ((cbp >> (5 - c)) & 1) && mt_is(M_TCOEF, mt_final);
+    uint2 o = pk[rd];                                         // uncoded: reconstruction = prediction
+    if (coded) {                                              // uniform over the 8 lanes of the block
+      // inverse quantise (transform.c:359-451): (2|l|+1)Q - ev with the sign of l, 0 stays 0; intra DC = 8 l
+      int v[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const int l = lv[rd][j], sg = l >> 31, aa = abs(l);
+        const int rr = aa ? aa * q2 + qo : 0;
+        v[j] = (rr ^ sg) - sg;
+      }
+      if (r == 0 && intra) v[0] = lv[rd][0] * 8;
+      transpose8(t0, r, v, gmask);
+      idct8<1>(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+      transpose8(t1, r, v, gmask);
+      idct8<0>(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+      int ob[8];                                              // ChenIDct rounding + Add*Compensate + BoundIDctMatrix
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        ob[j] = min(max(round_div16(v[j]) + ubyte(pk[rd].x, j), 0), 255);
+        ob[4 + j] = min(max(round_div16(v[4 + j]) + ubyte(pk[rd].y, j), 0), 255);
+      }
+      o = make_uint2(pack4(ob[0], ob[1], ob[2], ob[3]), pack4(ob[4], ob[5], ob[6], ob[7]));
     }
+    if (active) *reinterpret_cast<uint2*>(a.out + fo + off_[rd]) = o;
+  }
+  if (active && (lane & 15) == 0) {
+    const bool mf = mt_is(M_MF, mt_final);
+    uint32_t r0 = (uint32_t)mt_final | ((uint32_t)cbp << 8) | ((uint32_t)((mf ? mvx : 0) & 0xff) << 16) |
+                  ((uint32_t)((mf ? mvy : 0) & 0xff) << 24);
+    uint32_t r1 = (uint32_t)q | ((uint32_t)nz << 8);
+    *reinterpret_cast<uint2*>(a.mbs + mb_out) = make_uint2(r0, r1);
+    a.li_new[(size_t)s * g.nmb + mbi] = mt_is(M_INTRA, mt_final) ? 0 : (uint8_t)(li + 1);   // p64.c:909-910
   }
 }
 
