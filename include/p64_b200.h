@@ -125,6 +125,25 @@ int p64b_ctx_wait(p64b_ctx *ctx, int64_t ticket);
 int p64b_ctx_encode_frames_dev(p64b_ctx *ctx, const p64b_step *step, const uint8_t *src_dev,
                                p64b_mb *mbs_dev, int8_t *levels_dev);
 
+/* Device-side entropy coding: the same fixed-quantiser frame step, but the picture / GOB /
+ * macroblock headers and the run-level VLC (marker.c:103-354, codec.c:96-355) also run on the device, and what comes
+ * back is every stream's next whole bytes of the H.261 stream -- the host only appends them.  The stream's pending
+ * bits (< 8) stay on the device between frames.  submit_bits() enqueues like p64b_ctx_submit() (at most 3 steps in
+ * flight); wait_bits() blocks until the step's output is in pinned host memory owned by the context, valid until the
+ * third following submit.  temporal_reference = CurrentFrame % 32 (p64.c:637).  Records and levels are not downloaded. */
+typedef struct p64b_bits_out {
+  const uint8_t  *data;          /* packed chunks of all streams                                              */
+  const uint32_t *offset;        /* [n_streams+1] byte offset of stream s's chunk in data; [n_streams] = total */
+  const uint32_t *nbytes;        /* [n_streams] whole bytes of stream s's chunk                               */
+  const uint32_t *carry;         /* [n_streams] pending bits after this frame, left-aligned in the word       */
+  const uint32_t *carry_len;     /* [n_streams] how many (0..7)                                               */
+  const uint64_t *bit_position;  /* [n_streams] bits written so far (mwtell, stream.c:233-238)                */
+  size_t total_bytes;
+} p64b_bits_out;
+int p64b_ctx_submit_bits(p64b_ctx *ctx, const p64b_step *step, int temporal_reference, const uint8_t *src,
+                         int64_t *ticket);
+int p64b_ctx_wait_bits(p64b_ctx *ctx, int64_t ticket, p64b_bits_out *out);
+
 /* Rate-control split (-r / -x): the quantiser of GOB g is chosen by the host from the bits written so
  * far (ExecuteQuantization, p64.c:458-481, 697-702), so quantise..reconstruct runs per GOB.
  *   begin : upload + motion estimation for the whole frame (quantiser independent)
@@ -160,7 +179,8 @@ int p64b_ctx_last_intra(p64b_ctx *ctx, int stream, uint8_t *out);
 int64_t p64b_ctx_launches(const p64b_ctx *ctx);
 /* Per-kernel device timing (CUDA events on the launching stream around every launch) for the roofline report.
  * profile(ctx,1) clears and starts recording, profile(ctx,0) stops; profile_read sums the recorded launches:
- * ms_total[2], count[2] -- index 0 = motion-estimation kernel, 1 = macroblock (DCT/quant/recon) kernel. */
+ * ms_total[3], count[3] -- index 0 = motion-estimation kernel, 1 = macroblock (DCT/quant/recon) kernel,
+ * 2 = the entropy-coding kernels of p64b_ctx_submit_bits (one interval around the three of them). */
 int p64b_ctx_profile(p64b_ctx *ctx, int enable);
 int p64b_ctx_profile_read(p64b_ctx *ctx, double *ms_total, int32_t *count);
 /* Measured issue peak of the packed 4-byte SAD instruction (VABSDIFF4.U8.ACC) on this device, in
@@ -181,6 +201,8 @@ void p64b_bits_gob_header(p64b_bits *b, int gob, int gquant);
 /* WriteMDU's write half: WriteMBHeader (marker.c:288-354) + EncodeDC/EncodeAC/CBPEncodeAC (codec.c:96-205,
  * 346-355) for MB `mdu` (0..32) of the current GOB. */
 void p64b_bits_mb(p64b_bits *b, int mdu, const p64b_mb *rec, const int8_t *levels);
+/* mputv, stream.c:193-205: nbits (<= 32) raw bits, MSB first. */
+void p64b_bits_put(p64b_bits *b, uint32_t value, int nbits);
 /* mwtell, stream.c:233-238: bits written so far. */
 int64_t p64b_bits_tell(const p64b_bits *b);
 /* mwclose, stream.c:142-152: pad the last byte with 1-bits. Returns the byte count. */
@@ -208,7 +230,9 @@ typedef struct p64b_enc_params {
   int32_t search_limit;    /* -i (default 15)                                                      */
   int32_t force_intra;     /* `-o < test.intra`                                                    */
   int32_t vlc_threads;     /* host threads for the per-stream VLC (0 = one per core, capped)       */
-  int32_t reserved[3];
+  int32_t host_vlc;        /* 1: entropy-code on the host even with a fixed quantiser (default: on the device;
+                              rate control always codes on the host, its quantiser depends on the bits written) */
+  int32_t reserved[2];
 } p64b_enc_params;
 
 void p64b_enc_default_params(p64b_enc_params *p);

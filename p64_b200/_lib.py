@@ -29,7 +29,14 @@ class EncParams(C.Structure):
     """p64b_enc_params"""
     _fields_ = [(n, C.c_int32) for n in ("image_type", "n_streams", "device", "start_frame", "initial_quant", "rate",
                                          "frame_rate", "frame_rate_div", "frame_skip", "me_mode", "search_limit",
-                                         "force_intra", "vlc_threads")] + [("reserved", C.c_int32 * 3)]
+                                         "force_intra", "vlc_threads", "host_vlc")] + [("reserved", C.c_int32 * 2)]
+
+
+class BitsOut(C.Structure):
+    """p64b_bits_out"""
+    _fields_ = [("data", C.POINTER(C.c_uint8)), ("offset", C.POINTER(C.c_uint32)), ("nbytes", C.POINTER(C.c_uint32)),
+                ("carry", C.POINTER(C.c_uint32)), ("carry_len", C.POINTER(C.c_uint32)),
+                ("bit_position", C.POINTER(C.c_uint64)), ("total_bytes", C.c_size_t)]
 
 
 # name -> (restype, argtypes); every symbol include/p64_b200.h declares
@@ -49,6 +56,8 @@ SIGNATURES = {
     "p64b_ctx_submit": (_i, [_vp, C.POINTER(Step), _vp, _vp, _vp, C.POINTER(C.c_int64)]),
     "p64b_ctx_wait": (_i, [_vp, C.c_int64]),
     "p64b_ctx_encode_frames_dev": (_i, [_vp, C.POINTER(Step), _vp, _vp, _vp]),
+    "p64b_ctx_submit_bits": (_i, [_vp, C.POINTER(Step), _i, _vp, C.POINTER(C.c_int64)]),
+    "p64b_ctx_wait_bits": (_i, [_vp, C.c_int64, C.POINTER(BitsOut)]),
     "p64b_ctx_frame_begin": (_i, [_vp, C.POINTER(Step), _vp]),
     "p64b_ctx_encode_gob": (_i, [_vp, C.POINTER(Step), _i, _vp, _vp, _vp]),
     "p64b_ctx_frame_end": (_i, [_vp, _vp]),
@@ -66,6 +75,7 @@ SIGNATURES = {
     "p64b_bits_picture_header": (None, [_vp, _i]),
     "p64b_bits_gob_header": (None, [_vp, _i, _i]),
     "p64b_bits_mb": (None, [_vp, _i, _vp, _vp]),
+    "p64b_bits_put": (None, [_vp, C.c_uint32, _i]),
     "p64b_bits_tell": (C.c_int64, [_vp]),
     "p64b_bits_finish": (_sz, [_vp]),
     "p64b_bits_data": (C.POINTER(C.c_uint8), [_vp, C.POINTER(_sz)]),

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../include/p64_b200.h"
+#include "vlc_dev.h"
 #include "vlc_tables.h"
 
 namespace p64b {
@@ -43,6 +44,17 @@ static const uint8_t kCbpM[10]   = {0,0,1,1,0,1,1,0,1,1};
 static const uint8_t kIntraM[10] = {1,1,0,0,0,0,0,0,0,0};
 static const uint8_t kMfM[10]    = {0,0,0,0,1,1,1,1,1,1};
 static const uint8_t kTcoefM[10] = {1,1,1,1,0,1,1,0,1,1};
+
+void fill_dev_vlc_tables(DevVlcTables* d) {
+  const Tables& t = T();
+  memset(d, 0, sizeof(*d));
+  auto e = [](const Code& c) { return c.len ? ((uint32_t)c.len << 16) | c.bits : 0u; };
+  for (int r = 0; r < 32; r++)
+    for (int l = 0; l < 16; l++) d->tcoef[r * 16 + l] = e(t.tcoef[r][l]);
+  for (int i = 0; i < 10; i++) d->mtype[i] = e(t.mtype[i]);
+  for (int i = 0; i < 32; i++) d->mvd[i] = e(t.mvd[i]);
+  for (int i = 0; i < 64; i++) d->cbp[i] = e(t.cbp[i]);
+}
 
 }  // namespace p64b
 
@@ -154,6 +166,7 @@ void p64b_bits_mb(p64b_bits* b, int mdu, const p64b_mb* rec, const int8_t* level
   }
 }
 
+void p64b_bits_put(p64b_bits* b, uint32_t value, int nbits) { if (nbits > 0 && nbits <= 32) b->put(value, nbits); }
 int64_t p64b_bits_tell(const p64b_bits* b) { return b->tell(); }
 
 size_t p64b_bits_finish(p64b_bits* b) {

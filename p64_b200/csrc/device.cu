@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "vlc_kernels.cuh"
 
 namespace p64b {
 
@@ -68,9 +69,20 @@ struct p64b_ctx {
   int n_sm = 0;
   uint32_t* d_me_queue = nullptr;   // [2] work counters of the persistent ME kernel (alternating per launch)
   int64_t me_launches = 0;
+  // device-side entropy coding (p64b_ctx_submit_bits / p64b_ctx_wait_bits), allocated on first use
+  DevVlcTables* d_vlc_tables = nullptr;
+  uint32_t* d_gob_words = nullptr;          // [S][ngob][VLC_GOB_WORDS] GOB bit strings
+  uint32_t* d_gob_bits = nullptr;           // [S][ngob]
+  uint32_t *d_carry = nullptr, *d_carry_len = nullptr;     // [S] pending bits (< 8) of every stream
+  unsigned long long* d_bitpos = nullptr;   // [S] bits written so far
+  size_t bits_out_cap = 0;                  // bytes of one output buffer (worst case)
+  uint8_t* d_bits_out[NSLOT] = {};
+  uint8_t* h_bits_out[NSLOT] = {};          // pinned; grown on demand
+  size_t h_bits_cap[NSLOT] = {}, slot_copied[NSLOT] = {};
+  size_t bits_budget = 0;                   // data bytes downloaded with the first copy (adapts to the last frame's size)
   // optional per-kernel timing with CUDA events on the launching stream (bench.py roofline)
   bool prof = false;
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_ev[2];   // 0 = ME kernel, 1 = MB kernel
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_ev[3];   // 0 = ME kernel, 1 = MB kernel, 2 = entropy-coding kernels
 };
 
 struct ProfScope {   // records an event pair around one launch when profiling is on
@@ -286,6 +298,9 @@ void p64b_ctx_destroy(p64b_ctx* c) {
     if (c->ev_comp[i]) cudaEventDestroy(c->ev_comp[i]);
     if (c->ev_d2h[i]) cudaEventDestroy(c->ev_d2h[i]);
   }
+  cudaFree(c->d_vlc_tables); cudaFree(c->d_gob_words); cudaFree(c->d_gob_bits); cudaFree(c->d_carry); cudaFree(c->d_carry_len);
+  cudaFree(c->d_bitpos);
+  for (int i = 0; i < p64b_ctx::NSLOT; i++) { cudaFree(c->d_bits_out[i]); if (c->h_bits_out[i]) cudaFreeHost(c->h_bits_out[i]); }
   if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
   if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
   if (c->own) cudaStreamDestroy(c->own);
@@ -487,11 +502,132 @@ int p64b_ctx_profile_read(p64b_ctx* c, double* ms_total, int32_t* count) {
   int rc;
   if ((rc = use_device(c))) return rc;
   CU(cudaStreamSynchronize(c->stream));
-  for (int k = 0; k < 2; k++) {
+  for (int k = 0; k < 3; k++) {
     double t = 0;
     for (auto& e : c->prof_ev[k]) { float ms = 0; CU(cudaEventElapsedTime(&ms, e.first, e.second)); t += ms; }
     ms_total[k] = t; count[k] = (int32_t)c->prof_ev[k].size();
   }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Device-side entropy coding: the frame step that returns bytes
+// ---------------------------------------------------------------------------------------------------
+static int ensure_bits_buffers(p64b_ctx* c) {
+  if (c->d_vlc_tables) return 0;
+  const size_t S = (size_t)c->S, ng = (size_t)c->g.ngob;
+  DevVlcTables t;
+  fill_dev_vlc_tables(&t);
+  // worst case of one frame: every block escapes every coefficient (GOB slot size) + picture header + carry
+  c->bits_out_cap = vlc_data_offset(c->S) + S * (ng * VLC_GOB_WORDS * 4 + 16);
+#define ALLOCZ(p, bytes)                                                                                  \
+  if (cudaMalloc((void**)&(p), (bytes)) != cudaSuccess) { set_error("cudaMalloc failed (bit-stream buffers)"); return P64B_ENOMEM; } \
+  if (cudaMemsetAsync((p), 0, (bytes), c->stream) != cudaSuccess) { set_error("cudaMemset failed"); return P64B_ECUDA; }
+  ALLOCZ(c->d_gob_words, S * ng * VLC_GOB_WORDS * 4);
+  ALLOCZ(c->d_gob_bits, S * ng * 4);
+  ALLOCZ(c->d_carry, S * 4);
+  ALLOCZ(c->d_carry_len, S * 4);
+  ALLOCZ(c->d_bitpos, S * 8);
+  for (int i = 0; i < p64b_ctx::NSLOT; i++) { ALLOCZ(c->d_bits_out[i], c->bits_out_cap); }
+  ALLOCZ(c->d_vlc_tables, sizeof(DevVlcTables));
+#undef ALLOCZ
+  CU(cudaMemcpyAsync(c->d_vlc_tables, &t, sizeof t, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));          // `t` is on this stack frame
+  c->bits_budget = S * (c->image_type == P64B_IT_QCIF ? 12u : 40u) * 1024u;   // first frames are intra: generous start
+  return 0;
+}
+
+static int ensure_host_bits(p64b_ctx* c, int slot, size_t bytes) {
+  if (c->h_bits_cap[slot] >= bytes) return 0;
+  if (c->h_bits_out[slot]) { CU(cudaStreamSynchronize(c->s_d2h)); CU(cudaFreeHost(c->h_bits_out[slot])); c->h_bits_out[slot] = nullptr; c->h_bits_cap[slot] = 0; }
+  const size_t cap = std::min(c->bits_out_cap, bytes + bytes / 2);
+  if (cudaHostAlloc((void**)&c->h_bits_out[slot], cap, cudaHostAllocDefault) != cudaSuccess) { set_error("cudaHostAlloc failed (bit-stream buffer)"); return P64B_ENOMEM; }
+  c->h_bits_cap[slot] = cap;
+  return 0;
+}
+
+extern "C" int p64b_ctx_submit_bits(p64b_ctx* c, const p64b_step* st, int temporal_reference, const uint8_t* src, int64_t* ticket) {
+  if (!c || !src || !ticket) { set_error("NULL argument"); return P64B_EINVAL; }
+  if (c->frame_src) { set_error("p64b_ctx_submit_bits inside frame_begin/frame_end"); return P64B_EINVAL; }
+  int rc;
+  if ((rc = check_step(st)) || (rc = check_quant(st->gquant)) || (rc = use_device(c)) || (rc = ensure_bits_buffers(c))) return rc;
+  const int slot = (int)(c->submitted % p64b_ctx::NSLOT);
+  const size_t fb = (size_t)c->S * c->g.frame_bytes;
+  if (c->slot_used[slot]) {
+    CU(cudaStreamWaitEvent(c->s_h2d, c->ev_comp[slot], 0));    // the slot's source was consumed by its last kernels
+    CU(cudaStreamWaitEvent(c->stream, c->ev_d2h[slot], 0));    // its outputs were downloaded
+  }
+  CU(cudaMemcpyAsync(c->p_src[slot], src, fb, cudaMemcpyHostToDevice, c->s_h2d));
+  CU(cudaEventRecord(c->ev_h2d[slot], c->s_h2d));
+  CU(cudaStreamWaitEvent(c->stream, c->ev_h2d[slot], 0));
+  if ((rc = p64b_ctx_encode_frames_dev(c, st, c->p_src[slot], c->p_mbs[slot], c->p_levels[slot]))) return rc;
+  {
+    VlcArgs a;
+    a.tables = c->d_vlc_tables; a.mbs = c->p_mbs[slot]; a.levels = c->p_levels[slot];
+    a.gob_words = c->d_gob_words; a.gob_bits = c->d_gob_bits;
+    a.n_streams = c->S; a.ngob = c->g.ngob; a.nmb = c->g.nmb; a.qcif = c->g.qcif; a.gquant = st->gquant;
+    ProfScope ps(c, 2);
+    vlc_gob_kernel<<<c->S * c->g.ngob, VLC_THREADS, 0, c->stream>>>(a);
+    VlcFrameArgs f;
+    f.gob_words = c->d_gob_words; f.gob_bits = c->d_gob_bits; f.carry = c->d_carry; f.carry_len = c->d_carry_len;
+    f.bitpos = c->d_bitpos; f.out = c->d_bits_out[slot]; f.n_streams = c->S; f.ngob = c->g.ngob;
+    // WritePictureHeader, marker.c:103-137: PSC(20) TR(5) PTYPE(6) [PEI=1 PSPARE(8) for NTSC, p64.c:408-423] PEI=0
+    uint64_t h = (0x10ull << 44) | ((uint64_t)(temporal_reference & 31) << 39) |
+                 ((uint64_t)(c->image_type == P64B_IT_QCIF ? 0x00 : 0x04) << 33);
+    f.pic_hdr_bits = 32;
+    if (c->image_type == P64B_IT_NTSC) { h |= (1ull << 32) | (0x8cull << 24); f.pic_hdr_bits = 41; }
+    f.pic_hdr[0] = (uint32_t)(h >> 32); f.pic_hdr[1] = (uint32_t)h;
+    vlc_sizes_kernel<<<1, 1024, 0, c->stream>>>(f);
+    vlc_frame_kernel<<<c->S, VLC_THREADS, 0, c->stream>>>(f);
+    c->launches += 3;
+    CU(cudaGetLastError());
+  }
+  CU(cudaEventRecord(c->ev_comp[slot], c->stream));
+  CU(cudaStreamWaitEvent(c->s_d2h, c->ev_comp[slot], 0));
+  const size_t copy = std::min(c->bits_out_cap, vlc_data_offset(c->S) + c->bits_budget);
+  if ((rc = ensure_host_bits(c, slot, copy))) return rc;
+  CU(cudaMemcpyAsync(c->h_bits_out[slot], c->d_bits_out[slot], copy, cudaMemcpyDeviceToHost, c->s_d2h));
+  CU(cudaEventRecord(c->ev_d2h[slot], c->s_d2h));
+  c->slot_copied[slot] = copy;
+  c->slot_used[slot] = true;
+  *ticket = c->submitted++;
+  return 0;
+}
+
+extern "C" int p64b_ctx_wait_bits(p64b_ctx* c, int64_t ticket, p64b_bits_out* out) {
+  if (!c || !out || ticket < 0 || ticket >= c->submitted || ticket + p64b_ctx::NSLOT < c->submitted) { set_error("bad ticket"); return P64B_EINVAL; }
+  int rc;
+  if ((rc = use_device(c))) return rc;
+  const int slot = (int)(ticket % p64b_ctx::NSLOT);
+  if (!c->h_bits_out[slot]) { set_error("ticket was not issued by p64b_ctx_submit_bits"); return P64B_EINVAL; }
+  CU(cudaEventSynchronize(c->ev_d2h[slot]));
+  const size_t doff = vlc_data_offset(c->S);
+  size_t total = reinterpret_cast<const uint32_t*>(c->h_bits_out[slot])[c->S];
+  if (doff + total > c->slot_copied[slot]) {
+    // the frame was larger than the download budget: fetch the rest (rare; the budget follows the frame sizes)
+    const size_t have = c->slot_copied[slot];
+    if (c->h_bits_cap[slot] < doff + total) {
+      uint8_t* nb = nullptr;
+      const size_t cap = std::min(c->bits_out_cap, doff + total + total / 2);
+      if (cudaHostAlloc((void**)&nb, cap, cudaHostAllocDefault) != cudaSuccess) { set_error("cudaHostAlloc failed (bit-stream buffer)"); return P64B_ENOMEM; }
+      memcpy(nb, c->h_bits_out[slot], have);
+      CU(cudaFreeHost(c->h_bits_out[slot]));
+      c->h_bits_out[slot] = nb; c->h_bits_cap[slot] = cap;
+    }
+    CU(cudaMemcpyAsync(c->h_bits_out[slot] + have, c->d_bits_out[slot] + have, doff + total - have, cudaMemcpyDeviceToHost, c->s_d2h));
+    CU(cudaStreamSynchronize(c->s_d2h));
+    c->slot_copied[slot] = doff + total;
+  }
+  c->bits_budget = std::max<size_t>(total + total / 4 + 65536, 65536);
+  const uint8_t* b = c->h_bits_out[slot];
+  const size_t S = (size_t)c->S;
+  out->offset = reinterpret_cast<const uint32_t*>(b);
+  out->nbytes = out->offset + (S + 1);
+  out->carry = out->nbytes + S;
+  out->carry_len = out->carry + S;
+  out->bit_position = reinterpret_cast<const uint64_t*>(b + ((4 * S + 1) * 4 + 15) / 16 * 16);
+  out->data = b + doff;
+  out->total_bytes = total;
   return 0;
 }
 

@@ -22,6 +22,9 @@ struct StreamState {
   int gquant = 8;            // GQuant (p64.c:89)
   int64_t buffer_offset = 0; // BufferOffset (p64.c:140)
   int64_t total_bits = 0, first_frame_bits = 0, overflows = 0;
+  // device-side entropy coding: the stream's bytes as the device returned them, and its pending bits (< 8)
+  std::vector<uint8_t> dev_bytes;
+  uint32_t carry = 0, carry_len = 0;
 };
 
 }  // namespace
@@ -40,6 +43,7 @@ struct p64b_enc {
   uint8_t* h_src = nullptr;      // pinned staging [S][frame_bytes]
   std::vector<uint8_t> quant, overflow;
   int threads = 1;
+  bool device_vlc = false;       // fixed quantiser: headers + VLC run on the device (p64b_ctx_submit_bits)
 };
 
 namespace {
@@ -114,6 +118,7 @@ int p64b_enc_create(p64b_enc** out, const p64b_enc_params* p) {
   e->overflow.assign((size_t)e->S * e->nmb, 0);
   int hw = (int)std::thread::hardware_concurrency();
   e->threads = p->vlc_threads > 0 ? p->vlc_threads : std::max(1, std::min(hw, 64));
+  e->device_vlc = !p->rate && !p->host_vlc;
   *out = e;
   return 0;
 }
@@ -136,7 +141,19 @@ int p64b_enc_encode(p64b_enc* e, const uint8_t* src) {
   const int tr = e->current_frame % 32;            // p64.c:637
   memcpy(e->h_src, src, (size_t)e->S * e->frame_bytes);
   int rc;
-  if (!e->p.rate) {
+  if (e->device_vlc) {
+    // fixed quantiser, device-side entropy coding: one device step returns every stream's next whole bytes
+    step.gquant = e->st[0].gquant;
+    int64_t ticket;
+    p64b_bits_out o{};
+    if ((rc = p64b_ctx_submit_bits(e->ctx, &step, tr, e->h_src, &ticket)) || (rc = p64b_ctx_wait_bits(e->ctx, ticket, &o))) return rc;
+    parallel_streams(e, [&](int s) {
+      StreamState& ss = e->st[s];
+      ss.dev_bytes.insert(ss.dev_bytes.end(), o.data + o.offset[s], o.data + o.offset[s] + o.nbytes[s]);
+      ss.carry = o.carry[s]; ss.carry_len = o.carry_len[s];
+      ss.total_bits = (int64_t)o.bit_position[s];
+    });
+  } else if (!e->p.rate) {
     // fixed quantiser: one device step for the whole frame of every stream, then the VLC per stream
     step.gquant = e->st[0].gquant;
     if ((rc = p64b_ctx_encode_frames(e->ctx, &step, e->h_src, e->h_mbs, e->h_levels))) return rc;
@@ -185,7 +202,7 @@ int p64b_enc_encode(p64b_enc* e, const uint8_t* src) {
     if ((rc = p64b_ctx_frame_end(e->ctx, e->overflow.data()))) return rc;
   }
   for (auto& ss : e->st) {                          // p64.c:654-681
-    ss.total_bits = p64b_bits_tell(ss.bits);
+    if (!e->device_vlc) ss.total_bits = p64b_bits_tell(ss.bits);
     if (first) ss.first_frame_bits = ss.total_bits;
     if (e->p.rate) {
       if (first) ss.buffer_offset = buffer_size(e) / 2 - buffer_contents(e, ss, e->ngob, 0);
@@ -203,13 +220,23 @@ int p64b_enc_finish(p64b_enc* e) {
   // p64.c:600-605: limit file growth, trailing picture header, pad with 1-bits
   int last_plus_1 = e->p.start_frame + (e->frames_done ? (e->frames_done - 1) * e->p.frame_skip : 0) + 1;
   int cf = e->frames_done ? std::min(e->current_frame, last_plus_1) : e->current_frame;
-  for (auto& ss : e->st) { p64b_bits_picture_header(ss.bits, cf % 32); p64b_bits_finish(ss.bits); }
+  for (auto& ss : e->st) {
+    if (e->device_vlc && ss.carry_len) p64b_bits_put(ss.bits, ss.carry >> (32 - ss.carry_len), (int)ss.carry_len);   // the device's pending bits
+    p64b_bits_picture_header(ss.bits, cf % 32);
+    p64b_bits_finish(ss.bits);
+    if (e->device_vlc) {
+      size_t n = 0;
+      const uint8_t* t = p64b_bits_data(ss.bits, &n);
+      ss.dev_bytes.insert(ss.dev_bytes.end(), t, t + n);
+    }
+  }
   e->finished = true;
   return 0;
 }
 
 const uint8_t* p64b_enc_data(const p64b_enc* e, int stream, size_t* nbytes) {
   if (!e || stream < 0 || stream >= e->S) { if (nbytes) *nbytes = 0; return nullptr; }
+  if (e->device_vlc) { if (nbytes) *nbytes = e->st[stream].dev_bytes.size(); return e->st[stream].dev_bytes.data(); }
   return p64b_bits_data(e->st[stream].bits, nbytes);
 }
 p64b_ctx* p64b_enc_ctx(p64b_enc* e) { return e ? e->ctx : nullptr; }

@@ -11,7 +11,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import MB, ME, EncParams, Step, check
+from ._lib import MB, ME, BitsOut, EncParams, Step, check
 
 MB_DTYPE = np.dtype([("mtype", "u1"), ("cbp", "u1"), ("mvx", "i1"), ("mvy", "i1"), ("quant", "u1"),
                      ("nzmask", "u1"), ("reserved", "u2")])
@@ -73,6 +73,23 @@ class DeviceContext:
         t = C.c_int64()
         check(self.L.p64b_ctx_submit(self.h, C.byref(step), _ptr(src_ptr), _ptr(mbs_ptr), _ptr(levels_ptr), C.byref(t)))
         return t.value
+
+    def submit_bits(self, step: Step, temporal_reference: int, src_ptr: int) -> int:
+        """device-side entropy coding: enqueue one frame step of every stream; `src_ptr` = host address (pinned)"""
+        t = C.c_int64()
+        check(self.L.p64b_ctx_submit_bits(self.h, C.byref(step), int(temporal_reference), C.c_void_p(src_ptr), C.byref(t)))
+        return t.value
+
+    def wait_bits(self, ticket: int):
+        """-> (chunks: list of bytes per stream, carry, carry_len, bit_position) of that step"""
+        o = BitsOut()
+        check(self.L.p64b_ctx_wait_bits(self.h, ticket, C.byref(o)))
+        S = self.n_streams
+        off = np.ctypeslib.as_array(o.offset, (S + 1,)); nb = np.ctypeslib.as_array(o.nbytes, (S,))
+        data = np.ctypeslib.as_array(o.data, (max(int(o.total_bytes), 1),))
+        chunks = [data[off[s]:off[s] + nb[s]].tobytes() for s in range(S)]
+        return (chunks, np.ctypeslib.as_array(o.carry, (S,)).copy(), np.ctypeslib.as_array(o.carry_len, (S,)).copy(),
+                np.ctypeslib.as_array(o.bit_position, (S,)).copy())
 
     def wait(self, ticket: int):
         check(self.L.p64b_ctx_wait(self.h, ticket))
@@ -154,6 +171,7 @@ class BitWriter:
         levels = np.ascontiguousarray(levels, np.int8)
         self.L.p64b_bits_mb(self.h, mdu, _ptr(rec), _ptr(levels))
 
+    def put(self, value: int, nbits: int): self.L.p64b_bits_put(self.h, int(value), int(nbits))
     def tell(self) -> int: return int(self.L.p64b_bits_tell(self.h))
     def finish(self) -> int: return int(self.L.p64b_bits_finish(self.h))
 
@@ -174,13 +192,14 @@ class Encoder:
 
     def __init__(self, image_type: int, n_streams: int = 1, *, q: int = 0, rate: int = 0, me_mode: int = 0,
                  search_limit: int = 15, force_intra: bool = False, start_frame: int = 0, device: int = 0,
-                 frame_rate=(30000, 1001), frame_skip: int = 1, vlc_threads: int = 0):
+                 frame_rate=(30000, 1001), frame_skip: int = 1, vlc_threads: int = 0, host_vlc: bool = False):
         self.L = _lib.lib()
         p = default_params()
         p.image_type, p.n_streams, p.device, p.start_frame = image_type, n_streams, device, start_frame
         p.initial_quant, p.rate, p.me_mode, p.search_limit = q, rate, me_mode, search_limit
         p.force_intra, p.frame_rate, p.frame_rate_div, p.frame_skip = int(force_intra), frame_rate[0], frame_rate[1], frame_skip
         p.vlc_threads = vlc_threads
+        p.host_vlc = int(host_vlc)
         self.n_streams = n_streams
         self.geom = geometry(image_type)
         h = C.c_void_p()

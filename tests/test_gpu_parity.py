@@ -140,10 +140,14 @@ def test_adversarial_content_matches_oracle():
             ctx.close()
 
 
+@pytest.mark.parametrize("host_vlc", [False, True])
 @pytest.mark.parametrize("name", [n for n in GOLDEN if n != "qcif140_q10_tss"])
-def test_stream_bytes_match_reference_golden(name):
+def test_stream_bytes_match_reference_golden(name, host_vlc):
+    """fixed-quantiser cases run twice: headers + VLC on the device (the default) and on the host"""
     g, clip = golden_clip(name)
-    enc = Encoder(g["image_type"], 1, **golden_kwargs(g))
+    if host_vlc and g["args"].get("rate"):
+        pytest.skip("rate control always codes on the host")
+    enc = Encoder(g["image_type"], 1, host_vlc=host_vlc, **golden_kwargs(g))
     try:
         for fr in clip:
             enc.encode(fr[None])
@@ -280,3 +284,54 @@ def test_pipelined_submit_wait_equals_synchronous():
         assert np.array_equal(pipe.recon(S - 1), sync.recon(S - 1))
     finally:
         sync.close(); pipe.close()
+
+
+@pytest.mark.parametrize("it", [y4m.IT_QCIF, y4m.IT_CIF, y4m.IT_NTSC])
+@pytest.mark.parametrize("q", [1, 2, 8, 31])
+def test_device_vlc_equals_host_vlc_on_adversarial_content(it, q):
+    """noise at small quantisers: escapes everywhere, frames larger than the download budget (slow path of
+    p64b_ctx_wait_bits), maximal block lengths; flat frames: empty blocks, type-4 fallbacks"""
+    w, h = y4m.DIMS[it]
+    n = w * h * 3 // 2
+    rng = np.random.default_rng(17 + q)
+    frames = [rng.integers(0, 256, n).astype(np.uint8), rng.integers(0, 256, n).astype(np.uint8),
+              np.full(n, 128, np.uint8), np.full(n, 128, np.uint8), rng.integers(100, 140, n).astype(np.uint8),
+              np.full(n, 0, np.uint8), np.full(n, 255, np.uint8), rng.integers(0, 256, n).astype(np.uint8)]
+    for mode, limit in ((0, 15), (1, 31)):
+        got = encode_clip(it, np.stack(frames), q=q, me_mode=mode, search_limit=limit)
+        want = encode_clip(it, np.stack(frames), q=q, me_mode=mode, search_limit=limit, host_vlc=True)
+        assert got == want, (it, q, mode, len(got), len(want))
+
+
+def test_device_vlc_pipelined_multi_stream():
+    """p64b_ctx_submit_bits with three steps in flight, several streams: chunks + final carry reassemble the
+    bytes the sequence encoder writes"""
+    from p64_b200.encoder import BitWriter
+    it = y4m.IT_QCIF
+    S, nf = 5, 9
+    clips = [y4m.synth_clip(it, nf, seed=500 + s, pan=(s - 2, 1 - s)) for s in range(S)]
+    want = [encode_clip(it, clips[s], q=6, me_mode=1, search_limit=31, host_vlc=True) for s in range(S)]
+    ctx = DeviceContext(it, S)
+    try:
+        src = [np.stack([c[f] for c in clips]).copy() for f in range(nf)]
+        out = [b"" for _ in range(S)]
+        tickets = []
+        last = None
+        for f in range(nf):
+            if f >= 3:
+                chunks, carry, clen, pos = ctx.wait_bits(tickets[f - 3])
+                out = [o + c for o, c in zip(out, chunks)]
+            tickets.append(ctx.submit_bits(make_step(f == 0, 6, 1, 31), f % 32, src[f].ctypes.data))
+        for t in tickets[-3:]:
+            chunks, carry, clen, pos = ctx.wait_bits(t)
+            out = [o + c for o, c in zip(out, chunks)]
+        for s in range(S):
+            bw = BitWriter(it)
+            if clen[s]:
+                bw.put(int(carry[s]) >> (32 - int(clen[s])), int(clen[s]))
+            bw.picture_header(nf % 32)
+            bw.finish()
+            assert out[s] + bw.data() == want[s], s
+            assert pos[s] == 8 * len(out[s]) + clen[s]
+    finally:
+        ctx.close()
