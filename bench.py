@@ -11,8 +11,10 @@ Multi-GPU: streams are partitioned across ranks, no collective on the data path 
 
   value  device-resident: source frames already in HBM (a ring of distinct frame sets larger than L2), outputs left
          in HBM; timed with CUDA events on the launching stream, max over ranks.
-  e2e    the reference-facing C-ABI call with HOST buffers: p64b_ctx_encode_frames(): H2D of the step's source frames
-         from pinned memory + kernels + D2H of every macroblock record and level, every step.
+  e2e    the reference-facing C-ABI call with HOST buffers, p64b_ctx_submit_bits()/p64b_ctx_wait_bits(): H2D of the
+         step's source frames from pinned memory + the same kernels + the device-side headers/VLC + D2H of every
+         stream's finished H.261 bytes, every step (3 steps in flight).  `e2e_records` is the older variant that
+         downloads every macroblock record and level instead (p64b_ctx_submit/p64b_ctx_wait, host VLC not included).
 """
 from __future__ import annotations
 
@@ -41,6 +43,9 @@ IT_CIF = 1
 # algorithmic work per unit (DESIGN.md "Measurement")
 SAD_OPS_PER_CIF_FRAME = 343473 * 64          # legal candidates (me.c:212-213) x 64 packed 4-byte SADs each
 MB_BYTES_INTER = 384 + 384 + 384 + 384 + 8   # source + prediction + reconstruction + int8 levels + record
+# DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full` captures of
+# this very workload (profiles/r01_ncu_me_search_kernel.txt, profiles/r01_ncu_mb_encode_kernel.txt), bytes
+NCU_TRAFFIC = {"me_search_kernel": 51_940_096 + 1_754_368, "mb_encode_kernel": 81_226_752 + 41_383_680}
 
 
 def _clocks_sampler(stop, out, gpu_index):
@@ -226,6 +231,18 @@ def main_cuda(args):
         for t in tickets[-NOUT:]:
             ctx.wait(t)
 
+    def run_bits_steps(i0, n):
+        """n pipelined steps through p64b_ctx_submit_bits / p64b_ctx_wait_bits: source frames up, stream bytes down.
+        -> (bytes downloaded, bytes of H.261 stream produced)"""
+        tickets, down, used = [], 0, 0
+        for j in range(n):
+            if j >= NOUT:
+                o = ctx.wait_bits_raw(tickets[j - NOUT]); down += o.downloaded_bytes; used += o.total_bytes
+            tickets.append(ctx.submit_bits(make_step(False, QUANT, 1, SEARCH_LIMIT), (i0 + j) % 32, pin + ring(i0 + j) * set_bytes))
+        for t in tickets[-NOUT:]:
+            o = ctx.wait_bits_raw(t); down += o.downloaded_bytes; used += o.total_bytes
+        return down, used
+
     # ---- device-resident leg -----------------------------------------------------------------------------
     with torch.cuda.stream(stream):
         for i in range(W):
@@ -249,13 +266,22 @@ def main_cuda(args):
             step_dev(W + K + i)
         prof = ctx.profile_read()
         ctx.profile(False)
-        # ---- e2e leg: host buffers through the C-ABI call --------------------------------------------------
+        # ---- e2e legs: host buffers through the C-ABI calls -------------------------------------------------
         run_host_steps(W + 2 * K, 3)
         barrier()
         t0 = time.perf_counter()
         run_host_steps(W + 2 * K + 3, K)
         barrier()
-        ms_e2e = (time.perf_counter() - t0) * 1e3     # host wall clock between device-wide synchronisations (3 streams)
+        ms_e2e_rec = (time.perf_counter() - t0) * 1e3   # host wall clock between device-wide synchronisations (3 streams)
+        run_bits_steps(W + 3 * K + 3, 4)
+        barrier()
+        ctx.profile(True)
+        t0 = time.perf_counter()
+        bits_down, bits_used = run_bits_steps(W + 3 * K + 7, K)
+        barrier()
+        ms_e2e = (time.perf_counter() - t0) * 1e3
+        prof_bits = ctx.profile_read()
+        ctx.profile(False)
         extra = 0
         while len(samples) < 5 and extra < 400:        # short runs: keep the same load up until the sampler has rows
             step_dev(W + extra)
@@ -266,7 +292,7 @@ def main_cuda(args):
         stop.set()
         th.join(timeout=2)
 
-    ms, ms_e2e = shard.max_over_ranks([ms, ms_e2e], dist if world > 1 else None, device="cuda")
+    ms, ms_e2e, ms_e2e_rec = shard.max_over_ranks([ms, ms_e2e, ms_e2e_rec], dist if world > 1 else None, device="cuda")
 
     frames = world * S * K
     value = frames / (ms * 1e-3)
@@ -287,12 +313,14 @@ def main_cuda(args):
             pass
         me_roof = {"kernel": "me_search_kernel", "bound": "int_issue", "achieved": me_ops / (me_ms * 1e-3) / 1e9,
                    "peak": peak_ops.value / 1e9, "unit": "G packed-SAD ops/s", "frac": (me_ops / (me_ms * 1e-3)) / peak_ops.value,
-                   "traffic": None, "avg_launch_ms": me_ms, "launches_timed": prof["me"][1],
+                   "traffic": NCU_TRAFFIC["me_search_kernel"], "avg_launch_ms": me_ms, "launches_timed": prof["me"][1],
                    "peak_source": "measured live: VABSDIFF4.U8.ACC issue-rate probe (p64b_measure_sad_peak)",
                    "algorithmic": f"{SAD_OPS_PER_CIF_FRAME} packed SAD ops per CIF frame (343473 legal candidates x 64) x {S} frames per launch"}
         mb_roof = {"kernel": "mb_encode_kernel", "bound": "hbm", "achieved": mb_bytes / (mb_ms * 1e-3) / 1e9, "peak": hbm_peak,
-                   "unit": "GB/s", "frac": (mb_bytes / (mb_ms * 1e-3) / 1e9) / hbm_peak, "traffic": None, "avg_launch_ms": mb_ms,
+                   "unit": "GB/s", "frac": (mb_bytes / (mb_ms * 1e-3) / 1e9) / hbm_peak, "traffic": NCU_TRAFFIC["mb_encode_kernel"], "avg_launch_ms": mb_ms,
                    "launches_timed": prof["mb"][1], "peak_source": peak_src,
+                   "note": "integer-issue bound, not HBM bound: ncu shows the ALU pipe (adds, shifts, min/max, byte permutes) busy 69 % "
+                           "and the FMA pipe (IMAD) 25 % at 72 % issue utilisation (DESIGN.md 3.2)",
                    "algorithmic": f"{MB_BYTES_INTER} B per inter macroblock (384 source + 384 prediction + 384 reconstruction + 384 int8 levels + 8 record) x {nmb * S} macroblocks per launch"}
         dominant = me_roof if me_ms >= mb_ms else mb_roof
         cpu = None
@@ -309,8 +337,14 @@ def main_cuda(args):
                 "roofline": dominant, "roofline_kernels": {"me_search_kernel": me_roof, "mb_encode_kernel": mb_roof},
                 "kernel_share_of_step": {"me_search_kernel": me_ms / (me_ms + mb_ms), "mb_encode_kernel": mb_ms / (me_ms + mb_ms)},
                 "cpu_baseline": cpu,
-                "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": S * fb, "d2h_bytes_per_step": S * nmb * (384 + 8),
-                        "ms_per_step": ms_e2e / K, "api": "p64b_ctx_submit/p64b_ctx_wait (host buffers, pinned; 3 steps in flight)"},
+                "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": S * fb, "d2h_bytes_per_step": bits_down // K,
+                        "stream_bytes_per_step": bits_used // K, "ms_per_step": ms_e2e / K,
+                        "vlc_kernels_ms_per_step": prof_bits["vlc"][0] / max(1, prof_bits["vlc"][1]),
+                        "api": "p64b_ctx_submit_bits/p64b_ctx_wait_bits (host source frames in, finished H.261 stream bytes out; "
+                               "headers + VLC on the device; pinned buffers; 3 steps in flight)"},
+                "e2e_records": {"value": frames / (ms_e2e_rec * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": S * fb,
+                                "d2h_bytes_per_step": S * nmb * (384 + 8), "ms_per_step": ms_e2e_rec / K,
+                                "api": "p64b_ctx_submit/p64b_ctx_wait (records + levels out, host VLC NOT included)"},
                 "gpu_launches": int(launches), "clocks": _summarise_clocks(samples)}
         print(json.dumps(line))
     ctx.close()

@@ -139,6 +139,7 @@ typedef struct p64b_bits_out {
   const uint32_t *carry_len;     /* [n_streams] how many (0..7)                                               */
   const uint64_t *bit_position;  /* [n_streams] bits written so far (mwtell, stream.c:233-238)                */
   size_t total_bytes;
+  size_t downloaded_bytes;       /* what the device-to-host copies of this step moved (header + budgeted data)  */
 } p64b_bits_out;
 int p64b_ctx_submit_bits(p64b_ctx *ctx, const p64b_step *step, int temporal_reference, const uint8_t *src,
                          int64_t *ticket);

@@ -36,7 +36,7 @@ class BitsOut(C.Structure):
     """p64b_bits_out"""
     _fields_ = [("data", C.POINTER(C.c_uint8)), ("offset", C.POINTER(C.c_uint32)), ("nbytes", C.POINTER(C.c_uint32)),
                 ("carry", C.POINTER(C.c_uint32)), ("carry_len", C.POINTER(C.c_uint32)),
-                ("bit_position", C.POINTER(C.c_uint64)), ("total_bytes", C.c_size_t)]
+                ("bit_position", C.POINTER(C.c_uint64)), ("total_bytes", C.c_size_t), ("downloaded_bytes", C.c_size_t)]
 
 
 # name -> (restype, argtypes); every symbol include/p64_b200.h declares

@@ -628,6 +628,7 @@ extern "C" int p64b_ctx_wait_bits(p64b_ctx* c, int64_t ticket, p64b_bits_out* ou
   out->bit_position = reinterpret_cast<const uint64_t*>(b + ((4 * S + 1) * 4 + 15) / 16 * 16);
   out->data = b + doff;
   out->total_bytes = total;
+  out->downloaded_bytes = c->slot_copied[slot];
   return 0;
 }
 

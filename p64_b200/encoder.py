@@ -136,12 +136,17 @@ class DeviceContext:
     def profile(self, enable: bool):
         check(self.L.p64b_ctx_profile(self.h, int(enable)))
 
+    def wait_bits_raw(self, ticket: int) -> BitsOut:
+        o = BitsOut()
+        check(self.L.p64b_ctx_wait_bits(self.h, ticket, C.byref(o)))
+        return o
+
     def profile_read(self):
-        """-> {"me": (ms_total, launches), "mb": (ms_total, launches)}"""
-        ms = (C.c_double * 2)()
-        n = (C.c_int32 * 2)()
+        """-> {"me": (ms_total, launches), "mb": (...), "vlc": (ms_total, steps)}"""
+        ms = (C.c_double * 3)()
+        n = (C.c_int32 * 3)()
         check(self.L.p64b_ctx_profile_read(self.h, ms, n))
-        return {"me": (ms[0], n[0]), "mb": (ms[1], n[1])}
+        return {"me": (ms[0], n[0]), "mb": (ms[1], n[1]), "vlc": (ms[2], n[2])}
 
     @property
     def launches(self) -> int:
