@@ -96,7 +96,7 @@ def make_sources(streams, n_sets: int) -> np.ndarray:
 # --------------------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the unmodified reference encoder, one process per host core
 # --------------------------------------------------------------------------------------------------------------
-def run_reference_sample(frames_per_proc: int = 60, cores: int | None = None):
+def run_reference_sample(frames_per_proc: int = 60, cores: int | None = None, search: str = "full"):
     """-> (frames_per_s, cores, sample description). Uses oracle/_ref/p64_ref_fs (FastBME, -i 31) when built,
     else reports kind 'port' from the C oracle."""
     from oracle import oracle as O
@@ -106,7 +106,7 @@ def run_reference_sample(frames_per_proc: int = 60, cores: int | None = None):
     try:
         clip = y4m.synth_clip(IT_CIF, frames_per_proc, seed=1000)
         if O.have_ref():
-            exe = os.path.join(O.REF_DIR, "p64_ref_fs")
+            exe = os.path.join(O.REF_DIR, "p64_ref_fs" if search == "full" else "p64_ref")      # FastBME toggled | stock StepBME
             for c in range(cores):
                 y4m.write_y4m(f"{tmp}/c{c}.y4m", IT_CIF, clip)
             cmds = [[exe, "-y4m", "-CIF", "-a", "0", "-b", str(frames_per_proc - 1), "-q", str(QUANT), "-i", str(SEARCH_LIMIT),
@@ -120,7 +120,8 @@ def run_reference_sample(frames_per_proc: int = 60, cores: int | None = None):
             if any(rcs):
                 raise RuntimeError(f"reference encoder failed: {rcs}")
             kind = "reference"
-            what = (f"{cores} pinned processes of the unmodified reference (oracle/_ref/p64_ref_fs: FastBME, -q {QUANT} -i {SEARCH_LIMIT}), "
+            what = (f"{cores} pinned processes of the unmodified reference (oracle/_ref/{os.path.basename(exe)}: "
+                    f"{'FastBME' if search == 'full' else 'stock StepBME'}, -q {QUANT} -i {SEARCH_LIMIT}), "
                     f"each encoding its own {frames_per_proc}-frame synthetic CIF Y4M from tmpfs, incl. its VLC and file I/O")
             return cores * frames_per_proc / dt, cores, kind, what
         # no compiled reference: time the C oracle port, single thread
@@ -128,7 +129,7 @@ def run_reference_sample(frames_per_proc: int = 60, cores: int | None = None):
         n = min(frames_per_proc, 20)
         t0 = time.perf_counter()
         for f in range(n):
-            enc.encode_frame(clip[f], QUANT, O.ME_FULL, SEARCH_LIMIT)
+            enc.encode_frame(clip[f], QUANT, O.ME_FULL if search == "full" else 0, SEARCH_LIMIT)
         dt = time.perf_counter() - t0
         return n / dt, 1, "port", f"C oracle (oracle/p64_oracle.c), 1 thread, {n} synthetic CIF frames, hot path only (no VLC)"
     finally:
@@ -141,17 +142,18 @@ def main_reference(args):
         return 0
     vals = []
     if args.warmup > 0:
-        run_reference_sample(20)
+        run_reference_sample(20, search=args.search)
     t_all = time.perf_counter()
     for _ in range(args.steps):
-        fps, cores, kind, what = run_reference_sample(60)
+        fps, cores, kind, what = run_reference_sample(60, search=args.search)
         vals.append(fps)
     dt = time.perf_counter() - t_all
     v = float(np.mean(vals))
     line = {"impl": "reference", "metric": "CIF frames/sec encoded (ME+DCT+Q+recon)", "value": v, "unit": "frames/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 / max(1, args.steps),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "CIF 352x288 4:2:0 streams, fixed quantiser 8, full-search ME +-15 (-i 31), no rate control; "
+            "config": {"workload": "CIF 352x288 4:2:0 streams, fixed quantiser 8, " +
+                                   ("full-search ME +-15 (-i 31)" if args.search == "full" else "stock three-step search (StepBME)") + ", no rate control; "
                                    "bounded sample: " + what},
             "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": kind, "sample": what},
             "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -185,6 +187,7 @@ def main_cuda(args):
         torch.cuda.synchronize()
 
     S, K, W = STREAMS_PER_GPU, args.steps, args.warmup
+    ME_MODE = 1 if args.search == "full" else 0
     ctx = DeviceContext(IT_CIF, S, device=local)
     g = ctx.geom
     nmb, fb = g["num_mb"], g["frame_bytes"]
@@ -211,7 +214,7 @@ def main_cuda(args):
         return j if j < n_sets else 2 * n_sets - 2 - j
 
     def step_dev(i, first=False):
-        ctx.encode_frames_dev(make_step(first, QUANT, 1, SEARCH_LIMIT), dev_sets.data_ptr() + ring(i) * set_bytes,
+        ctx.encode_frames_dev(make_step(first, QUANT, ME_MODE, SEARCH_LIMIT), dev_sets.data_ptr() + ring(i) * set_bytes,
                               d_mbs.data_ptr(), d_lv.data_ptr())
 
     NOUT = 3
@@ -227,7 +230,7 @@ def main_cuda(args):
             if j >= NOUT:
                 ctx.wait(tickets[j - NOUT])          # the output set about to be reused has landed
             om, ol = pin_outs[j % NOUT]
-            tickets.append(ctx.submit(make_step(False, QUANT, 1, SEARCH_LIMIT), pin + ring(i0 + j) * set_bytes, om, ol))
+            tickets.append(ctx.submit(make_step(False, QUANT, ME_MODE, SEARCH_LIMIT), pin + ring(i0 + j) * set_bytes, om, ol))
         for t in tickets[-NOUT:]:
             ctx.wait(t)
 
@@ -238,7 +241,7 @@ def main_cuda(args):
         for j in range(n):
             if j >= NOUT:
                 o = ctx.wait_bits_raw(tickets[j - NOUT]); down += o.downloaded_bytes; used += o.total_bytes
-            tickets.append(ctx.submit_bits(make_step(False, QUANT, 1, SEARCH_LIMIT), (i0 + j) % 32, pin + ring(i0 + j) * set_bytes))
+            tickets.append(ctx.submit_bits(make_step(False, QUANT, ME_MODE, SEARCH_LIMIT), (i0 + j) % 32, pin + ring(i0 + j) * set_bytes))
         for t in tickets[-NOUT:]:
             o = ctx.wait_bits_raw(t); down += o.downloaded_bytes; used += o.total_bytes
         return down, used
@@ -303,7 +306,7 @@ def main_cuda(args):
         _lib.check(L.p64b_measure_sad_peak(local, C.byref(peak_ops), C.byref(clk)))
         me_ms = prof["me"][0] / max(1, prof["me"][1])
         mb_ms = prof["mb"][0] / max(1, prof["mb"][1])
-        me_ops = SAD_OPS_PER_CIF_FRAME * S
+        me_ops = (SAD_OPS_PER_CIF_FRAME if ME_MODE else 396 * 33 * 64) * S      # tss: at most 33 probes per macroblock
         mb_bytes = MB_BYTES_INTER * nmb * S
         hbm_peak, peak_src = 6650.0, "fallback"
         try:
@@ -315,7 +318,8 @@ def main_cuda(args):
                    "peak": peak_ops.value / 1e9, "unit": "G packed-SAD ops/s", "frac": (me_ops / (me_ms * 1e-3)) / peak_ops.value,
                    "traffic": NCU_TRAFFIC["me_search_kernel"], "avg_launch_ms": me_ms, "launches_timed": prof["me"][1],
                    "peak_source": "measured live: VABSDIFF4.U8.ACC issue-rate probe (p64b_measure_sad_peak)",
-                   "algorithmic": f"{SAD_OPS_PER_CIF_FRAME} packed SAD ops per CIF frame (343473 legal candidates x 64) x {S} frames per launch"}
+                   "algorithmic": (f"{SAD_OPS_PER_CIF_FRAME} packed SAD ops per CIF frame (343473 legal candidates x 64) x {S} frames per launch" if ME_MODE
+                                   else f"three-step search: at most 33 probes x 64 packed SAD ops per macroblock (upper bound) x {396 * S} macroblocks per launch")}
         mb_roof = {"kernel": "mb_encode_kernel", "bound": "hbm", "achieved": mb_bytes / (mb_ms * 1e-3) / 1e9, "peak": hbm_peak,
                    "unit": "GB/s", "frac": (mb_bytes / (mb_ms * 1e-3) / 1e9) / hbm_peak, "traffic": NCU_TRAFFIC["mb_encode_kernel"], "avg_launch_ms": mb_ms,
                    "launches_timed": prof["mb"][1], "peak_source": peak_src,
@@ -325,13 +329,14 @@ def main_cuda(args):
         dominant = me_roof if me_ms >= mb_ms else mb_roof
         cpu = None
         if world == 1:
-            fps, cores, kind, what = run_reference_sample(60)
+            fps, cores, kind, what = run_reference_sample(60, search=args.search)
             cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind, "sample": what}
         line = {"metric": "CIF frames/sec encoded (ME+DCT+Q+recon)", "value": value, "unit": "frames/s", "n_gpus": world,
                 "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                 "config": {"workload": f"{S} independent synthetic CIF 352x288 4:2:0 streams per GPU (BASELINE configs[4] per-GPU share), "
-                                       f"one step = one inter frame of every stream, fixed quantiser {QUANT}, full-search ME +-15 (-i {SEARCH_LIMIT}), no rate control",
+                                       f"one step = one inter frame of every stream, fixed quantiser {QUANT}, " +
+                                       (f"full-search ME +-15 (-i {SEARCH_LIMIT})" if ME_MODE else "stock three-step search (StepBME)") + ", no rate control",
                            "streams_per_gpu": S, "frames_per_step": world * S, "parallelism": f"streams partitioned over {world} GPU(s), no collective",
                            "l2": f"inputs larger than L2: ring of {n_sets} source sets ({n_sets * set_bytes >> 20} MiB) + frame stores + outputs = {(n_sets + 3) * set_bytes >> 20} MiB per GPU"},
                 "roofline": dominant, "roofline_kernels": {"me_search_kernel": me_roof, "mb_encode_kernel": mb_roof},
@@ -362,6 +367,8 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--search", default="full", choices=["full", "tss"],
+                    help="full = exhaustive FastBME -i 31 (the north-star configuration, default); tss = the stock three-step StepBME")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
     return main_reference(args) if args.impl == "reference" else main_cuda(args)

@@ -159,13 +159,14 @@ static int launch_me(p64b_ctx* c, const uint8_t* ref, const uint8_t* cur, size_t
   if (!c->me_attr_done) {
     CU(cudaFuncSetAttribute(me_search_kernel<ME_V_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, ME_SMEM_FULL));
     CU(cudaFuncSetAttribute(me_search_kernel<ME_V_SURF>, cudaFuncAttributeMaxDynamicSharedMemorySize, ME_SMEM_SURF));
+    CU(cudaFuncSetAttribute(me_search_kernel<ME_V_TSS>, cudaFuncAttributeMaxDynamicSharedMemorySize, ME_SMEM_FULL));
     CU(cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, c->device));
     c->me_attr_done = true;
   }
   CUtensorMap tm_ref, tm_cur;
   if ((rc = make_plane_map(&tm_ref, ref, c->g.W, c->g.H, stride, n_pairs, 48, ME_WIN_ROWS))) return rc;
   if ((rc = make_plane_map(&tm_cur, cur, c->g.W, c->g.H, stride, n_pairs, 16, 16))) return rc;
-  const bool surf = !(me_mode == P64B_ME_FULL && !surface);
+  const bool surf = surface != nullptr;
   MeArgs a;
   a.rg = me_ranges(c->g, me_mode, search_limit);
   a.me_mode = me_mode; a.mbw = c->g.mbw; a.mbh = c->g.mbh; a.n_pairs = n_pairs; a.out = out; a.surface = surface;
@@ -183,8 +184,9 @@ static int launch_me(p64b_ctx* c, const uint8_t* ref, const uint8_t* cur, size_t
   a.queue = c->d_me_queue; a.parity = (int)(c->me_launches++ & 1);
   a.m8 = 1u << 8; a.m16 = 1u << 16; a.m24 = 1u << 24; a.m2048 = 2048u;
   ProfScope ps(c, 0);
-  if (!surf) me_search_kernel<ME_V_FULL><<<grid, ME_THREADS, ME_SMEM_FULL, c->stream>>>(tm_ref, tm_cur, a);
-  else       me_search_kernel<ME_V_SURF><<<grid, ME_THREADS, ME_SMEM_SURF, c->stream>>>(tm_ref, tm_cur, a);
+  if (surf)                          me_search_kernel<ME_V_SURF><<<grid, ME_THREADS, ME_SMEM_SURF, c->stream>>>(tm_ref, tm_cur, a);
+  else if (me_mode == P64B_ME_FULL)  me_search_kernel<ME_V_FULL><<<grid, ME_THREADS, ME_SMEM_FULL, c->stream>>>(tm_ref, tm_cur, a);
+  else                               me_search_kernel<ME_V_TSS><<<grid, ME_THREADS, ME_SMEM_FULL, c->stream>>>(tm_ref, tm_cur, a);
   c->launches++;
   CU(cudaGetLastError());
   return 0;

@@ -110,7 +110,7 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, in
       ::"r"(smem_u32(dst)), "l"(tm), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
 }
 
-constexpr int ME_V_FULL = 0, ME_V_SURF = 1;
+constexpr int ME_V_FULL = 0, ME_V_SURF = 1, ME_V_TSS = 2;
 
 // One pass: this thread's NC candidates at dy positions yb .. yb+NC-1 (accumulators start at 0 or ME_ILLEGAL from the
 // row table).  Returns min_j (SAD_j << 11 | yb + j): the dy part of the exhaustive-search key.  ME_V_SURF also
@@ -148,14 +148,16 @@ __device__ __forceinline__ uint32_t sweep_pass(const uint32_t* __restrict__ colb
 }
 
 // tm_ref / tm_cur: u8 tensors {W, H, n_pairs}; boxes {48,47,1} and {16,16,1}.  grid = worker CTAs (persistent).
-// VARIANT: ME_V_FULL exhaustive argmin straight from registers; ME_V_SURF additionally stages the 31x31 surface in
-// shared memory for the three-step walk (me_mode == TSS) and the test hook (surface != nullptr).
+// VARIANT: ME_V_FULL exhaustive argmin straight from registers; ME_V_TSS the stock three-step search evaluating only
+// the <= 33 positions it probes (8 candidates x 4 row quarters per step across the lanes, unaligned window words by
+// funnel shift, no shifted copies); ME_V_SURF the whole surface in shared memory + a three-step walk over it (test
+// hook, surface != nullptr: the two TSS implementations check each other).
 template <int VARIANT>
 __global__ void __launch_bounds__(ME_THREADS, 4)
 me_search_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constant__ CUtensorMap tm_cur,
                  const __grid_constant__ MeArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  constexpr int WARP_WORDS = VARIANT == ME_V_FULL ? ME_WARP_WORDS_FULL : ME_WARP_WORDS_SURF;
+  constexpr int WARP_WORDS = VARIANT == ME_V_SURF ? ME_WARP_WORDS_SURF : ME_WARP_WORDS_FULL;
   uint32_t* sm = reinterpret_cast<uint32_t*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
   const int lane = threadIdx.x & 31;
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);      // warp-uniform for the compiler
@@ -225,7 +227,7 @@ me_search_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_consta
     mbar_wait(bars + b, (it >> 1) & 1);
     // byte-shifted copies 1..3: each 16-byte quad + the following word yields the three shifted quads
 #pragma unroll 1
-    for (int u = lane; u < ME_WIN_ROWS * 3; u += 32) {
+    for (int u = lane; VARIANT != ME_V_TSS && u < ME_WIN_ROWS * 3; u += 32) {
       const int idx = 4 * u;                          // row (u/3) * 12 + 4 * (u%3)
       const uint4 v = *reinterpret_cast<const uint4*>(win + idx);
       const uint32_t nx = win[idx + 4];
@@ -241,10 +243,12 @@ me_search_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_consta
       }
     }
     uint32_t c[16][4];
+    if (VARIANT != ME_V_TSS) {
 #pragma unroll
-    for (int i = 0; i < 16; i++) {
-      const uint4 v = reinterpret_cast<const uint4*>(s_cur)[i];
-      c[i][0] = v.x; c[i][1] = v.y; c[i][2] = v.z; c[i][3] = v.w;
+      for (int i = 0; i < 16; i++) {
+        const uint4 v = reinterpret_cast<const uint4*>(s_cur)[i];
+        c[i][0] = v.x; c[i][1] = v.y; c[i][2] = v.z; c[i][3] = v.w;
+      }
     }
     // SAD(0,0) = OMV (me.c:203, 271): two packed SADs per lane
     uint32_t omv;
@@ -257,12 +261,14 @@ me_search_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_consta
     __syncwarp();
 
     // ---- SAD sweep over the legal rectangle
-    const int o = xi + 1, k = o & 3;                             // o = dx + 16
-    const uint32_t* colbase = (k ? shifted + (k - 1) * ME_COPY_WORDS : win) + (o >> 2);
     uint32_t best = 0xffffffffu;
-    for (int done = 0; done < rpg;) {
-      if (rpg - done > 5) { best = min(best, sweep_pass<VARIANT, 10>(colbase, c, pen, s_sad, xi, min(ystart + done, 22), xok, a.m2048)); done += 10; }
-      else                { best = min(best, sweep_pass<VARIANT, 5>(colbase, c, pen, s_sad, xi, min(ystart + done, 27), xok, a.m2048)); done += 5; }
+    if (VARIANT != ME_V_TSS) {
+      const int o = xi + 1, k = o & 3;                             // o = dx + 16
+      const uint32_t* colbase = (k ? shifted + (k - 1) * ME_COPY_WORDS : win) + (o >> 2);
+      for (int done = 0; done < rpg;) {
+        if (rpg - done > 5) { best = min(best, sweep_pass<VARIANT, 10>(colbase, c, pen, s_sad, xi, min(ystart + done, 22), xok, a.m2048)); done += 10; }
+        else                { best = min(best, sweep_pass<VARIANT, 5>(colbase, c, pen, s_sad, xi, min(ystart + done, 27), xok, a.m2048)); done += 5; }
+      }
     }
 
     const size_t mb_index = (size_t)n;
@@ -285,6 +291,45 @@ me_search_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_consta
       mv = best >> 11;
       const int ord = best & 2047;
       if (ord) { mx = ((ord - 1) >> 5) - 15; my = ((ord - 1) & 31) - 15; }
+    } else if (VARIANT == ME_V_TSS) {
+      // StepBME (me.c:273-311) evaluating only what it probes: steps 8,4,2,1; the 8 neighbours of the centre in
+      // (diry outer, dirx inner) order = candidate slot lane>>2; lane&3 = which four rows of the block this lane sums.
+      // Legality me.c:292-294; strict < keeps the earlier candidate on ties and the centre on equality.
+      const int cand = lane >> 2, qr = lane & 3, nn = cand < 4 ? cand : cand + 1;
+      uint32_t cq[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const uint4 v = reinterpret_cast<const uint4*>(s_cur)[4 * qr + i];
+        cq[i][0] = v.x; cq[i][1] = v.y; cq[i][2] = v.z; cq[i][3] = v.w;
+      }
+      for (int step = 8; step >= 1; step >>= 1) {
+        const int dxi = mx + (nn % 3 - 1) * step + 15, dyi = my + (nn / 3 - 1) * step + 15;
+        const bool legal = dxi >= lxlo && dxi <= lxhi && dyi >= lylo && dyi <= lyhi;
+        uint32_t sad = 0;
+        if (legal) {
+          const int o = dxi + 1, sh = (o & 3) * 8;
+          const uint32_t* p = win + (dyi + 4 * qr) * ME_ROW_WORDS + (o >> 2);
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const uint32_t w0 = p[i * ME_ROW_WORDS], w1 = p[i * ME_ROW_WORDS + 1], w2 = p[i * ME_ROW_WORDS + 2],
+                           w3 = p[i * ME_ROW_WORDS + 3], w4 = p[i * ME_ROW_WORDS + 4];
+            sad = sad4(__funnelshift_r(w0, w1, sh), cq[i][0], sad);
+            sad = sad4(__funnelshift_r(w1, w2, sh), cq[i][1], sad);
+            sad = sad4(__funnelshift_r(w2, w3, sh), cq[i][2], sad);
+            sad = sad4(__funnelshift_r(w3, w4, sh), cq[i][3], sad);
+          }
+        }
+        sad += __shfl_xor_sync(0xffffffffu, sad, 1);
+        sad += __shfl_xor_sync(0xffffffffu, sad, 2);
+        const uint32_t key = legal ? min((sad << 4) | (uint32_t)(cand + 1), mv << 4) : (mv << 4);
+        const uint32_t bk = __reduce_min_sync(0xffffffffu, key);
+        const int ord = bk & 15;
+        if (ord) {
+          const int n2 = ord - 1 < 4 ? ord - 1 : ord;
+          mx += (n2 % 3 - 1) * step; my += (n2 / 3 - 1) * step;
+          mv = bk >> 4;
+        }
+      }
     } else if (VARIANT == ME_V_SURF) {
       // StepBME (me.c:273-311): steps 8,4,2,1; 8 neighbours in (diry outer, dirx inner) order; the centre
       // moves once per step; strict < keeps the earlier candidate on ties.  Lanes 0..7 probe in parallel.
@@ -311,9 +356,9 @@ me_search_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_consta
     // ---- statistics over the best-match reference block (me.c:230-245), on packed words, two per lane:
     // sum r = SAD(r,0); sum r^2 = dp4a(r,r); sum (r-c)^2 = dp4a(r,r) - 2 dp4a(r,c) + dp4a(c,c)
     {
-      const int i = lane >> 1, wc = (lane & 1) * 2, oo = mx + 16, kk = oo & 3;
-      const uint32_t* rp = (kk ? shifted + (kk - 1) * ME_COPY_WORDS : win) + (my + 15 + i) * ME_ROW_WORDS + (oo >> 2) + wc;
-      const uint32_t ra = rp[0], rb = rp[1];
+      const int i = lane >> 1, wc = (lane & 1) * 2, oo = mx + 16, sh = (oo & 3) * 8;
+      const uint32_t* rp = win + (my + 15 + i) * ME_ROW_WORDS + (oo >> 2) + wc;      // unaligned: three words, two funnel shifts
+      const uint32_t ra = __funnelshift_r(rp[0], rp[1], sh), rb = __funnelshift_r(rp[1], rp[2], sh);
       const uint2 cw = *reinterpret_cast<const uint2*>(s_cur + i * 4 + wc);
       uint32_t smm = sad4(rb, 0u, sad4(ra, 0u, 0u));
       uint32_t so = __dp4a(rb, rb, __dp4a(ra, ra, 0u));
