@@ -65,7 +65,7 @@ struct p64b_ctx {
   uint8_t* d_ovf = nullptr;       // [S][nmb]
   const uint8_t* frame_src = nullptr;   // source of the frame in flight (frame_begin .. frame_end)
   int64_t launches = 0;
-  bool me_attr_done = false;
+  bool me_attr_done = false, mb_attr_done = false;
   int n_sm = 0;
   uint32_t* d_me_queue = nullptr;   // [2] work counters of the persistent ME kernel (alternating per launch)
   int64_t me_launches = 0;
@@ -208,7 +208,11 @@ static int launch_mb(p64b_ctx* c, const p64b_step* st, const uint8_t* src, int g
     a.mps_shift = sh; a.mps_magic = (uint32_t)(((1ull << (32 + sh)) + mps - 1) / mps);
   }
   ProfScope ps(c, 1);
-  mb_encode_kernel<<<(n + MB_PER_CTA - 1) / MB_PER_CTA, MBK_THREADS, 0, c->stream>>>(a);
+  if (!c->mb_attr_done) {
+    CU(cudaFuncSetAttribute(mb_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MB4_SMEM));
+    c->mb_attr_done = true;
+  }
+  mb_encode_kernel<<<(n + MB4_PER_CTA - 1) / MB4_PER_CTA, MB4_THREADS, MB4_SMEM, c->stream>>>(a);
   c->launches++;
   CU(cudaGetLastError());
   return 0;

@@ -384,11 +384,15 @@ me_search_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_consta
 // ---------------------------------------------------------------------------------------------------
 #define P64B_MS(e) ((e) >> 9)     // MSCALE: arithmetic shift = floor (chendct.c:46-53, NO_MULTIPLY)
 
-// Chen forward butterfly on 8 values (chendct.c:119-158 / 165-197). PRE: 1 = column pass (<<2), 0 = row pass (>>1)
+// Chen forward butterfly on 8 values (chendct.c:119-158 / 165-197). PRE: 1 = column pass (<<2), 0 = row pass (>>1),
+// 2 = column pass on inputs that already carry the <<2 (exact: the shift distributes over the sums)
 template <int PRE>
 __device__ __forceinline__ void fdct8(int& x0, int& x1, int& x2, int& x3, int& x4, int& x5, int& x6, int& x7) {
   int a0, a1, a2, a3, b0, b1, b2, b3, c0, c1, c2, c3;
-  if (PRE) {
+  if (PRE == 2) {
+    a0 = x0 + x7; c3 = x0 - x7; a1 = x1 + x6; c2 = x1 - x6;
+    a2 = x2 + x5; c1 = x2 - x5; a3 = x3 + x4; c0 = x3 - x4;
+  } else if (PRE) {
     a0 = (x0 + x7) << 2; c3 = (x0 - x7) << 2; a1 = (x1 + x6) << 2; c2 = (x1 - x6) << 2;
     a2 = (x2 + x5) << 2; c1 = (x2 - x5) << 2; a3 = (x3 + x4) << 2; c0 = (x3 - x4) << 2;
   } else {
@@ -409,10 +413,11 @@ __device__ __forceinline__ void fdct8(int& x0, int& x1, int& x2, int& x3, int& x
   x7 = P64B_MS(100 * a3 - 502 * a0);
 }
 
-// Chen inverse butterfly (chendct.c:236-299 / 305-363). PRE: 1 = column pass (<<2)
+// Chen inverse butterfly (chendct.c:236-299 / 305-363). PRE: 1 = column pass (<<2); 2 = column pass on inputs that
+// already carry the <<2
 template <int PRE>
 __device__ __forceinline__ void idct8(int& x0, int& x1, int& x2, int& x3, int& x4, int& x5, int& x6, int& x7) {
-  const int sh = PRE ? 2 : 0;
+  const int sh = PRE == 1 ? 2 : 0;
   int b0 = x0 << sh, a0 = x1 << sh, b2 = x2 << sh, a1 = x3 << sh;
   int b1 = x4 << sh, a2 = x5 << sh, b3 = x6 << sh, a3 = x7 << sh;
   int c0 = P64B_MS(100 * a0 - 502 * a3);
@@ -449,6 +454,7 @@ __host__ __device__ constexpr ZigTable make_zig() {
   return z;
 }
 __constant__ ZigTable c_zig = make_zig();
+__host__ __device__ constexpr int c_zig_at(int i) { return make_zig().pos[i]; }
 
 __device__ __forceinline__ int ubyte(uint32_t w, int k) { return (int)__byte_perm(w, 0, 0x4440 + k); }   // PRMT, zero-extended byte k
 __device__ __forceinline__ uint32_t pack4(int a, int b, int c, int d) {                                   // low bytes of a,b,c,d
@@ -477,29 +483,6 @@ struct MbArgs {
   uint32_t mps_magic, mps_shift;  // n / (gob_count*33) = umulhi(n, mps_magic) >> mps_shift
 };
 
-// ---------------------------------------------------------------------------------------------------
-// Transform chain: 8 lanes per 8x8 block (lane = row), a warp = two macroblocks = 12 blocks in three rounds of four:
-//   round 0: Y(0,0) Y(1,0) of both macroblocks   (32 contiguous bytes per pixel row when the two are neighbours)
-//   round 1: Y(0,1) Y(1,1)                       round 2: U, V
-// Each Chen pass works on the 8 values a lane holds; the column passes (which the reference runs FIRST, chendct.c:
-// 119-158 / 236-299 -- the >>9 floors make the order matter) are reached by transposing the block through a padded
-// shared-memory tile (8 STS.32 + 2 LDS.128, conflict-free).  Nothing is synchronised wider than the 8 lanes of a block.
-// ---------------------------------------------------------------------------------------------------
-constexpr int MBK_WARPS = 8;
-constexpr int MBK_THREADS = 32 * MBK_WARPS;
-constexpr int MB_PER_CTA = 2 * MBK_WARPS;
-constexpr int MBK_TILE = 104;     // [8][12] words + 8: the four lane groups of a warp start 8 banks apart
-
-// lane r of the group holds v[c] = element (r, c)  ->  v[i] = element (i, r)
-__device__ __forceinline__ void transpose8(uint32_t* tile, int r, int (&v)[8], uint32_t gmask) {
-#pragma unroll
-  for (int c = 0; c < 8; c++) tile[c * 12 + r] = (uint32_t)v[c];
-  __syncwarp(gmask);
-  const uint4 lo = *reinterpret_cast<const uint4*>(tile + r * 12), hi = *reinterpret_cast<const uint4*>(tile + r * 12 + 4);
-  v[0] = (int)lo.x; v[1] = (int)lo.y; v[2] = (int)lo.z; v[3] = (int)lo.w;
-  v[4] = (int)hi.x; v[5] = (int)hi.y; v[6] = (int)hi.z; v[7] = (int)hi.w;
-}
-
 // One 8-byte row of the prediction at any byte alignment: aligned 8-byte loads + funnel shift
 // (frame stores carry slack at the end).
 __device__ __forceinline__ uint2 fetch_row8(const uint8_t* p) {
@@ -514,76 +497,121 @@ __device__ __forceinline__ uint2 fetch_row8(const uint8_t* p) {
   return make_uint2(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh));
 }
 
-// H.261 loop filter (LoadFilterMatrix, io.c:323-372) for row r of a block whose rows live in the 8 lanes of a group.
-// Separable 1-2-1 with the block's edge rows / columns passed through in that dimension; the reference's two-stage
-// rounding equals (S16+8)>>4 on the scale-16 sum (tests/test_oracle_vs_ref.py), so the vertical pass can run first:
-// on the neighbours' packed bytes widened to 16-bit pairs.
-__device__ __forceinline__ uint2 loop_filter_row(uint2 pk, int r, uint32_t gmask) {
-  uint2 up, dn;
-  up.x = __shfl_up_sync(gmask, pk.x, 1, 8); up.y = __shfl_up_sync(gmask, pk.y, 1, 8);
-  dn.x = __shfl_down_sync(gmask, pk.x, 1, 8); dn.y = __shfl_down_sync(gmask, pk.y, 1, 8);
-  if (r == 0 || r == 7) { up = pk; dn = pk; }             // edge rows: 4 * own sample
-  int V[8];
-#pragma unroll
-  for (int h = 0; h < 2; h++) {
-    const uint32_t cw = h ? pk.y : pk.x, uw = h ? up.y : up.x, dw = h ? dn.y : dn.x;
-    const uint32_t lo = __byte_perm(uw, 0, 0x4140) + 2u * __byte_perm(cw, 0, 0x4140) + __byte_perm(dw, 0, 0x4140);
-    const uint32_t hi = __byte_perm(uw, 0, 0x4342) + 2u * __byte_perm(cw, 0, 0x4342) + __byte_perm(dw, 0, 0x4342);
-    V[4 * h] = (int)(lo & 0xffffu); V[4 * h + 1] = (int)(lo >> 16);
-    V[4 * h + 2] = (int)(hi & 0xffffu); V[4 * h + 3] = (int)(hi >> 16);
-  }
-  int o[8];
-  o[0] = (4 * V[0] + 8) >> 4; o[7] = (4 * V[7] + 8) >> 4;
-#pragma unroll
-  for (int j = 1; j < 7; j++) o[j] = (V[j - 1] + 2 * V[j] + V[j + 1] + 8) >> 4;
-  return make_uint2(pack4(o[0], o[1], o[2], o[3]), pack4(o[4], o[5], o[6], o[7]));
+// ---------------------------------------------------------------------------------------------------
+// Transform chain: one thread per 8x8 block with the block in a private shared-memory tile.
+// CTA = 6 warps x 32 macroblocks (warp c = block index c of p64.c:77-79, lane = macroblock): a warp is homogeneous
+// in plane handling.  The column passes (first in the reference, chendct.c:119-158 / 236-299) run on half blocks --
+// 8 rows x 4 columns = 32 registers -- read and written as 16-byte rows of the tile; the row passes stream one row at
+// a time.  That keeps the thread at <= 80 registers (24 warps per SM) without the transposes and per-lane overheads of
+// the 8-lanes-per-block layout, and the instruction count at the one-thread-per-block level (~3 700 per block).
+// Tile stride 84 words (== 20 mod 32): a quarter warp's 16-byte row accesses fall into 8 different 4-bank groups.
+// ---------------------------------------------------------------------------------------------------
+constexpr int MB4_PER_CTA = 32;
+constexpr int MB4_THREADS = 6 * MB4_PER_CTA;
+constexpr int MB4_TILE = 84;                      // words per thread: [8][8] int32 block + 16 words packed prediction + 4 pad
+constexpr int MB4_SMEM = MB4_THREADS * MB4_TILE * 4;
+
+// sum_j ubyte(a, j) * sbyte(b, j) + c  (IDP.4A.U8.S8): with b = k << 8j this is k * (byte j of a) + c on the FMA pipe
+__device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c) {
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+// byte 0 of v into byte position b of w (PRMT, selector known at compile time)
+template <int B>
+__device__ __forceinline__ uint32_t put_byte(uint32_t w, int v) {
+  return __byte_perm(w, (uint32_t)v, B == 0 ? 0x3214 : (B == 1 ? 0x3240 : (B == 2 ? 0x3410 : 0x4210)));
+}
+template <int K>
+__device__ __forceinline__ void zig_insert(uint32_t (&out)[16], int v) { out[K >> 2] = put_byte<K & 3>(out[K >> 2], v); }
+
+__device__ __forceinline__ void st_row(int* tile, int r, int h, const int (&v)[4]) {
+  *reinterpret_cast<int4*>(tile + 8 * r + 4 * h) = make_int4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void ld_row(const int* tile, int r, int h, int (&v)[4]) {
+  const int4 q = *reinterpret_cast<const int4*>(tile + 8 * r + 4 * h);
+  v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
 }
 
-#ifndef MBK_MINB
-#define MBK_MINB 3
-#endif
-__global__ void __launch_bounds__(MBK_THREADS, MBK_MINB)
+// forward row pass of row R: Chen row butterfly, then ChenDct's final rounding + BoundDctMatrix + CCITT[Flat]Quantize +
+// [Flat]BoundQuantizeMatrix (chendct.c:204-205, transform.c:271-350, 460-537) in sign-magnitude form on the RAW output v:
+//   |x| = (|v|+4)>>3 clamped to 1023  ==  (min(|v|,8187)+4)>>3
+//   |level| = floor((|x| + ev) / 2Q) = floor((min(|v|,8187) + 4 + 8ev) / 16Q)          (ev = 1 for even Q; nested floors)
+//           = ((a*M + K) >> 22) with M = floor(2^22/16Q)+1, K = (4+8ev)*M   -- exact because (a+12)*16Q < 2^22
+// (tests/test_abi_and_host.py checks the identity exhaustively).  Levels go back into the tile, their low bytes into the
+// transmission-order words.
+template <int R>
+__device__ __forceinline__ int fwd_row(int* tile, uint32_t (&out)[16], uint32_t M, uint32_t K, uint32_t ev, bool intra) {
+  int v[8];
+  {
+    int a[4], b[4];
+    ld_row(tile, R, 0, a); ld_row(tile, R, 1, b);
+    v[0] = a[0]; v[1] = a[1]; v[2] = a[2]; v[3] = a[3]; v[4] = b[0]; v[5] = b[1]; v[6] = b[2]; v[7] = b[3];
+  }
+  fdct8<0>(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+  int l[8], sum = 0;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    if (R == 0 && j == 0) {                                   // the DC term (clamped from above only, transform.c:464-466)
+      const int x = min(round_div8(v[0]), 2047);
+      int d;
+      if (intra) d = min(max((x + 4) >> 3, 1), 254);          // (x-4)/8 <= 0 for x <= 0 and is clamped to 1 anyway
+      else { d = min((int)(((uint32_t)(abs(x) + (int)ev) * M) >> 19), 127); d = x < 0 ? -d : d; }
+      l[0] = d; sum += abs(d);
+    } else {
+      const int x = v[j], sg = x >> 31;
+      const uint32_t aa = (uint32_t)min(abs(x), 8187);
+      const int q = min((int)((aa * M + K) >> 22), 127);
+      sum += q;
+      l[j] = (q ^ sg) - sg;
+    }
+  }
+  zig_insert<c_zig_at(8 * R + 0)>(out, l[0]); zig_insert<c_zig_at(8 * R + 1)>(out, l[1]);
+  zig_insert<c_zig_at(8 * R + 2)>(out, l[2]); zig_insert<c_zig_at(8 * R + 3)>(out, l[3]);
+  zig_insert<c_zig_at(8 * R + 4)>(out, l[4]); zig_insert<c_zig_at(8 * R + 5)>(out, l[5]);
+  zig_insert<c_zig_at(8 * R + 6)>(out, l[6]); zig_insert<c_zig_at(8 * R + 7)>(out, l[7]);
+  {
+    const int a[4] = {l[0], l[1], l[2], l[3]}, b[4] = {l[4], l[5], l[6], l[7]};
+    st_row(tile, R, 0, a); st_row(tile, R, 1, b);
+  }
+  return sum;
+}
+
+__global__ void __launch_bounds__(MB4_THREADS, 3)
 mb_encode_kernel(const __grid_constant__ MbArgs a) {
-  __shared__ __align__(16) uint32_t s_tile[MBK_WARPS][4][2][MBK_TILE];
-  __shared__ __align__(8) uint8_t s_lev[MBK_WARPS][4][64];
+  extern __shared__ __align__(16) uint32_t s_dyn[];
+  __shared__ int s_acc[6][MB4_PER_CTA];
   __shared__ uint32_t s_qm[32];
   const Geom& g = a.g;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int grp = lane >> 3, r = lane & 7, half = lane >> 4, g1 = grp & 1;
-  const uint32_t gmask = 0xffu << (8 * grp);
-  // multiply-shift quantiser constant per quantiser value: M = floor(2^22 / 16Q) + 1 = floor(2^18 / Q) + 1 (see quantise below)
+  const int lane = threadIdx.x & 31, c = threadIdx.x >> 5;        // block index within the MB: p64.c:77-79
+  int* tile = reinterpret_cast<int*>(s_dyn) + threadIdx.x * MB4_TILE;
+  uint32_t* s_pk = reinterpret_cast<uint32_t*>(tile) + 64;        // packed prediction, 8 rows x 2 words
   if (threadIdx.x < 32) s_qm[threadIdx.x] = threadIdx.x ? (1u << 18) / threadIdx.x + 1u : 0u;
-  __syncthreads();
 
   const int n_total = a.n_streams * a.gob_count * 33;
-  const int n = (blockIdx.x * MBK_WARPS + warp) * 2 + half;
+  const int n = blockIdx.x * MB4_PER_CTA + lane;
   const bool active = n < n_total;
   const int nn = active ? n : n_total - 1;
-  const int mps = a.gob_count * 33;                               // macroblocks per stream in this launch
+  const int mps = a.gob_count * 33;
   const int s = (int)(__umulhi((uint32_t)nn, a.mps_magic) >> a.mps_shift), rem = nn - s * mps;
   const int gob = a.gob_first + rem / 33, m = rem % 33;
   int col, row;                                                    // MoveTo, io.c:730-741
   if (g.qcif) { col = m % 11; row = gob * 3 + m / 11; }
   else { col = (gob & 1) * 11 + m % 11; row = (gob >> 1) * 3 + m / 11; }
   const int mbi = gob * 33 + m;                                    // GOB-major index
+  const bool chroma = c >= 4;
+  const int w = chroma ? g.W >> 1 : g.W, wq = w >> 3;
+  const int off = chroma ? g.W * g.H + (c - 4) * (g.W * g.H >> 2) + row * 8 * w + col * 8
+                         : (row * 16 + (c >> 1) * 8) * w + col * 16 + (c & 1) * 8;
   const size_t fo = (size_t)s * g.frame_bytes;
-  uint32_t* t0 = s_tile[warp][grp][0];
-  uint32_t* t1 = s_tile[warp][grp][1];
-  uint8_t* levp = s_lev[warp][grp];
-  const uint2 zz = reinterpret_cast<const uint2*>(c_zig.pos)[r];     // transmission positions of raster 8r .. 8r+7
 
-  // per round: plane geometry of this lane's block (p64.c:77-79: blocks 0..3 = Y(h,v), 4 = U, 5 = V)
-  int w_[3], off_[3];                                               // row pitch; byte offset of the row's first pixel in the frame
+  // ---- source block (ReadBlock, io.c:793-820): issued first, it does not depend on the decision
+  uint2 srow[8];
+  {
+    const uint2* sp = reinterpret_cast<const uint2*>(a.src + fo + off);
 #pragma unroll
-  for (int rd = 0; rd < 3; rd++) {
-    if (rd < 2) { w_[rd] = g.W; off_[rd] = (row * 16 + rd * 8 + r) * g.W + col * 16 + g1 * 8; }
-    else { w_[rd] = g.W >> 1; off_[rd] = g.W * g.H + g1 * (g.W * g.H >> 2) + (row * 8 + r) * (g.W >> 1) + col * 8; }
+    for (int i = 0; i < 8; i++) srow[i] = __ldg(sp + i * wq);
   }
-
-  // ---- source rows (ReadBlock, io.c:793-820): issued first, they do not depend on the decision
-  uint2 sv[3];
-#pragma unroll
-  for (int rd = 0; rd < 3; rd++) sv[rd] = __ldg(reinterpret_cast<const uint2*>(a.src + fo + off_[rd]));
 
   // ---- MTYPE decision (p64.c:734-773), double arithmetic exactly as written
   int4 me0 = make_int4(0, 0, 0, 0), me1 = me0;
@@ -607,92 +635,102 @@ mb_encode_kernel(const __grid_constant__ MbArgs a) {
   if (li > 131) mt = 0;
   const int q = a.quant ? a.quant[s] : a.gquant;
   const bool intra = mt_is(M_INTRA, mt);
-
-  // ---- prediction rows: SubOverlay / SubCompensate / HalfSubCompensate addressing (io.c:142-313); chroma vector =
-  // MV/2 with C truncation (io.c:268-269); loop filter for the filter types
-  auto fetch_pred = [&](int rd, bool mc) -> uint2 {
-    int dx = 0, dy = 0;
-    if (mc) { dx = rd == 2 ? mvx / 2 : mvx; dy = rd == 2 ? mvy / 2 : mvy; }
-    return fetch_row8(a.ref + fo + off_[rd] + dy * w_[rd] + dx);
-  };
-  uint2 pk[3];
-#pragma unroll
-  for (int rd = 0; rd < 3; rd++) {
-    pk[rd] = make_uint2(0u, 0u);
-    if (!intra) {
-      pk[rd] = fetch_pred(rd, mt_is(M_MF, mt));
-      if (mt_is(M_FILTER, mt)) pk[rd] = loop_filter_row(pk[rd], r, gmask);
-    }
-  }
-
-  // ---- ReadCompressMDU (p64.c:823-886): residual, Chen DCT, bound, quantise, zig-zag.
-  // ChenDct's final rounding + BoundDctMatrix + CCITT[Flat]Quantize + [Flat]BoundQuantizeMatrix (chendct.c:204-205,
-  // transform.c:271-350, 460-537) in sign-magnitude form on the RAW transform output v:
-  //   |x| = (|v|+4)>>3 clamped to 1023  ==  (min(|v|,8187)+4)>>3
-  //   |level| = floor((|x| + ev) / 2Q) = floor((min(|v|,8187) + 4 + 8ev) / 16Q)          (ev = 1 for even Q; nested floors)
-  //           = ((a*M + K) >> 22) with M = floor(2^22/16Q)+1, K = (4+8ev)*M   -- exact because (a+12)*16Q < 2^22
-  // (tests/test_abi_and_host.py checks the identity exhaustively).  The DC term keeps the reference's two steps
-  // (it is clamped from above only, transform.c:464-466).
+  __syncthreads();                                  // s_qm
   const uint32_t ev = (q & 1) ? 0u : 1u, M = s_qm[q], K = (4u + 8u * ev) * M;
-  int lv[3][8], acc[3];
-  const size_t mb_out = (size_t)s * a.out_mb_per_stream + (mbi - a.gob_first * 33);
+
+  // ---- prediction (SubOverlay / SubCompensate / HalfSubCompensate addressing, io.c:142-313; chroma vector = MV/2 with C
+  // truncation, io.c:268-269), as packed bytes: pk[2r], pk[2r+1] = row r
+  uint32_t pk[16];
 #pragma unroll
-  for (int rd = 0; rd < 3; rd++) {
-    int v[8];
+  for (int i = 0; i < 16; i++) pk[i] = 0;
+  auto fetch_pred = [&](bool mc) {
+    int dx = 0, dy = 0;
+    if (mc) { dx = chroma ? mvx / 2 : mvx; dy = chroma ? mvy / 2 : mvy; }
+    const uint8_t* b = a.ref + fo + off + dy * w + dx;
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-      v[j] = ubyte(sv[rd].x, j) - ubyte(pk[rd].x, j);
-      v[4 + j] = ubyte(sv[rd].y, j) - ubyte(pk[rd].y, j);
+    for (int i = 0; i < 8; i++) { const uint2 r = fetch_row8(b + i * w); pk[2 * i] = r.x; pk[2 * i + 1] = r.y; }
+  };
+  if (!intra) {
+    fetch_pred(mt_is(M_MF, mt));
+    if (mt_is(M_FILTER, mt)) {
+      // H.261 loop filter (LoadFilterMatrix, io.c:323-372): horizontal 1-2-1 per row (block-edge columns x4) into the tile,
+      // vertical 1-2-1 on half blocks (block-edge rows x4), single rounding (S16+8)>>4 (identity in tests/test_oracle_vs_ref.py)
+#pragma unroll
+      for (int r = 0; r < 8; r++) {
+        int p[8], h0[4], h1[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) { p[j] = ubyte(pk[2 * r], j); p[4 + j] = ubyte(pk[2 * r + 1], j); }
+        h0[0] = p[0] << 2; h0[1] = p[0] + 2 * p[1] + p[2]; h0[2] = p[1] + 2 * p[2] + p[3]; h0[3] = p[2] + 2 * p[3] + p[4];
+        h1[0] = p[3] + 2 * p[4] + p[5]; h1[1] = p[4] + 2 * p[5] + p[6]; h1[2] = p[5] + 2 * p[6] + p[7]; h1[3] = p[7] << 2;
+        st_row(tile, r, 0, h0); st_row(tile, r, 1, h1);
+      }
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        int v[8][4];
+#pragma unroll
+        for (int r = 0; r < 8; r++) ld_row(tile, r, h, v[r]);
+        int o[8][4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          o[0][j] = (4 * v[0][j] + 8) >> 4; o[7][j] = (4 * v[7][j] + 8) >> 4;
+#pragma unroll
+          for (int r = 1; r < 7; r++) o[r][j] = (v[r - 1][j] + 2 * v[r][j] + v[r + 1][j] + 8) >> 4;
+        }
+#pragma unroll
+        for (int r = 0; r < 8; r++) pk[2 * r + h] = pack4(o[r][0], o[r][1], o[r][2], o[r][3]);
+      }
     }
-    transpose8(t0, r, v, gmask);
-    fdct8<1>(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
-    transpose8(t1, r, v, gmask);
-    fdct8<0>(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
-    int sum = 0;
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-      const int x = v[j], sg = x >> 31;
-      const uint32_t aa = (uint32_t)min(abs(x), 8187);
-      const int l = min((int)((aa * M + K) >> 22), 127);
-      sum += l;
-      lv[rd][j] = (l ^ sg) - sg;
-    }
-    if (r == 0) {                                             // the DC term of the block
-      sum -= abs(lv[rd][0]);
-      int x = min(round_div8(v[0]), 2047), l;
-      if (intra) l = min(max((x + 4) >> 3, 1), 254);          // (x-4)/8 <= 0 for x <= 0 and is clamped to 1 anyway
-      else { l = min((int)(((uint32_t)(abs(x) + (int)ev) * M) >> 19), 127); l = x < 0 ? -l : l; }
-      lv[rd][0] = l;
-      sum += abs(l);
-    }
-#pragma unroll
-    for (int d = 1; d < 8; d <<= 1) sum += __shfl_xor_sync(gmask, sum, d);
-    acc[rd] = sum;                                            // sum |level| of the block (p64.c:892), in all its lanes
-    // levels out in transmission order (transform.c:561-568), int8 (intra DC as uint8)
-#pragma unroll
-    for (int j = 0; j < 8; j++) levp[((j < 4 ? zz.x : zz.y) >> (8 * (j & 3))) & 0xff] = (uint8_t)lv[rd][j];
-    __syncwarp(gmask);
-    const uint2 lw = *reinterpret_cast<const uint2*>(levp + 8 * r);
-    const int c = rd < 2 ? 2 * rd + g1 : 4 + g1;
-    if (active) *reinterpret_cast<uint2*>(a.levels + mb_out * 384 + c * 64 + 8 * r) = lw;
   }
 
-  // ---- CBP and the type-4 / type-7 fallback (p64.c:887-908): block c of the macroblock sits in round c/2 (4,5: round 2)
-  // of lane group c&1
+  // ---- ReadCompressMDU (p64.c:823-886): residual + Chen column pass on half blocks, into the tile
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    int v[8][4];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      // 4 (s_j - p_j) by two byte dot products (IDP.4A, FMA pipe) instead of two byte extractions, a subtraction and the
+      // column pass's <<2 on the ALU pipe, which is this kernel's bottleneck
+      const uint32_t sw = h ? srow[r].y : srow[r].x, pw = pk[2 * r + h];
+#pragma unroll
+      for (int j = 0; j < 4; j++) v[r][j] = dp4a_us(sw, 4 << (8 * j), dp4a_us(pw, (int)(0xfcu << (8 * j)), 0));
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) fdct8<2>(v[0][j], v[1][j], v[2][j], v[3][j], v[4][j], v[5][j], v[6][j], v[7][j]);
+#pragma unroll
+    for (int r = 0; r < 8; r++) st_row(tile, r, h, v[r]);
+  }
+  // the prediction moves to shared memory: it is needed again only row by row in the reconstruction
+#pragma unroll
+  for (int i = 0; i < 4; i++) reinterpret_cast<uint4*>(s_pk)[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+
+  // ---- row pass, bound, quantise, zig-zag (transform.c:561-568): byte k of the output = level at raster izig(k)
+  uint32_t out[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) out[i] = 0;
+  int acc = 0;
+  acc += fwd_row<0>(tile, out, M, K, ev, intra); acc += fwd_row<1>(tile, out, M, K, ev, intra);
+  acc += fwd_row<2>(tile, out, M, K, ev, intra); acc += fwd_row<3>(tile, out, M, K, ev, intra);
+  acc += fwd_row<4>(tile, out, M, K, ev, intra); acc += fwd_row<5>(tile, out, M, K, ev, intra);
+  acc += fwd_row<6>(tile, out, M, K, ev, intra); acc += fwd_row<7>(tile, out, M, K, ev, intra);
+  const size_t mb_out = (size_t)s * a.out_mb_per_stream + (mbi - a.gob_first * 33);
+  if (active) {
+    uint4* lp = reinterpret_cast<uint4*>(a.levels + mb_out * 384 + c * 64);
+#pragma unroll
+    for (int i = 0; i < 4; i++) lp[i] = make_uint4(out[4 * i], out[4 * i + 1], out[4 * i + 2], out[4 * i + 3]);
+  }
+
+  // ---- CBP and the type-4 / type-7 fallback (p64.c:887-908)
+  s_acc[c][lane] = acc;
+  __syncthreads();
   int cbp = 0x3f, nz = 0;
   {
     int pm = 0, cb = 0;
 #pragma unroll
-    for (int rd = 0; rd < 3; rd++) {
-      const int other = __shfl_xor_sync(0xffffffffu, acc[rd], 8);
-      const int a0 = g1 ? other : acc[rd], a1 = g1 ? acc[rd] : other;      // blocks 2rd, 2rd+1
-      const int b0 = 1 << (5 - 2 * rd), b1 = b0 >> 1;
-      if (a0 && !pm) pm = b0;
-      if (a0 > 1) cb |= b0;
-      if (a0) nz |= b0;
-      if (a1 && !pm) pm = b1;
-      if (a1 > 1) cb |= b1;
-      if (a1) nz |= b1;
+    for (int k = 0; k < 6; k++) {
+      const int ak = s_acc[k][lane];
+      if (ak && !pm) pm = 1 << (5 - k);
+      if (ak > 1) cb |= 1 << (5 - k);
+      if (ak) nz |= 1 << (5 - k);
     }
     if (mt_is(M_CBP, mt)) {
       cbp = cb ? cb : pm;
@@ -702,42 +740,62 @@ mb_encode_kernel(const __grid_constant__ MbArgs a) {
   const int mt_final = mt;
 
   // ---- inverse half (p64.c:935-959) + DecodeSaveMDU (p64.c:971-1013)
+  const bool coded = ((cbp >> (5 - c)) & 1) && mt_is(M_TCOEF, mt_final);
   // a type-2 MB that fell back to type 4 predicts with the ME vector (p64.c:904, marker.c:339-342)
   if (!intra && mt_final == 4 && (mvx | mvy)) {
+    fetch_pred(true);
 #pragma unroll
-    for (int rd = 0; rd < 3; rd++) pk[rd] = fetch_pred(rd, true);
+    for (int i = 0; i < 4; i++) reinterpret_cast<uint4*>(s_pk)[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
   }
-  const int q2 = 2 * q, qo = q - (int)ev;
+  uint2* op = reinterpret_cast<uint2*>(a.out + fo + off);
+  if (coded) {
+    // inverse quantise (transform.c:359-451): (2|l|+1)Q - ev with the sign of l, 0 stays 0; intra DC = 8 l; Chen column pass
+    // (the column pass's <<2 is folded into the constants)
+    const int q2 = 8 * q, qo = 4 * (q - (int)ev);
+#pragma unroll 1
+    for (int h = 0; h < 2; h++) {
+      int v[8][4];
 #pragma unroll
-  for (int rd = 0; rd < 3; rd++) {
-    const int c = rd < 2 ? 2 * rd + g1 : 4 + g1;
-    const bool coded = ((cbp >> (5 - c)) & 1) && mt_is(M_TCOEF, mt_final);
-    uint2 o = pk[rd];                                         // uncoded: reconstruction = prediction
-    if (coded) {                                              // uniform over the 8 lanes of the block
-      // inverse quantise (transform.c:359-451): (2|l|+1)Q - ev with the sign of l, 0 stays 0; intra DC = 8 l
-      int v[8];
+      for (int r = 0; r < 8; r++) {
+        ld_row(tile, r, h, v[r]);
 #pragma unroll
-      for (int j = 0; j < 8; j++) {
-        const int l = lv[rd][j], sg = l >> 31, aa = abs(l);
-        const int rr = aa ? aa * q2 + qo : 0;
-        v[j] = (rr ^ sg) - sg;
+        for (int j = 0; j < 4; j++) {
+          const int l = v[r][j], sg = l >> 31, aa = abs(l);
+          const int rr = aa ? aa * q2 + qo : 0;
+          v[r][j] = (rr ^ sg) - sg;
+        }
       }
-      if (r == 0 && intra) v[0] = lv[rd][0] * 8;
-      transpose8(t0, r, v, gmask);
-      idct8<1>(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
-      transpose8(t1, r, v, gmask);
-      idct8<0>(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
-      int ob[8];                                              // ChenIDct rounding + Add*Compensate + BoundIDctMatrix
+      if (h == 0 && intra) v[0][0] = ((const int*)tile)[0] * 32;
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
-        ob[j] = min(max(round_div16(v[j]) + ubyte(pk[rd].x, j), 0), 255);
-        ob[4 + j] = min(max(round_div16(v[4 + j]) + ubyte(pk[rd].y, j), 0), 255);
-      }
-      o = make_uint2(pack4(ob[0], ob[1], ob[2], ob[3]), pack4(ob[4], ob[5], ob[6], ob[7]));
+      for (int j = 0; j < 4; j++) idct8<2>(v[0][j], v[1][j], v[2][j], v[3][j], v[4][j], v[5][j], v[6][j], v[7][j]);
+      __syncwarp();                                 // (no cross-thread hazard: keeps the loads of the rolled loop above the stores)
+#pragma unroll
+      for (int r = 0; r < 8; r++) st_row(tile, r, h, v[r]);
     }
-    if (active) *reinterpret_cast<uint2*>(a.out + fo + off_[rd]) = o;
+    // row pass, ChenIDct rounding + Add*Compensate + BoundIDctMatrix, row by row
+#pragma unroll 1
+    for (int r = 0; r < 8; r++) {
+      int x[8];
+      {
+        int p0[4], p1[4];
+        ld_row(tile, r, 0, p0); ld_row(tile, r, 1, p1);
+        x[0] = p0[0]; x[1] = p0[1]; x[2] = p0[2]; x[3] = p0[3]; x[4] = p1[0]; x[5] = p1[1]; x[6] = p1[2]; x[7] = p1[3];
+      }
+      idct8<0>(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);
+      const uint2 pw = *reinterpret_cast<const uint2*>(s_pk + 2 * r);
+      int o[8];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {              // + prediction byte j by a byte dot product (FMA pipe)
+        o[j] = min(max(dp4a_us(pw.x, 1 << (8 * j), round_div16(x[j])), 0), 255);
+        o[4 + j] = min(max(dp4a_us(pw.y, 1 << (8 * j), round_div16(x[4 + j])), 0), 255);
+      }
+      if (active) op[r * wq] = make_uint2(pack4(o[0], o[1], o[2], o[3]), pack4(o[4], o[5], o[6], o[7]));
+    }
+  } else if (active) {
+#pragma unroll
+    for (int r = 0; r < 8; r++) op[r * wq] = *reinterpret_cast<const uint2*>(s_pk + 2 * r);   // reconstruction = prediction
   }
-  if (active && (lane & 15) == 0) {
+  if (active && c == 0) {
     const bool mf = mt_is(M_MF, mt_final);
     uint32_t r0 = (uint32_t)mt_final | ((uint32_t)cbp << 8) | ((uint32_t)((mf ? mvx : 0) & 0xff) << 16) |
                   ((uint32_t)((mf ? mvy : 0) & 0xff) << 24);

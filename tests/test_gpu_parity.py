@@ -335,3 +335,32 @@ def test_device_vlc_pipelined_multi_stream():
             assert pos[s] == 8 * len(out[s]) + clen[s]
     finally:
         ctx.close()
+
+
+def test_me_microbenchmark_size_1024_pairs():
+    """BASELINE configs[3]: 1024 CIF frame pairs in one motion-estimation call (405 504 macroblocks through the work
+    queue).  Pairs cycle through 8 distinct seeded pairs: every copy must give the same records, and the distinct ones
+    must equal the oracle's -- for the exhaustive search and for the three-step search."""
+    import torch
+    it = y4m.IT_CIF
+    w, h = y4m.DIMS[it]
+    base = [y4m.random_pair(it, 40 + k, shift=(k - 4, 3 - k), noise=k) for k in range(8)]
+    n_pairs = 1024
+    ref = torch.from_numpy(np.stack([base[k % 8][0] for k in range(n_pairs)])).cuda()
+    cur = torch.from_numpy(np.stack([base[k % 8][1] for k in range(n_pairs)])).cuda()
+    ctx = DeviceContext(it, 1)
+    try:
+        nmb = ctx.geom["num_mb"]
+        out = torch.zeros(n_pairs * nmb * 8, dtype=torch.int32, device="cuda")
+        ctx.set_cuda_stream(torch.cuda.current_stream().cuda_stream)
+        for mode, limit in ((1, 31), (0, 15)):
+            out.zero_()
+            torch.cuda.synchronize()
+            ctx.motion_estimation_dev(ref.data_ptr(), cur.data_ptr(), n_pairs, mode, limit, out.data_ptr())
+            torch.cuda.synchronize()
+            got = out.cpu().numpy().reshape(n_pairs, nmb, 8)[:, :, :7]
+            for k in range(8):
+                assert np.array_equal(got[k], O.me_frame(base[k][0], base[k][1], mode, limit)), (mode, k)
+            assert np.array_equal(got, np.tile(got[:8], (n_pairs // 8, 1, 1))), mode
+    finally:
+        ctx.close()

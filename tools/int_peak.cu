@@ -23,6 +23,15 @@ __global__ void __launch_bounds__(256) kern(uint32_t* out, int iters, uint32_t s
         if (MODE == 1) asm volatile("add.u32 %0,%0,%1;" : "+r"(acc[i]) : "r"(a[i]));
         if (MODE == 2) asm volatile("mad.lo.u32 %0,%1,%2,%0;" : "+r"(acc[i]) : "r"(a[i]), "r"(b));
         if (MODE == 3) { uint32_t v; asm volatile("ld.shared.u32 %0,[%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(&sm[(threadIdx.x + 32 * i + u) & 1023]))); acc[i] ^= v; }
+        if (MODE == 5) asm volatile("dp4a.u32.s32 %0,%1,%2,%0;" : "+r"(acc[i]) : "r"(a[i]), "r"(b));
+        if (MODE == 6) asm volatile("mul.hi.s32 %0,%0,%1;" : "+r"(acc[i]) : "r"(a[i]));
+        if (MODE == 7) asm volatile("prmt.b32 %0,%0,%1,%2;" : "+r"(acc[i]) : "r"(a[i]), "r"(b & 0x7777));
+        if (MODE == 8) asm volatile("min.s32 %0,%0,%1;" : "+r"(acc[i]) : "r"(a[i]));
+        if (MODE == 9) asm volatile("shf.r.clamp.b32 %0,%0,%1,%2;" : "+r"(acc[i]) : "r"(a[i]), "r"(b & 31));
+        if (MODE == 10) { // 1 IMAD : 1 ALU(min) alternating on independent chains: do the two pipes overlap?
+          if (i & 1) asm volatile("mad.lo.u32 %0,%1,%2,%0;" : "+r"(acc[i]) : "r"(a[i]), "r"(b));
+          else asm volatile("min.s32 %0,%0,%1;" : "+r"(acc[i]) : "r"(a[i]));
+        }
         if (MODE == 4) { // mix: 4 VABSDIFF4 : 1 IMAD-ish
           asm volatile("vabsdiff4.u32.u32.u32.add %0,%1,%2,%0;" : "+r"(acc[i]) : "r"(a[i]), "r"(b));
           if ((i & 3) == 0) asm volatile("mad.lo.u32 %0,%1,%2,%0;" : "+r"(a[i]) : "r"(a[i]), "r"(b));
@@ -61,5 +70,11 @@ int main() {
   if (run<2>("imad", sms, 64)) return 1;
   if (run<3>("lds32", sms, 64)) return 1;
   if (run<4>("vabsdiff4+imad(4:1)", sms, 64)) return 1;
+  if (run<5>("dp4a", sms, 64)) return 1;
+  if (run<6>("mul.hi.s32", sms, 64)) return 1;
+  if (run<7>("prmt", sms, 64)) return 1;
+  if (run<8>("min.s32", sms, 64)) return 1;
+  if (run<9>("shf.r", sms, 64)) return 1;
+  if (run<10>("imad+min(1:1)", sms, 64)) return 1;
   return 0;
 }
