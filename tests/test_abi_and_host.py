@@ -212,3 +212,31 @@ def test_cli_builds_and_reports_missing_gpu(tmp_path):
     r = subprocess.run([cli, "-y4m", "-QCIF", "-a", "0", "-b", "0", "-q", "8", str(tmp_path / "c"), "-s", str(tmp_path / "o.p64")],
                        capture_output=True, text=True)
     assert r.returncode == 2 and "no CPU fallback" in r.stderr
+
+
+def test_bits_put_and_carry_join(L):
+    """p64b_bits_put = mputv (stream.c:193-205); a stream cut at an arbitrary bit and resumed from the carried bits
+    (what the sequence driver does with the device coder's pending bits at the end) gives the same bytes"""
+    from p64_b200.encoder import BitWriter
+    rng = np.random.default_rng(3)
+    fields = [(int(rng.integers(0, 1 << n)), n) for n in rng.integers(1, 33, 200)]
+    whole = BitWriter(1)
+    for v, n in fields:
+        whole.put(v, int(n))
+    total = whole.tell()
+    whole.finish()
+    want = whole.data()
+    bits = "".join(f"{v:0{n}b}" for v, n in fields)
+    assert total == len(bits)
+    assert want == int(bits + "1" * (-len(bits) % 8), 2).to_bytes((len(bits) + 7) // 8, "big")
+    for cut in (1, 7, 8, 9, 31, 333, total - 3):
+        head, rest = bits[:cut - cut % 8], bits[cut - cut % 8:]
+        carry_len = cut % 8
+        tail = BitWriter(1)
+        if carry_len:
+            tail.put(int(rest[:carry_len], 2), carry_len)
+        for i in range(carry_len, len(rest), 16):
+            tail.put(int(rest[i:i + 16], 2), len(rest[i:i + 16]))
+        tail.finish()
+        head_bytes = int(head, 2).to_bytes(len(head) // 8, "big") if head else b""
+        assert head_bytes + tail.data() == want, cut
