@@ -53,6 +53,7 @@ struct p64b_ctx {
   int8_t* p_levels[NSLOT] = {};
   cudaEvent_t ev_h2d[NSLOT] = {}, ev_comp[NSLOT] = {}, ev_d2h[NSLOT] = {};
   bool slot_used[NSLOT] = {};
+  bool slot_bits[NSLOT] = {};      // the slot's last step came from p64b_ctx_submit_bits
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
   int64_t submitted = 0;
   uint8_t* d_fs[2] = {nullptr, nullptr};   // frame stores; d_fs[cur] = CFS (reference), d_fs[cur^1] = OFS
@@ -372,6 +373,7 @@ int p64b_ctx_submit(p64b_ctx* c, const p64b_step* st, const uint8_t* src, p64b_m
   CU(cudaMemcpyAsync(levels, c->p_levels[slot], nm * P64B_LEVELS_PER_MB, cudaMemcpyDeviceToHost, c->s_d2h));
   CU(cudaEventRecord(c->ev_d2h[slot], c->s_d2h));
   c->slot_used[slot] = true;
+  c->slot_bits[slot] = false;
   *ticket = c->submitted++;
   return 0;
 }
@@ -596,6 +598,7 @@ extern "C" int p64b_ctx_submit_bits(p64b_ctx* c, const p64b_step* st, int tempor
   CU(cudaEventRecord(c->ev_d2h[slot], c->s_d2h));
   c->slot_copied[slot] = copy;
   c->slot_used[slot] = true;
+  c->slot_bits[slot] = true;
   *ticket = c->submitted++;
   return 0;
 }
@@ -605,7 +608,7 @@ extern "C" int p64b_ctx_wait_bits(p64b_ctx* c, int64_t ticket, p64b_bits_out* ou
   int rc;
   if ((rc = use_device(c))) return rc;
   const int slot = (int)(ticket % p64b_ctx::NSLOT);
-  if (!c->h_bits_out[slot]) { set_error("ticket was not issued by p64b_ctx_submit_bits"); return P64B_EINVAL; }
+  if (!c->slot_bits[slot] || !c->h_bits_out[slot]) { set_error("ticket was not issued by p64b_ctx_submit_bits"); return P64B_EINVAL; }
   CU(cudaEventSynchronize(c->ev_d2h[slot]));
   const size_t doff = vlc_data_offset(c->S);
   size_t total = reinterpret_cast<const uint32_t*>(c->h_bits_out[slot])[c->S];
