@@ -140,10 +140,29 @@ typedef struct p64b_bits_out {
   const uint64_t *bit_position;  /* [n_streams] bits written so far (mwtell, stream.c:233-238)                */
   size_t total_bytes;
   size_t downloaded_bytes;       /* what the device-to-host copies of this step moved (header + budgeted data)  */
+  const uint32_t *gquant;        /* [n_streams] GQuant after this frame (p64.c:89; varies under rate control)   */
+  const uint32_t *overflows;     /* [n_streams] NumberOvfl so far (p64.c:780; 0 without rate control)          */
 } p64b_bits_out;
 int p64b_ctx_submit_bits(p64b_ctx *ctx, const p64b_step *step, int temporal_reference, const uint8_t *src,
                          int64_t *ticket);
 int p64b_ctx_wait_bits(p64b_ctx *ctx, int64_t ticket, p64b_bits_out *out);
+
+/* Rate control on the device (-r).  Once configured (before the first frame), p64b_ctx_submit_bits()
+ * runs the reference's buffer model per stream ON THE DEVICE: motion estimation once per frame, then GOB by GOB
+ * quantise..reconstruct with the stream's own GQUANT, entropy-code, count the bits, pick the next GOB's GQUANT
+ * (BufferContents / ExecuteQuantization, p64.c:233-237, 458-481, 697-702) and apply the per-macroblock overflow override
+ * (p64.c:776-783) -- the dependency "quantiser of GOB g <- bits of GOBs < g" is kept, it just no longer crosses PCIe.
+ * step->gquant of the FIRST frame is the initial quantiser (InitialQuant, p64.c:574-590); later frames ignore it. */
+typedef struct p64b_rate_control {
+  int32_t rate;            /* Rate, bits/s (-r); 0 = off                                   */
+  int32_t frame_rate;      /* FrameRate / FrameRateDiv (-f, p64.c:128-129)                 */
+  int32_t frame_rate_div;
+  int32_t frame_skip;      /* FrameSkip (-k)                                               */
+  int32_t qdfact;          /* QDFact = Rate/320 under -r (p64.c:576)                       */
+  int32_t qoffs;           /* QOffs  = 1 (p64.c:577)                                       */
+  int32_t reserved[2];
+} p64b_rate_control;
+int p64b_ctx_set_rate_control(p64b_ctx *ctx, const p64b_rate_control *rc);
 
 /* Rate-control split (-r / -x): the quantiser of GOB g is chosen by the host from the bits written so
  * far (ExecuteQuantization, p64.c:458-481, 697-702), so quantise..reconstruct runs per GOB.
@@ -231,8 +250,8 @@ typedef struct p64b_enc_params {
   int32_t search_limit;    /* -i (default 15)                                                      */
   int32_t force_intra;     /* `-o < test.intra`                                                    */
   int32_t vlc_threads;     /* host threads for the per-stream VLC (0 = one per core, capped)       */
-  int32_t host_vlc;        /* 1: entropy-code on the host even with a fixed quantiser (default: on the device;
-                              rate control always codes on the host, its quantiser depends on the bits written) */
+  int32_t host_vlc;        /* 1: entropy-code (and, under -r, run the rate control) on the host through the per-GOB
+                              calls; default 0: both on the device (p64b_ctx_submit_bits)                       */
   int32_t reserved[2];
 } p64b_enc_params;
 

@@ -36,7 +36,14 @@ class BitsOut(C.Structure):
     """p64b_bits_out"""
     _fields_ = [("data", C.POINTER(C.c_uint8)), ("offset", C.POINTER(C.c_uint32)), ("nbytes", C.POINTER(C.c_uint32)),
                 ("carry", C.POINTER(C.c_uint32)), ("carry_len", C.POINTER(C.c_uint32)),
-                ("bit_position", C.POINTER(C.c_uint64)), ("total_bytes", C.c_size_t), ("downloaded_bytes", C.c_size_t)]
+                ("bit_position", C.POINTER(C.c_uint64)), ("total_bytes", C.c_size_t), ("downloaded_bytes", C.c_size_t),
+                ("gquant", C.POINTER(C.c_uint32)), ("overflows", C.POINTER(C.c_uint32))]
+
+
+class RateControl(C.Structure):
+    """p64b_rate_control"""
+    _fields_ = [(n, C.c_int32) for n in ("rate", "frame_rate", "frame_rate_div", "frame_skip", "qdfact", "qoffs")] + \
+               [("reserved", C.c_int32 * 2)]
 
 
 # name -> (restype, argtypes); every symbol include/p64_b200.h declares
@@ -58,6 +65,7 @@ SIGNATURES = {
     "p64b_ctx_encode_frames_dev": (_i, [_vp, C.POINTER(Step), _vp, _vp, _vp]),
     "p64b_ctx_submit_bits": (_i, [_vp, C.POINTER(Step), _i, _vp, C.POINTER(C.c_int64)]),
     "p64b_ctx_wait_bits": (_i, [_vp, C.c_int64, C.POINTER(BitsOut)]),
+    "p64b_ctx_set_rate_control": (_i, [_vp, C.POINTER(RateControl)]),
     "p64b_ctx_frame_begin": (_i, [_vp, C.POINTER(Step), _vp]),
     "p64b_ctx_encode_gob": (_i, [_vp, C.POINTER(Step), _i, _vp, _vp, _vp]),
     "p64b_ctx_frame_end": (_i, [_vp, _vp]),

@@ -81,6 +81,12 @@ struct p64b_ctx {
   uint8_t* h_bits_out[NSLOT] = {};          // pinned; grown on demand
   size_t h_bits_cap[NSLOT] = {}, slot_copied[NSLOT] = {};
   size_t bits_budget = 0;                   // data bytes downloaded with the first copy (adapts to the last frame's size)
+  // rate control on the device (p64b_ctx_set_rate_control)
+  p64b_rate_control rate{};                 // rate.rate == 0: off
+  uint32_t* d_frame_bits = nullptr;         // [S] bits of the frame in flight so far
+  long long* d_buffer_offset = nullptr;     // [S] BufferOffset
+  uint32_t* d_overflows = nullptr;          // [S] NumberOvfl
+  bool rc_started = false;                  // the initial quantiser has been loaded
   // optional per-kernel timing with CUDA events on the launching stream (bench.py roofline)
   bool prof = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_ev[3];   // 0 = ME kernel, 1 = MB kernel, 2 = entropy-coding kernels
@@ -193,13 +199,17 @@ static int launch_me(p64b_ctx* c, const uint8_t* ref, const uint8_t* cur, size_t
   return 0;
 }
 
+// frame_layout: the outputs of a partial launch land at their position in the whole-frame arrays [S][nmb] instead of
+// being packed [S][gob_count*33]
 static int launch_mb(p64b_ctx* c, const p64b_step* st, const uint8_t* src, int gob_first, int gob_count,
-                     const uint8_t* d_quant, p64b_mb* mbs, int8_t* levels) {
+                     const uint8_t* d_quant, p64b_mb* mbs, int8_t* levels, bool frame_layout = false) {
   MbArgs a;
   a.g = c->g; a.src = src; a.ref = c->d_fs[c->cur]; a.out = c->d_fs[c->cur ^ 1];
   a.me = c->d_me; a.li_prev = c->d_li[c->cur]; a.li_new = c->d_li[c->cur ^ 1];
   a.quant = d_quant; a.mbs = mbs; a.levels = levels; a.n_streams = c->S;
-  a.gob_first = gob_first; a.gob_count = gob_count; a.out_mb_per_stream = gob_count * 33;
+  a.gob_first = gob_first; a.gob_count = gob_count;
+  a.out_mb_per_stream = frame_layout ? c->g.nmb : gob_count * 33;
+  if (frame_layout) { a.mbs += gob_first * 33; a.levels += (size_t)gob_first * 33 * P64B_LEVELS_PER_MB; }
   a.first_frame = st->first_frame; a.force_intra = st->force_intra; a.gquant = st->gquant;
   const int n = c->S * gob_count * 33;
   {   // n / mps by multiply-high, exact for n < 2^31 (same construction as in launch_me)
@@ -306,7 +316,7 @@ void p64b_ctx_destroy(p64b_ctx* c) {
     if (c->ev_d2h[i]) cudaEventDestroy(c->ev_d2h[i]);
   }
   cudaFree(c->d_vlc_tables); cudaFree(c->d_gob_words); cudaFree(c->d_gob_bits); cudaFree(c->d_carry); cudaFree(c->d_carry_len);
-  cudaFree(c->d_bitpos);
+  cudaFree(c->d_bitpos); cudaFree(c->d_frame_bits); cudaFree(c->d_buffer_offset); cudaFree(c->d_overflows);
   for (int i = 0; i < p64b_ctx::NSLOT; i++) { cudaFree(c->d_bits_out[i]); if (c->h_bits_out[i]) cudaFreeHost(c->h_bits_out[i]); }
   if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
   if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
@@ -536,6 +546,9 @@ static int ensure_bits_buffers(p64b_ctx* c) {
   ALLOCZ(c->d_carry, S * 4);
   ALLOCZ(c->d_carry_len, S * 4);
   ALLOCZ(c->d_bitpos, S * 8);
+  ALLOCZ(c->d_frame_bits, S * 4);
+  ALLOCZ(c->d_buffer_offset, S * 8);
+  ALLOCZ(c->d_overflows, S * 4);
   for (int i = 0; i < p64b_ctx::NSLOT; i++) { ALLOCZ(c->d_bits_out[i], c->bits_out_cap); }
   ALLOCZ(c->d_vlc_tables, sizeof(DevVlcTables));
 #undef ALLOCZ
@@ -554,6 +567,16 @@ static int ensure_host_bits(p64b_ctx* c, int slot, size_t bytes) {
   return 0;
 }
 
+extern "C" int p64b_ctx_set_rate_control(p64b_ctx* c, const p64b_rate_control* r) {
+  if (!c || !r) { set_error("NULL argument"); return P64B_EINVAL; }
+  if (c->submitted || c->frame_src) { set_error("rate control must be configured before the first frame"); return P64B_EINVAL; }
+  if (r->rate < 0 || (r->rate && (r->frame_rate < 1 || r->frame_rate_div < 1 || r->frame_skip < 1 || r->qdfact < 1))) {
+    set_error("bad rate-control parameters"); return P64B_EINVAL;
+  }
+  c->rate = *r;
+  return 0;
+}
+
 extern "C" int p64b_ctx_submit_bits(p64b_ctx* c, const p64b_step* st, int temporal_reference, const uint8_t* src, int64_t* ticket) {
   if (!c || !src || !ticket) { set_error("NULL argument"); return P64B_EINVAL; }
   if (c->frame_src) { set_error("p64b_ctx_submit_bits inside frame_begin/frame_end"); return P64B_EINVAL; }
@@ -568,25 +591,70 @@ extern "C" int p64b_ctx_submit_bits(p64b_ctx* c, const p64b_step* st, int tempor
   CU(cudaMemcpyAsync(c->p_src[slot], src, fb, cudaMemcpyHostToDevice, c->s_h2d));
   CU(cudaEventRecord(c->ev_h2d[slot], c->s_h2d));
   CU(cudaStreamWaitEvent(c->stream, c->ev_h2d[slot], 0));
-  if ((rc = p64b_ctx_encode_frames_dev(c, st, c->p_src[slot], c->p_mbs[slot], c->p_levels[slot]))) return rc;
+  // WritePictureHeader, marker.c:103-137: PSC(20) TR(5) PTYPE(6) [PEI=1 PSPARE(8) for NTSC, p64.c:408-423] PEI=0
+  VlcFrameArgs f{};
   {
-    VlcArgs a;
-    a.tables = c->d_vlc_tables; a.mbs = c->p_mbs[slot]; a.levels = c->p_levels[slot];
-    a.gob_words = c->d_gob_words; a.gob_bits = c->d_gob_bits;
-    a.n_streams = c->S; a.ngob = c->g.ngob; a.nmb = c->g.nmb; a.qcif = c->g.qcif; a.gquant = st->gquant;
-    ProfScope ps(c, 2);
-    vlc_gob_kernel<<<c->S * c->g.ngob, VLC_THREADS, 0, c->stream>>>(a);
-    VlcFrameArgs f;
-    f.gob_words = c->d_gob_words; f.gob_bits = c->d_gob_bits; f.carry = c->d_carry; f.carry_len = c->d_carry_len;
-    f.bitpos = c->d_bitpos; f.out = c->d_bits_out[slot]; f.n_streams = c->S; f.ngob = c->g.ngob;
-    // WritePictureHeader, marker.c:103-137: PSC(20) TR(5) PTYPE(6) [PEI=1 PSPARE(8) for NTSC, p64.c:408-423] PEI=0
     uint64_t h = (0x10ull << 44) | ((uint64_t)(temporal_reference & 31) << 39) |
                  ((uint64_t)(c->image_type == P64B_IT_QCIF ? 0x00 : 0x04) << 33);
     f.pic_hdr_bits = 32;
     if (c->image_type == P64B_IT_NTSC) { h |= (1ull << 32) | (0x8cull << 24); f.pic_hdr_bits = 41; }
     f.pic_hdr[0] = (uint32_t)(h >> 32); f.pic_hdr[1] = (uint32_t)h;
+  }
+  f.gob_words = c->d_gob_words; f.gob_bits = c->d_gob_bits; f.carry = c->d_carry; f.carry_len = c->d_carry_len;
+  f.bitpos = c->d_bitpos; f.out = c->d_bits_out[slot]; f.n_streams = c->S; f.ngob = c->g.ngob; f.gquant = st->gquant;
+  VlcArgs a{};
+  a.tables = c->d_vlc_tables; a.mbs = c->p_mbs[slot]; a.levels = c->p_levels[slot];
+  a.gob_words = c->d_gob_words; a.gob_bits = c->d_gob_bits;
+  a.n_streams = c->S; a.ngob = c->g.ngob; a.nmb = c->g.nmb; a.qcif = c->g.qcif; a.gquant = st->gquant;
+  if (!c->rate.rate) {
+    if ((rc = p64b_ctx_encode_frames_dev(c, st, c->p_src[slot], c->p_mbs[slot], c->p_levels[slot]))) return rc;
+    a.gob_first = 0; a.gob_count = c->g.ngob;
+    ProfScope ps(c, 2);
+    vlc_gob_kernel<false><<<c->S * c->g.ngob, VLC_THREADS, 0, c->stream>>>(a);
     vlc_sizes_kernel<<<1, 1024, 0, c->stream>>>(f);
     vlc_frame_kernel<<<c->S, VLC_THREADS, 0, c->stream>>>(f);
+    c->launches += 3;
+    CU(cudaGetLastError());
+  } else {
+    // Rate control (-r): motion estimation once per frame; then GOB by GOB {quantise..reconstruct with the stream's GQUANT,
+    // entropy-code, count the bits, choose the next GOB's GQUANT} -- all on the device, no host round trip.  Macroblocks the
+    // overflow test overrode are re-reconstructed as copies at the end (macroblocks of a frame do not depend on each other).
+    RcArgs r{};
+    r.rate = c->rate.rate; r.frame_skip = c->rate.frame_skip; r.frame_rate = c->rate.frame_rate;
+    r.frame_rate_div = c->rate.frame_rate_div; r.qdfact = c->rate.qdfact; r.qoffs = c->rate.qoffs;
+    r.denom = c->g.ngob * 33 * c->rate.frame_rate / c->rate.frame_rate_div;
+    r.first_frame = st->first_frame; r.pic_hdr_bits = f.pic_hdr_bits;
+    r.bitpos = c->d_bitpos; r.frame_bits = c->d_frame_bits; r.buffer_offset = c->d_buffer_offset;
+    r.quant = c->d_quant; r.ovf = c->d_ovf; r.overflows = c->d_overflows;
+    a.rc = r; f.rc = r;
+    const uint8_t* src_dev = c->p_src[slot];
+    if (!st->first_frame) {
+      if ((rc = launch_me(c, c->d_fs[c->cur], src_dev, (size_t)c->g.frame_bytes, c->S, st->me_mode, st->search_limit, c->d_me))) return rc;
+    } else {
+      CU(cudaMemsetAsync(c->d_me, 0, (size_t)c->S * c->g.nmb * sizeof(p64b_me), c->stream));
+    }
+    CU(cudaMemsetAsync(c->d_ovf, 0, (size_t)c->S * c->g.nmb, c->stream));
+    rc_frame_begin_kernel<<<(c->S + 255) / 256, 256, 0, c->stream>>>(r, c->S, c->rc_started ? 0 : st->gquant);
+    c->rc_started = true;
+    c->launches++;
+    for (int g = 0; g < c->g.ngob; g++) {
+      if ((rc = launch_mb(c, st, src_dev, g, 1, c->d_quant, c->p_mbs[slot], c->p_levels[slot], true))) return rc;
+      a.gob_first = g; a.gob_count = 1;
+      ProfScope ps(c, 2);
+      vlc_gob_kernel<true><<<c->S, VLC_THREADS, 0, c->stream>>>(a);
+      c->launches++;
+    }
+    {
+      const int warps = c->S * c->g.nmb, threads = 256;
+      overflow_patch_kernel<<<(warps * 32 + threads - 1) / threads, threads, 0, c->stream>>>(
+          c->g, c->d_ovf, c->d_fs[c->cur], c->d_fs[c->cur ^ 1], c->d_li[c->cur], c->d_li[c->cur ^ 1], c->S);
+    }
+    swap_stores(c);
+    {
+      ProfScope ps(c, 2);
+      vlc_sizes_kernel<<<1, 1024, 0, c->stream>>>(f);
+      vlc_frame_kernel<<<c->S, VLC_THREADS, 0, c->stream>>>(f);
+    }
     c->launches += 3;
     CU(cudaGetLastError());
   }
@@ -634,7 +702,9 @@ extern "C" int p64b_ctx_wait_bits(p64b_ctx* c, int64_t ticket, p64b_bits_out* ou
   out->nbytes = out->offset + (S + 1);
   out->carry = out->nbytes + S;
   out->carry_len = out->carry + S;
-  out->bit_position = reinterpret_cast<const uint64_t*>(b + ((4 * S + 1) * 4 + 15) / 16 * 16);
+  out->bit_position = reinterpret_cast<const uint64_t*>(b + vlc_bitpos_offset(c->S));
+  out->gquant = reinterpret_cast<const uint32_t*>(b + vlc_bitpos_offset(c->S) + S * 8);
+  out->overflows = out->gquant + S;
   out->data = b + doff;
   out->total_bytes = total;
   out->downloaded_bytes = c->slot_copied[slot];

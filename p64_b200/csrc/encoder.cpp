@@ -43,7 +43,7 @@ struct p64b_enc {
   uint8_t* h_src = nullptr;      // pinned staging [S][frame_bytes]
   std::vector<uint8_t> quant, overflow;
   int threads = 1;
-  bool device_vlc = false;       // fixed quantiser: headers + VLC run on the device (p64b_ctx_submit_bits)
+  bool device_vlc = false;       // headers + VLC (+ rate control) run on the device (p64b_ctx_submit_bits)
 };
 
 namespace {
@@ -118,7 +118,13 @@ int p64b_enc_create(p64b_enc** out, const p64b_enc_params* p) {
   e->overflow.assign((size_t)e->S * e->nmb, 0);
   int hw = (int)std::thread::hardware_concurrency();
   e->threads = p->vlc_threads > 0 ? p->vlc_threads : std::max(1, std::min(hw, 64));
-  e->device_vlc = !p->rate && !p->host_vlc;
+  e->device_vlc = !p->host_vlc;
+  if (e->device_vlc && p->rate) {                  // the buffer model runs on the device, per stream
+    p64b_rate_control r{};
+    r.rate = p->rate; r.frame_rate = p->frame_rate; r.frame_rate_div = p->frame_rate_div; r.frame_skip = p->frame_skip;
+    r.qdfact = e->qdfact; r.qoffs = e->qoffs;
+    if ((rc = p64b_ctx_set_rate_control(e->ctx, &r))) { p64b_enc_destroy(e); return rc; }
+  }
   *out = e;
   return 0;
 }
@@ -142,7 +148,7 @@ int p64b_enc_encode(p64b_enc* e, const uint8_t* src) {
   memcpy(e->h_src, src, (size_t)e->S * e->frame_bytes);
   int rc;
   if (e->device_vlc) {
-    // fixed quantiser, device-side entropy coding: one device step returns every stream's next whole bytes
+    // device-side entropy coding (and rate control, if any): one device step returns every stream's next whole bytes
     step.gquant = e->st[0].gquant;
     int64_t ticket;
     p64b_bits_out o{};
@@ -152,6 +158,7 @@ int p64b_enc_encode(p64b_enc* e, const uint8_t* src) {
       ss.dev_bytes.insert(ss.dev_bytes.end(), o.data + o.offset[s], o.data + o.offset[s] + o.nbytes[s]);
       ss.carry = o.carry[s]; ss.carry_len = o.carry_len[s];
       ss.total_bits = (int64_t)o.bit_position[s];
+      ss.gquant = (int)o.gquant[s]; ss.overflows = (int64_t)o.overflows[s];
     });
   } else if (!e->p.rate) {
     // fixed quantiser: one device step for the whole frame of every stream, then the VLC per stream
@@ -204,7 +211,7 @@ int p64b_enc_encode(p64b_enc* e, const uint8_t* src) {
   for (auto& ss : e->st) {                          // p64.c:654-681
     if (!e->device_vlc) ss.total_bits = p64b_bits_tell(ss.bits);
     if (first) ss.first_frame_bits = ss.total_bits;
-    if (e->p.rate) {
+    if (e->p.rate && !e->device_vlc) {
       if (first) ss.buffer_offset = buffer_size(e) / 2 - buffer_contents(e, ss, e->ngob, 0);
       ss.buffer_offset -= (int)((int64_t)e->p.rate * e->p.frame_skip * e->p.frame_rate_div / e->p.frame_rate);
     }

@@ -28,6 +28,38 @@ constexpr int VLC_MBHDR_MAX_BITS = 1 + 10 + 5 + 11 + 11 + 9;
 constexpr int VLC_GOB_WORDS = (26 + 33 * (VLC_MBHDR_MAX_BITS + 6 * VLC_BLOCK_MAX_BITS) + 31) / 32 + 8;   // slot size, words
 constexpr int VLC_PIC_HDR_MAX_BITS = 41;
 
+// Rate control on the device ("exact per-MB bit counts on device let GQUANT selection and the overflow
+// test run without a per-GOB host round trip").  Restates, per stream,
+//   BufferContents()  p64.c:233-236   mwtell() + BufferOffset - ((CurrentGOB*33 + CurrentMDU) * Rate*FrameSkip / denom)
+//   BufferSize()      p64.c:237       Rate / 4
+//   ExecuteQuantization p64.c:458-481 GQuant = clamp(BufferContents()/QDFact + QOffs, 1, 31), every GOB but not on the
+//                                     first frame (p64.c:697-702)
+//   the per-macroblock overflow override p64.c:776-783 (MType 4, zero vector; also on the first frame)
+//   the end-of-frame BufferOffset update p64.c:670-680
+// in the reference's integer types (int, with the long->int truncations where the reference has them).
+struct RcArgs {
+  int rate;                        // -r bits/s; 0 = rate control off
+  int frame_skip, frame_rate, frame_rate_div, qdfact, qoffs;
+  int denom;                       // NumberGOB*NumberMDU*FrameRate/FrameRateDiv (p64.c:236)
+  int first_frame;
+  int pic_hdr_bits;
+  const unsigned long long* bitpos;  // [S] mwtell() at the end of the previous frame
+  uint32_t* frame_bits;            // [S] bits of this frame so far: picture header + the GOBs already coded
+  long long* buffer_offset;        // [S] BufferOffset (p64.c:136)
+  uint8_t* quant;                  // [S] GQuant: read for this GOB, written for the next one
+  uint8_t* ovf;                    // [S][nmb] macroblocks overridden in this frame (for the reconstruction patch)
+  uint32_t* overflows;             // [S] NumberOvfl, cumulative (p64.c:780)
+};
+__host__ __device__ inline long long rc_buffer_contents(const RcArgs& r, long long tell, long long offset, int g, int m) {
+  const int num = (int)((long long)(g * 33 + m) * r.rate * r.frame_skip);
+  return tell + offset - (r.denom ? num / r.denom : 0);
+}
+__host__ __device__ inline int rc_execute_quantization(const RcArgs& r, long long tell, long long offset, int g) {
+  const int cur = (int)rc_buffer_contents(r, tell, offset, g, 0);
+  const int q = cur / r.qdfact + r.qoffs;
+  return q < 1 ? 1 : (q > 31 ? 31 : q);
+}
+
 struct VlcArgs {
   const DevVlcTables* tables;
   const p64b_mb* mbs;        // [S][nmb] GOB-major
@@ -36,7 +68,9 @@ struct VlcArgs {
   uint32_t* gob_bits;        // [S][ngob]
   int n_streams, ngob, nmb;
   int qcif;                  // GOB numbers 1,3,5 (p64.c:709-711)
-  int gquant;
+  int gquant;                // GQUANT of every stream when rc.rate == 0
+  int gob_first, gob_count;  // CTA b -> stream b / gob_count, GOB gob_first + b % gob_count
+  RcArgs rc;
 };
 
 // MType property tables (p64.c:217-222) as bit masks over type 0..9
@@ -146,15 +180,46 @@ __device__ __forceinline__ uint64_t vlc_mb_header(const p64b_mb& r, const p64b_m
   return b;
 }
 
+// exclusive scan of one value per thread over the CTA; *total = sum.  Two barriers.
+__device__ __forceinline__ uint32_t vlc_cta_scan(uint32_t len, uint32_t* s_wsum, uint32_t* s_total, uint32_t* total) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t x = len;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+  __syncthreads();                                     // s_wsum / s_total of an earlier scan have been read
+  if (lane == 31) s_wsum[warp] = x;
+  __syncthreads();
+  uint32_t base = 0;
+  for (int w = 0; w < warp; w++) base += s_wsum[w];
+  if (tid == VLC_THREADS - 1) *s_total = base + x;
+  __syncthreads();
+  *total = *s_total;
+  return base + x - len;
+}
+
+// RC = true: one GOB of every stream under rate control.  Pieces are first measured as if no macroblock were
+// overridden; the bit position of every macroblock header then gives the overflow test (p64.c:776) of all 33 macroblocks at
+// once, exact up to and including the first one that fires.  Only when one fires does thread 0 walk the GOB in order
+// (an overridden macroblock is MType 4 with a zero vector and no coefficients, which also changes the MVD predictor of
+// its successor, marker.c:310-338), after which the pieces are re-placed.  The CTA then publishes the GOB's length and
+// the next GOB's GQUANT (ExecuteQuantization, p64.c:458-481).
+template <bool RC>
 __global__ void __launch_bounds__(VLC_THREADS)
 vlc_gob_kernel(const __grid_constant__ VlcArgs a) {
   __shared__ uint32_t s_buf[VLC_GOB_WORDS];
   __shared__ DevVlcTables s_t;
-  __shared__ uint32_t s_off[VLC_THREADS + 1];
+  __shared__ uint32_t s_total;
   __shared__ uint32_t s_wsum[VLC_THREADS / 32];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int s = blockIdx.x / a.ngob, gob = blockIdx.x % a.ngob;
+  __shared__ uint32_t s_len[RC ? VLC_THREADS : 1];
+  __shared__ uint2 s_rec[RC ? 33 : 1];
+  __shared__ unsigned long long s_hb[RC ? 33 : 1];
+  __shared__ uint8_t s_hl[RC ? 33 : 1], s_ovf[RC ? 33 : 1];
+  const int tid = threadIdx.x;
+  const int s = blockIdx.x / a.gob_count, gob = a.gob_first + blockIdx.x % a.gob_count;
   for (int i = tid; i < DEV_VLC_WORDS; i += VLC_THREADS) reinterpret_cast<uint32_t*>(&s_t)[i] = reinterpret_cast<const uint32_t*>(a.tables)[i];
+  const int gquant = RC ? (int)a.rc.quant[s] : a.gquant;
+  long long tell0 = 0, boff = 0;                      // mwtell() before this GOB's header; BufferOffset
+  if (RC) { tell0 = (long long)a.rc.bitpos[s] + a.rc.frame_bits[s]; boff = a.rc.buffer_offset[s]; }
   __syncthreads();
 
   // ---- this thread's piece
@@ -170,13 +235,14 @@ vlc_gob_kernel(const __grid_constant__ VlcArgs a) {
   if (is_piece) {
     if (piece == 0) {                                 // WriteGOBHeader, marker.c:182-209: GBSC, GN, GQUANT, no GSPARE
       const int gn = (a.qcif ? (gob << 1) : gob) + 1;
-      hbits = (1ull << 10) | ((uint64_t)gn << 6) | ((uint64_t)a.gquant << 1);
+      hbits = (1ull << 10) | ((uint64_t)gn << 6) | ((uint64_t)gquant << 1);
       len = 26;
     } else {
       rec = a.mbs[mbi];
       if (k == 0) {
         if (m) prev = a.mbs[mbi - 1];
         hbits = vlc_mb_header(rec, prev, m, &s_t, &len);
+        if (RC) s_rec[m] = *reinterpret_cast<const uint2*>(&rec);
       } else {
         coded = vt(V_TCOEF, rec.mtype) && ((rec.cbp >> (6 - k)) & 1);      // block c = k-1: bit 5-c
         if (coded) len = vlc_block<false>(lv, vt(V_CBP, rec.mtype), s_t.tcoef, nullptr);
@@ -184,18 +250,44 @@ vlc_gob_kernel(const __grid_constant__ VlcArgs a) {
     }
   }
 
-  // ---- exclusive scan of the piece lengths
-  uint32_t x = (uint32_t)len;
+  // ---- placement: exclusive scan of the piece lengths
+  uint32_t total;
+  uint32_t off = vlc_cta_scan((uint32_t)len, s_wsum, &s_total, &total);
+  if (RC) {
+    const int bsize = a.rc.rate / 4;                   // BufferSize(), p64.c:237
+    s_len[tid] = (uint32_t)len;
+    const bool fires = is_piece && piece && k == 0 && rc_buffer_contents(a.rc, tell0 + off, boff, gob, m) > bsize;
+    if (__syncthreads_or(fires)) {
+      if (tid == 0) {
+        uint32_t bits = 26;
+        p64b_mb pe{};
+        for (int i = 0; i < 33; i++) {
+          p64b_mb r = *reinterpret_cast<const p64b_mb*>(&s_rec[i]);
+          const bool o = rc_buffer_contents(a.rc, tell0 + bits, boff, gob, i) > bsize;
+          if (o) { r = p64b_mb{}; r.mtype = 4; r.cbp = 0x3f; r.quant = (uint8_t)gquant; }      // p64.c:778-779
+          int n;
+          s_hb[i] = vlc_mb_header(r, pe, i, &s_t, &n);
+          s_hl[i] = (uint8_t)n; s_ovf[i] = o;
+          bits += (uint32_t)n;
+          if (!o) for (int c = 0; c < 6; c++) bits += s_len[1 + 7 * i + 1 + c];
+          pe = r;
+        }
+      }
+      __syncthreads();
+      if (is_piece && piece) {
+        if (k == 0) { hbits = s_hb[m]; len = s_hl[m]; a.rc.ovf[mbi] = s_ovf[m]; }
+        else if (s_ovf[m]) len = 0;
+      }
+      off = vlc_cta_scan((uint32_t)len, s_wsum, &s_total, &total);
+      if (tid < 32) {                                  // NumberOvfl
+        uint32_t n = (uint32_t)s_ovf[tid] + (tid == 0 ? (uint32_t)s_ovf[32] : 0u);
 #pragma unroll
-  for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
-  if (lane == 31) s_wsum[warp] = x;
-  __syncthreads();
-  uint32_t base = 0;
-  for (int w = 0; w < warp; w++) base += s_wsum[w];
-  const uint32_t off = base + x - (uint32_t)len;
-  if (tid == VLC_THREADS - 1) s_off[0] = base + x;     // total bits of the GOB
-  __syncthreads();
-  const uint32_t total = s_off[0], nwords = (total + 31) >> 5;
+        for (int d = 16; d; d >>= 1) n += __shfl_xor_sync(0xffffffffu, n, d);
+        if (tid == 0) a.rc.overflows[s] += n;
+      }
+    }
+  }
+  const uint32_t nwords = (total + 31) >> 5;
   for (uint32_t i = tid; i < nwords + 1; i += VLC_THREADS) s_buf[i] = 0;
   __syncthreads();
 
@@ -213,7 +305,25 @@ vlc_gob_kernel(const __grid_constant__ VlcArgs a) {
   __syncthreads();
   uint32_t* dst = a.gob_words + ((size_t)s * a.ngob + gob) * VLC_GOB_WORDS;
   for (uint32_t i = tid; i < nwords + 1; i += VLC_THREADS) dst[i] = s_buf[i];      // + one zero word for the gather's look-ahead
-  if (tid == 0) a.gob_bits[(size_t)s * a.ngob + gob] = total;
+  if (tid == 0) {
+    a.gob_bits[(size_t)s * a.ngob + gob] = total;
+    if (RC) {
+      const uint32_t fb = a.rc.frame_bits[s] + total;
+      a.rc.frame_bits[s] = fb;
+      if (!a.rc.first_frame && gob + 1 < a.ngob)       // GQUANT of the next GOB (p64.c:697-702)
+        a.rc.quant[s] = (uint8_t)rc_execute_quantization(a.rc, (long long)a.rc.bitpos[s] + fb, boff, gob + 1);
+    }
+  }
+}
+
+// Start of a frame under rate control: the picture header is written before GOB 0 asks for its quantiser.
+__global__ void rc_frame_begin_kernel(RcArgs r, int n_streams, int initial_quant) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_streams) return;
+  r.frame_bits[s] = (uint32_t)r.pic_hdr_bits;
+  if (initial_quant) r.quant[s] = (uint8_t)initial_quant;                 // first frame of the sequence (p64.c:574-590)
+  else if (!r.first_frame)
+    r.quant[s] = (uint8_t)rc_execute_quantization(r, (long long)r.bitpos[s] + r.pic_hdr_bits, r.buffer_offset[s], 0);
 }
 
 // Output of one frame step, one buffer (copied to the host in one piece):
@@ -222,8 +332,11 @@ vlc_gob_kernel(const __grid_constant__ VlcArgs a) {
 //   uint32 carry[S]      the stream's pending bits (< 8) after this frame, left-aligned in the word
 //   uint32 carry_len[S]
 //   uint64 bitpos[S]     bits written so far (mwtell, stream.c:233-238)
+//   uint32 gquant[S]     GQuant after this frame (rate control; else the step's quantiser)
+//   uint32 overflows[S]  NumberOvfl so far (rate control; else 0)
 //   uint8  data[]        at byte vlc_data_offset(S)
-__host__ __device__ constexpr size_t vlc_data_offset(int S) { return (((size_t)(4 * S + 1) * 4 + 15) / 16) * 16 + (size_t)S * 8; }
+__host__ __device__ constexpr size_t vlc_bitpos_offset(int S) { return (((size_t)(4 * S + 1) * 4 + 15) / 16) * 16; }
+__host__ __device__ constexpr size_t vlc_data_offset(int S) { return vlc_bitpos_offset(S) + (size_t)S * 16; }
 struct VlcFrameArgs {
   const uint32_t* gob_words;   // [S][ngob][VLC_GOB_WORDS]
   const uint32_t* gob_bits;    // [S][ngob]
@@ -234,10 +347,15 @@ struct VlcFrameArgs {
   int n_streams, ngob;
   uint32_t pic_hdr[2];         // picture header bits (MSB first), pic_hdr_bits long
   int pic_hdr_bits;
+  int gquant;                  // reported when rc.rate == 0
+  RcArgs rc;
 };
 __device__ __forceinline__ uint32_t* vlc_out_u32(uint8_t* out, int S, int field) { return reinterpret_cast<uint32_t*>(out) + (field == 0 ? 0 : (S + 1) + (field - 1) * S); }
 __device__ __forceinline__ unsigned long long* vlc_out_bitpos(uint8_t* out, int S) {
-  return reinterpret_cast<unsigned long long*>(out + (((size_t)(4 * S + 1) * 4 + 15) / 16) * 16);
+  return reinterpret_cast<unsigned long long*>(out + vlc_bitpos_offset(S));
+}
+__device__ __forceinline__ uint32_t* vlc_out_rc(uint8_t* out, int S, int field) {     // 0: gquant, 1: overflows
+  return reinterpret_cast<uint32_t*>(out + vlc_bitpos_offset(S) + (size_t)S * 8) + field * S;
 }
 
 // chunk sizes and their packed offsets: one CTA, streams in blocks of blockDim.x with a running base
@@ -322,6 +440,16 @@ vlc_frame_kernel(const __grid_constant__ VlcFrameArgs a) {
     vlc_out_u32(a.out, a.n_streams, 2)[s] = cbits;
     vlc_out_u32(a.out, a.n_streams, 3)[s] = rem;
     vlc_out_bitpos(a.out, a.n_streams)[s] = pos;
+    uint32_t gq = (uint32_t)a.gquant, novf = 0;
+    if (a.rc.rate) {                                   // end of frame, p64.c:670-680
+      long long bo = a.rc.buffer_offset[s];
+      if (a.rc.first_frame) bo = (a.rc.rate / 4) / 2 - rc_buffer_contents(a.rc, (long long)pos, bo, a.ngob, 0);
+      bo -= (int)((long long)a.rc.rate * a.rc.frame_skip * a.rc.frame_rate_div / a.rc.frame_rate);
+      a.rc.buffer_offset[s] = bo;
+      gq = a.rc.quant[s]; novf = a.rc.overflows[s];
+    }
+    vlc_out_rc(a.out, a.n_streams, 0)[s] = gq;
+    vlc_out_rc(a.out, a.n_streams, 1)[s] = novf;
   }
 }
 

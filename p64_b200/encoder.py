@@ -11,7 +11,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import MB, ME, BitsOut, EncParams, Step, check
+from ._lib import MB, ME, BitsOut, EncParams, RateControl, Step, check
 
 MB_DTYPE = np.dtype([("mtype", "u1"), ("cbp", "u1"), ("mvx", "i1"), ("mvy", "i1"), ("quant", "u1"),
                      ("nzmask", "u1"), ("reserved", "u2")])
@@ -74,6 +74,12 @@ class DeviceContext:
         check(self.L.p64b_ctx_submit(self.h, C.byref(step), _ptr(src_ptr), _ptr(mbs_ptr), _ptr(levels_ptr), C.byref(t)))
         return t.value
 
+    def set_rate_control(self, rate: int, frame_rate=(30000, 1001), frame_skip: int = 1, qdfact: int = 0, qoffs: int = 1):
+        """Rate control on the device for submit_bits (p64.c:233-237, 458-481, 776-783); QDFact defaults to Rate/320."""
+        r = RateControl(int(rate), int(frame_rate[0]), int(frame_rate[1]), int(frame_skip),
+                        int(qdfact) if qdfact else max(int(rate) // 320, 1), int(qoffs))
+        check(self.L.p64b_ctx_set_rate_control(self.h, C.byref(r)))
+
     def submit_bits(self, step: Step, temporal_reference: int, src_ptr: int) -> int:
         """device-side entropy coding: enqueue one frame step of every stream; `src_ptr` = host address (pinned)"""
         t = C.c_int64()
@@ -88,6 +94,8 @@ class DeviceContext:
         off = np.ctypeslib.as_array(o.offset, (S + 1,)); nb = np.ctypeslib.as_array(o.nbytes, (S,))
         data = np.ctypeslib.as_array(o.data, (max(int(o.total_bytes), 1),))
         chunks = [data[off[s]:off[s] + nb[s]].tobytes() for s in range(S)]
+        self.last_gquant = np.ctypeslib.as_array(o.gquant, (S,)).copy()
+        self.last_overflows = np.ctypeslib.as_array(o.overflows, (S,)).copy()
         return (chunks, np.ctypeslib.as_array(o.carry, (S,)).copy(), np.ctypeslib.as_array(o.carry_len, (S,)).copy(),
                 np.ctypeslib.as_array(o.bit_position, (S,)).copy())
 

@@ -143,10 +143,9 @@ def test_adversarial_content_matches_oracle():
 @pytest.mark.parametrize("host_vlc", [False, True])
 @pytest.mark.parametrize("name", [n for n in GOLDEN if n != "qcif140_q10_tss"])
 def test_stream_bytes_match_reference_golden(name, host_vlc):
-    """fixed-quantiser cases run twice: headers + VLC on the device (the default) and on the host"""
+    """every case runs twice: headers + VLC (and, for the -r cases, the rate control: per-GOB GQUANT, overflow overrides)
+    on the device -- the default -- and on the host through the per-GOB calls"""
     g, clip = golden_clip(name)
-    if host_vlc and g["args"].get("rate"):
-        pytest.skip("rate control always codes on the host")
     enc = Encoder(g["image_type"], 1, host_vlc=host_vlc, **golden_kwargs(g))
     try:
         for fr in clip:
@@ -335,6 +334,58 @@ def test_device_vlc_pipelined_multi_stream():
             assert pos[s] == 8 * len(out[s]) + clen[s]
     finally:
         ctx.close()
+
+
+@pytest.mark.parametrize("it,rate,nf", [(y4m.IT_QCIF, 64000, 10), (y4m.IT_QCIF, 48000, 8), (y4m.IT_CIF, 128000, 6),
+                                        (y4m.IT_CIF, 1500000, 5), (y4m.IT_NTSC, 96000, 5)])
+def test_device_rate_control_multi_stream_pipelined(it, rate, nf):
+    """Rate control on the device (p64b_ctx_set_rate_control + submit_bits, three steps in flight): streams with different
+    content take different GQUANT / overflow paths; each must equal the host-side rate control of the sequence encoder
+    run on that stream alone (which the golden tests pin to the reference's bytes)."""
+    from p64_b200._lib import P64Error
+    from p64_b200.encoder import BitWriter
+    S = 4
+    w, h = y4m.DIMS[it]
+    n = w * h * 3 // 2
+    rng = np.random.default_rng(rate + nf)
+    clips = [y4m.synth_clip(it, nf, seed=900 + s, pan=(2 * s - 3, s - 1)) for s in range(S - 1)]
+    clips.append(np.stack([rng.integers(0, 256, n).astype(np.uint8) if f % 3 != 2 else np.full(n, 90, np.uint8) for f in range(nf)]))
+    want, want_ovf = [], []
+    for s in range(S):
+        enc = Encoder(it, 1, rate=rate, me_mode=1, search_limit=31, host_vlc=True)
+        for fr in clips[s]:
+            enc.encode(fr[None])
+        enc.finish()
+        want.append(enc.data(0)); want_ovf.append(enc.overflows(0))
+        enc.close()
+    iq = min(max(10000000 // rate, 1), 31)
+    ctx = DeviceContext(it, S)
+    try:
+        ctx.set_rate_control(rate)
+        src = [np.stack([c[f] for c in clips]).copy() for f in range(nf)]
+        out = [b"" for _ in range(S)]
+        tickets = []
+        for f in range(nf):
+            if f >= 3:
+                chunks, carry, clen, pos = ctx.wait_bits(tickets[f - 3])
+                out = [o + c for o, c in zip(out, chunks)]
+            tickets.append(ctx.submit_bits(make_step(f == 0, iq, 1, 31), f % 32, src[f].ctypes.data))
+        for t in tickets[-3:]:
+            chunks, carry, clen, pos = ctx.wait_bits(t)
+            out = [o + c for o, c in zip(out, chunks)]
+        for s in range(S):
+            bw = BitWriter(it)
+            if clen[s]:
+                bw.put(int(carry[s]) >> (32 - int(clen[s])), int(clen[s]))
+            bw.picture_header(nf % 32)
+            bw.finish()
+            assert out[s] + bw.data() == want[s], (s, len(out[s]), len(want[s]))
+            assert int(ctx.last_overflows[s]) == want_ovf[s], s
+        with pytest.raises(P64Error):
+            ctx.set_rate_control(rate)          # only before the first frame
+    finally:
+        ctx.close()
+    assert sum(want_ovf) > 0 or rate >= 1000000
 
 
 def test_me_microbenchmark_size_1024_pairs():
