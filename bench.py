@@ -285,6 +285,10 @@ def main_cuda(args):
         ms_e2e = (time.perf_counter() - t0) * 1e3
         prof_bits = ctx.profile_read()
         ctx.profile(False)
+        # ---- BASELINE configs[2]: the same streams under rate control (-r), buffer model on the device ----------
+        rc_line = None
+        if not args.no_rate_control:
+            rc_line = rate_control_leg(L, local, S, K, pin, set_bytes, ring, ME_MODE, barrier)
         extra = 0
         while len(samples) < 5 and extra < 400:        # short runs: keep the same load up until the sampler has rows
             step_dev(W + extra)
@@ -295,7 +299,8 @@ def main_cuda(args):
         stop.set()
         th.join(timeout=2)
 
-    ms, ms_e2e, ms_e2e_rec = shard.max_over_ranks([ms, ms_e2e, ms_e2e_rec], dist if world > 1 else None, device="cuda")
+    rc_ms = [rc_line["ms_dev"], rc_line["ms_host"]] if rc_line else [0.0, 0.0]
+    ms, ms_e2e, ms_e2e_rec, rc_ms[0], rc_ms[1] = shard.max_over_ranks([ms, ms_e2e, ms_e2e_rec] + rc_ms, dist if world > 1 else None, device="cuda")
 
     frames = world * S * K
     value = frames / (ms * 1e-3)
@@ -351,6 +356,18 @@ def main_cuda(args):
                                 "d2h_bytes_per_step": S * nmb * (384 + 8), "ms_per_step": ms_e2e_rec / K,
                                 "api": "p64b_ctx_submit/p64b_ctx_wait (records + levels out, host VLC NOT included)"},
                 "gpu_launches": int(launches), "clocks": _summarise_clocks(samples)}
+        if rc_line:
+            line["e2e_rate_control"] = {
+                "value": world * S * K / (rc_ms[0] * 1e-3), "unit": "frames/s", "ms_per_step": rc_ms[0] / K,
+                "h2d_bytes_per_step": S * fb, "d2h_bytes_per_step": rc_line["down"] // K, "stream_bytes_per_step": rc_line["used"] // K,
+                "rate": RATE, "gquant_range_last_step": rc_line["gquant"], "overflow_mbs": rc_line["overflows"],
+                "kernel_launches_per_step": rc_line["launches"] // K,
+                "api": "p64b_ctx_set_rate_control + p64b_ctx_submit_bits/p64b_ctx_wait_bits (BASELINE configs[2]: -r; per-GOB GQUANT "
+                       "and the overflow override chosen on the device from exact bit counts; 3 steps in flight)",
+                "host_round_trip_path": {"value": world * S * rc_line["host_steps"] / (rc_ms[1] * 1e-3), "unit": "frames/s",
+                                         "ms_per_step": rc_ms[1] / rc_line["host_steps"], "steps": rc_line["host_steps"],
+                                         "api": "p64b_enc_encode with host_vlc=1: p64b_ctx_frame_begin / 12 x p64b_ctx_encode_gob / "
+                                                "p64b_ctx_frame_end, rate control + VLC on the host cores"}}
         print(json.dumps(line))
     ctx.close()
     L.p64b_host_free(pin)
@@ -361,6 +378,56 @@ def main_cuda(args):
     return 0
 
 
+RATE = 384000                 # -r of BASELINE configs[2]
+
+
+def rate_control_leg(L, local, S, K, pin, set_bytes, ring, me_mode, barrier):
+    """BASELINE configs[2] (CIF inter encode with rate control) for the same S streams, end to end with host buffers:
+    (a) buffer model on the device, (b) the per-GOB host round-trip path of the sequence encoder, a few steps."""
+    from p64_b200.encoder import DeviceContext, Encoder, make_step
+    iq = min(max(10000000 // RATE, 1), 31)
+    ctx = DeviceContext(IT_CIF, S, device=local)
+    ctx.set_rate_control(RATE)
+    NOUT = 3
+
+    def run(i0, n, first):
+        tickets, down, used = [], 0, 0
+        for j in range(n):
+            if j >= NOUT:
+                o = ctx.wait_bits_raw(tickets[j - NOUT]); down += o.downloaded_bytes; used += o.total_bytes
+            tickets.append(ctx.submit_bits(make_step(first and j == 0, iq, me_mode, SEARCH_LIMIT), (i0 + j) % 32, pin + ring(i0 + j) * set_bytes))
+        for t in tickets[-NOUT:]:
+            o = ctx.wait_bits_raw(t); down += o.downloaded_bytes; used += o.total_bytes
+        return down, used, o
+
+    run(0, 6, True)
+    barrier()
+    l0 = ctx.launches
+    t0 = time.perf_counter()
+    down, used, o = run(6, K, False)
+    barrier()
+    ms_dev = (time.perf_counter() - t0) * 1e3
+    launches = ctx.launches - l0
+    gq = np.ctypeslib.as_array(o.gquant, (S,)); ov = np.ctypeslib.as_array(o.overflows, (S,))
+    out = {"ms_dev": ms_dev, "down": int(down), "used": int(used), "gquant": [int(gq.min()), int(gq.max())],
+           "overflows": int(ov.sum()), "launches": int(launches)}
+    ctx.close()
+    # (b) host round trips: 12 synchronous per-GOB calls per frame, VLC and rate control on the host cores
+    hs = max(2, min(K, 8))
+    enc = Encoder(IT_CIF, S, rate=RATE, me_mode=me_mode, search_limit=SEARCH_LIMIT, host_vlc=True, device=local)
+    frames = [np.ctypeslib.as_array(C.cast(pin + ring(i) * set_bytes, C.POINTER(C.c_uint8)), (set_bytes,)) for i in range(hs + 2)]
+    enc.encode(frames[0]); enc.encode(frames[1])
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(hs):
+        enc.encode(frames[2 + i])
+    barrier()
+    out["ms_host"] = (time.perf_counter() - t0) * 1e3
+    out["host_steps"] = hs
+    enc.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -369,6 +436,7 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--search", default="full", choices=["full", "tss"],
                     help="full = exhaustive FastBME -i 31 (the north-star configuration, default); tss = the stock three-step StepBME")
+    ap.add_argument("--no-rate-control", action="store_true", help="skip the extra rate-control (-r) end-to-end leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
     return main_reference(args) if args.impl == "reference" else main_cuda(args)
