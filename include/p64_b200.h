@@ -46,6 +46,16 @@ extern "C" {
 
 #define P64B_MDU_PER_GOB 33 /* NumberMDU, p64.c:1478 */
 
+/* Y4M chroma types the reference's reader accepts (y4m_input.c:587-655) */
+#define P64B_CHROMA_420JPEG  0 /* "420", "420jpeg": no conversion                                   */
+#define P64B_CHROMA_420MPEG2 1 /* horizontal re-siting filter (y4m_input.c:195-229)                 */
+#define P64B_CHROMA_420PALDV 2 /* horizontal + vertical re-siting (y4m_input.c:274-376)             */
+#define P64B_CHROMA_422      3 /* the 420mpeg2 filter on full-height planes (y4m_input.c:617-624)   */
+#define P64B_CHROMA_411      4 /* 4:1:1 -> 4:2:2 (y4m_input.c:417-459)                              */
+#define P64B_CHROMA_444      5 /* no conversion                                                     */
+#define P64B_CHROMA_444ALPHA 6 /* no conversion, alpha plane dropped                                */
+#define P64B_CHROMA_MONO     7 /* chroma = 128 (y4m_input.c:463-471)                                */
+
 /* One macroblock as the host VLC needs it (the globals WriteMBHeader()/WriteMDU() read:
  * MType, CBP, MVDH, MVDV, UseQuant -- p64.c:85-98, marker.c:288-354).  8 bytes. */
 typedef struct p64b_mb {
@@ -102,6 +112,18 @@ int p64b_ctx_set_cuda_stream(p64b_ctx *ctx, void *cuda_stream);
 /* Pinned host memory for source/record/level buffers (cudaHostAlloc); plain malloc'd buffers also work. */
 void *p64b_host_alloc(size_t bytes);
 void p64b_host_free(void *p);
+
+/* Ingest.  By default `src` frames are 4:2:0 with "jpeg" chroma siting.  After
+ * p64b_ctx_set_input_chroma() (before the first frame) every host `src` argument of this context is instead the
+ * unconverted Y4M frame payload, [n_streams][p64b_raw_frame_bytes(image_type, chroma)], and the chroma conversion the
+ * reference's reader applies on the CPU (y4m_input.c:195-545) runs on the device after the upload.  What the encoder
+ * reads of 4:2:2 / 4:1:1 / 4:4:4 input is what the reference reads (the first (W/2)*(H/2) bytes of each converted chroma
+ * plane: ReadIob io.c:636-645 + ReadBlock io.c:793-803), so streams stay byte-identical.  Device-pointer entry points
+ * (*_dev) always take converted 4:2:0 frames. */
+int p64b_raw_frame_bytes(int image_type, int chroma);
+int p64b_ctx_set_input_chroma(p64b_ctx *ctx, int chroma);
+/* Upload + convert only: raw [n_streams][raw_frame_bytes] -> out420 [n_streams][frame_bytes] (what ReadIob would install). */
+int p64b_ctx_convert_frames(p64b_ctx *ctx, const uint8_t *raw, uint8_t *out420);
 
 /* One frame step for every stream, host buffers in and out.  Replaces the body of p64EncodeFrame()
  * between ReadIob() and SwapFS() (p64.c:633-661) in fixed-quantiser mode: GlobalMC/MotionEstimation
@@ -232,6 +254,26 @@ const uint8_t *p64b_bits_data(const p64b_bits *b, size_t *nbytes);
 void p64b_bits_reset(p64b_bits *b);
 
 /* ---------------------------------------------------------------------------------------------
+ * (2b) YUV4MPEG2 reader of the ingest path (vidinput.c / y4m_input.c:556-768): parses the header and FRAME markers
+ * with the reference reader's rules and reads each frame's payload, unconverted, into the caller's staging buffer.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct p64b_y4m p64b_y4m;
+typedef struct p64b_y4m_info {
+  int32_t width, height;      /* W, H                                                   */
+  int32_t fps_n, fps_d;       /* F                                                      */
+  int32_t par_n, par_d;       /* A (0:0 when absent)                                    */
+  int32_t chroma;             /* P64B_CHROMA_* from the C tag ("420" when absent)       */
+  int32_t interlace;          /* I tag character, '?' when absent                       */
+  int64_t frame_bytes;        /* payload bytes per frame in the file                    */
+} p64b_y4m_info;
+int p64b_y4m_open(p64b_y4m **out, const char *path /* "-" = stdin */);
+void p64b_y4m_close(p64b_y4m *y);
+int p64b_y4m_get_info(const p64b_y4m *y, p64b_y4m_info *info);
+/* 1 = a frame was read into dst[frame_bytes], 0 = end of file, < 0 = error */
+int p64b_y4m_read_frame(p64b_y4m *y, uint8_t *dst);
+int64_t p64b_y4m_payload_bytes(int width, int height, int chroma);
+
+/* ---------------------------------------------------------------------------------------------
  * (3) sequence driver: p64EncodeSequence / p64EncodeFrame / p64EncodeGOB (p64.c:524-786) for a batch
  * ------------------------------------------------------------------------------------------- */
 typedef struct p64b_enc p64b_enc;
@@ -252,14 +294,18 @@ typedef struct p64b_enc_params {
   int32_t vlc_threads;     /* host threads for the per-stream VLC (0 = one per core, capped)       */
   int32_t host_vlc;        /* 1: entropy-code (and, under -r, run the rate control) on the host through the per-GOB
                               calls; default 0: both on the device (p64b_ctx_submit_bits)                       */
-  int32_t reserved[2];
+  int32_t input_chroma;    /* P64B_CHROMA_*: layout of the frames given to p64b_enc_encode (default 420jpeg)    */
+  int32_t reserved[1];
 } p64b_enc_params;
 
 void p64b_enc_default_params(p64b_enc_params *p);
 int p64b_enc_create(p64b_enc **out, const p64b_enc_params *p);
 void p64b_enc_destroy(p64b_enc *e);
-/* Encode the next frame of every stream: src [n_streams][frame_bytes] (host). */
+/* Encode the next frame of every stream: src [n_streams][frame_bytes] (host); with input_chroma set,
+ * [n_streams][p64b_raw_frame_bytes()] unconverted Y4M payloads.  p64b_enc_staging() is the encoder's own pinned
+ * upload buffer of that size: a reader may fill it in place and pass it as `src` (no extra copy). */
 int p64b_enc_encode(p64b_enc *e, const uint8_t *src);
+uint8_t *p64b_enc_staging(p64b_enc *e);
 /* Trailing picture header + padding (p64.c:600-605) for every stream. Call once after the last frame. */
 int p64b_enc_finish(p64b_enc *e);
 /* The stream's bytes so far (complete after p64b_enc_finish). */

@@ -205,6 +205,97 @@ class Encoder:
 
 
 # ------------------------------------------------------------------------------------------------
+# ingest: the Y4M reader's chroma conversions (y4m_input.c:195-545), restated in NumPy
+# ------------------------------------------------------------------------------------------------
+CHROMA = {"420jpeg": 0, "420": 0, "420mpeg2": 1, "420paldv": 2, "422": 3, "411": 4, "444": 5, "444alpha": 6, "mono": 7}
+
+
+def payload_bytes(w: int, h: int, chroma: str) -> int:
+    """dst_buf_read_sz + aux_buf_read_sz (y4m_input.c:587-655)"""
+    c = CHROMA[chroma]
+    cw, ch = (w + 1) // 2, (h + 1) // 2
+    return {0: w * h + 2 * cw * ch, 1: w * h + 2 * cw * ch, 2: w * h + 2 * cw * ch, 3: w * h + 2 * cw * h,
+            4: w * h + 2 * ((w + 3) // 4) * h, 5: 3 * w * h, 6: 4 * w * h, 7: w * h}[c]
+
+
+def _taps(a, axis, taps, first):
+    """sum_k taps[k] * a[index + first + k] along `axis`, indices clamped to the plane edge -- the three loops per row of
+    the reference (y4m_input.c:211-224 etc.) are exactly edge clamping; (s + 64) >> 7 floors; clamp to [0,255]."""
+    a = a.astype(np.int64)
+    n = a.shape[axis]
+    idx = np.arange(n)
+    acc = 0
+    for k, t in enumerate(taps):
+        acc = acc + t * np.take(a, np.clip(idx + first + k, 0, n - 1), axis=axis)
+    return np.clip((acc + 64) >> 7, 0, 255)
+
+
+def y4m_payload_to_encoder_frame(raw: np.ndarray, w: int, h: int, chroma: str) -> np.ndarray:
+    """One Y4M frame payload -> the 4:2:0 frame the reference ENCODER reads: the reader's conversion
+    (y4m_convert_*, y4m_input.c:195-471), then ReadIob/ReadBlock's view of the planes (io.c:636-645, 793-803): the first
+    (w/2)*(h/2) bytes of each converted chroma plane."""
+    c = CHROMA[chroma]
+    raw = np.ascontiguousarray(raw, np.uint8)
+    assert raw.size == payload_bytes(w, h, chroma)
+    y = raw[:w * h]
+    cw, ch = w // 2, h // 2
+    H6 = (4, -17, 114, 35, -9, 1)                       # y4m_input.c:209-210, first tap at x-2
+    planes = []
+    if c == 0:
+        planes = [raw[w * h:w * h + cw * ch], raw[w * h + cw * ch:]]
+    elif c in (1, 3):                                   # y4m_convert_42xmpeg2_42xjpeg, y4m_input.c:195-229
+        sh = ch if c == 1 else h
+        for pl in range(2):
+            src = raw[w * h + pl * cw * sh:w * h + (pl + 1) * cw * sh].reshape(sh, cw)
+            planes.append(_taps(src, 1, H6, -2).astype(np.uint8).ravel())
+    elif c == 2:                                        # y4m_convert_42xpaldv_42xjpeg, y4m_input.c:274-376
+        for pl in range(2):
+            src = raw[w * h + pl * cw * ch:w * h + (pl + 1) * cw * ch].reshape(ch, cw)
+            tmp = _taps(src, 1, H6, -2)
+            if pl == 0:                                 # Cb up a quarter pel: [1 -9 35 114 -17 4], first tap at y-3
+                out = _taps(tmp, 0, (1, -9, 35, 114, -17, 4), -3)
+            else:                                       # Cr down: the horizontal filter, vertically
+                out = _taps(tmp, 0, H6, -2)
+            planes.append(out.astype(np.uint8).ravel())
+    elif c == 4:                                        # y4m_convert_411_422jpeg, y4m_input.c:417-459
+        sw = (w + 3) // 4
+        for pl in range(2):
+            src = raw[w * h + pl * sw * h:w * h + (pl + 1) * sw * h].reshape(h, sw)
+            even = _taps(src, 1, (1, 110, 18, -1), -1)
+            odd = _taps(src, 1, (-3, 50, 86, -5), -1)
+            out = np.empty((h, cw), np.int64)
+            out[:, 0::2] = even[:, :(cw + 1) // 2]
+            out[:, 1::2] = odd[:, :cw // 2]
+            planes.append(out.astype(np.uint8).ravel())
+    elif c in (5, 6):                                   # y4m_convert_null on full-size planes
+        planes = [raw[w * h:2 * w * h], raw[2 * w * h:3 * w * h]]
+    else:                                               # y4m_convert_mono_420jpeg, y4m_input.c:463-471
+        planes = [np.full(cw * ch, 128, np.uint8)] * 2
+    return np.concatenate([y, planes[0][:cw * ch], planes[1][:cw * ch]])
+
+
+def write_y4m_raw(path: str, w: int, h: int, payloads, chroma: str, rate=(30000, 1001), frame_params: bytes = b"") -> None:
+    with open(path, "wb") as f:
+        f.write(f"YUV4MPEG2 W{w} H{h} F{rate[0]}:{rate[1]} Ip C{chroma}\n".encode())
+        for fr in payloads:
+            f.write(b"FRAME" + frame_params + b"\n")
+            f.write(np.ascontiguousarray(fr, dtype=np.uint8).tobytes())
+
+
+def ref_y4m_frames(path: str, w: int, h: int, max_frames: int = 1000) -> np.ndarray:
+    """The reference's OWN Y4M reader (vidinput.c / y4m_input.c in oracle/_ref/libp64ref.so) through oracle/ref_shim.c:
+    uint8 [n, w*h*3/2], what ReadIob hands the encoder."""
+    L = C.CDLL(os.path.join(REF_DIR, "libp64ref.so"))
+    L.ref_y4m_frames.restype = C.c_int
+    L.ref_y4m_frames.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    out = np.zeros((max_frames, w * h * 3 // 2), np.uint8)
+    n = L.ref_y4m_frames(path.encode(), max_frames, w, h, _p(out))
+    if n < 0:
+        raise RuntimeError("reference Y4M reader failed")
+    return out[:n].copy()
+
+
+# ------------------------------------------------------------------------------------------------
 # the compiled reference
 # ------------------------------------------------------------------------------------------------
 def have_ref() -> bool:

@@ -29,7 +29,13 @@ class EncParams(C.Structure):
     """p64b_enc_params"""
     _fields_ = [(n, C.c_int32) for n in ("image_type", "n_streams", "device", "start_frame", "initial_quant", "rate",
                                          "frame_rate", "frame_rate_div", "frame_skip", "me_mode", "search_limit",
-                                         "force_intra", "vlc_threads", "host_vlc")] + [("reserved", C.c_int32 * 2)]
+                                         "force_intra", "vlc_threads", "host_vlc", "input_chroma")] + [("reserved", C.c_int32 * 1)]
+
+
+class Y4mInfo(C.Structure):
+    """p64b_y4m_info"""
+    _fields_ = [(n, C.c_int32) for n in ("width", "height", "fps_n", "fps_d", "par_n", "par_d", "chroma", "interlace")] + \
+               [("frame_bytes", C.c_int64)]
 
 
 class BitsOut(C.Structure):
@@ -66,6 +72,15 @@ SIGNATURES = {
     "p64b_ctx_submit_bits": (_i, [_vp, C.POINTER(Step), _i, _vp, C.POINTER(C.c_int64)]),
     "p64b_ctx_wait_bits": (_i, [_vp, C.c_int64, C.POINTER(BitsOut)]),
     "p64b_ctx_set_rate_control": (_i, [_vp, C.POINTER(RateControl)]),
+    "p64b_raw_frame_bytes": (_i, [_i, _i]),
+    "p64b_ctx_set_input_chroma": (_i, [_vp, _i]),
+    "p64b_ctx_convert_frames": (_i, [_vp, _vp, _vp]),
+    "p64b_y4m_open": (_i, [C.POINTER(_vp), C.c_char_p]),
+    "p64b_y4m_close": (None, [_vp]),
+    "p64b_y4m_get_info": (_i, [_vp, C.POINTER(Y4mInfo)]),
+    "p64b_y4m_read_frame": (_i, [_vp, _vp]),
+    "p64b_y4m_payload_bytes": (C.c_int64, [_i, _i, _i]),
+    "p64b_enc_staging": (_vp, [_vp]),
     "p64b_ctx_frame_begin": (_i, [_vp, C.POINTER(Step), _vp]),
     "p64b_ctx_encode_gob": (_i, [_vp, C.POINTER(Step), _i, _vp, _vp, _vp]),
     "p64b_ctx_frame_end": (_i, [_vp, _vp]),

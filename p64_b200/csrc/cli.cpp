@@ -22,32 +22,6 @@ static void help() {
          "(motion estimation, DCT, quantisation, reconstruction) runs on the GPU. There is no CPU fallback.\n");
 }
 
-struct Y4m {
-  FILE* f = nullptr;
-  int w = 0, h = 0;
-  bool open(const char* path) {
-    f = strcmp(path, "-") ? fopen(path, "rb") : stdin;
-    if (!f) return false;
-    char hdr[256];
-    if (!fgets(hdr, sizeof hdr, f) || strncmp(hdr, "YUV4MPEG2", 9)) return false;
-    for (char* t = strtok(hdr + 9, " \n"); t; t = strtok(nullptr, " \n")) {
-      if (t[0] == 'W') w = atoi(t + 1);
-      else if (t[0] == 'H') h = atoi(t + 1);
-      else if (t[0] == 'C' && strcmp(t, "C420jpeg") && strcmp(t, "C420")) {
-        fprintf(stderr, "p64b: chroma format %s needs the reference's re-siting filters (y4m_input.c:195-545), not supported\n", t);
-        return false;
-      }
-    }
-    return w > 0 && h > 0;
-  }
-  bool frame(uint8_t* dst) {
-    char line[128];
-    if (!fgets(line, sizeof line, f) || strncmp(line, "FRAME", 5)) return false;
-    size_t n = (size_t)w * h * 3 / 2;
-    return fread(dst, 1, n, f) == n;
-  }
-};
-
 int main(int argc, char** argv) {
   p64b_enc_params p;
   p64b_enc_default_params(&p);
@@ -95,27 +69,32 @@ int main(int argc, char** argv) {
   p.start_frame = start;
   if (stream_file.empty()) stream_file = prefix + ".p64";
 
-  Y4m in;
+  // ingest: the library's Y4M reader fills the encoder's pinned staging buffer in place; chroma types other than
+  // 420jpeg are converted on the device (y4m_input.c:195-545)
+  p64b_y4m* in = nullptr;
   std::string path = prefix == "-" ? "-" : prefix + ".y4m";
-  if (!in.open(path.c_str())) { fprintf(stderr, "Unable to open '%s'.\n", path.c_str()); return -1; }
-  if (in.w != p64b_width(p.image_type) || in.h != p64b_height(p.image_type)) {
-    fprintf(stderr, "p64b: %dx%d input does not match the selected image type (%dx%d)\n", in.w, in.h,
+  if (p64b_y4m_open(&in, path.c_str())) { fprintf(stderr, "Unable to open '%s': %s\n", path.c_str(), p64b_last_error()); return -1; }
+  p64b_y4m_info info;
+  p64b_y4m_get_info(in, &info);
+  if (info.width != p64b_width(p.image_type) || info.height != p64b_height(p.image_type)) {
+    fprintf(stderr, "p64b: %dx%d input does not match the selected image type (%dx%d)\n", info.width, info.height,
             p64b_width(p.image_type), p64b_height(p.image_type));
     return 3;
   }
+  p.input_chroma = info.chroma;
   p64b_enc* enc = nullptr;
   if (p64b_enc_create(&enc, &p)) { fprintf(stderr, "p64b: %s\n", p64b_last_error()); return 2; }
-  std::vector<uint8_t> frame(p64b_frame_bytes(p.image_type));
+  uint8_t* frame = p64b_enc_staging(enc);
   for (int i = start; i > 0; --i)                           // seek to StartFrame (p64.c:562-565)
-    if (!in.frame(frame.data())) return 3;
+    if (p64b_y4m_read_frame(in, frame) != 1) return 3;
   if (p.rate) {
     printf("Rate: %d   QDFact: %d  QOffs: %d\n", p.rate, p.rate / 320, 1);
   }
   printf("START>SEQUENCE\n");
   for (int cf = start; cf <= last; cf += p.frame_skip) {
     printf("START>Frame: %d\n", cf);
-    if (!in.frame(frame.data())) { p64b_enc_destroy(enc); return 3; }
-    if (p64b_enc_encode(enc, frame.data())) { fprintf(stderr, "p64b: %s\n", p64b_last_error()); return 2; }
+    if (p64b_y4m_read_frame(in, frame) != 1) { p64b_enc_destroy(enc); return 3; }
+    if (p64b_enc_encode(enc, frame)) { fprintf(stderr, "p64b: %s\n", p64b_last_error()); return 2; }
     printf("END>Frame: %d\n", cf);
   }
   p64b_enc_finish(enc);
@@ -128,5 +107,6 @@ int main(int argc, char** argv) {
   printf("Bits for first frame: %lld   Number of buffer overflows: %lld\n", (long long)p64b_enc_first_frame_bits(enc, 0),
          (long long)p64b_enc_overflows(enc, 0));
   p64b_enc_destroy(enc);
+  p64b_y4m_close(in);
   return 0;
 }

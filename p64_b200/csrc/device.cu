@@ -9,6 +9,7 @@
 #include <utility>
 #include <vector>
 
+#include "ingest.cuh"
 #include "kernels.cuh"
 #include "vlc_kernels.cuh"
 
@@ -81,6 +82,10 @@ struct p64b_ctx {
   uint8_t* h_bits_out[NSLOT] = {};          // pinned; grown on demand
   size_t h_bits_cap[NSLOT] = {}, slot_copied[NSLOT] = {};
   size_t bits_budget = 0;                   // data bytes downloaded with the first copy (adapts to the last frame's size)
+  // ingest (p64b_ctx_set_input_chroma): host sources are unconverted Y4M payloads; chroma converted on the device
+  int chroma = P64B_CHROMA_420JPEG;
+  size_t raw_bytes = 0, aux_bytes = 0;      // per frame: whole payload; the part of its chroma the conversion reads
+  uint8_t* d_aux[NSLOT] = {};               // [S][aux_bytes] uploaded chroma payload per pipeline slot
   // rate control on the device (p64b_ctx_set_rate_control)
   p64b_rate_control rate{};                 // rate.rate == 0: off
   uint32_t* d_frame_bits = nullptr;         // [S] bits of the frame in flight so far
@@ -316,6 +321,7 @@ void p64b_ctx_destroy(p64b_ctx* c) {
     if (c->ev_d2h[i]) cudaEventDestroy(c->ev_d2h[i]);
   }
   cudaFree(c->d_vlc_tables); cudaFree(c->d_gob_words); cudaFree(c->d_gob_bits); cudaFree(c->d_carry); cudaFree(c->d_carry_len);
+  for (int i = 0; i < p64b_ctx::NSLOT; i++) cudaFree(c->d_aux[i]);
   cudaFree(c->d_bitpos); cudaFree(c->d_frame_bits); cudaFree(c->d_buffer_offset); cudaFree(c->d_overflows);
   for (int i = 0; i < p64b_ctx::NSLOT; i++) { cudaFree(c->d_bits_out[i]); if (c->h_bits_out[i]) cudaFreeHost(c->h_bits_out[i]); }
   if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
@@ -340,6 +346,32 @@ void* p64b_host_alloc(size_t bytes) {
 void p64b_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 static void swap_stores(p64b_ctx* c) { c->cur ^= 1; }    // SwapFS(CFS,OFS), p64.c:661
+
+// H2D of one step's host source frames into `dst` (a staging slot) on `copy_stream`.  420jpeg: one contiguous copy.
+// Otherwise the luma planes go straight into the frames and the chroma payload into the slot's aux buffer (two strided
+// copies); ingest_source() then converts it on the compute stream.
+static int upload_source(p64b_ctx* c, int slot, uint8_t* dst, const uint8_t* src, cudaStream_t copy_stream) {
+  const size_t fb = (size_t)c->g.frame_bytes, wh = (size_t)c->g.W * c->g.H;
+  if (c->chroma == P64B_CHROMA_420JPEG) {
+    CU(cudaMemcpyAsync(dst, src, (size_t)c->S * fb, cudaMemcpyHostToDevice, copy_stream));
+    return 0;
+  }
+  CU(cudaMemcpy2DAsync(dst, fb, src, c->raw_bytes, wh, (size_t)c->S, cudaMemcpyHostToDevice, copy_stream));
+  if (c->aux_bytes)
+    CU(cudaMemcpy2DAsync(c->d_aux[slot], c->aux_bytes, src + wh, c->raw_bytes, c->aux_bytes, (size_t)c->S, cudaMemcpyHostToDevice, copy_stream));
+  return 0;
+}
+static int ingest_source(p64b_ctx* c, int slot, uint8_t* dst) {
+  if (c->chroma == P64B_CHROMA_420JPEG) return 0;
+  IngestArgs a;
+  a.aux = c->d_aux[slot]; a.aux_stride = c->aux_bytes; a.dst = dst; a.dst_stride = (size_t)c->g.frame_bytes;
+  a.W = c->g.W; a.H = c->g.H; a.n_streams = c->S; a.chroma = c->chroma;
+  const long long threads = (long long)c->S * 2 * (c->g.H / 2) * (c->g.W / 8);
+  ingest_chroma_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(a);
+  c->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
 
 int p64b_ctx_encode_frames_dev(p64b_ctx* c, const p64b_step* st, const uint8_t* src_dev, p64b_mb* mbs_dev,
                                int8_t* levels_dev) {
@@ -373,9 +405,10 @@ int p64b_ctx_submit(p64b_ctx* c, const p64b_step* st, const uint8_t* src, p64b_m
     CU(cudaStreamWaitEvent(c->s_h2d, c->ev_comp[slot], 0));    // the slot's source was consumed by its last kernels
     CU(cudaStreamWaitEvent(c->stream, c->ev_d2h[slot], 0));    // its outputs were downloaded
   }
-  CU(cudaMemcpyAsync(c->p_src[slot], src, fb, cudaMemcpyHostToDevice, c->s_h2d));
+  if ((rc = upload_source(c, slot, c->p_src[slot], src, c->s_h2d))) return rc;
   CU(cudaEventRecord(c->ev_h2d[slot], c->s_h2d));
   CU(cudaStreamWaitEvent(c->stream, c->ev_h2d[slot], 0));
+  if ((rc = ingest_source(c, slot, c->p_src[slot]))) return rc;
   if ((rc = p64b_ctx_encode_frames_dev(c, st, c->p_src[slot], c->p_mbs[slot], c->p_levels[slot]))) return rc;
   CU(cudaEventRecord(c->ev_comp[slot], c->stream));
   CU(cudaStreamWaitEvent(c->s_d2h, c->ev_comp[slot], 0));
@@ -408,7 +441,7 @@ int p64b_ctx_frame_begin(p64b_ctx* c, const p64b_step* st, const uint8_t* src) {
   if ((rc = check_step(st)) || (rc = use_device(c))) return rc;
   CU(cudaStreamSynchronize(c->s_h2d));      // drain any pipelined steps still in flight (they share staging slot 0)
   CU(cudaStreamSynchronize(c->s_d2h));
-  CU(cudaMemcpyAsync(c->d_src, src, (size_t)c->S * c->g.frame_bytes, cudaMemcpyHostToDevice, c->stream));
+  if ((rc = upload_source(c, 0, c->d_src, src, c->stream)) || (rc = ingest_source(c, 0, c->d_src))) return rc;
   if (!st->first_frame) {
     if ((rc = launch_me(c, c->d_fs[c->cur], c->d_src, (size_t)c->g.frame_bytes, c->S, st->me_mode, st->search_limit, c->d_me))) return rc;
   } else {
@@ -567,6 +600,37 @@ static int ensure_host_bits(p64b_ctx* c, int slot, size_t bytes) {
   return 0;
 }
 
+extern "C" int p64b_ctx_set_input_chroma(p64b_ctx* c, int chroma) {
+  if (!c) { set_error("NULL argument"); return P64B_EINVAL; }
+  if (c->submitted || c->frame_src) { set_error("the input format must be configured before the first frame"); return P64B_EINVAL; }
+  const int raw = p64b_raw_frame_bytes(c->image_type, chroma);
+  if (raw < 0) { set_error("unknown chroma type"); return P64B_EINVAL; }
+  int rc;
+  if ((rc = use_device(c))) return rc;
+  const size_t wh = (size_t)c->g.W * c->g.H;
+  c->chroma = chroma; c->raw_bytes = (size_t)raw;
+  c->aux_bytes = chroma == P64B_CHROMA_444ALPHA ? 2 * wh : (size_t)raw - wh;       // the alpha plane is never uploaded
+  for (int i = 0; i < p64b_ctx::NSLOT; i++) {
+    cudaFree(c->d_aux[i]); c->d_aux[i] = nullptr;
+    if (chroma != P64B_CHROMA_420JPEG && c->aux_bytes)
+      if (cudaMalloc((void**)&c->d_aux[i], (size_t)c->S * c->aux_bytes + 64) != cudaSuccess) { set_error("cudaMalloc failed (ingest buffers)"); return P64B_ENOMEM; }
+  }
+  return 0;
+}
+
+extern "C" int p64b_ctx_convert_frames(p64b_ctx* c, const uint8_t* raw, uint8_t* out420) {
+  if (!c || !raw || !out420) { set_error("NULL argument"); return P64B_EINVAL; }
+  if (c->frame_src) { set_error("p64b_ctx_convert_frames inside frame_begin/frame_end"); return P64B_EINVAL; }
+  int rc;
+  if ((rc = use_device(c))) return rc;
+  CU(cudaStreamSynchronize(c->s_h2d));      // staging slot 0 may still be in use by pipelined steps
+  CU(cudaStreamSynchronize(c->stream));
+  if ((rc = upload_source(c, 0, c->d_src, raw, c->stream)) || (rc = ingest_source(c, 0, c->d_src))) return rc;
+  CU(cudaMemcpyAsync(out420, c->d_src, (size_t)c->S * c->g.frame_bytes, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
 extern "C" int p64b_ctx_set_rate_control(p64b_ctx* c, const p64b_rate_control* r) {
   if (!c || !r) { set_error("NULL argument"); return P64B_EINVAL; }
   if (c->submitted || c->frame_src) { set_error("rate control must be configured before the first frame"); return P64B_EINVAL; }
@@ -588,9 +652,10 @@ extern "C" int p64b_ctx_submit_bits(p64b_ctx* c, const p64b_step* st, int tempor
     CU(cudaStreamWaitEvent(c->s_h2d, c->ev_comp[slot], 0));    // the slot's source was consumed by its last kernels
     CU(cudaStreamWaitEvent(c->stream, c->ev_d2h[slot], 0));    // its outputs were downloaded
   }
-  CU(cudaMemcpyAsync(c->p_src[slot], src, fb, cudaMemcpyHostToDevice, c->s_h2d));
+  if ((rc = upload_source(c, slot, c->p_src[slot], src, c->s_h2d))) return rc;
   CU(cudaEventRecord(c->ev_h2d[slot], c->s_h2d));
   CU(cudaStreamWaitEvent(c->stream, c->ev_h2d[slot], 0));
+  if ((rc = ingest_source(c, slot, c->p_src[slot]))) return rc;
   // WritePictureHeader, marker.c:103-137: PSC(20) TR(5) PTYPE(6) [PEI=1 PSPARE(8) for NTSC, p64.c:408-423] PEI=0
   VlcFrameArgs f{};
   {

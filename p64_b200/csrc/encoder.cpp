@@ -33,6 +33,7 @@ struct p64b_enc {
   p64b_enc_params p{};
   p64b_ctx* ctx = nullptr;
   int S = 0, ngob = 0, nmb = 0, frame_bytes = 0;
+  int src_bytes = 0;             // bytes per stream of one input frame: frame_bytes, or the raw Y4M payload (input_chroma)
   int current_frame = 0;         // CurrentFrame (p64.c:121)
   int frames_done = 0;
   int qdfact = 1, qoffs = 1;     // QDFact, QOffs (p64.c:141-142)
@@ -101,6 +102,14 @@ int p64b_enc_create(p64b_enc** out, const p64b_enc_params* p) {
   if (rc) { delete e; return rc; }
   e->S = p->n_streams; e->ngob = p64b_num_gob(p->image_type); e->nmb = p64b_num_mb(p->image_type);
   e->frame_bytes = p64b_frame_bytes(p->image_type);
+  e->src_bytes = e->frame_bytes;
+  if (p->input_chroma != P64B_CHROMA_420JPEG) {      // ingest: chroma conversion on the device (y4m_input.c:195-545)
+    e->src_bytes = p64b_raw_frame_bytes(p->image_type, p->input_chroma);
+    if (e->src_bytes < 0 || (rc = p64b_ctx_set_input_chroma(e->ctx, p->input_chroma))) {
+      if (e->src_bytes < 0) p64b::set_error("unknown input chroma type");
+      p64b_ctx_destroy(e->ctx); delete e; return rc ? rc : P64B_EINVAL;
+    }
+  }
   e->current_frame = p->start_frame;
   int iq = p->initial_quant;                       // p64.c:574-590
   if (p->rate) {
@@ -112,7 +121,7 @@ int p64b_enc_create(p64b_enc** out, const p64b_enc_params* p) {
   for (auto& s : e->st) { s.bits = p64b_bits_create(p->image_type); s.gquant = iq; }
   e->h_mbs = (p64b_mb*)p64b_host_alloc((size_t)e->S * e->nmb * sizeof(p64b_mb));
   e->h_levels = (int8_t*)p64b_host_alloc((size_t)e->S * e->nmb * P64B_LEVELS_PER_MB);
-  e->h_src = (uint8_t*)p64b_host_alloc((size_t)e->S * e->frame_bytes);
+  e->h_src = (uint8_t*)p64b_host_alloc((size_t)e->S * e->src_bytes);
   if (!e->h_mbs || !e->h_levels || !e->h_src) { p64b_enc_destroy(e); return P64B_ENOMEM; }
   e->quant.assign(e->S, (uint8_t)iq);
   e->overflow.assign((size_t)e->S * e->nmb, 0);
@@ -145,7 +154,7 @@ int p64b_enc_encode(p64b_enc* e, const uint8_t* src) {
   step.first_frame = first; step.me_mode = e->p.me_mode; step.search_limit = e->p.search_limit;
   step.force_intra = e->p.force_intra;
   const int tr = e->current_frame % 32;            // p64.c:637
-  memcpy(e->h_src, src, (size_t)e->S * e->frame_bytes);
+  if (src != e->h_src) memcpy(e->h_src, src, (size_t)e->S * e->src_bytes);
   int rc;
   if (e->device_vlc) {
     // device-side entropy coding (and rate control, if any): one device step returns every stream's next whole bytes
@@ -247,6 +256,7 @@ const uint8_t* p64b_enc_data(const p64b_enc* e, int stream, size_t* nbytes) {
   return p64b_bits_data(e->st[stream].bits, nbytes);
 }
 p64b_ctx* p64b_enc_ctx(p64b_enc* e) { return e ? e->ctx : nullptr; }
+uint8_t* p64b_enc_staging(p64b_enc* e) { return e ? e->h_src : nullptr; }
 int64_t p64b_enc_overflows(const p64b_enc* e, int stream) {
   return (e && stream >= 0 && stream < e->S) ? e->st[stream].overflows : -1;
 }

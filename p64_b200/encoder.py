@@ -11,7 +11,9 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import MB, ME, BitsOut, EncParams, RateControl, Step, check
+from ._lib import MB, ME, BitsOut, EncParams, RateControl, Step, Y4mInfo, check
+
+CHROMA = {"420jpeg": 0, "420": 0, "420mpeg2": 1, "420paldv": 2, "422": 3, "411": 4, "444": 5, "444alpha": 6, "mono": 7}
 
 MB_DTYPE = np.dtype([("mtype", "u1"), ("cbp", "u1"), ("mvx", "i1"), ("mvy", "i1"), ("quant", "u1"),
                      ("nzmask", "u1"), ("reserved", "u2")])
@@ -63,7 +65,7 @@ class DeviceContext:
 
     def encode_frames(self, step: Step, src: np.ndarray):
         """src uint8 [n_streams, frame_bytes] (host) -> (mbs [S,nmb], levels int8 [S,nmb,6,64])."""
-        src = np.ascontiguousarray(src, np.uint8).reshape(self.n_streams, self.geom["frame_bytes"])
+        src = np.ascontiguousarray(src, np.uint8).reshape(self.n_streams, getattr(self, "raw_frame_bytes", self.geom["frame_bytes"]))
         mbs, levels = self._outputs(self.geom["num_mb"])
         check(self.L.p64b_ctx_encode_frames(self.h, C.byref(step), _ptr(src), _ptr(mbs), _ptr(levels)))
         return mbs, levels
@@ -73,6 +75,21 @@ class DeviceContext:
         t = C.c_int64()
         check(self.L.p64b_ctx_submit(self.h, C.byref(step), _ptr(src_ptr), _ptr(mbs_ptr), _ptr(levels_ptr), C.byref(t)))
         return t.value
+
+    def set_input_chroma(self, chroma):
+        """Host sources become unconverted Y4M payloads; the reader's chroma conversion (y4m_input.c:195-545) runs on the
+        device.  `chroma`: a Y4M C-tag name ("420mpeg2", ...) or a P64B_CHROMA_* id."""
+        cid = CHROMA[chroma] if isinstance(chroma, str) else int(chroma)
+        check(self.L.p64b_ctx_set_input_chroma(self.h, cid))
+        self.raw_frame_bytes = int(self.L.p64b_raw_frame_bytes(self.image_type, cid))
+
+    def convert_frames(self, raw: np.ndarray) -> np.ndarray:
+        """raw uint8 [n_streams, raw_frame_bytes] -> uint8 [n_streams, frame_bytes] (what ReadIob would install)"""
+        nb = getattr(self, "raw_frame_bytes", self.geom["frame_bytes"])
+        raw = np.ascontiguousarray(raw, np.uint8).reshape(self.n_streams, nb)
+        out = np.zeros((self.n_streams, self.geom["frame_bytes"]), np.uint8)
+        check(self.L.p64b_ctx_convert_frames(self.h, _ptr(raw), _ptr(out)))
+        return out
 
     def set_rate_control(self, rate: int, frame_rate=(30000, 1001), frame_skip: int = 1, qdfact: int = 0, qoffs: int = 1):
         """Rate control on the device for submit_bits (p64.c:233-237, 458-481, 776-783); QDFact defaults to Rate/320."""
@@ -205,7 +222,8 @@ class Encoder:
 
     def __init__(self, image_type: int, n_streams: int = 1, *, q: int = 0, rate: int = 0, me_mode: int = 0,
                  search_limit: int = 15, force_intra: bool = False, start_frame: int = 0, device: int = 0,
-                 frame_rate=(30000, 1001), frame_skip: int = 1, vlc_threads: int = 0, host_vlc: bool = False):
+                 frame_rate=(30000, 1001), frame_skip: int = 1, vlc_threads: int = 0, host_vlc: bool = False,
+                 input_chroma="420jpeg"):
         self.L = _lib.lib()
         p = default_params()
         p.image_type, p.n_streams, p.device, p.start_frame = image_type, n_streams, device, start_frame
@@ -213,8 +231,10 @@ class Encoder:
         p.force_intra, p.frame_rate, p.frame_rate_div, p.frame_skip = int(force_intra), frame_rate[0], frame_rate[1], frame_skip
         p.vlc_threads = vlc_threads
         p.host_vlc = int(host_vlc)
+        p.input_chroma = CHROMA[input_chroma] if isinstance(input_chroma, str) else int(input_chroma)
         self.n_streams = n_streams
         self.geom = geometry(image_type)
+        self.src_bytes = int(self.L.p64b_raw_frame_bytes(image_type, p.input_chroma))
         h = C.c_void_p()
         check(self.L.p64b_enc_create(C.byref(h), C.byref(p)))
         self.h = h
@@ -227,7 +247,7 @@ class Encoder:
     __del__ = close
 
     def encode(self, frames: np.ndarray):
-        frames = np.ascontiguousarray(frames, np.uint8).reshape(self.n_streams, self.geom["frame_bytes"])
+        frames = np.ascontiguousarray(frames, np.uint8).reshape(self.n_streams, self.src_bytes)
         check(self.L.p64b_enc_encode(self.h, _ptr(frames)))
 
     def finish(self):
@@ -243,6 +263,33 @@ class Encoder:
 
     def context_handle(self):
         return C.c_void_p(self.L.p64b_enc_ctx(self.h))
+
+
+class Y4mReader:
+    """p64b_y4m_*: the ingest path's YUV4MPEG2 reader (header / FRAME parsing as y4m_input.c:75-134, 556-586, 708-740)."""
+
+    def __init__(self, path: str):
+        self.L = _lib.lib()
+        h = C.c_void_p()
+        check(self.L.p64b_y4m_open(C.byref(h), path.encode()))
+        self.h = h
+        self.info = Y4mInfo()
+        check(self.L.p64b_y4m_get_info(self.h, C.byref(self.info)))
+
+    def read_frame(self):
+        """-> uint8 [frame_bytes] payload, or None at end of file"""
+        buf = np.empty(int(self.info.frame_bytes), np.uint8)
+        r = self.L.p64b_y4m_read_frame(self.h, _ptr(buf))
+        if r < 0:
+            check(r)
+        return buf if r == 1 else None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.p64b_y4m_close(self.h)
+            self.h = None
+
+    __del__ = close
 
 
 def encode_clip(image_type: int, clip: np.ndarray, **kw) -> bytes:

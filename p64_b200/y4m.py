@@ -62,10 +62,38 @@ def random_pair(image_type: int, seed: int, shift=(0, 0), noise: int = 4):
     return ref.astype(np.uint8), cur.astype(np.uint8)
 
 
-def write_y4m(path: str, image_type: int, frames: np.ndarray, rate=(30000, 1001)) -> None:
+def synth_payloads(image_type: int, n_frames: int, seed: int, chroma: str) -> np.ndarray:
+    """Seeded synthetic clip as unconverted Y4M frame payloads of chroma type `chroma` (uint8 [n_frames, payload]):
+    the luma of synth_clip(); chroma planes of the type's own shape (the 4:2:0 planes stretched, plus seeded noise so
+    the re-siting filters have something to do); an alpha ramp for 444alpha."""
+    w, h = DIMS[image_type]
+    base = synth_clip(image_type, n_frames, seed)
+    if chroma in ("420", "420jpeg"):
+        return base
+    rng = np.random.default_rng(seed + 7919)
+    cw, ch = w // 2, h // 2
+    shape = {"420mpeg2": (ch, cw), "420paldv": (ch, cw), "422": (h, cw), "411": (h, (w + 3) // 4), "444": (h, w),
+             "444alpha": (h, w), "mono": None}[chroma]
+    out = []
+    for f in range(n_frames):
+        parts = [base[f, :w * h]]
+        if shape is not None:
+            for pl in range(2):
+                c = base[f, w * h + pl * cw * ch:w * h + (pl + 1) * cw * ch].reshape(ch, cw).astype(np.int64)
+                c = np.repeat(c, shape[0] // ch, axis=0)
+                c = np.repeat(c, 2, axis=1) if shape[1] == w else (c[:, ::2] if shape[1] < cw else c)
+                c = np.clip(c + rng.integers(-24, 25, size=c.shape), 0, 255)
+                parts.append(c.astype(np.uint8).ravel())
+            if chroma == "444alpha":
+                parts.append((np.arange(w * h) % 251).astype(np.uint8))
+        out.append(np.concatenate(parts))
+    return np.stack(out)
+
+
+def write_y4m(path: str, image_type: int, frames: np.ndarray, rate=(30000, 1001), chroma: str = "420jpeg") -> None:
     w, h = DIMS[image_type]
     with open(path, "wb") as f:
-        f.write(f"YUV4MPEG2 W{w} H{h} F{rate[0]}:{rate[1]} Ip C420jpeg\n".encode())
+        f.write(f"YUV4MPEG2 W{w} H{h} F{rate[0]}:{rate[1]} Ip C{chroma}\n".encode())
         for fr in frames:
             f.write(b"FRAME\n")
             f.write(np.ascontiguousarray(fr, dtype=np.uint8).tobytes())

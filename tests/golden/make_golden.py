@@ -32,6 +32,14 @@ CASES = [
     ("cif12_r128000_tss", y4m.IT_CIF, 12, 1234, dict(rate=128000)),  # buffer-overflow branch (p64.c:776-783)
     ("cif12_r64000_full31", y4m.IT_CIF, 12, 1234, dict(rate=64000, full_search=True, search_limit=31)),
     ("qcif20_r64000_tss", y4m.IT_QCIF, 20, 4321, dict(rate=64000)),
+    # ingest: Y4M chroma types the reference's reader converts (y4m_input.c:195-545) before the encoder sees the frame
+    ("cif5_q8_tss_420mpeg2", y4m.IT_CIF, 5, 31, dict(q=8, chroma="420mpeg2")),
+    ("qcif6_q6_full31_420paldv", y4m.IT_QCIF, 6, 32, dict(q=6, full_search=True, search_limit=31, chroma="420paldv")),
+    ("cif4_q8_tss_422", y4m.IT_CIF, 4, 33, dict(q=8, chroma="422")),
+    ("qcif5_q8_tss_411", y4m.IT_QCIF, 5, 34, dict(q=8, chroma="411")),
+    ("qcif4_q8_tss_444", y4m.IT_QCIF, 4, 35, dict(q=8, chroma="444")),
+    ("ntsc3_q8_tss_444alpha", y4m.IT_NTSC, 3, 36, dict(q=8, chroma="444alpha")),
+    ("qcif5_r64000_tss_mono", y4m.IT_QCIF, 5, 37, dict(rate=64000, chroma="mono")),
 ]
 
 
@@ -41,9 +49,13 @@ def main():
     out = {}
     tmp = tempfile.mkdtemp()
     for name, it, nf, seed, kw in CASES:
-        clip = y4m.synth_clip(it, nf, seed)
-        y4m.write_y4m(f"{tmp}/c.y4m", it, clip)
+        kw = dict(kw)
+        chroma = kw.pop("chroma", "420jpeg")
+        clip = y4m.synth_payloads(it, nf, seed, chroma)
+        y4m.write_y4m(f"{tmp}/c.y4m", it, clip, chroma=chroma)
         log = O.ref_encode(f"{tmp}/c.y4m", f"{tmp}/o.p64", it, nf, **kw)
+        if chroma != "420jpeg":
+            kw["chroma"] = chroma
         data = open(f"{tmp}/o.p64", "rb").read()
         O.ref_decode(f"{tmp}/o.p64", f"{tmp}/dec")
         _, _, dec = y4m.read_y4m(f"{tmp}/dec.y4m")

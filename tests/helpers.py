@@ -15,7 +15,7 @@ GOLDEN = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)),
 
 def golden_clip(name):
     g = GOLDEN[name]
-    clip = y4m.synth_clip(g["image_type"], g["n_frames"], g["seed"])
+    clip = y4m.synth_payloads(g["image_type"], g["n_frames"], g["seed"], g["args"].get("chroma", "420jpeg"))
     assert hashlib.md5(clip.tobytes()).hexdigest() == g["clip_md5"], "synthetic clip generator drifted"
     return g, clip
 
@@ -24,7 +24,8 @@ def golden_kwargs(g):
     """reference CLI arguments of a golden case -> keyword arguments of p64_b200.encoder.Encoder"""
     a = g["args"]
     return dict(q=a.get("q", 0), rate=a.get("rate", 0), me_mode=1 if a.get("full_search") else 0,
-                search_limit=a.get("search_limit") or 15, force_intra=bool(a.get("intra_only")))
+                search_limit=a.get("search_limit") or 15, force_intra=bool(a.get("intra_only")),
+                **({"input_chroma": a["chroma"]} if a.get("chroma") else {}))
 
 
 def recs_to_mb(recs):
@@ -39,8 +40,11 @@ def levels_to_i8(levels):
 
 
 def oracle_encode_stream(image_type, clip, *, q=0, rate=0, me_mode=0, search_limit=15, force_intra=False,
-                         frame_rate=(30000, 1001), frame_skip=1, start_frame=0):
-    """Returns (.p64 bytes, per-frame recon list, overflow count)."""
+                         frame_rate=(30000, 1001), frame_skip=1, start_frame=0, input_chroma=None):
+    """Returns (.p64 bytes, per-frame recon list, overflow count).  input_chroma: `clip` holds unconverted Y4M payloads."""
+    if input_chroma:
+        w, h = y4m.DIMS[image_type]
+        clip = np.stack([O.y4m_payload_to_encoder_frame(fr, w, h, input_chroma) for fr in clip])
     enc = O.Encoder(image_type)
     bw = BitWriter(image_type)
     ngob = enc.ngob
