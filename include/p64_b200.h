@@ -219,6 +219,11 @@ int p64b_ctx_download_recon(p64b_ctx *ctx, int stream, uint8_t *yuv);
 int p64b_ctx_last_intra(p64b_ctx *ctx, int stream, uint8_t *out);
 /* number of kernel launches issued by this context so far */
 int64_t p64b_ctx_launches(const p64b_ctx *ctx);
+/* Packed 4-byte SAD operations (VABSDIFF4.U8.ACC lane-instructions) the motion-estimation kernel has EXECUTED so far in
+ * its search sweeps, counted on the device; reset != 0 zeroes the counter.  The exhaustive search leaves a pass early when
+ * no candidate of the pass can still win (the warp-wide form of ComputeError's early exit, me.c:122-170), so this is what
+ * the issue-rate roofline is measured with; the algorithmic count (every legal candidate in full) is content independent. */
+int p64b_ctx_me_executed(p64b_ctx *ctx, uint64_t *packed_sad_ops, int reset);
 /* Per-kernel device timing (CUDA events on the launching stream around every launch) for the roofline report.
  * profile(ctx,1) clears and starts recording, profile(ctx,0) stops; profile_read sums the recorded launches:
  * ms_total[3], count[3] -- index 0 = motion-estimation kernel, 1 = macroblock (DCT/quant/recon) kernel,
@@ -228,6 +233,9 @@ int p64b_ctx_profile_read(p64b_ctx *ctx, double *ms_total, int32_t *count);
 /* Measured issue peak of the packed 4-byte SAD instruction (VABSDIFF4.U8.ACC) on this device, in
  * packed ops per second: the denominator of the ME roofline (no datasheet figure exists). */
 int p64b_measure_sad_peak(int device, double *ops_per_s, double *sm_clock_mhz);
+/* Measured host-to-device copy rate (GB/s) of `reps` back-to-back copies of `bytes` from `host` (pinned): the ceiling of
+ * the upload-bound end-to-end path. */
+int p64b_measure_h2d(int device, const void *host, size_t bytes, int reps, double *gb_per_s);
 
 /* ---------------------------------------------------------------------------------------------
  * (2) host bit stream: headers + VLC (marker.c, codec.c, huffman.c, stream.c)

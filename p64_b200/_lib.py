@@ -90,9 +90,11 @@ SIGNATURES = {
     "p64b_ctx_download_recon": (_i, [_vp, _i, _vp]),
     "p64b_ctx_last_intra": (_i, [_vp, _i, _vp]),
     "p64b_ctx_launches": (C.c_int64, [_vp]),
+    "p64b_ctx_me_executed": (_i, [_vp, C.POINTER(C.c_uint64), _i]),
     "p64b_ctx_profile": (_i, [_vp, _i]),
     "p64b_ctx_profile_read": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
     "p64b_measure_sad_peak": (_i, [_i, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "p64b_measure_h2d": (_i, [_i, _vp, _sz, _i, C.POINTER(C.c_double)]),
     "p64b_bits_create": (_vp, [_i]),
     "p64b_bits_destroy": (None, [_vp]),
     "p64b_bits_picture_header": (None, [_vp, _i]),

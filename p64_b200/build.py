@@ -33,18 +33,19 @@ def _stale(target: str, deps) -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build_lib(force: bool = False, verbose: bool = False) -> str:
+def build_lib(force: bool = False, verbose: bool = False, out: str = LIB, defines=()) -> str:
+    """`out` / `defines` (-D...) build experiment variants next to the product library (selected with P64B_LIB)."""
     srcs = [os.path.join(CSRC, s) for s in LIB_SOURCES]
     deps = srcs + [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
-    if force or _stale(LIB, deps):
+    if force or _stale(out, deps):
         cmd = [_nvcc(), *ARCH, "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-Wall", "-shared",
-               "-Xptxas", "-v" if verbose else "-warn-spills", "-o", LIB, *srcs, "-lpthread"]
+               "-Xptxas", "-v" if verbose else "-warn-spills", *[f"-D{d}" for d in defines], "-o", out, *srcs, "-lpthread"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if verbose or r.returncode:
             sys.stderr.write(r.stdout + r.stderr)
         if r.returncode:
             raise RuntimeError("nvcc failed building libp64b200.so")
-    return LIB
+    return out
 
 
 def build_cli(force: bool = False) -> str:

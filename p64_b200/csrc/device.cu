@@ -194,6 +194,7 @@ static int launch_me(p64b_ctx* c, const uint8_t* ref, const uint8_t* cur, size_t
   a.magic_pp = (uint32_t)(((1ull << (32 + sh)) + per_pair - 1) / per_pair);
   a.magic_w = 65536u / (uint32_t)a.mbw + 1u;               // r / mbw for r < per_pair <= 1024
   a.queue = c->d_me_queue; a.parity = (int)(c->me_launches++ & 1);
+  a.executed = reinterpret_cast<unsigned long long*>(c->d_me_queue + 2);
   a.m8 = 1u << 8; a.m16 = 1u << 16; a.m24 = 1u << 24; a.m2048 = 2048u;
   ProfScope ps(c, 0);
   if (surf)                          me_search_kernel<ME_V_SURF><<<grid, ME_THREADS, ME_SMEM_SURF, c->stream>>>(tm_ref, tm_cur, a);
@@ -285,7 +286,7 @@ int p64b_ctx_create(p64b_ctx** out, int device, int image_type, int n_streams) {
   ALLOC(c->d_levels, nm * P64B_LEVELS_PER_MB);
   ALLOC(c->d_quant, (size_t)n_streams);
   ALLOC(c->d_ovf, nm);
-  ALLOC(c->d_me_queue, 2 * sizeof(uint32_t));
+  ALLOC(c->d_me_queue, 4 * sizeof(uint32_t));   // two work counters + the 64-bit executed-work counter
   c->p_src[0] = c->d_src; c->p_mbs[0] = c->d_mbs; c->p_levels[0] = c->d_levels;
   for (int i = 1; i < p64b_ctx::NSLOT; i++) {
     ALLOC(c->p_src[i], fb + slack);
@@ -538,6 +539,18 @@ int p64b_ctx_last_intra(p64b_ctx* c, int stream, uint8_t* out) {
 
 int64_t p64b_ctx_launches(const p64b_ctx* c) { return c ? c->launches : 0; }
 
+int p64b_ctx_me_executed(p64b_ctx* c, uint64_t* packed_sad_ops, int reset) {
+  if (!c || !packed_sad_ops) { set_error("NULL argument"); return P64B_EINVAL; }
+  int rc;
+  if ((rc = use_device(c))) return rc;
+  CU(cudaStreamSynchronize(c->stream));
+  unsigned long long rows = 0;
+  CU(cudaMemcpy(&rows, c->d_me_queue + 2, sizeof rows, cudaMemcpyDeviceToHost));
+  if (reset) CU(cudaMemset(c->d_me_queue + 2, 0, sizeof rows));
+  *packed_sad_ops = (uint64_t)rows * 32u * 4u;      // a candidate row = 4 packed SADs in each of the warp's 32 lanes
+  return 0;
+}
+
 int p64b_ctx_profile(p64b_ctx* c, int enable) {
   if (!c) return P64B_EINVAL;
   int rc;
@@ -773,6 +786,31 @@ extern "C" int p64b_ctx_wait_bits(p64b_ctx* c, int64_t ticket, p64b_bits_out* ou
   out->data = b + doff;
   out->total_bytes = total;
   out->downloaded_bytes = c->slot_copied[slot];
+  return 0;
+}
+
+// Host-to-device copy rate of `bytes` from (pinned) host memory, `reps` copies back to back on one stream: what the PCIe
+// link gives the upload-bound end-to-end path.
+int p64b_measure_h2d(int device, const void* host, size_t bytes, int reps, double* gb_per_s) {
+  if (!host || !gb_per_s || !bytes || reps < 1) return P64B_EINVAL;
+  CU(cudaSetDevice(device));
+  void* d = nullptr;
+  CU(cudaMalloc(&d, bytes));
+  cudaStream_t st;
+  CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int r = 0; r < 3; r++) {
+    CU(cudaEventRecord(e0, st));
+    for (int i = 0; i < reps; i++) CU(cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, st));
+    CU(cudaEventRecord(e1, st));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0; CU(cudaEventElapsedTime(&ms, e0, e1));
+    if (ms < best) best = ms;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaStreamDestroy(st); cudaFree(d);
+  *gb_per_s = (double)bytes * reps / (best * 1e-3) / 1e9;
   return 0;
 }
 

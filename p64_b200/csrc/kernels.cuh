@@ -77,6 +77,7 @@ struct MeArgs {
   uint32_t m8, m16, m24, m2048;   // 1<<8, 1<<16, 1<<24, 2048 in registers: keeps those multiplies on the FMA pipe
   p64b_me* out;
   uint32_t* surface;
+  unsigned long long* executed;   // += candidate rows accumulated per lane, summed over warps (nullptr: not counted)
 };
 
 __device__ __forceinline__ uint32_t sad4(uint32_t a, uint32_t b, uint32_t c) {
@@ -115,26 +116,70 @@ constexpr int ME_V_FULL = 0, ME_V_SURF = 1, ME_V_TSS = 2;
 // One pass: this thread's NC candidates at dy positions yb .. yb+NC-1 (accumulators start at 0 or ME_ILLEGAL from the
 // row table).  Returns min_j (SAD_j << 11 | yb + j): the dy part of the exhaustive-search key.  ME_V_SURF also
 // stores the legal entries into the surface.
-template <int VARIANT, int NC>
-__device__ __forceinline__ uint32_t sweep_pass(const uint32_t* __restrict__ colbase, const uint32_t (&c)[16][4],
-                                               const uint32_t* pen, uint32_t* s_sad, int xi, int yb, bool xok,
-                                               uint32_t m2048) {
-  const uint32_t* base = colbase + yb * ME_ROW_WORDS;
-  uint32_t a[NC];
+//
+// PRUNE (exhaustive search only): the reference's ComputeError leaves a candidate as soon as its partial sum reaches the
+// best SAD so far (me.c:65, 122, 133, 170) -- which never changes a decision, because acceptance needs a strictly smaller
+// FULL sum (me.c:220).  The warp-wide form of that early exit: the pass first accumulates block rows 0..R1-1 of all its
+// candidates, and if every legal candidate of every lane is already strictly above `bound` (the smallest full SAD
+// found so far, SAD(0,0) included) none of them can win or tie, and the remaining rows are skipped.  There are two such
+// check points (after R1 and R2 rows).  Exact for any content; on content without a good match nothing is skipped and a
+// pass costs 2 (NC-1) extra row loads.
+#ifndef P64B_ME_PRUNE_R1
+#define P64B_ME_PRUNE_R1 4
+#endif
+#ifndef P64B_ME_PRUNE_R2
+#define P64B_ME_PRUNE_R2 8
+#endif
+constexpr int ME_PRUNE_R1 = P64B_ME_PRUNE_R1, ME_PRUNE_R2 = P64B_ME_PRUNE_R2;   // check points (block rows done); R2 == R1: one check
+
+// block rows [R0, R1) of all NC candidates: window rows R0 .. R1-1+NC-1
+template <int NC, int R0, int R1>
+__device__ __forceinline__ void sweep_rows(const uint32_t* __restrict__ base, const uint32_t (&c)[16][4], uint32_t (&a)[NC]) {
 #pragma unroll
-  for (int j = 0; j < NC; j++) a[j] = pen[yb + j];
-#pragma unroll
-  for (int t = 0; t < 15 + NC; t++) {
+  for (int t = R0; t < R1 - 1 + NC; t++) {
     const uint32_t r0 = base[t * ME_ROW_WORDS + 0], r1 = base[t * ME_ROW_WORDS + 1];
     const uint32_t r2 = base[t * ME_ROW_WORDS + 2], r3 = base[t * ME_ROW_WORDS + 3];
 #pragma unroll
     for (int j = 0; j < NC; j++) {
       const int i = t - j;
-      if (i >= 0 && i < 16) {
+      if (i >= R0 && i < R1) {
         a[j] = sad4(r0, c[i][0], a[j]); a[j] = sad4(r1, c[i][1], a[j]);
         a[j] = sad4(r2, c[i][2], a[j]); a[j] = sad4(r3, c[i][3], a[j]);
       }
     }
+  }
+}
+template <int NC>
+__device__ __forceinline__ bool sweep_hopeless(const uint32_t (&a)[NC], bool xok, uint32_t bound) {
+  uint32_t m = a[0];
+#pragma unroll
+  for (int j = 1; j < NC; j++) m = min(m, a[j]);
+  return __reduce_min_sync(0xffffffffu, xok ? m : 0xffffffffu) > bound;
+}
+
+template <int VARIANT, int NC, bool PRUNE>
+__device__ __forceinline__ uint32_t sweep_pass(const uint32_t* __restrict__ colbase, const uint32_t (&c)[16][4],
+                                               const uint32_t* pen, uint32_t* s_sad, int xi, int yb, bool xok,
+                                               uint32_t m2048, uint32_t bound, uint32_t& units) {
+  const uint32_t* base = colbase + yb * ME_ROW_WORDS;
+  uint32_t a[NC];
+#pragma unroll
+  for (int j = 0; j < NC; j++) a[j] = pen[yb + j];
+  if (PRUNE) {
+    constexpr int R1 = ME_PRUNE_R1, R2 = ME_PRUNE_R2;
+    sweep_rows<NC, 0, R1>(base, c, a);
+    units += (uint32_t)(NC * R1);
+    if (sweep_hopeless<NC>(a, xok, bound)) return 0xffffffffu;
+    if (R2 > R1) {
+      sweep_rows<NC, R1, R2>(base, c, a);
+      units += (uint32_t)(NC * (R2 - R1));
+      if (sweep_hopeless<NC>(a, xok, bound)) return 0xffffffffu;
+    }
+    sweep_rows<NC, R2, 16>(base, c, a);
+    units += (uint32_t)(NC * (16 - R2));
+  } else {
+    sweep_rows<NC, 0, 16>(base, c, a);
+    units += (uint32_t)(NC * 16);
   }
   if (VARIANT == ME_V_SURF) {
 #pragma unroll
@@ -194,6 +239,7 @@ me_search_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_consta
     ticket = atomicAdd(a.queue + a.parity, 1u);
   }
 
+  uint32_t units = 0;                             // candidate rows (16 pixels each) this warp's lanes actually accumulated
   for (int it = 0; n < total; it++) {
     // ---- the warp's next macroblock: start its loads into the other buffer, request the one after it
     const int b = it & 1;
@@ -265,9 +311,23 @@ me_search_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_consta
     if (VARIANT != ME_V_TSS) {
       const int o = xi + 1, k = o & 3;                             // o = dx + 16
       const uint32_t* colbase = (k ? shifted + (k - 1) * ME_COPY_WORDS : win) + (o >> 2);
-      for (int done = 0; done < rpg;) {
-        if (rpg - done > 5) { best = min(best, sweep_pass<VARIANT, 10>(colbase, c, pen, s_sad, xi, min(ystart + done, 22), xok, a.m2048)); done += 10; }
-        else                { best = min(best, sweep_pass<VARIANT, 5>(colbase, c, pen, s_sad, xi, min(ystart + done, 27), xok, a.m2048)); done += 5; }
+      // passes of 10 (a last one of 5) dy rows.  Exhaustive search: the pass that holds dy = 0 goes first, then outwards, so
+      // that the bound of the early exit is good as soon as possible (the order of evaluation does not matter: the
+      // winner is the minimum of a key that carries the reference's scan order).  The two-half mapping of edge columns
+      // keeps the plain order (the halves would disagree about the centre; control flow must stay warp-uniform).
+      constexpr bool PR = VARIANT == ME_V_FULL;
+      const int np = rpg <= 0 ? 0 : (rpg - 1) / 10 + 1;                 // passes k = 0..np-1 start at row 10k
+      const int kc = (PR && !xr) ? min(max((15 - lylo) / 10, 0), max(np - 1, 0)) : 0;
+      uint32_t bound = omv;                                             // smallest full SAD so far
+      for (int v = 0; v < 2 * np; v++) {
+        const int k = (PR && !xr) ? kc + ((v + 1) >> 1) * ((v & 1) ? -1 : 1) : v;
+        if (k < 0 || k >= np) continue;
+        const int done = 10 * k;
+        uint32_t r;
+        if (rpg - done > 5) r = sweep_pass<VARIANT, 10, PR>(colbase, c, pen, s_sad, xi, min(ystart + done, 22), xok, a.m2048, bound, units);
+        else                r = sweep_pass<VARIANT, 5, PR>(colbase, c, pen, s_sad, xi, min(ystart + done, 27), xok, a.m2048, bound, units);
+        best = min(best, r);
+        if (PR) bound = min(bound, __reduce_min_sync(0xffffffffu, xok ? r : 0xffffffffu) >> 11);
       }
     }
 
@@ -286,7 +346,7 @@ me_search_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_consta
     if (full) {
       // FastBME (me.c:206-227) scans dx outer, dy inner with strict <, after probing (0,0): winner = min of
       // SAD<<11 | (1 + (dx+15)*32 + (dy+15)); (0,0) enters with order 0 so that it wins ties
-      best = xok ? best + (uint32_t)(1 + xi * 32) : 0xffffffffu;
+      best = (xok && best != 0xffffffffu) ? best + (uint32_t)(1 + xi * 32) : 0xffffffffu;     // (all passes may have been left early)
       best = min(__reduce_min_sync(0xffffffffu, best), omv << 11);
       mv = best >> 11;
       const int ord = best & 2047;
@@ -377,6 +437,8 @@ me_search_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_consta
     __syncwarp();          // every lane is done with this buffer and the shifted copies
     n = n_next;
   }
+  // executed work of this launch, in warp-wide candidate rows (x 32 lanes x 4 packed SADs): the roofline's numerator
+  if (a.executed && lane == 0) atomicAdd(a.executed, (unsigned long long)units);
 }
 
 // ---------------------------------------------------------------------------------------------------

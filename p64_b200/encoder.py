@@ -158,6 +158,12 @@ class DeviceContext:
         check(self.L.p64b_ctx_last_intra(self.h, stream, _ptr(out)))
         return out
 
+    def me_executed(self, reset: bool = False) -> int:
+        """packed SAD operations the ME kernel's sweeps have executed so far (device counter)"""
+        n = C.c_uint64()
+        check(self.L.p64b_ctx_me_executed(self.h, C.byref(n), int(reset)))
+        return int(n.value)
+
     def profile(self, enable: bool):
         check(self.L.p64b_ctx_profile(self.h, int(enable)))
 
