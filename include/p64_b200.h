@@ -215,6 +215,20 @@ int p64b_ctx_me_records(p64b_ctx *ctx, int stream, p64b_me *out);
 /* The current reference frame store (= last reconstructed frame, CFS after SwapFS), for -l statistics
  * (stat.c:52) and closed-loop tests. */
 int p64b_ctx_download_recon(p64b_ctx *ctx, int stream, uint8_t *yuv);
+/* Frame statistics (Statistics / StatisticsMem, stat.c:52-130, printed by -l): the exact integer sums of
+ * the last coded frame of every stream, source frame vs its reconstruction (CFS after SwapFS), per plane Y, Cb, Cr --
+ * accumulated on the device; p64b_stat_from_sums() turns one record into the doubles the reference prints. */
+typedef struct p64b_plane_stats {
+  uint64_t n;            /* samples: width*height of the plane (top)                      */
+  uint64_t sum_src;      /* sum of the source samples             (rvalue,   stat.c:97)  */
+  uint64_t sum_rec;      /* sum of the reconstructed samples      (value,    stat.c:98)  */
+  uint64_t sum_sq_err;   /* sum of (reconstruction - source)^2    (squared,  stat.c:99)  */
+  uint64_t sum_sq_src;   /* sum of source^2                       (rsquared, stat.c:100) */
+  uint32_t hist[256];    /* histogram of the reconstruction       (Values,   stat.c:102) */
+} p64b_plane_stats;
+typedef struct p64b_stat { double mean, mse, snr, mrsnr, psnr, entropy; } p64b_stat;   /* STAT, globals.h */
+int p64b_ctx_statistics(p64b_ctx *ctx, p64b_plane_stats *out /* [n_streams][3] */);
+void p64b_stat_from_sums(const p64b_plane_stats *sums, p64b_stat *out);
 /* LastIntra counters [num_mb] GOB-major (p64.c:213). */
 int p64b_ctx_last_intra(p64b_ctx *ctx, int stream, uint8_t *out);
 /* number of kernel launches issued by this context so far */
@@ -258,7 +272,22 @@ int64_t p64b_bits_tell(const p64b_bits *b);
 /* mwclose, stream.c:142-152: pad the last byte with 1-bits. Returns the byte count. */
 size_t p64b_bits_finish(p64b_bits *b);
 const uint8_t *p64b_bits_data(const p64b_bits *b, size_t *nbytes);
-/* per-category bit counters of the current frame (p64.c:1299-1332 statistics) */
+/* The per-frame counters PrintFrameStatistics() reports (p64.c:198-211, 640-649, 1299-1332), accumulated by
+ * p64b_bits_mb() since the last p64b_bits_counters_reset(). */
+typedef struct p64b_frame_counters {
+  int32_t mb_attribute_bits;    /* MacroAttributeBits, marker.c:354 */
+  int32_t mv_bits;              /* MotionVectorBits,   marker.c:344 */
+  int32_t eob_bits;             /* EOBBits,            codec.c:129, 204 */
+  int32_t y_bits, u_bits, v_bits;   /* Y/U/VCoefBits,  p64.c:949-951 */
+  int32_t number_nz;            /* NumberNZ,           codec.c:125, 169, 200, 351 */
+  int32_t q_sum, q_use;         /* QSum, QUse,         p64.c:804-805 */
+  int32_t macro_type_freq[10], y_type_freq[10], uv_type_freq[10];   /* p64.c:807, 937-938 */
+  int32_t total_bits, last_bits;            /* TotalBits, LastBits (p64.c:654-658); filled by p64b_enc_frame_counters */
+  int32_t buffer_contents, buffer_size;     /* BufferContents(), BufferSize() as printed under -r (p64.c:1304-1308) */
+} p64b_frame_counters;
+void p64b_bits_counters(const p64b_bits *b, p64b_frame_counters *out);
+void p64b_bits_counters_reset(p64b_bits *b);
+/* empties the writer (bytes, predictors, counters) */
 void p64b_bits_reset(p64b_bits *b);
 
 /* ---------------------------------------------------------------------------------------------
@@ -322,6 +351,9 @@ p64b_ctx *p64b_enc_ctx(p64b_enc *e);
 /* Statistics the reference prints: buffer overflows (p64.c:779), bits of the first frame (p64.c:668). */
 int64_t p64b_enc_overflows(const p64b_enc *e, int stream);
 int64_t p64b_enc_first_frame_bits(const p64b_enc *e, int stream);
+/* PrintFrameStatistics()'s counters for the frame just coded (-l).  Needs host_vlc = 1 (the categories are counted by
+ * the host bit writer); P64B_EINVAL otherwise. */
+int p64b_enc_frame_counters(const p64b_enc *e, int stream, p64b_frame_counters *out);
 
 #ifdef __cplusplus
 }

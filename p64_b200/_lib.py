@@ -46,6 +46,24 @@ class BitsOut(C.Structure):
                 ("gquant", C.POINTER(C.c_uint32)), ("overflows", C.POINTER(C.c_uint32))]
 
 
+class PlaneStats(C.Structure):
+    """p64b_plane_stats"""
+    _fields_ = [(n, C.c_uint64) for n in ("n", "sum_src", "sum_rec", "sum_sq_err", "sum_sq_src")] + [("hist", C.c_uint32 * 256)]
+
+
+class Stat(C.Structure):
+    """p64b_stat"""
+    _fields_ = [(n, C.c_double) for n in ("mean", "mse", "snr", "mrsnr", "psnr", "entropy")]
+
+
+class FrameCounters(C.Structure):
+    """p64b_frame_counters"""
+    _fields_ = [(n, C.c_int32) for n in ("mb_attribute_bits", "mv_bits", "eob_bits", "y_bits", "u_bits", "v_bits",
+                                         "number_nz", "q_sum", "q_use")] + \
+               [(n, C.c_int32 * 10) for n in ("macro_type_freq", "y_type_freq", "uv_type_freq")] + \
+               [(n, C.c_int32) for n in ("total_bits", "last_bits", "buffer_contents", "buffer_size")]
+
+
 class RateControl(C.Structure):
     """p64b_rate_control"""
     _fields_ = [(n, C.c_int32) for n in ("rate", "frame_rate", "frame_rate_div", "frame_skip", "qdfact", "qoffs")] + \
@@ -89,6 +107,8 @@ SIGNATURES = {
     "p64b_ctx_me_records": (_i, [_vp, _i, _vp]),
     "p64b_ctx_download_recon": (_i, [_vp, _i, _vp]),
     "p64b_ctx_last_intra": (_i, [_vp, _i, _vp]),
+    "p64b_ctx_statistics": (_i, [_vp, _vp]),
+    "p64b_stat_from_sums": (None, [C.POINTER(PlaneStats), C.POINTER(Stat)]),
     "p64b_ctx_launches": (C.c_int64, [_vp]),
     "p64b_ctx_me_executed": (_i, [_vp, C.POINTER(C.c_uint64), _i]),
     "p64b_ctx_profile": (_i, [_vp, _i]),
@@ -105,6 +125,9 @@ SIGNATURES = {
     "p64b_bits_finish": (_sz, [_vp]),
     "p64b_bits_data": (C.POINTER(C.c_uint8), [_vp, C.POINTER(_sz)]),
     "p64b_bits_reset": (None, [_vp]),
+    "p64b_bits_counters": (None, [_vp, C.POINTER(FrameCounters)]),
+    "p64b_bits_counters_reset": (None, [_vp]),
+    "p64b_enc_frame_counters": (_i, [_vp, _i, C.POINTER(FrameCounters)]),
     "p64b_enc_default_params": (None, [C.POINTER(EncParams)]),
     "p64b_enc_create": (_i, [C.POINTER(_vp), C.POINTER(EncParams)]),
     "p64b_enc_destroy": (None, [_vp]),

@@ -67,6 +67,7 @@ struct p64b_bits {
   int nacc = 0;       // number of pending bits (< 8 after every put)
   // MB-header predictors (marker.c:63-68, p64.c:716)
   int last_mba = -1, last_mtype = 0, last_mvx = 0, last_mvy = 0;
+  p64b_frame_counters cnt{};   // the reference's per-frame statistics counters (p64.c:198-211, 640-649)
 
   inline void put(uint32_t v, int n) {         // mputv, stream.c:193-205 (n <= 32)
     acc = (acc << n) | (uint64_t)(v & (n >= 32 ? 0xffffffffu : ((1u << n) - 1)));
@@ -117,10 +118,14 @@ void p64b_bits_mb(p64b_bits* b, int mdu, const p64b_mb* rec, const int8_t* level
   const Tables& t = T();
   const int mt = rec->mtype;
   const int mba = mdu - b->last_mba;                  // p64.c:928
+  p64b_frame_counters& cn = b->cnt;
+  const int64_t start = b->tell();
+  int64_t mv0 = start, mv1 = start;
   b->put(t.mba[mba]);
   b->put(t.mtype[mt]);
   if (kQuantM[mt]) b->put(rec->quant, 5);
   if (kMfM[mt]) {                                     // marker.c:310-338
+    mv0 = b->tell();
     int h = rec->mvx, v = rec->mvy;
     if (!kMfM[b->last_mtype] || mba != 1 || b->last_mba == -1 || b->last_mba == 10 || b->last_mba == 21) {
       b->put(t.mvd[h & 31]); b->put(t.mvd[v & 31]);
@@ -133,23 +138,31 @@ void p64b_bits_mb(p64b_bits* b, int mdu, const p64b_mb* rec, const int8_t* level
       b->put(t.mvd[dh & 31]); b->put(t.mvd[dv & 31]);
     }
     b->last_mvx = h; b->last_mvy = v;
+    mv1 = b->tell();
   } else {
     b->last_mvx = b->last_mvy = 0;
   }
   if (kCbpM[mt]) b->put(t.cbp[rec->cbp]);
   b->last_mba = mdu;
   b->last_mtype = mt;
+  cn.mv_bits += (int32_t)(mv1 - mv0);                 // MotionVectorBits, marker.c:344
+  cn.mb_attribute_bits += (int32_t)(b->tell() - start);   // MacroAttributeBits, marker.c:354
+  cn.q_use++; cn.q_sum += rec->quant;                 // p64.c:804-805
+  if (mt < 10) cn.macro_type_freq[mt]++;              // p64.c:806-807
   if (!kTcoefM[mt]) return;
   for (int c = 0; c < 6; c++) {                       // p64.c:931-950
     if (!(rec->cbp & (1 << (5 - c)))) continue;
     const int8_t* l = levels + 64 * c;
     int k = 0;
     bool first = false;
+    (c < 4 ? cn.y_type_freq : cn.uv_type_freq)[mt]++;     // p64.c:937-938
+    const int64_t bstart = b->tell();
     if (kCbpM[mt]) first = true;                      // CBPEncodeAC(0,.)  codec.c:140-205
     else {                                            // EncodeDC + EncodeAC(1,.)  codec.c:346-355, 96-130
       int dc = (uint8_t)l[0];
       if (dc > 254) dc = 254;
       if (dc < 1) dc = 1;
+      if (dc != 1) cn.number_nz++;                     // codec.c:351
       if (dc == 128) dc = 255;
       b->put((uint32_t)dc, 8);
       k = 1;
@@ -161,7 +174,10 @@ void p64b_bits_mb(p64b_bits* b, int mdu, const p64b_mb* rec, const int8_t* level
       if (!v) { run++; continue; }
       put_tcoef(b, t, run, v, first);
       first = false; any = true; run = 0;
+      cn.number_nz++;                                 // codec.c:125, 169, 200
     }
+    (c < 4 ? cn.y_bits : (c == 4 ? cn.u_bits : cn.v_bits)) += (int32_t)(b->tell() - bstart);   // CodedBlockBits, p64.c:949-951
+    if (any) cn.eob_bits += t.eob.len;                // codec.c:129, 204
     if (any) b->put(t.eob);                           // an all-zero CBP block gets no EOB (codec.c:169-174)
   }
 }
@@ -177,7 +193,10 @@ const uint8_t* p64b_bits_data(const p64b_bits* b, size_t* n) {
   if (n) *n = b->buf.size();
   return b->buf.data();
 }
+void p64b_bits_counters(const p64b_bits* b, p64b_frame_counters* out) { if (b && out) *out = b->cnt; }
+void p64b_bits_counters_reset(p64b_bits* b) { if (b) b->cnt = p64b_frame_counters{}; }   // p64.c:640-649
 void p64b_bits_reset(p64b_bits* b) {
+  b->cnt = p64b_frame_counters{};
   b->buf.clear(); b->acc = 0; b->nacc = 0; b->last_mba = -1; b->last_mtype = 0; b->last_mvx = b->last_mvy = 0;
 }
 

@@ -22,10 +22,40 @@ static void help() {
          "(motion estimation, DCT, quantisation, reconstruction) runs on the GPU. There is no CPU fallback.\n");
 }
 
+// PrintFrameStatistics (p64.c:1299-1332) + Statistics (stat.c:52-63): the block `-l 1` prints after every frame; the plane
+// statistics come from the device (p64b_ctx_statistics), the bit counters from the host bit writer.
+static void print_frame_statistics(p64b_enc* enc, const p64b_enc_params& p) {
+  p64b_frame_counters c;
+  if (p64b_enc_frame_counters(enc, 0, &c)) return;
+  const int nmb = p64b_num_mb(p.image_type);
+  printf("Total No of Bits: %8d  Bits for Frame: %8d\n", c.total_bits, c.last_bits);
+  if (p.rate) printf("Buffer Contents: %8d  out of: %8d\n", c.buffer_contents, c.buffer_size);
+  printf("MB Attribute Bits: %6d  MV Bits: %6d   EOB Bits: %6d\n", c.mb_attribute_bits, c.mv_bits, c.eob_bits);
+  printf("Y Bits: %7d  U Bits: %7d  V Bits: %7d  Total Bits: %7d\n", c.y_bits, c.u_bits, c.v_bits, c.y_bits + c.u_bits + c.v_bits);
+  printf("MV StepSize: %f  MV NumberNonZero: %f  MV NumberZero: %f\n", (double)c.q_sum / (double)c.q_use,
+         (double)c.number_nz / (double)(nmb * 6), (double)(nmb * 6 * 64 - c.number_nz) / (double)(nmb * 6));
+  printf("Code MType: ");
+  for (int x = 0; x < 10; x++) printf("%5d", x);
+  printf("\nMacro Freq: ");
+  for (int x = 0; x < 10; x++) printf("%5d", c.macro_type_freq[x]);
+  printf("\nY     Freq: ");
+  for (int x = 0; x < 10; x++) printf("%5d", c.y_type_freq[x]);
+  printf("\nUV    Freq: ");
+  for (int x = 0; x < 10; x++) printf("%5d", c.uv_type_freq[x]);
+  printf("\n");
+  p64b_plane_stats sums[3];
+  if (p64b_ctx_statistics(p64b_enc_ctx(enc), sums)) return;
+  for (int i = 0; i < 3; i++) {
+    p64b_stat s;
+    p64b_stat_from_sums(&sums[i], &s);
+    printf("Comp: %d  MRSNR: %2.2f  SNR: %2.2f  PSNR: %2.2f  MSE: %4.2f  Entropy: %1.2f\n", i, s.mrsnr, s.snr, s.psnr, s.mse, s.entropy);
+  }
+}
+
 int main(int argc, char** argv) {
   p64b_enc_params p;
   p64b_enc_default_params(&p);
-  int start = 0, last = 0, file_size_bits = 0;
+  int start = 0, last = 0, file_size_bits = 0, loud = 0;
   std::string prefix, stream_file;
   if (argc == 1) { help(); return -1; }
   for (int i = 1; i < argc; i++) {
@@ -55,7 +85,8 @@ int main(int argc, char** argv) {
     else if (a == "-r") p.rate = atoi(next());
     else if (a == "-x") file_size_bits = atoi(next());
     else if (a == "-s") stream_file = next();
-    else if (a == "-l" || a == "-z") next();               // accepted, ignored (statistics / suffixes)
+    else if (a == "-l") loud = atoi(next());               // Loud (p64.c:348-350): > 0 prints the frame statistics
+    else if (a == "-z") next();                            // accepted, ignored (component file suffixes)
     else if (a == "-v" || a == "-c" || a == "-p") {}
     else if (a == "-") prefix = "-";
     else if (a[0] == '-') { printf("Illegal Option %s\n", a.c_str()); return 3; }
@@ -82,6 +113,7 @@ int main(int argc, char** argv) {
     return 3;
   }
   p.input_chroma = info.chroma;
+  if (loud > 0) p.host_vlc = 1;                            // the per-category bit counters live in the host bit writer
   p64b_enc* enc = nullptr;
   if (p64b_enc_create(&enc, &p)) { fprintf(stderr, "p64b: %s\n", p64b_last_error()); return 2; }
   uint8_t* frame = p64b_enc_staging(enc);
@@ -95,6 +127,7 @@ int main(int argc, char** argv) {
     printf("START>Frame: %d\n", cf);
     if (p64b_y4m_read_frame(in, frame) != 1) { p64b_enc_destroy(enc); return 3; }
     if (p64b_enc_encode(enc, frame)) { fprintf(stderr, "p64b: %s\n", p64b_last_error()); return 2; }
+    if (loud > 0) print_frame_statistics(enc, p);
     printf("END>Frame: %d\n", cf);
   }
   p64b_enc_finish(enc);

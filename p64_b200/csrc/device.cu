@@ -2,6 +2,7 @@
 // of independent streams, kernel launches, host<->device staging.  No CPU fallback: every entry point
 // fails with P64B_ECUDA when no CUDA device is usable.
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -66,6 +67,8 @@ struct p64b_ctx {
   uint8_t* d_quant = nullptr;     // [S]
   uint8_t* d_ovf = nullptr;       // [S][nmb]
   const uint8_t* frame_src = nullptr;   // source of the frame in flight (frame_begin .. frame_end)
+  const uint8_t* last_src = nullptr;    // device source frames of the last coded frame (for p64b_ctx_statistics)
+  p64b_plane_stats* d_stats = nullptr;  // [S][3], allocated on first use
   int64_t launches = 0;
   bool me_attr_done = false, mb_attr_done = false;
   int n_sm = 0;
@@ -321,6 +324,7 @@ void p64b_ctx_destroy(p64b_ctx* c) {
     if (c->ev_comp[i]) cudaEventDestroy(c->ev_comp[i]);
     if (c->ev_d2h[i]) cudaEventDestroy(c->ev_d2h[i]);
   }
+  cudaFree(c->d_stats);
   cudaFree(c->d_vlc_tables); cudaFree(c->d_gob_words); cudaFree(c->d_gob_bits); cudaFree(c->d_carry); cudaFree(c->d_carry_len);
   for (int i = 0; i < p64b_ctx::NSLOT; i++) cudaFree(c->d_aux[i]);
   cudaFree(c->d_bitpos); cudaFree(c->d_frame_bits); cudaFree(c->d_buffer_offset); cudaFree(c->d_overflows);
@@ -386,6 +390,7 @@ int p64b_ctx_encode_frames_dev(p64b_ctx* c, const p64b_step* st, const uint8_t* 
   }
   if ((rc = launch_mb(c, st, src_dev, 0, c->g.ngob, nullptr, mbs_dev, levels_dev))) return rc;
   swap_stores(c);
+  c->last_src = src_dev;
   return 0;
 }
 
@@ -489,6 +494,7 @@ int p64b_ctx_frame_end(p64b_ctx* c, const uint8_t* overflow) {
     }
   }
   swap_stores(c);
+  c->last_src = c->frame_src;
   c->frame_src = nullptr;
   return 0;
 }
@@ -526,6 +532,46 @@ int p64b_ctx_download_recon(p64b_ctx* c, int stream, uint8_t* yuv) {
   CU(cudaStreamSynchronize(c->stream));
   CU(cudaMemcpy(yuv, c->d_fs[c->cur] + (size_t)stream * c->g.frame_bytes, c->g.frame_bytes, cudaMemcpyDeviceToHost));
   return 0;
+}
+
+int p64b_ctx_statistics(p64b_ctx* c, p64b_plane_stats* out) {
+  if (!c || !out) { set_error("NULL argument"); return P64B_EINVAL; }
+  if (!c->last_src || c->frame_src) { set_error("p64b_ctx_statistics needs a completely coded frame"); return P64B_EINVAL; }
+  int rc;
+  if ((rc = use_device(c))) return rc;
+  const size_t bytes = (size_t)c->S * 3 * sizeof(p64b_plane_stats);
+  if (!c->d_stats && cudaMalloc((void**)&c->d_stats, bytes) != cudaSuccess) { set_error("cudaMalloc failed (statistics)"); return P64B_ENOMEM; }
+  CU(cudaMemsetAsync(c->d_stats, 0, bytes, c->stream));
+  const int wh = c->g.W * c->g.H;
+  const int per_stream = (wh + STATS_CHUNK - 1) / STATS_CHUNK + 2 * ((wh / 4 + STATS_CHUNK - 1) / STATS_CHUNK);
+  plane_stats_kernel<<<c->S * per_stream, 256, 0, c->stream>>>(c->g, c->last_src, c->d_fs[c->cur], c->d_stats, c->S);
+  c->launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out, c->d_stats, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+// StatisticsMem's derived quantities (stat.c:104-129) from the integer sums; the reference accumulates the same
+// integers in double, which is exact below 2^53.
+void p64b_stat_from_sums(const p64b_plane_stats* m, p64b_stat* s) {
+  if (!m || !s) return;
+  const double top = (double)m->n, value = (double)m->sum_rec, squared = (double)m->sum_sq_err;
+  const double rsquared = (double)m->sum_sq_src, rvalue = (double)m->sum_src;
+  s->mean = value / top;
+  s->mse = squared / top;
+  if (squared) {
+    s->snr = rsquared ? 10 * log10(rsquared / squared) : -99.99;
+    const double mr = rsquared - (rvalue * rvalue / top);
+    s->mrsnr = mr ? 10 * log10(mr / squared) : -99.99;
+    s->psnr = m->n ? 10 * log10((65025.0 * top) / squared) : -99.99;
+  } else {
+    s->snr = s->mrsnr = s->psnr = 99.99;
+  }
+  double e = 0;
+  for (int i = 0; i < 256; i++)
+    if (m->hist[i]) { const double p = (double)m->hist[i] / top; e += p * log(p); }
+  s->entropy = -e / log(2.0);
 }
 
 int p64b_ctx_last_intra(p64b_ctx* c, int stream, uint8_t* out) {
@@ -728,6 +774,7 @@ extern "C" int p64b_ctx_submit_bits(p64b_ctx* c, const p64b_step* st, int tempor
           c->g, c->d_ovf, c->d_fs[c->cur], c->d_fs[c->cur ^ 1], c->d_li[c->cur], c->d_li[c->cur ^ 1], c->S);
     }
     swap_stores(c);
+    c->last_src = src_dev;
     {
       ProfScope ps(c, 2);
       vlc_sizes_kernel<<<1, 1024, 0, c->stream>>>(f);

@@ -22,6 +22,7 @@ struct StreamState {
   int gquant = 8;            // GQuant (p64.c:89)
   int64_t buffer_offset = 0; // BufferOffset (p64.c:140)
   int64_t total_bits = 0, first_frame_bits = 0, overflows = 0;
+  int64_t last_bits = 0, buffer_contents_at_end = 0;   // LastBits; BufferContents() when PrintFrameStatistics runs
   // device-side entropy coding: the stream's bytes as the device returned them, and its pending bits (< 8)
   std::vector<uint8_t> dev_bytes;
   uint32_t carry = 0, carry_len = 0;
@@ -154,6 +155,7 @@ int p64b_enc_encode(p64b_enc* e, const uint8_t* src) {
   step.first_frame = first; step.me_mode = e->p.me_mode; step.search_limit = e->p.search_limit;
   step.force_intra = e->p.force_intra;
   const int tr = e->current_frame % 32;            // p64.c:637
+  if (!e->device_vlc) for (auto& ss : e->st) p64b_bits_counters_reset(ss.bits);      // p64.c:640-649
   if (src != e->h_src) memcpy(e->h_src, src, (size_t)e->S * e->src_bytes);
   int rc;
   if (e->device_vlc) {
@@ -218,8 +220,11 @@ int p64b_enc_encode(p64b_enc* e, const uint8_t* src) {
     if ((rc = p64b_ctx_frame_end(e->ctx, e->overflow.data()))) return rc;
   }
   for (auto& ss : e->st) {                          // p64.c:654-681
+    const int64_t before = ss.total_bits;
     if (!e->device_vlc) ss.total_bits = p64b_bits_tell(ss.bits);
+    ss.last_bits = ss.total_bits - before;
     if (first) ss.first_frame_bits = ss.total_bits;
+    if (e->p.rate && !e->device_vlc) ss.buffer_contents_at_end = buffer_contents(e, ss, e->ngob, 0);   // p64.c:663, before 670-680
     if (e->p.rate && !e->device_vlc) {
       if (first) ss.buffer_offset = buffer_size(e) / 2 - buffer_contents(e, ss, e->ngob, 0);
       ss.buffer_offset -= (int)((int64_t)e->p.rate * e->p.frame_skip * e->p.frame_rate_div / e->p.frame_rate);
@@ -259,6 +264,15 @@ p64b_ctx* p64b_enc_ctx(p64b_enc* e) { return e ? e->ctx : nullptr; }
 uint8_t* p64b_enc_staging(p64b_enc* e) { return e ? e->h_src : nullptr; }
 int64_t p64b_enc_overflows(const p64b_enc* e, int stream) {
   return (e && stream >= 0 && stream < e->S) ? e->st[stream].overflows : -1;
+}
+int p64b_enc_frame_counters(const p64b_enc* e, int stream, p64b_frame_counters* out) {
+  if (!e || !out || stream < 0 || stream >= e->S) { p64b::set_error("bad arguments"); return P64B_EINVAL; }
+  if (e->device_vlc) { p64b::set_error("frame counters need host_vlc = 1"); return P64B_EINVAL; }
+  const StreamState& ss = e->st[stream];
+  p64b_bits_counters(ss.bits, out);
+  out->total_bits = (int32_t)ss.total_bits; out->last_bits = (int32_t)ss.last_bits;
+  out->buffer_contents = (int32_t)ss.buffer_contents_at_end; out->buffer_size = e->p.rate / 4;
+  return 0;
 }
 int64_t p64b_enc_first_frame_bits(const p64b_enc* e, int stream) {
   return (e && stream >= 0 && stream < e->S) ? e->st[stream].first_frame_bits : -1;

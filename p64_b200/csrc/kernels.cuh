@@ -893,6 +893,58 @@ __global__ void overflow_patch_kernel(Geom g, const uint8_t* __restrict__ ovf, c
   if (lane == 0) li_new[wid] = (uint8_t)(li_prev[wid] + 1);
 }
 
+// Frame statistics (StatisticsMem, stat.c:73-130): per (stream, plane) the exact integer sums the reference
+// accumulates in double -- sum of the source, sum of the reconstruction, sum of squared differences, sum of squared source
+// samples -- and the 256-bin histogram of the reconstruction.  One CTA per 4 KB chunk of a plane: packed-byte dot
+// products for the sums, a shared-memory histogram, one atomic per value into the plane's record.  The host derives
+// mean / MSE / SNR / MRSNR / PSNR / entropy from the sums exactly as stat.c does (p64b_stat_from_sums).
+constexpr int STATS_CHUNK = 4096;
+__global__ void __launch_bounds__(256) plane_stats_kernel(Geom g, const uint8_t* __restrict__ src, const uint8_t* __restrict__ rec,
+                                                          p64b_plane_stats* __restrict__ out, int n_streams) {
+  __shared__ uint32_t s_hist[256];
+  __shared__ unsigned long long s_sum[4];
+  const int wh = g.W * g.H, cq = wh >> 2;
+  const int chunks_y = (wh + STATS_CHUNK - 1) / STATS_CHUNK, chunks_c = (cq + STATS_CHUNK - 1) / STATS_CHUNK;
+  const int per_stream = chunks_y + 2 * chunks_c;
+  const int s = blockIdx.x / per_stream;
+  int r = blockIdx.x - s * per_stream;
+  if (s >= n_streams) return;
+  int pl = 0, plane_off = 0, plane_n = wh;
+  if (r >= chunks_y) { r -= chunks_y; pl = 1 + r / chunks_c; r -= (pl - 1) * chunks_c; plane_off = wh + (pl - 1) * cq; plane_n = cq; }
+  const int begin = r * STATS_CHUNK, end = min(begin + STATS_CHUNK, plane_n);
+  s_hist[threadIdx.x] = 0;
+  if (threadIdx.x < 4) s_sum[threadIdx.x] = 0;
+  __syncthreads();
+  const size_t base = (size_t)s * g.frame_bytes + plane_off;
+  uint32_t a_src = 0, a_rec = 0, a_err = 0, a_sq = 0;
+  for (int i = begin + 4 * threadIdx.x; i < end; i += 4 * blockDim.x) {      // planes and chunks are multiples of 4 bytes
+    const uint32_t sv = __ldg(reinterpret_cast<const uint32_t*>(src + base + i));
+    const uint32_t rv = __ldg(reinterpret_cast<const uint32_t*>(rec + base + i));
+    a_src = __dp4a(sv, 0x01010101u, a_src);
+    a_rec = __dp4a(rv, 0x01010101u, a_rec);
+    a_sq = __dp4a(sv, sv, a_sq);
+    a_err += __dp4a(sv, sv, 0u) + __dp4a(rv, rv, 0u) - 2u * __dp4a(sv, rv, 0u);
+#pragma unroll
+    for (int k = 0; k < 4; k++) atomicAdd(&s_hist[(rv >> (8 * k)) & 0xffu], 1u);
+  }
+  a_src = __reduce_add_sync(0xffffffffu, a_src); a_rec = __reduce_add_sync(0xffffffffu, a_rec);
+  a_err = __reduce_add_sync(0xffffffffu, a_err); a_sq = __reduce_add_sync(0xffffffffu, a_sq);
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&s_sum[0], (unsigned long long)a_src); atomicAdd(&s_sum[1], (unsigned long long)a_rec);
+    atomicAdd(&s_sum[2], (unsigned long long)a_err); atomicAdd(&s_sum[3], (unsigned long long)a_sq);
+  }
+  __syncthreads();
+  p64b_plane_stats* o = out + (size_t)s * 3 + pl;
+  if (s_hist[threadIdx.x]) atomicAdd(&o->hist[threadIdx.x], s_hist[threadIdx.x]);
+  if (threadIdx.x == 0) {
+    atomicAdd(reinterpret_cast<unsigned long long*>(&o->sum_src), s_sum[0]);
+    atomicAdd(reinterpret_cast<unsigned long long*>(&o->sum_rec), s_sum[1]);
+    atomicAdd(reinterpret_cast<unsigned long long*>(&o->sum_sq_err), s_sum[2]);
+    atomicAdd(reinterpret_cast<unsigned long long*>(&o->sum_sq_src), s_sum[3]);
+    if (r == 0) o->n = (uint64_t)plane_n;
+  }
+}
+
 // Register-only issue-rate probe for VABSDIFF4.U8.ACC (ME roofline denominator)
 __global__ void __launch_bounds__(256) sad_peak_kernel(uint32_t* out, int iters, uint32_t seed) {
   uint32_t x[8], acc[8];

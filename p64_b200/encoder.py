@@ -11,7 +11,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import MB, ME, BitsOut, EncParams, RateControl, Step, Y4mInfo, check
+from ._lib import MB, ME, BitsOut, EncParams, PlaneStats, RateControl, Stat, Step, Y4mInfo, check
 
 CHROMA = {"420jpeg": 0, "420": 0, "420mpeg2": 1, "420paldv": 2, "422": 3, "411": 4, "444": 5, "444alpha": 6, "mono": 7}
 
@@ -158,6 +158,12 @@ class DeviceContext:
         check(self.L.p64b_ctx_last_intra(self.h, stream, _ptr(out)))
         return out
 
+    def statistics(self):
+        """Statistics of the last coded frame (stat.c:52-130): -> ((PlaneStats * 3) * n_streams) of exact integer sums"""
+        arr = ((PlaneStats * 3) * self.n_streams)()
+        check(self.L.p64b_ctx_statistics(self.h, C.cast(arr, C.c_void_p)))
+        return arr
+
     def me_executed(self, reset: bool = False) -> int:
         """packed SAD operations the ME kernel's sweeps have executed so far (device counter)"""
         n = C.c_uint64()
@@ -215,6 +221,22 @@ class BitWriter:
         n = C.c_size_t()
         p = self.L.p64b_bits_data(self.h, C.byref(n))
         return C.string_at(p, n.value)
+
+
+def stat_from_sums(sums: PlaneStats) -> Stat:
+    st = Stat()
+    _lib.lib().p64b_stat_from_sums(C.byref(sums), C.byref(st))
+    return st
+
+
+def format_statistics(planes) -> list:
+    """the `Comp:` lines Statistics() prints (stat.c:60-62) for one stream's (PlaneStats * 3)"""
+    out = []
+    for i in range(3):
+        s = stat_from_sums(planes[i])
+        out.append("Comp: %d  MRSNR: %2.2f  SNR: %2.2f  PSNR: %2.2f  MSE: %4.2f  Entropy: %1.2f" %
+                   (i, s.mrsnr, s.snr, s.psnr, s.mse, s.entropy))
+    return out
 
 
 def default_params() -> EncParams:
