@@ -199,6 +199,14 @@ int p64b_ctx_encode_gob(p64b_ctx *ctx, const p64b_step *step, int gob, const uin
                         int8_t *levels);
 int p64b_ctx_frame_end(p64b_ctx *ctx, const uint8_t *overflow);
 
+/* Decoder's inverse half (DecompressMDU p64.c:1179-1237 + DecodeSaveMDU p64.c:971-1013) for one picture of
+ * every stream: inverse quantise, Chen IDCT, prediction (overlay / MC / half-vector chroma / loop filter), clamp, store.
+ *   mbs    [n_streams][num_mb] GOB-major: mtype, cbp, mvx/mvy (full vectors, MVD prediction already undone), quant = UseQuant;
+ *          bit 0 of `reserved` set iff the stream transmitted the macroblock -- others keep the previous picture's samples
+ *   levels [n_streams][num_mb][6][64] transmission order, as the VLC decoder delivers them (intra DC as uint8)
+ * The decoded picture becomes the reference store: p64b_ctx_download_recon() reads it. */
+int p64b_ctx_decode_frames(p64b_ctx *ctx, const p64b_mb *mbs, const int8_t *levels);
+
 /* Motion estimation alone on device-resident luma planes (config 4 microbenchmark):
  * ref/cur [n_pairs][W*H], out [n_pairs][num_mb raster]. n_pairs may exceed the context's stream count. */
 int p64b_ctx_motion_estimation_dev(p64b_ctx *ctx, const uint8_t *ref_dev, const uint8_t *cur_dev, int n_pairs,
@@ -309,6 +317,27 @@ int p64b_y4m_get_info(const p64b_y4m *y, p64b_y4m_info *info);
 /* 1 = a frame was read into dst[frame_bytes], 0 = end of file, < 0 = error */
 int p64b_y4m_read_frame(p64b_y4m *y, uint8_t *dst);
 int64_t p64b_y4m_payload_bytes(int width, int height, int chroma);
+
+/* ---------------------------------------------------------------------------------------------
+ * (2c) decoder: the sequential bit-stream parser (ReadPictureHeader / ReadGOBHeader / ReadMBHeader marker.c:144-450,
+ * DecodeDC / DecodeAC / CBPDecodeAC codec.c:214-340) on the host + the inverse half on the device, driven like
+ * p64DecodeSequence (p64.c:1022-1126).  One stream per decoder object.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct p64b_dec p64b_dec;
+/* `data` must stay valid for the decoder's life time.  The image type comes from the first picture header (p64.c:1071-1081). */
+int p64b_dec_create(p64b_dec **out, int device, const uint8_t *data, size_t nbytes);
+void p64b_dec_destroy(p64b_dec *d);
+int p64b_dec_image_type(const p64b_dec *d);
+/* Decodes the next picture into yuv[frame_bytes].  Returns 1 with *repeat = how many times p64DecodeSequence writes it
+ * (temporal-reference gaps repeat a picture, p64.c:1047-1054), 0 at the end of the stream, < 0 on error. */
+int p64b_dec_next_picture(p64b_dec *d, uint8_t *yuv, int *repeat);
+/* The parser alone (no device): fills mbs[num_mb] / levels[num_mb][6][64] for the next picture as p64b_ctx_decode_frames
+ * wants them; *temporal_reference = TR of its picture header.  Returns 1 / 0 / < 0 like p64b_dec_next_picture. */
+typedef struct p64b_parser p64b_parser;
+int p64b_parser_create(p64b_parser **out, const uint8_t *data, size_t nbytes);
+void p64b_parser_destroy(p64b_parser *p);
+int p64b_parser_image_type(const p64b_parser *p);
+int p64b_parser_next_picture(p64b_parser *p, p64b_mb *mbs, int8_t *levels, int *temporal_reference, int *repeat);
 
 /* ---------------------------------------------------------------------------------------------
  * (3) sequence driver: p64EncodeSequence / p64EncodeFrame / p64EncodeGOB (p64.c:524-786) for a batch

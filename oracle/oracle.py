@@ -196,6 +196,15 @@ class Encoder:
     def last_intra(self):
         return np.ctypeslib.as_array(lib().orc_last_intra(self._h), shape=(self.nmb,)).copy()
 
+    def set_recon(self, frame):
+        """Overwrite the current reference picture (decoder tests: skipped macroblocks change the prediction source)."""
+        frame = np.ascontiguousarray(frame, np.uint8).reshape(-1)
+        n, off = self.w * self.h, 0
+        for j in range(3):
+            sz = n if j == 0 else n // 4
+            np.ctypeslib.as_array(lib().orc_ref_plane(self._h, j), shape=(sz,))[:] = frame[off:off + sz]
+            off += sz
+
     def recon(self):
         """Reconstructed frame most recently completed (the current reference), planar uint8."""
         n = self.w * self.h

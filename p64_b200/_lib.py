@@ -93,6 +93,15 @@ SIGNATURES = {
     "p64b_raw_frame_bytes": (_i, [_i, _i]),
     "p64b_ctx_set_input_chroma": (_i, [_vp, _i]),
     "p64b_ctx_convert_frames": (_i, [_vp, _vp, _vp]),
+    "p64b_ctx_decode_frames": (_i, [_vp, _vp, _vp]),
+    "p64b_dec_create": (_i, [C.POINTER(_vp), _i, _vp, _sz]),
+    "p64b_dec_destroy": (None, [_vp]),
+    "p64b_dec_image_type": (_i, [_vp]),
+    "p64b_dec_next_picture": (_i, [_vp, _vp, C.POINTER(_i)]),
+    "p64b_parser_create": (_i, [C.POINTER(_vp), _vp, _sz]),
+    "p64b_parser_destroy": (None, [_vp]),
+    "p64b_parser_image_type": (_i, [_vp]),
+    "p64b_parser_next_picture": (_i, [_vp, _vp, _vp, C.POINTER(_i), C.POINTER(_i)]),
     "p64b_y4m_open": (_i, [C.POINTER(_vp), C.c_char_p]),
     "p64b_y4m_close": (None, [_vp]),
     "p64b_y4m_get_info": (_i, [_vp, C.POINTER(Y4mInfo)]),

@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libp64b200.so")
 CLI = os.path.join(HERE, "p64b")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-LIB_SOURCES = ["device.cu", "bits.cpp", "encoder.cpp", "y4m.cpp"]
+LIB_SOURCES = ["device.cu", "bits.cpp", "encoder.cpp", "y4m.cpp", "decoder.cpp"]
 HEADERS = ["kernels.cuh", "vlc_kernels.cuh", "ingest.cuh", "vlc_dev.h", "vlc_tables.h", os.path.join("..", "..", "include", "p64_b200.h")]
 
 

@@ -1,6 +1,6 @@
-// p64b -- command line with the reference encoder's flags (p64.c:262-449, Help() p64.c:1537-1568) on top of the
-// B200 hot path.  Encoder only (the decoder is out of scope); input is Y4M (the reference's raw-component path
-// crashes at end of sequence).  Extra flags that the reference lacks are spelled with two dashes:
+// p64b -- command line with the reference's flags (p64.c:262-449, Help() p64.c:1537-1568) on top of the B200 hot path.
+// Encoder, and with -d the decoder (host parser + the device's inverse half); video I/O is Y4M (the reference's
+// raw-component path crashes at end of sequence).  Extra flags that the reference lacks are spelled with two dashes:
 //   --me tss|full   the stock three-step search (me.c:352) or the exhaustive FastBME (me.c:351)   [default tss]
 //   --intra-only    stand-in for `-o < test.intra` (every macroblock intra)
 //   --device N      CUDA device
@@ -17,7 +17,7 @@
 static void help() {
   printf("p64b -a StartFrame -b LastFrame [-NTSC] [-CIF] [-QCIF] [-y4m]\n"
          "     [-f FrameRate[/Div]] [-i SearchLimit] [-k FrameSkip] [-q Quantization] [-r Rate] [-x FileSizeBits]\n"
-         "     [-s StreamFile] [--me tss|full] [--intra-only] [--device N] Y4MFilePrefix\n"
+         "     [-s StreamFile] [-l 1] [-d] [--me tss|full] [--intra-only] [--device N] Y4MFilePrefix\n"
          "Encodes PrefixYUV4MPEG2 file `Prefix.y4m` (or `-` for stdin) into an H.261 stream; the data-parallel hot path\n"
          "(motion estimation, DCT, quantisation, reconstruction) runs on the GPU. There is no CPU fallback.\n");
 }
@@ -52,10 +52,43 @@ static void print_frame_statistics(p64b_enc* enc, const p64b_enc_params& p) {
   }
 }
 
+// -d: p64DecodeSequence (p64.c:1022-1126) -- StreamFile -> Prefix.y4m with the reference's Y4M header (p64.c:249-251, 1104)
+// and its START>Frame / END> Frame markers.
+static int decode_stream(const std::string& stream_file, const std::string& prefix, const p64b_enc_params& p) {
+  FILE* f = fopen(stream_file.c_str(), "rb");
+  if (!f) { printf("Cannot Open Input File\n"); return 1; }
+  std::vector<uint8_t> data;
+  uint8_t buf[65536];
+  for (size_t n; (n = fread(buf, 1, sizeof buf, f)) > 0;) data.insert(data.end(), buf, buf + n);
+  fclose(f);
+  p64b_dec* dec = nullptr;
+  if (p64b_dec_create(&dec, p.device, data.data(), data.size())) { fprintf(stderr, "p64b: %s\n", p64b_last_error()); return 2; }
+  const int it = p64b_dec_image_type(dec);
+  FILE* out = fopen((prefix + ".y4m").c_str(), "wb");
+  if (!out) { printf("Cannot Open Output File\n"); return 1; }
+  fprintf(out, "YUV4MPEG2 W%d H%d C420jpeg Ip F%i:%i\n", p64b_width(it), p64b_height(it), p.frame_rate, p.frame_rate_div);
+  std::vector<uint8_t> frame(p64b_frame_bytes(it));
+  int cf = 0, rep = 0, rc;
+  printf("START>Frame: %d\n", cf);
+  while ((rc = p64b_dec_next_picture(dec, frame.data(), &rep)) == 1) {
+    for (int i = 0; i < rep; i++) {
+      printf("END> Frame: %d\n", cf++);
+      fwrite("FRAME\n", 1, 6, out);
+      fwrite(frame.data(), 1, frame.size(), out);
+    }
+    printf("START>Frame: %d\n", cf);
+  }
+  fclose(out);
+  p64b_dec_destroy(dec);
+  if (rc < 0) { fprintf(stderr, "p64b: %s\n", p64b_last_error()); return 2; }
+  return 0;
+}
+
 int main(int argc, char** argv) {
   p64b_enc_params p;
   p64b_enc_default_params(&p);
   int start = 0, last = 0, file_size_bits = 0, loud = 0;
+  bool decode = false;
   std::string prefix, stream_file;
   if (argc == 1) { help(); return -1; }
   for (int i = 1; i < argc; i++) {
@@ -65,6 +98,7 @@ int main(int argc, char** argv) {
     else if (a == "-CIF") p.image_type = P64B_IT_CIF;
     else if (a == "-QCIF") p.image_type = P64B_IT_QCIF;
     else if (a == "-y4m") {}
+    else if (a == "-d") decode = true;                     // p64.c:307-309
     else if (a == "--me") { std::string m = next(); p.me_mode = m == "full" ? P64B_ME_FULL : P64B_ME_TSS; }
     else if (a == "--intra-only" || a == "-o") p.force_intra = 1;
     else if (a == "--device") p.device = atoi(next());
@@ -93,6 +127,7 @@ int main(int argc, char** argv) {
     else prefix = a;
   }
   if (prefix.empty()) { printf("A file prefix should be specified.\n"); return 3; }
+  if (decode) return decode_stream(stream_file.empty() ? prefix + ".p64" : stream_file, prefix, p);
   if (start > last) { printf("Need positive number of frames.\n"); return 3; }
   if (p.search_limit < 1 || p.search_limit > 31 || p.initial_quant < 0 || p.initial_quant > 31) { printf("Parameter out of bounds.\n"); return 3; }
   if (file_size_bits)                                       // p64.c:572-573

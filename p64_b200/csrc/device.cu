@@ -406,7 +406,7 @@ int p64b_ctx_submit(p64b_ctx* c, const p64b_step* st, const uint8_t* src, p64b_m
   int rc;
   if ((rc = check_step(st)) || (rc = check_quant(st->gquant)) || (rc = use_device(c))) return rc;
   const int slot = (int)(c->submitted % p64b_ctx::NSLOT);
-  const size_t fb = (size_t)c->S * c->g.frame_bytes, nm = (size_t)c->S * c->g.nmb;
+  const size_t nm = (size_t)c->S * c->g.nmb;
   if (c->slot_used[slot]) {
     CU(cudaStreamWaitEvent(c->s_h2d, c->ev_comp[slot], 0));    // the slot's source was consumed by its last kernels
     CU(cudaStreamWaitEvent(c->stream, c->ev_d2h[slot], 0));    // its outputs were downloaded
@@ -531,6 +531,31 @@ int p64b_ctx_download_recon(p64b_ctx* c, int stream, uint8_t* yuv) {
   if ((rc = use_device(c))) return rc;
   CU(cudaStreamSynchronize(c->stream));
   CU(cudaMemcpy(yuv, c->d_fs[c->cur] + (size_t)stream * c->g.frame_bytes, c->g.frame_bytes, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// Decoder's inverse half for one picture of every stream: records + levels (from the bit-stream parser) up, mb_decode_kernel,
+// SwapFS.  The decoded picture is then the context's reference store (p64b_ctx_download_recon).
+int p64b_ctx_decode_frames(p64b_ctx* c, const p64b_mb* mbs, const int8_t* levels) {
+  if (!c || !mbs || !levels) { set_error("NULL argument"); return P64B_EINVAL; }
+  if (c->frame_src) { set_error("p64b_ctx_decode_frames inside frame_begin/frame_end"); return P64B_EINVAL; }
+  int rc;
+  if ((rc = use_device(c))) return rc;
+  CU(cudaStreamSynchronize(c->s_h2d));      // slot 0 buffers may still be in use by pipelined encode steps
+  CU(cudaStreamSynchronize(c->s_d2h));
+  const size_t nm = (size_t)c->S * c->g.nmb;
+  CU(cudaMemcpyAsync(c->d_mbs, mbs, nm * sizeof(p64b_mb), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->d_levels, levels, nm * P64B_LEVELS_PER_MB, cudaMemcpyHostToDevice, c->stream));
+  MbDecArgs a;
+  a.g = c->g; a.ref = c->d_fs[c->cur]; a.out = c->d_fs[c->cur ^ 1]; a.mbs = c->d_mbs; a.levels = c->d_levels; a.n_streams = c->S;
+  static bool attr_done = false;
+  if (!attr_done) { CU(cudaFuncSetAttribute(mb_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MB4_SMEM)); attr_done = true; }
+  mb_decode_kernel<<<((int)nm + MB4_PER_CTA - 1) / MB4_PER_CTA, MB4_THREADS, MB4_SMEM, c->stream>>>(a);
+  c->launches++;
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(c->stream));     // mbs / levels are caller memory
+  swap_stores(c);
+  c->last_src = nullptr;
   return 0;
 }
 
@@ -706,7 +731,6 @@ extern "C" int p64b_ctx_submit_bits(p64b_ctx* c, const p64b_step* st, int tempor
   int rc;
   if ((rc = check_step(st)) || (rc = check_quant(st->gquant)) || (rc = use_device(c)) || (rc = ensure_bits_buffers(c))) return rc;
   const int slot = (int)(c->submitted % p64b_ctx::NSLOT);
-  const size_t fb = (size_t)c->S * c->g.frame_bytes;
   if (c->slot_used[slot]) {
     CU(cudaStreamWaitEvent(c->s_h2d, c->ev_comp[slot], 0));    // the slot's source was consumed by its last kernels
     CU(cudaStreamWaitEvent(c->stream, c->ev_d2h[slot], 0));    // its outputs were downloaded

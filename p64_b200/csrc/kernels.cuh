@@ -867,6 +867,158 @@ mb_encode_kernel(const __grid_constant__ MbArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Decoder's inverse half (DecompressMDU p64.c:1179-1237 + DecodeSaveMDU p64.c:971-1013): the same
+// inverse quantise / Chen IDCT / prediction (overlay, MC, half-vector chroma, loop filter) / clamp / store as the
+// encoder's reconstruction, driven by macroblock records and levels a bit-stream PARSER produced (decoder.cpp) instead of
+// by the forward half.  Thread = one 8x8 block, CTA = 6 warps x 32 macroblocks, block in a private shared-memory tile
+// (layout of mb_encode_kernel).  A macroblock the stream did not transmit (MBA skipped it, or its whole GOB is missing)
+// keeps the previous picture's samples: the decoder writes into a persistent picture buffer (CopyIob2FS, p64.c:1046).
+// ---------------------------------------------------------------------------------------------------
+struct MbDecArgs {
+  Geom g;
+  const uint8_t* ref;      // [S][frame_bytes] previous decoded picture (CFS)
+  uint8_t* out;            // [S][frame_bytes] picture being decoded
+  const p64b_mb* mbs;      // [S][nmb] GOB-major; reserved bit 0 = the macroblock was transmitted
+  const int8_t* levels;    // [S][nmb][6][64] transmission order (intra DC as uint8)
+  int n_streams;
+};
+
+template <int I>
+__device__ __forceinline__ int level_at(const uint32_t (&w)[16]) {      // raster coefficient I = byte c_zig_at(I) (IZigzagMatrix, transform.c:546-553)
+  constexpr int pos = c_zig_at(I);
+  return (int)(int8_t)(w[pos >> 2] >> (8 * (pos & 3)));
+}
+template <int R>
+__device__ __forceinline__ void dequant_row(int* tile, const uint32_t (&w)[16], int q2, int qo) {
+  int v[8] = {level_at<8 * R + 0>(w), level_at<8 * R + 1>(w), level_at<8 * R + 2>(w), level_at<8 * R + 3>(w),
+              level_at<8 * R + 4>(w), level_at<8 * R + 5>(w), level_at<8 * R + 6>(w), level_at<8 * R + 7>(w)};
+#pragma unroll
+  for (int j = 0; j < 8; j++) {                     // ICCITT[Flat]Quantize (transform.c:359-451) with the column pass's <<2 folded in
+    const int l = v[j], sg = l >> 31, aa = abs(l);
+    const int rr = aa ? aa * q2 + qo : 0;
+    v[j] = (rr ^ sg) - sg;
+  }
+  const int a[4] = {v[0], v[1], v[2], v[3]}, b[4] = {v[4], v[5], v[6], v[7]};
+  st_row(tile, R, 0, a); st_row(tile, R, 1, b);
+}
+
+__global__ void __launch_bounds__(MB4_THREADS, 3)
+mb_decode_kernel(const __grid_constant__ MbDecArgs a) {
+  extern __shared__ __align__(16) uint32_t s_dyn[];
+  const Geom& g = a.g;
+  const int lane = threadIdx.x & 31, c = threadIdx.x >> 5;
+  int* tile = reinterpret_cast<int*>(s_dyn) + threadIdx.x * MB4_TILE;
+  const int n_total = a.n_streams * g.nmb;
+  const int n = blockIdx.x * MB4_PER_CTA + lane;
+  if (n >= n_total) return;                          // no CTA-wide barrier below
+  const int s = n / g.nmb, mbi = n - s * g.nmb;
+  const int gob = mbi / 33, m = mbi - gob * 33;
+  int col, row;                                      // MoveTo, io.c:730-741
+  if (g.qcif) { col = m % 11; row = gob * 3 + m / 11; }
+  else { col = (gob & 1) * 11 + m % 11; row = (gob >> 1) * 3 + m / 11; }
+  const bool chroma = c >= 4;
+  const int w = chroma ? g.W >> 1 : g.W, wq = w >> 3;
+  const int off = chroma ? g.W * g.H + (c - 4) * (g.W * g.H >> 2) + row * 8 * w + col * 8
+                         : (row * 16 + (c >> 1) * 8) * w + col * 16 + (c & 1) * 8;
+  const size_t fo = (size_t)s * g.frame_bytes;
+  uint2* op = reinterpret_cast<uint2*>(a.out + fo + off);
+  const uint2 rw = __ldg(reinterpret_cast<const uint2*>(a.mbs + n));
+  const int mt = rw.x & 0xff, cbp_raw = (rw.x >> 8) & 0xff, q = rw.y & 0xff;
+  const int mvx = (int)(int8_t)(rw.x >> 16), mvy = (int)(int8_t)(rw.x >> 24);
+  const bool present = (rw.y >> 16) & 1u;
+  if (!present) {                                    // not transmitted: the picture buffer keeps the previous samples
+    const uint2* rp = reinterpret_cast<const uint2*>(a.ref + fo + off);
+#pragma unroll
+    for (int r = 0; r < 8; r++) op[r * wq] = __ldg(rp + r * wq);
+    return;
+  }
+  const bool intra = mt_is(M_INTRA, mt);
+  const int cbp = mt_is(M_CBP, mt) ? cbp_raw : 0x3f;                       // p64.c:1196
+  const bool coded = ((cbp >> (5 - c)) & 1) && mt_is(M_TCOEF, mt);
+
+  // ---- prediction as packed bytes (Add*Compensate addressing, io.c:142-313; chroma vector = MV/2 truncating)
+  uint32_t pk[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) pk[i] = 0;
+  if (!intra) {
+    int dx = 0, dy = 0;
+    if (mt_is(M_MF, mt)) { dx = chroma ? mvx / 2 : mvx; dy = chroma ? mvy / 2 : mvy; }
+    const uint8_t* b = a.ref + fo + off + dy * w + dx;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { const uint2 r = fetch_row8(b + i * w); pk[2 * i] = r.x; pk[2 * i + 1] = r.y; }
+    if (mt_is(M_FILTER, mt)) {                       // LoadFilterMatrix, io.c:323-372 (single rounding (S16+8)>>4)
+#pragma unroll
+      for (int r = 0; r < 8; r++) {
+        int p[8], h0[4], h1[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) { p[j] = ubyte(pk[2 * r], j); p[4 + j] = ubyte(pk[2 * r + 1], j); }
+        h0[0] = p[0] << 2; h0[1] = p[0] + 2 * p[1] + p[2]; h0[2] = p[1] + 2 * p[2] + p[3]; h0[3] = p[2] + 2 * p[3] + p[4];
+        h1[0] = p[3] + 2 * p[4] + p[5]; h1[1] = p[4] + 2 * p[5] + p[6]; h1[2] = p[5] + 2 * p[6] + p[7]; h1[3] = p[7] << 2;
+        st_row(tile, r, 0, h0); st_row(tile, r, 1, h1);
+      }
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        int v[8][4], o[8][4];
+#pragma unroll
+        for (int r = 0; r < 8; r++) ld_row(tile, r, h, v[r]);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          o[0][j] = (4 * v[0][j] + 8) >> 4; o[7][j] = (4 * v[7][j] + 8) >> 4;
+#pragma unroll
+          for (int r = 1; r < 7; r++) o[r][j] = (v[r - 1][j] + 2 * v[r][j] + v[r + 1][j] + 8) >> 4;
+        }
+#pragma unroll
+        for (int r = 0; r < 8; r++) pk[2 * r + h] = pack4(o[r][0], o[r][1], o[r][2], o[r][3]);
+      }
+    }
+  }
+  if (!coded) {                                      // reconstruction = prediction (zero residual)
+#pragma unroll
+    for (int r = 0; r < 8; r++) op[r * wq] = make_uint2(pk[2 * r], pk[2 * r + 1]);
+    return;
+  }
+  // ---- levels -> raster order -> inverse quantise -> tile
+  {
+    uint32_t lw[16];
+    const uint4* lp = reinterpret_cast<const uint4*>(a.levels + ((size_t)n * 6 + c) * 64);
+#pragma unroll
+    for (int i = 0; i < 4; i++) { const uint4 v = __ldg(lp + i); lw[4 * i] = v.x; lw[4 * i + 1] = v.y; lw[4 * i + 2] = v.z; lw[4 * i + 3] = v.w; }
+    const int ev = (q & 1) ? 0 : 1, q2 = 8 * q, qo = 4 * (q - ev);
+    dequant_row<0>(tile, lw, q2, qo); dequant_row<1>(tile, lw, q2, qo); dequant_row<2>(tile, lw, q2, qo); dequant_row<3>(tile, lw, q2, qo);
+    dequant_row<4>(tile, lw, q2, qo); dequant_row<5>(tile, lw, q2, qo); dequant_row<6>(tile, lw, q2, qo); dequant_row<7>(tile, lw, q2, qo);
+    if (intra) tile[0] = (int)(lw[0] & 0xffu) * 32;                        // intra DC = 8 l (transform.c:362), x4 for the column pass
+  }
+  // ---- Chen IDCT: column pass on half blocks, then row pass + rounding + prediction + clamp, row by row
+#pragma unroll 1
+  for (int h = 0; h < 2; h++) {
+    int v[8][4];
+#pragma unroll
+    for (int r = 0; r < 8; r++) ld_row(tile, r, h, v[r]);
+#pragma unroll
+    for (int j = 0; j < 4; j++) idct8<2>(v[0][j], v[1][j], v[2][j], v[3][j], v[4][j], v[5][j], v[6][j], v[7][j]);
+#pragma unroll
+    for (int r = 0; r < 8; r++) st_row(tile, r, h, v[r]);
+  }
+#pragma unroll
+  for (int r = 0; r < 8; r++) {
+    int x[8];
+    {
+      int p0[4], p1[4];
+      ld_row(tile, r, 0, p0); ld_row(tile, r, 1, p1);
+      x[0] = p0[0]; x[1] = p0[1]; x[2] = p0[2]; x[3] = p0[3]; x[4] = p1[0]; x[5] = p1[1]; x[6] = p1[2]; x[7] = p1[3];
+    }
+    idct8<0>(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);
+    int o[8];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      o[j] = min(max(dp4a_us(pk[2 * r], 1 << (8 * j), round_div16(x[j])), 0), 255);
+      o[4 + j] = min(max(dp4a_us(pk[2 * r + 1], 1 << (8 * j), round_div16(x[4 + j])), 0), 255);
+    }
+    op[r * wq] = make_uint2(pack4(o[0], o[1], o[2], o[3]), pack4(o[4], o[5], o[6], o[7]));
+  }
+}
+
 // MBs overridden by the host to MType 4 with a zero vector when the rate buffer overflowed (p64.c:776-783):
 // reconstruction = copy of the reference MB (AddCompensate at (0,0), TCoeffMType[4]=0), LastIntra++.
 // One warp per (stream, MB); exits immediately when the MB was not overridden.

@@ -158,6 +158,12 @@ class DeviceContext:
         check(self.L.p64b_ctx_last_intra(self.h, stream, _ptr(out)))
         return out
 
+    def decode_frames(self, mbs: np.ndarray, levels: np.ndarray):
+        """decoder's inverse half for one picture of every stream (records with reserved bit 0 = transmitted)"""
+        mbs = np.ascontiguousarray(mbs, MB_DTYPE).reshape(self.n_streams, self.geom["num_mb"])
+        levels = np.ascontiguousarray(levels, np.int8).reshape(self.n_streams, self.geom["num_mb"], 6, 64)
+        check(self.L.p64b_ctx_decode_frames(self.h, _ptr(mbs), _ptr(levels)))
+
     def statistics(self):
         """Statistics of the last coded frame (stat.c:52-130): -> ((PlaneStats * 3) * n_streams) of exact integer sums"""
         arr = ((PlaneStats * 3) * self.n_streams)()
@@ -315,6 +321,69 @@ class Y4mReader:
     def close(self):
         if getattr(self, "h", None):
             self.L.p64b_y4m_close(self.h)
+            self.h = None
+
+    __del__ = close
+
+
+class Parser:
+    """p64b_parser_*: the decoder's sequential half alone (no device) -- pictures as records + levels"""
+
+    def __init__(self, data: bytes):
+        self.L = _lib.lib()
+        self._data = np.frombuffer(data, np.uint8).copy()       # must outlive the parser
+        h = C.c_void_p()
+        check(self.L.p64b_parser_create(C.byref(h), _ptr(self._data), len(self._data)))
+        self.h = h
+        self.image_type = int(self.L.p64b_parser_image_type(self.h))
+        self.num_mb = int(self.L.p64b_num_mb(self.image_type))
+
+    def next_picture(self):
+        """-> (mbs [nmb], levels int8 [nmb,6,64], temporal_reference, repeat) or None at the end"""
+        mbs = np.zeros(self.num_mb, MB_DTYPE)
+        lv = np.zeros((self.num_mb, 6, 64), np.int8)
+        tr, rep = C.c_int(), C.c_int()
+        r = self.L.p64b_parser_next_picture(self.h, _ptr(mbs), _ptr(lv), C.byref(tr), C.byref(rep))
+        if r < 0:
+            check(r)
+        return (mbs, lv, tr.value, rep.value) if r == 1 else None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.p64b_parser_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+
+class Decoder:
+    """p64b_dec_*: p64DecodeSequence (p64.c:1022-1126) -- host parser + the device's inverse half"""
+
+    def __init__(self, data: bytes, device: int = 0):
+        self.L = _lib.lib()
+        self._data = np.frombuffer(data, np.uint8).copy()
+        h = C.c_void_p()
+        check(self.L.p64b_dec_create(C.byref(h), device, _ptr(self._data), len(self._data)))
+        self.h = h
+        self.image_type = int(self.L.p64b_dec_image_type(self.h))
+        self.frame_bytes = int(self.L.p64b_frame_bytes(self.image_type))
+
+    def frames(self):
+        """every frame p64DecodeSequence writes, in order (a picture repeated for temporal-reference gaps)"""
+        out = []
+        while True:
+            buf = np.zeros(self.frame_bytes, np.uint8)
+            rep = C.c_int()
+            r = self.L.p64b_dec_next_picture(self.h, _ptr(buf), C.byref(rep))
+            if r < 0:
+                check(r)
+            if r != 1:
+                return out
+            out += [buf] * rep.value
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.p64b_dec_destroy(self.h)
             self.h = None
 
     __del__ = close
