@@ -371,8 +371,8 @@ static int ingest_source(p64b_ctx* c, int slot, uint8_t* dst) {
   IngestArgs a;
   a.aux = c->d_aux[slot]; a.aux_stride = c->aux_bytes; a.dst = dst; a.dst_stride = (size_t)c->g.frame_bytes;
   a.W = c->g.W; a.H = c->g.H; a.n_streams = c->S; a.chroma = c->chroma;
-  const long long threads = (long long)c->S * 2 * (c->g.H / 2) * (c->g.W / 8);
-  ingest_chroma_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(a);
+  const size_t smem = c->chroma == P64B_CHROMA_420PALDV ? (size_t)(c->g.W / 2) * (c->g.H / 2) : 0;   // the intermediate plane
+  ingest_chroma_kernel<<<c->S * 2, INGEST_THREADS, smem, c->stream>>>(a);
   c->launches++;
   CU(cudaGetLastError());
   return 0;

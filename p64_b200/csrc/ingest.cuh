@@ -32,68 +32,102 @@ struct IngestArgs {
 };
 
 __device__ __forceinline__ int clamp255(int v) { return min(max(v, 0), 255); }
-
-// horizontal [4 -17 114 35 -9 1]/128 at x of a row of n samples
-__device__ __forceinline__ int hshift6(const uint8_t* __restrict__ r, int x, int n) {
-  auto at = [&](int i) { return (int)__ldg(r + min(max(i, 0), n - 1)); };
-  return clamp255((4 * at(x - 2) - 17 * at(x - 1) + 114 * at(x) + 35 * at(x + 1) - 9 * at(x + 2) + at(x + 3) + 64) >> 7);
+__device__ __forceinline__ int byte_of(uint32_t w, int k) { return (int)((w >> (8 * k)) & 0xffu); }
+__device__ __forceinline__ uint32_t pack_u8x4(const int (&o)[4]) {
+  return (uint32_t)o[0] | ((uint32_t)o[1] << 8) | ((uint32_t)o[2] << 16) | ((uint32_t)o[3] << 24);
 }
 
-__global__ void __launch_bounds__(256) ingest_chroma_kernel(const IngestArgs a) {
-  const int cw = a.W >> 1, ch = a.H >> 1, q = cw >> 2;                  // 4 output samples per thread
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long per_stream = 2ll * ch * q;
-  if (t >= per_stream * a.n_streams) return;
-  const int s = (int)(t / per_stream);
-  int r = (int)(t - (long long)s * per_stream);
-  const int pl = r / (ch * q); r -= pl * ch * q;
-  const int y = r / q, x0 = (r - y * q) * 4;
+// Samples x0-4 .. x0+7 of a row of n bytes (n and x0 multiples of 4, row 4-byte aligned) as 12 ints, indices clamped to
+// the row: three aligned word loads; beyond the ends the edge sample is replicated.
+template <typename Load>
+__device__ __forceinline__ void row12(Load ld, int x0, int n, int (&p)[12]) {
+  const uint32_t w1 = ld(x0 >> 2);
+  const uint32_t w0 = x0 ? ld((x0 >> 2) - 1) : (w1 & 0xffu) * 0x01010101u;
+  const uint32_t w2 = x0 + 4 < n ? ld((x0 >> 2) + 1) : (w1 >> 24) * 0x01010101u;
+#pragma unroll
+  for (int k = 0; k < 4; k++) { p[k] = byte_of(w0, k); p[4 + k] = byte_of(w1, k); p[8 + k] = byte_of(w2, k); }
+}
+// [4 -17 114 35 -9 1]/128 at x0 .. x0+3 (first tap at x-2): the quarter-pel shift of y4m_input.c:209-224
+__device__ __forceinline__ void hshift6x4(const int (&p)[12], int (&o)[4]) {
+#pragma unroll
+  for (int j = 0; j < 4; j++)
+    o[j] = clamp255((4 * p[j + 2] - 17 * p[j + 3] + 114 * p[j + 4] + 35 * p[j + 5] - 9 * p[j + 6] + p[j + 7] + 64) >> 7);
+}
+
+// One CTA per (stream, chroma plane).  4 output samples per thread and step; word loads only.  420paldv keeps the whole
+// horizontally filtered plane (8-bit, as the reference's intermediate buffer) in shared memory -- 25 KB for CIF -- and
+// filters it vertically from there, so every intermediate sample is computed once.
+constexpr int INGEST_THREADS = 256;
+__global__ void __launch_bounds__(INGEST_THREADS) ingest_chroma_kernel(const IngestArgs a) {
+  extern __shared__ __align__(16) uint32_t s_tmp[];                      // paldv only: [ch][cw] bytes
+  const int cw = a.W >> 1, ch = a.H >> 1, q = cw >> 2, nwords = ch * q;
+  const int s = blockIdx.x >> 1, pl = blockIdx.x & 1;
   const uint8_t* aux = a.aux + (size_t)s * a.aux_stride;
-  int o[4];
+  uint32_t* dst = reinterpret_cast<uint32_t*>(a.dst + (size_t)s * a.dst_stride + (size_t)a.W * a.H + (size_t)pl * cw * ch);
   switch (a.chroma) {
     case P64B_CHROMA_420MPEG2:
-    case P64B_CHROMA_422: {
-      const int sh = a.chroma == P64B_CHROMA_422 ? a.H : ch;            // source plane height; only its first ch rows are read
-      const uint8_t* row = aux + (size_t)pl * cw * sh + (size_t)y * cw;
-#pragma unroll
-      for (int j = 0; j < 4; j++) o[j] = hshift6(row, x0 + j, cw);
-      break;
-    }
+    case P64B_CHROMA_422:
     case P64B_CHROMA_420PALDV: {
-      const uint8_t* plane = aux + (size_t)pl * cw * ch;
+      const int sh = a.chroma == P64B_CHROMA_422 ? a.H : ch;            // source plane height; only its first ch rows are read
+      const uint32_t* plane = reinterpret_cast<const uint32_t*>(aux + (size_t)pl * cw * sh);
+      uint32_t* hout = a.chroma == P64B_CHROMA_420PALDV ? s_tmp : dst;
+      for (int i = threadIdx.x; i < nwords; i += INGEST_THREADS) {
+        const int y = i / q, x0 = (i - y * q) * 4;
+        const uint32_t* row = plane + y * q;
+        int p[12], o[4];
+        row12([&](int w) { return __ldg(row + w); }, x0, cw, p);
+        hshift6x4(p, o);
+        hout[i] = pack_u8x4(o);
+      }
+      if (a.chroma != P64B_CHROMA_420PALDV) break;
+      __syncthreads();
+      // vertical quarter-pel shift of the intermediate: Cb up [1 -9 35 114 -17 4] (first tap at y-3), Cr down
+      // [4 -17 114 35 -9 1] (first tap at y-2); row indices clamped (y4m_input.c:313-359)
+      for (int i = threadIdx.x; i < nwords; i += INGEST_THREADS) {
+        const int y = i / q, xw = i - y * q;
+        uint32_t t[6];
+        const int first = pl == 0 ? y - 3 : y - 2;
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
-        auto tmp = [&](int yy) { return hshift6(plane + (size_t)min(max(yy, 0), ch - 1) * cw, x0 + j, cw); };
-        const int x = x0 + j; (void)x;
-        o[j] = pl == 0 ? clamp255((tmp(y - 3) - 9 * tmp(y - 2) + 35 * tmp(y - 1) + 114 * tmp(y) - 17 * tmp(y + 1) + 4 * tmp(y + 2) + 64) >> 7)
-                       : clamp255((4 * tmp(y - 2) - 17 * tmp(y - 1) + 114 * tmp(y) + 35 * tmp(y + 1) - 9 * tmp(y + 2) + tmp(y + 3) + 64) >> 7);
+        for (int k = 0; k < 6; k++) t[k] = s_tmp[min(max(first + k, 0), ch - 1) * q + xw];
+        int o[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int v0 = byte_of(t[0], j), v1 = byte_of(t[1], j), v2 = byte_of(t[2], j), v3 = byte_of(t[3], j), v4 = byte_of(t[4], j), v5 = byte_of(t[5], j);
+          o[j] = pl == 0 ? clamp255((v0 - 9 * v1 + 35 * v2 + 114 * v3 - 17 * v4 + 4 * v5 + 64) >> 7)
+                         : clamp255((4 * v0 - 17 * v1 + 114 * v2 + 35 * v3 - 9 * v4 + v5 + 64) >> 7);
+        }
+        dst[i] = pack_u8x4(o);
       }
       break;
     }
     case P64B_CHROMA_411: {
-      const int sw = (a.W + 3) >> 2;                                    // source samples per row; plane height H
-      const uint8_t* row = aux + (size_t)pl * sw * a.H + (size_t)y * sw;
-      auto at = [&](int i) { return (int)__ldg(row + min(max(i, 0), sw - 1)); };
+      const int sw = (a.W + 3) >> 2;                                    // source samples per row (plane height H); 2 of them per 4 outputs
+      const uint8_t* plane = aux + (size_t)pl * sw * a.H;
+      for (int i = threadIdx.x; i < nwords; i += INGEST_THREADS) {
+        const int y = i / q, x0 = (i - y * q) * 4, k0 = x0 >> 1;
+        const uint8_t* row = plane + (size_t)y * sw;
+        int p[5];                                                       // samples k0-1 .. k0+3, clamped
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const int k = (x0 + j) >> 1;
-        o[j] = ((x0 + j) & 1) ? clamp255((-3 * at(k - 1) + 50 * at(k) + 86 * at(k + 1) - 5 * at(k + 2) + 64) >> 7)
-                              : clamp255((at(k - 1) + 110 * at(k) + 18 * at(k + 1) - at(k + 2) + 64) >> 7);
+        for (int k = 0; k < 5; k++) p[k] = (int)__ldg(row + min(max(k0 - 1 + k, 0), sw - 1));
+        int o[4];
+#pragma unroll
+        for (int j = 0; j < 2; j++) {                                   // [1 110 18 -1] and [-3 50 86 -5], first tap at k-1 (y4m_input.c:434-455)
+          o[2 * j] = clamp255((p[j] + 110 * p[j + 1] + 18 * p[j + 2] - p[j + 3] + 64) >> 7);
+          o[2 * j + 1] = clamp255((-3 * p[j] + 50 * p[j + 1] + 86 * p[j + 2] - 5 * p[j + 3] + 64) >> 7);
+        }
+        dst[i] = pack_u8x4(o);
       }
       break;
     }
     case P64B_CHROMA_444:
     case P64B_CHROMA_444ALPHA: {
-      const uint8_t* p = aux + (size_t)pl * a.W * a.H + (size_t)y * cw + x0;   // the plane's first cw*ch bytes, linearly
-#pragma unroll
-      for (int j = 0; j < 4; j++) o[j] = __ldg(p + j);
+      const uint32_t* plane = reinterpret_cast<const uint32_t*>(aux + (size_t)pl * a.W * a.H);   // the plane's first cw*ch bytes, linearly
+      for (int i = threadIdx.x; i < nwords; i += INGEST_THREADS) dst[i] = __ldg(plane + i);
       break;
     }
     default:                                                            // mono
-      o[0] = o[1] = o[2] = o[3] = 128;
+      for (int i = threadIdx.x; i < nwords; i += INGEST_THREADS) dst[i] = 0x80808080u;
   }
-  uint8_t* d = a.dst + (size_t)s * a.dst_stride + (size_t)a.W * a.H + (size_t)pl * cw * ch + (size_t)y * cw + x0;
-  *reinterpret_cast<uint32_t*>(d) = (uint32_t)o[0] | ((uint32_t)o[1] << 8) | ((uint32_t)o[2] << 16) | ((uint32_t)o[3] << 24);
 }
 
 }  // namespace p64b
