@@ -174,6 +174,10 @@ def main_cuda(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly one JSON line: whatever libraries print there (NCCL's version banner ...) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; p64_b200 has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
@@ -383,7 +387,9 @@ def main_cuda(args):
                                          "ms_per_step": rc_ms[1] / rc_line["host_steps"], "steps": rc_line["host_steps"],
                                          "api": "p64b_enc_encode with host_vlc=1: p64b_ctx_frame_begin / 12 x p64b_ctx_encode_gob / "
                                                 "p64b_ctx_frame_end, rate control + VLC on the host cores"}}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
     ctx.close()
     L.p64b_host_free(pin)
     for a, b in pin_outs:
