@@ -154,8 +154,11 @@ int main(int argc, char** argv) {
   uint8_t* frame = p64b_enc_staging(enc);
   for (int i = start; i > 0; --i)                           // seek to StartFrame (p64.c:562-565)
     if (p64b_y4m_read_frame(in, frame) != 1) return 3;
-  if (p.rate) {
+  if (p.rate && !p.initial_quant) {                        // p64.c:574-586
+    int iq = 10000000 / p.rate;
+    iq = iq > 31 ? 31 : (iq < 1 ? 1 : iq);
     printf("Rate: %d   QDFact: %d  QOffs: %d\n", p.rate, p.rate / 320, 1);
+    printf("Starting Quantization: %d\n", iq);
   }
   printf("START>SEQUENCE\n");
   for (int cf = start; cf <= last; cf += p.frame_skip) {

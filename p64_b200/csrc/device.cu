@@ -70,7 +70,7 @@ struct p64b_ctx {
   const uint8_t* last_src = nullptr;    // device source frames of the last coded frame (for p64b_ctx_statistics)
   p64b_plane_stats* d_stats = nullptr;  // [S][3], allocated on first use
   int64_t launches = 0;
-  bool me_attr_done = false, mb_attr_done = false;
+  bool me_attr_done = false, mb_attr_done = false, dec_attr_done = false;   // per context: function attributes are per device
   int n_sm = 0;
   uint32_t* d_me_queue = nullptr;   // [2] work counters of the persistent ME kernel (alternating per launch)
   int64_t me_launches = 0;
@@ -548,8 +548,7 @@ int p64b_ctx_decode_frames(p64b_ctx* c, const p64b_mb* mbs, const int8_t* levels
   CU(cudaMemcpyAsync(c->d_levels, levels, nm * P64B_LEVELS_PER_MB, cudaMemcpyHostToDevice, c->stream));
   MbDecArgs a;
   a.g = c->g; a.ref = c->d_fs[c->cur]; a.out = c->d_fs[c->cur ^ 1]; a.mbs = c->d_mbs; a.levels = c->d_levels; a.n_streams = c->S;
-  static bool attr_done = false;
-  if (!attr_done) { CU(cudaFuncSetAttribute(mb_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MB4_SMEM)); attr_done = true; }
+  if (!c->dec_attr_done) { CU(cudaFuncSetAttribute(mb_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MB4_SMEM)); c->dec_attr_done = true; }
   mb_decode_kernel<<<((int)nm + MB4_PER_CTA - 1) / MB4_PER_CTA, MB4_THREADS, MB4_SMEM, c->stream>>>(a);
   c->launches++;
   CU(cudaGetLastError());
