@@ -35,8 +35,9 @@ def synth_clip(image_type: int, n_frames: int, seed: int = 1234, pan=(3, 2), noi
     patch = rng.integers(0, 256, size=(48, 48)).astype(np.float64)
     out = np.empty((n_frames, w * h * 3 // 2), dtype=np.uint8)
     cy, cx = np.mgrid[0:h // 2, 0:w // 2].astype(np.float64)
+    by, bx = max(32, -pan[1] * (n_frames - 1)), max(32, -pan[0] * (n_frames - 1))     # long clips panning up / left start further in
     for f in range(n_frames):
-        oy, ox = 32 + pan[1] * f, 32 + pan[0] * f
+        oy, ox = by + pan[1] * f, bx + pan[0] * f
         y = tex[oy:oy + h, ox:ox + w].copy()
         py, px = (20 + 5 * f) % (h - 48), (30 + 7 * f) % (w - 48)
         y[py:py + 48, px:px + 48] = patch

@@ -237,6 +237,73 @@ def test_full_size_batch_properties():
         ctx.close()
 
 
+@pytest.mark.parametrize("rate", [0, 384000])
+def test_full_size_batch_round_trip_all_streams(rate):
+    """BASELINE configs[4]-shaped batch: 256 CIF streams with DIFFERENT content (the bench's clip bank and phases), 10
+    frames, pipelined device-side entropy coding (and, rate != 0, the device-side rate control).  Size-independent
+    properties for every one of the 256 streams: (1) the stream parses, picture by picture, into as many pictures as were
+    coded; (2) decoding it (host parser + the device's inverse half, all streams as one batch) reproduces the ENCODER's
+    reconstruction of the last frame bit for bit -- encoder and decoder stay in lock step; (3) streams fed the same clip
+    at the same phase are byte-identical; and for a sample of streams (4) the bytes equal a single-stream encode."""
+    import bench
+    from p64_b200.encoder import BitWriter, Parser
+    it, S, nf = y4m.IT_CIF, 256, 10
+    frames = bench.make_sources(range(S), nf)                         # [nf, S, frame_bytes]
+    iq = 8 if not rate else min(max(10000000 // rate, 1), 31)
+    ctx = DeviceContext(it, S)
+    try:
+        if rate:
+            ctx.set_rate_control(rate)
+        out = [bytearray() for _ in range(S)]
+        tickets = []
+        src = [np.ascontiguousarray(frames[f]) for f in range(nf)]
+        for f in range(nf):
+            if f >= 3:
+                chunks, carry, clen, pos = ctx.wait_bits(tickets[f - 3])
+                for s in range(S):
+                    out[s] += chunks[s]
+            tickets.append(ctx.submit_bits(make_step(f == 0, iq, 1, 31), f % 32, src[f].ctypes.data))
+        for t in tickets[-3:]:
+            chunks, carry, clen, pos = ctx.wait_bits(t)
+            for s in range(S):
+                out[s] += chunks[s]
+        streams = []
+        for s in range(S):
+            bw = BitWriter(it)
+            if clen[s]:
+                bw.put(int(carry[s]) >> (32 - int(clen[s])), int(clen[s]))
+            bw.picture_header(nf % 32)
+            bw.finish()
+            streams.append(bytes(out[s]) + bw.data())
+            assert pos[s] == 8 * len(out[s]) + clen[s]
+        enc_recon = [ctx.recon(s) for s in range(S)]
+    finally:
+        ctx.close()
+    # (3) same clip, same phase -> same bytes (stream s plays clip s % 8 at phase (s // 8) % 8)
+    for s in range(64, S):
+        assert streams[s] == streams[s - 64], s
+    assert len({hashlib.md5(x).hexdigest() for x in streams[:64]}) == 64
+    # (1) + (2): parse all streams, decode them as one batch
+    parsers = [Parser(x) for x in streams]
+    dec = DeviceContext(it, S)
+    try:
+        for f in range(nf):
+            pics = [p.next_picture() for p in parsers]
+            assert all(pic is not None and pic[2] == f % 32 and pic[3] == 1 for pic in pics), f
+            dec.decode_frames(np.stack([pic[0] for pic in pics]), np.stack([pic[1] for pic in pics]))
+        assert all(p.next_picture() is None for p in parsers)
+        for s in range(S):
+            assert np.array_equal(dec.recon(s), enc_recon[s]), s
+    finally:
+        dec.close()
+        for p in parsers:
+            p.close()
+    # (4) a sample against single-stream encodes
+    for s in (0, 37, 63, 255):
+        want = encode_clip(it, frames[:, s], q=0 if rate else 8, rate=rate, me_mode=1, search_limit=31)
+        assert streams[s] == want, s
+
+
 def test_cli_matches_reference_golden(tmp_path):
     """the p64b command line (reference flags) writes the reference's bytes"""
     import subprocess
