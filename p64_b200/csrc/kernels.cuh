@@ -523,6 +523,14 @@ __device__ __forceinline__ uint32_t pack4(int a, int b, int c, int d) {         
   return __byte_perm(__byte_perm((uint32_t)a, (uint32_t)b, 0x0040), __byte_perm((uint32_t)c, (uint32_t)d, 0x0040), 0x5410);
 }
 
+// four ints -> four bytes (a lowest) with saturation to [0,255]: two I2IP (cvt.pack.sat) instead of 4 x min/max + 3 PRMT
+__device__ __forceinline__ uint32_t pack4_sat(int a, int b, int c, int d) {
+  uint32_t hi, r;
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(d), "r"(c), "r"(0));
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(b), "r"(a), "r"(hi));
+  return r;
+}
+
 // MType property tables (p64.c:217-222) as bit masks over type 0..9
 constexpr uint32_t M_CBP = 0x36c, M_INTRA = 0x003, M_MF = 0x3f0, M_FILTER = 0x380, M_TCOEF = 0x36f;
 __device__ __forceinline__ bool mt_is(uint32_t mask, int mt) { return (mask >> mt) & 1u; }
@@ -596,14 +604,18 @@ __device__ __forceinline__ void ld_row(const int* tile, int r, int h, int (&v)[4
 }
 
 // forward row pass of row R: Chen row butterfly, then ChenDct's final rounding + BoundDctMatrix + CCITT[Flat]Quantize +
-// [Flat]BoundQuantizeMatrix (chendct.c:204-205, transform.c:271-350, 460-537) in sign-magnitude form on the RAW output v:
+// [Flat]BoundQuantizeMatrix (chendct.c:204-205, transform.c:271-350, 460-537) as ONE signed multiply-shift on the RAW output v:
 //   |x| = (|v|+4)>>3 clamped to 1023  ==  (min(|v|,8187)+4)>>3
-//   |level| = floor((|x| + ev) / 2Q) = floor((min(|v|,8187) + 4 + 8ev) / 16Q)          (ev = 1 for even Q; nested floors)
-//           = ((a*M + K) >> 22) with M = floor(2^22/16Q)+1, K = (4+8ev)*M   -- exact because (a+12)*16Q < 2^22
-// (tests/test_abi_and_host.py checks the identity exhaustively).  Levels go back into the tile, their low bytes into the
+//   |level| = min(127, floor((|x| + ev) / 2Q)) = min(127, (a*M + K) >> 22),  a = min(|v|,8187), M = floor(2^22/16Q)+1,
+//             K = (4+8ev)*M                                                  (ev = 1 for even Q; nested floors)
+//   both clamps become one clamp of v to +-A(Q), A = the largest a <= 8187 whose level is <= 127, and the sign moves into
+//   the rounding constant:  level = (clamp(v,-A,A)*M + (v < 0 ? K ^ 0x3fffff : K)) >> 22   (arithmetic shift)
+// because -((a*M+K) >> 22) == (-a*M + (2^22-1-K)) >> 22 and K < 2^22 (tests/test_abi_and_host.py checks the identity
+// for every raw value and every Q).  Sum |level| is only ever compared with 0 and 1 (p64.c:887-903); sum level^2 gives the
+// same two answers and is one IMAD per coefficient.  Levels go back into the tile, their low bytes into the
 // transmission-order words.
 template <int R>
-__device__ __forceinline__ int fwd_row(int* tile, uint32_t (&out)[16], uint32_t M, uint32_t K, uint32_t ev, bool intra) {
+__device__ __forceinline__ int fwd_row(int* tile, uint32_t (&out)[16], int M, int K, int A, uint32_t ev, bool intra) {
   int v[8];
   {
     int a[4], b[4];
@@ -618,15 +630,13 @@ __device__ __forceinline__ int fwd_row(int* tile, uint32_t (&out)[16], uint32_t 
       const int x = min(round_div8(v[0]), 2047);
       int d;
       if (intra) d = min(max((x + 4) >> 3, 1), 254);          // (x-4)/8 <= 0 for x <= 0 and is clamped to 1 anyway
-      else { d = min((int)(((uint32_t)(abs(x) + (int)ev) * M) >> 19), 127); d = x < 0 ? -d : d; }
-      l[0] = d; sum += abs(d);
+      else { d = min((int)(((uint32_t)(abs(x) + (int)ev) * (uint32_t)M) >> 19), 127); d = x < 0 ? -d : d; }
+      l[0] = d;
     } else {
       const int x = v[j], sg = x >> 31;
-      const uint32_t aa = (uint32_t)min(abs(x), 8187);
-      const int q = min((int)((aa * M + K) >> 22), 127);
-      sum += q;
-      l[j] = (q ^ sg) - sg;
+      l[j] = (min(max(x, -A), A) * M + (K ^ (sg & 0x3fffff))) >> 22;
     }
+    sum += l[j] * l[j];
   }
   zig_insert<c_zig_at(8 * R + 0)>(out, l[0]); zig_insert<c_zig_at(8 * R + 1)>(out, l[1]);
   zig_insert<c_zig_at(8 * R + 2)>(out, l[2]); zig_insert<c_zig_at(8 * R + 3)>(out, l[3]);
@@ -639,16 +649,43 @@ __device__ __forceinline__ int fwd_row(int* tile, uint32_t (&out)[16], uint32_t 
   return sum;
 }
 
+// H.261 loop filter (LoadFilterMatrix, io.c:323-372) of one output row on packed bytes: the separable 1-2-1 filter with
+// block-edge rows / columns passed through is one 2-D kernel with a single rounding (S16+8)>>4 (identity checked in
+// tests/test_oracle_vs_ref.py), so every output sample is a chain of byte dot products (IDP.4A, FMA pipe) over the row
+// above, the row and the row below with the column weights folded into the coefficient bytes.  wa/wb/wc = vertical
+// weights of the three rows ((1,2,1) inside the block, (0,4,0) on its first and last row).
+template <int WA, int WB, int WC>
+__device__ __forceinline__ void filter_row(const uint32_t (&pk)[16], int ra, int rb, int rc, uint32_t& o0, uint32_t& o1) {
+  // horizontal coefficient bytes per output column j for the two words of a row (columns 0-3, 4-7)
+  constexpr int C0[8] = {0x00000004, 0x00010201, 0x01020100, 0x02010000, 0x01000000, 0, 0, 0};
+  constexpr int C1[8] = {0, 0, 0, 0x00000001, 0x00000102, 0x00010201, 0x01020100, 0x04000000};
+  int o[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    int acc = 8;
+    if (WA) { if (C0[j]) acc = dp4a_us(pk[2 * ra], C0[j] * WA, acc); if (C1[j]) acc = dp4a_us(pk[2 * ra + 1], C1[j] * WA, acc); }
+    if (WB) { if (C0[j]) acc = dp4a_us(pk[2 * rb], C0[j] * WB, acc); if (C1[j]) acc = dp4a_us(pk[2 * rb + 1], C1[j] * WB, acc); }
+    if (WC) { if (C0[j]) acc = dp4a_us(pk[2 * rc], C0[j] * WC, acc); if (C1[j]) acc = dp4a_us(pk[2 * rc + 1], C1[j] * WC, acc); }
+    o[j] = acc >> 4;
+  }
+  o0 = pack4_sat(o[0], o[1], o[2], o[3]); o1 = pack4_sat(o[4], o[5], o[6], o[7]);
+}
+
 __global__ void __launch_bounds__(MB4_THREADS, 3)
 mb_encode_kernel(const __grid_constant__ MbArgs a) {
   extern __shared__ __align__(16) uint32_t s_dyn[];
   __shared__ int s_acc[6][MB4_PER_CTA];
-  __shared__ uint32_t s_qm[32];
+  __shared__ uint32_t s_qm[32], s_qa[32];
+  __shared__ uint8_t s_mt[MB4_PER_CTA];
   const Geom& g = a.g;
   const int lane = threadIdx.x & 31, c = threadIdx.x >> 5;        // block index within the MB: p64.c:77-79
   int* tile = reinterpret_cast<int*>(s_dyn) + threadIdx.x * MB4_TILE;
   uint32_t* s_pk = reinterpret_cast<uint32_t*>(tile) + 64;        // packed prediction, 8 rows x 2 words
-  if (threadIdx.x < 32) s_qm[threadIdx.x] = threadIdx.x ? (1u << 18) / threadIdx.x + 1u : 0u;
+  if (threadIdx.x < 32) {                                           // per quantiser: M and the clamp A(Q) of fwd_row
+    const uint32_t qq = threadIdx.x, m = qq ? (1u << 18) / qq + 1u : 0u, k = ((qq & 1) ? 4u : 12u) * m;
+    s_qm[qq] = m;
+    s_qa[qq] = qq ? min(8187u, ((1u << 29) - 1u - k) / m) : 0u;
+  }
 
   const int n_total = a.n_streams * a.gob_count * 33;
   const int n = blockIdx.x * MB4_PER_CTA + lane;
@@ -683,22 +720,27 @@ mb_encode_kernel(const __grid_constant__ MbArgs a) {
   }
   const int mvx = me0.x, mvy = me0.y;
   const int li = a.li_prev[(size_t)s * g.nmb + mbi];
-  int mt = 0;
-  if (!a.first_frame) {
-    double x = (double)me0.w / 256.0, y = (double)me0.z / 256.0;
-    int var = me1.x, varor = me1.y;
-    if (var < 64 || varor > var) {
-      if (x < 1.0 || (x < 3.0 && y > x * 0.5) || y > __ddiv_rn(x, 1.1)) mt = 2;
-      else if (var < 6) mt = 5;
-      else mt = 8;
-    } else mt = 0;
-    if (a.force_intra) mt = 0;
+  if (c == 0) {                                     // once per macroblock; the other five warps read it after the barrier
+    int mt0 = 0;
+    if (!a.first_frame) {
+      double x = (double)me0.w / 256.0, y = (double)me0.z / 256.0;
+      int var = me1.x, varor = me1.y;
+      if (var < 64 || varor > var) {
+        if (x < 1.0 || (x < 3.0 && y > x * 0.5) || y > __ddiv_rn(x, 1.1)) mt0 = 2;
+        else if (var < 6) mt0 = 5;
+        else mt0 = 8;
+      } else mt0 = 0;
+      if (a.force_intra) mt0 = 0;
+    }
+    if (li > 131) mt0 = 0;
+    s_mt[lane] = (uint8_t)mt0;
   }
-  if (li > 131) mt = 0;
   const int q = a.quant ? a.quant[s] : a.gquant;
+  __syncthreads();                                  // s_qm, s_qa, s_mt
+  int mt = s_mt[lane];
   const bool intra = mt_is(M_INTRA, mt);
-  __syncthreads();                                  // s_qm
-  const uint32_t ev = (q & 1) ? 0u : 1u, M = s_qm[q], K = (4u + 8u * ev) * M;
+  const uint32_t ev = (q & 1) ? 0u : 1u;
+  const int M = (int)s_qm[q], K = (int)(4u + 8u * ev) * M, A = (int)s_qa[q];
 
   // ---- prediction (SubOverlay / SubCompensate / HalfSubCompensate addressing, io.c:142-313; chroma vector = MV/2 with C
   // truncation, io.c:268-269), as packed bytes: pk[2r], pk[2r+1] = row r
@@ -715,32 +757,14 @@ mb_encode_kernel(const __grid_constant__ MbArgs a) {
   if (!intra) {
     fetch_pred(mt_is(M_MF, mt));
     if (mt_is(M_FILTER, mt)) {
-      // H.261 loop filter (LoadFilterMatrix, io.c:323-372): horizontal 1-2-1 per row (block-edge columns x4) into the tile,
-      // vertical 1-2-1 on half blocks (block-edge rows x4), single rounding (S16+8)>>4 (identity in tests/test_oracle_vs_ref.py)
+      uint32_t f[16];
+      filter_row<0, 4, 0>(pk, 0, 0, 0, f[0], f[1]);
+      filter_row<1, 2, 1>(pk, 0, 1, 2, f[2], f[3]);   filter_row<1, 2, 1>(pk, 1, 2, 3, f[4], f[5]);
+      filter_row<1, 2, 1>(pk, 2, 3, 4, f[6], f[7]);   filter_row<1, 2, 1>(pk, 3, 4, 5, f[8], f[9]);
+      filter_row<1, 2, 1>(pk, 4, 5, 6, f[10], f[11]); filter_row<1, 2, 1>(pk, 5, 6, 7, f[12], f[13]);
+      filter_row<0, 4, 0>(pk, 7, 7, 7, f[14], f[15]);
 #pragma unroll
-      for (int r = 0; r < 8; r++) {
-        int p[8], h0[4], h1[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) { p[j] = ubyte(pk[2 * r], j); p[4 + j] = ubyte(pk[2 * r + 1], j); }
-        h0[0] = p[0] << 2; h0[1] = p[0] + 2 * p[1] + p[2]; h0[2] = p[1] + 2 * p[2] + p[3]; h0[3] = p[2] + 2 * p[3] + p[4];
-        h1[0] = p[3] + 2 * p[4] + p[5]; h1[1] = p[4] + 2 * p[5] + p[6]; h1[2] = p[5] + 2 * p[6] + p[7]; h1[3] = p[7] << 2;
-        st_row(tile, r, 0, h0); st_row(tile, r, 1, h1);
-      }
-#pragma unroll
-      for (int h = 0; h < 2; h++) {
-        int v[8][4];
-#pragma unroll
-        for (int r = 0; r < 8; r++) ld_row(tile, r, h, v[r]);
-        int o[8][4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          o[0][j] = (4 * v[0][j] + 8) >> 4; o[7][j] = (4 * v[7][j] + 8) >> 4;
-#pragma unroll
-          for (int r = 1; r < 7; r++) o[r][j] = (v[r - 1][j] + 2 * v[r][j] + v[r + 1][j] + 8) >> 4;
-        }
-#pragma unroll
-        for (int r = 0; r < 8; r++) pk[2 * r + h] = pack4(o[r][0], o[r][1], o[r][2], o[r][3]);
-      }
+      for (int i = 0; i < 16; i++) pk[i] = f[i];
     }
   }
 
@@ -770,10 +794,10 @@ mb_encode_kernel(const __grid_constant__ MbArgs a) {
 #pragma unroll
   for (int i = 0; i < 16; i++) out[i] = 0;
   int acc = 0;
-  acc += fwd_row<0>(tile, out, M, K, ev, intra); acc += fwd_row<1>(tile, out, M, K, ev, intra);
-  acc += fwd_row<2>(tile, out, M, K, ev, intra); acc += fwd_row<3>(tile, out, M, K, ev, intra);
-  acc += fwd_row<4>(tile, out, M, K, ev, intra); acc += fwd_row<5>(tile, out, M, K, ev, intra);
-  acc += fwd_row<6>(tile, out, M, K, ev, intra); acc += fwd_row<7>(tile, out, M, K, ev, intra);
+  acc += fwd_row<0>(tile, out, M, K, A, ev, intra); acc += fwd_row<1>(tile, out, M, K, A, ev, intra);
+  acc += fwd_row<2>(tile, out, M, K, A, ev, intra); acc += fwd_row<3>(tile, out, M, K, A, ev, intra);
+  acc += fwd_row<4>(tile, out, M, K, A, ev, intra); acc += fwd_row<5>(tile, out, M, K, A, ev, intra);
+  acc += fwd_row<6>(tile, out, M, K, A, ev, intra); acc += fwd_row<7>(tile, out, M, K, A, ev, intra);
   const size_t mb_out = (size_t)s * a.out_mb_per_stream + (mbi - a.gob_first * 33);
   if (active) {
     uint4* lp = reinterpret_cast<uint4*>(a.levels + mb_out * 384 + c * 64);
@@ -847,11 +871,11 @@ mb_encode_kernel(const __grid_constant__ MbArgs a) {
       const uint2 pw = *reinterpret_cast<const uint2*>(s_pk + 2 * r);
       int o[8];
 #pragma unroll
-      for (int j = 0; j < 4; j++) {              // + prediction byte j by a byte dot product (FMA pipe)
-        o[j] = min(max(dp4a_us(pw.x, 1 << (8 * j), round_div16(x[j])), 0), 255);
-        o[4 + j] = min(max(dp4a_us(pw.y, 1 << (8 * j), round_div16(x[4 + j])), 0), 255);
+      for (int j = 0; j < 4; j++) {              // + prediction byte j by a byte dot product (FMA pipe); the clamp is in the pack
+        o[j] = dp4a_us(pw.x, 1 << (8 * j), round_div16(x[j]));
+        o[4 + j] = dp4a_us(pw.y, 1 << (8 * j), round_div16(x[4 + j]));
       }
-      if (active) op[r * wq] = make_uint2(pack4(o[0], o[1], o[2], o[3]), pack4(o[4], o[5], o[6], o[7]));
+      if (active) op[r * wq] = make_uint2(pack4_sat(o[0], o[1], o[2], o[3]), pack4_sat(o[4], o[5], o[6], o[7]));
     }
   } else if (active) {
 #pragma unroll
@@ -947,30 +971,15 @@ mb_decode_kernel(const __grid_constant__ MbDecArgs a) {
     const uint8_t* b = a.ref + fo + off + dy * w + dx;
 #pragma unroll
     for (int i = 0; i < 8; i++) { const uint2 r = fetch_row8(b + i * w); pk[2 * i] = r.x; pk[2 * i + 1] = r.y; }
-    if (mt_is(M_FILTER, mt)) {                       // LoadFilterMatrix, io.c:323-372 (single rounding (S16+8)>>4)
+    if (mt_is(M_FILTER, mt)) {                       // LoadFilterMatrix, io.c:323-372 (filter_row: single rounding (S16+8)>>4)
+      uint32_t f[16];
+      filter_row<0, 4, 0>(pk, 0, 0, 0, f[0], f[1]);
+      filter_row<1, 2, 1>(pk, 0, 1, 2, f[2], f[3]);   filter_row<1, 2, 1>(pk, 1, 2, 3, f[4], f[5]);
+      filter_row<1, 2, 1>(pk, 2, 3, 4, f[6], f[7]);   filter_row<1, 2, 1>(pk, 3, 4, 5, f[8], f[9]);
+      filter_row<1, 2, 1>(pk, 4, 5, 6, f[10], f[11]); filter_row<1, 2, 1>(pk, 5, 6, 7, f[12], f[13]);
+      filter_row<0, 4, 0>(pk, 7, 7, 7, f[14], f[15]);
 #pragma unroll
-      for (int r = 0; r < 8; r++) {
-        int p[8], h0[4], h1[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) { p[j] = ubyte(pk[2 * r], j); p[4 + j] = ubyte(pk[2 * r + 1], j); }
-        h0[0] = p[0] << 2; h0[1] = p[0] + 2 * p[1] + p[2]; h0[2] = p[1] + 2 * p[2] + p[3]; h0[3] = p[2] + 2 * p[3] + p[4];
-        h1[0] = p[3] + 2 * p[4] + p[5]; h1[1] = p[4] + 2 * p[5] + p[6]; h1[2] = p[5] + 2 * p[6] + p[7]; h1[3] = p[7] << 2;
-        st_row(tile, r, 0, h0); st_row(tile, r, 1, h1);
-      }
-#pragma unroll
-      for (int h = 0; h < 2; h++) {
-        int v[8][4], o[8][4];
-#pragma unroll
-        for (int r = 0; r < 8; r++) ld_row(tile, r, h, v[r]);
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          o[0][j] = (4 * v[0][j] + 8) >> 4; o[7][j] = (4 * v[7][j] + 8) >> 4;
-#pragma unroll
-          for (int r = 1; r < 7; r++) o[r][j] = (v[r - 1][j] + 2 * v[r][j] + v[r + 1][j] + 8) >> 4;
-        }
-#pragma unroll
-        for (int r = 0; r < 8; r++) pk[2 * r + h] = pack4(o[r][0], o[r][1], o[r][2], o[r][3]);
-      }
+      for (int i = 0; i < 16; i++) pk[i] = f[i];
     }
   }
   if (!coded) {                                      // reconstruction = prediction (zero residual)
@@ -1012,10 +1021,10 @@ mb_decode_kernel(const __grid_constant__ MbDecArgs a) {
     int o[8];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-      o[j] = min(max(dp4a_us(pk[2 * r], 1 << (8 * j), round_div16(x[j])), 0), 255);
-      o[4 + j] = min(max(dp4a_us(pk[2 * r + 1], 1 << (8 * j), round_div16(x[4 + j])), 0), 255);
+      o[j] = dp4a_us(pk[2 * r], 1 << (8 * j), round_div16(x[j]));
+      o[4 + j] = dp4a_us(pk[2 * r + 1], 1 << (8 * j), round_div16(x[4 + j]));
     }
-    op[r * wq] = make_uint2(pack4(o[0], o[1], o[2], o[3]), pack4(o[4], o[5], o[6], o[7]));
+    op[r * wq] = make_uint2(pack4_sat(o[0], o[1], o[2], o[3]), pack4_sat(o[4], o[5], o[6], o[7]));
   }
 }
 

@@ -169,6 +169,12 @@ def test_multiply_shift_dividers_are_exact(orc):
         assert int(prod.max()) < 2 ** 32                                 # fits the uint32 arithmetic used on device
         got = np.minimum((prod >> np.uint64(22)).astype(np.int64), 127) * np.sign(v)
         assert np.array_equal(got, want), q
+        # the signed one-clamp form the kernel uses (kernels.cuh fwd_row): level = (clamp(v,-A,A)*M + (v<0 ? K^0x3fffff : K)) >> 22
+        assert K < (1 << 22)
+        A = min(8187, ((1 << 29) - 1 - K) // M)                           # s_qa[q] in mb_encode_kernel
+        t = np.clip(v, -A, A) * M + np.where(v < 0, K ^ 0x3fffff, K)
+        assert int(t.max()) < 2 ** 31 and int(t.min()) >= -2 ** 31          # fits the int32 arithmetic used on device
+        assert np.array_equal(t >> 22, want), q
         # the DC path keeps (x*rcp)>>19
         aa = np.arange(0, 4097, dtype=np.int64)
         rcp = (1 << 19) // (2 * q) + 1
@@ -184,6 +190,11 @@ def test_multiply_shift_dividers_are_exact(orc):
             M = (1 << 22) // (16 * q) + 1
             got = min(((min(abs(val), 8187) * M + (4 + 8 * ev) * M) & 0xffffffff) >> 22, 127) * (1 if val > 0 else -1 if val < 0 else 0)
             assert got == want, (q, val)
+    # sum |level| vs sum level^2: the same answers to "!= 0" and "> 1" (p64.c:887-903)
+    rng = np.random.default_rng(0)
+    for _ in range(2000):
+        lv = rng.integers(-2, 3, 64) * (rng.random(64) < rng.choice([0.02, 0.05, 0.5]))
+        assert (np.abs(lv).sum() != 0) == ((lv * lv).sum() != 0) and (np.abs(lv).sum() > 1) == ((lv * lv).sum() > 1)
     # rounding identities (chendct.c:205, 374)
     w = np.arange(-5000, 5001, dtype=np.int64)
     assert np.array_equal((w + 4 + (w >> 63)) >> 3, np.where(w < 0, -((-w + 4) // 8), (w + 4) // 8))
