@@ -251,3 +251,45 @@ def test_bits_put_and_carry_join(L):
         tail.finish()
         head_bytes = int(head, 2).to_bytes(len(head) // 8, "big") if head else b""
         assert head_bytes + tail.data() == want, cut
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """the drop-in boundary is a C ABI: the header compiles as C89/C99 and a C program links against the library, sees the
+    geometry of SetCCITT (p64.c:1476-1514) and gets a clean error -- not a crash, not a fallback -- when no GPU is usable"""
+    import shutil
+    import subprocess
+    from p64_b200 import build
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("no C compiler")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = os.path.join(root, "include", "p64_b200.h")
+    for std in ("c89", "c99"):
+        subprocess.run([gcc, f"-std={std}", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", hdr], check=True)
+    src = tmp_path / "t.c"
+    src.write_text('''
+#include <stdio.h>
+#include "p64_b200.h"
+int main(void) {
+  p64b_ctx *ctx = 0; p64b_enc_params p; int rc;
+  if (p64b_version() != P64B_VERSION) return 10;
+  if (p64b_width(P64B_IT_CIF) != 352 || p64b_height(P64B_IT_CIF) != 288 || p64b_num_gob(P64B_IT_CIF) != 12) return 11;
+  if (p64b_frame_bytes(P64B_IT_QCIF) != 38016 || p64b_num_mb(P64B_IT_NTSC) != 330) return 12;
+  if (p64b_raw_frame_bytes(P64B_IT_CIF, P64B_CHROMA_422) != 352 * 288 * 2) return 13;
+  p64b_enc_default_params(&p);
+  if (p.image_type != P64B_IT_NTSC || p.search_limit != 15 || p.frame_rate != 30000 || p.frame_rate_div != 1001) return 14;
+  rc = p64b_ctx_create(&ctx, 0, P64B_IT_CIF, 1);
+  printf("%d %s\\n", rc, rc ? p64b_last_error() : "ok");
+  if (!rc) p64b_ctx_destroy(ctx);
+  return 0;
+}
+''')
+    lib_dir = os.path.dirname(build.build_lib())
+    exe = tmp_path / "t"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-I", os.path.join(root, "include"), str(src), "-L", lib_dir, "-lp64b200",
+                    f"-Wl,-rpath,{lib_dir}", "-o", str(exe)], check=True)
+    r = subprocess.run([str(exe)], stdout=subprocess.PIPE, check=True)
+    rc, msg = r.stdout.decode().split(" ", 1)
+    import torch
+    if not torch.cuda.is_available():
+        assert int(rc) == -2 and "no CPU fallback" in msg
