@@ -44,8 +44,8 @@ IT_CIF = 1
 SAD_OPS_PER_CIF_FRAME = 343473 * 64          # legal candidates (me.c:212-213) x 64 packed 4-byte SADs each
 MB_BYTES_INTER = 384 + 384 + 384 + 384 + 8   # source + prediction + reconstruction + int8 levels + record
 # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full` captures of
-# this very workload (profiles/r01_ncu_me_search_kernel.txt, profiles/r01_ncu_mb_encode_kernel.txt), bytes
-NCU_TRAFFIC = {"me_search_kernel": 51_940_096 + 1_754_368, "mb_encode_kernel": 81_230_592 + 34_341_632}
+# this very workload (profiles/r01_ncu_me_search_kernel_v6.txt, profiles/r01_ncu_mb_encode_kernel_v5.txt), bytes
+NCU_TRAFFIC = {"me_search_kernel": 51_943_168 + 1_667_328, "mb_encode_kernel": 81_309_952 + 35_024_384}
 
 
 def _clocks_sampler(stop, out, gpu_index):
@@ -346,8 +346,8 @@ def main_cuda(args):
         mb_roof = {"kernel": "mb_encode_kernel", "bound": "hbm", "achieved": mb_bytes / (mb_ms * 1e-3) / 1e9, "peak": hbm_peak,
                    "unit": "GB/s", "frac": (mb_bytes / (mb_ms * 1e-3) / 1e9) / hbm_peak, "traffic": NCU_TRAFFIC["mb_encode_kernel"], "avg_launch_ms": mb_ms,
                    "launches_timed": prof["mb"][1], "peak_source": peak_src,
-                   "note": "integer-issue bound, not HBM bound: ncu shows the ALU pipe (shifts, byte permutes, min/max, shift-adds) busy 69 % "
-                           "and the FMA pipe (IMAD, IDP.4A) 25 % at 64 % issue utilisation (DESIGN.md 3.2)",
+                   "note": "integer-issue bound, not HBM bound: ncu shows the ALU pipe (shifts, byte permutes, min/max, shift-adds) busy 58 % "
+                           "and the FMA pipe (IMAD, IDP.4A) 32 % at 66 % issue utilisation, 3850 instructions per 8x8 block (DESIGN.md 3.2)",
                    "algorithmic": f"{MB_BYTES_INTER} B per inter macroblock (384 source + 384 prediction + 384 reconstruction + 384 int8 levels + 8 record) x {nmb * S} macroblocks per launch"}
         dominant = me_roof if me_ms >= mb_ms else mb_roof
         cpu = None
