@@ -1,7 +1,7 @@
-"""Randomised parity soak (not part of the test suite: it runs for minutes).  Random picture size, content, quantiser or
+"""TEST INFRASTRUCTURE.  Randomised parity soak (not collected by pytest: it runs for minutes).  Random picture size, content, quantiser or
 bit rate, search mode / range, input chroma type, stream count; the device path (device-side VLC / rate control, batch of
 streams) must give, stream by stream, the bytes of the CPU oracle + host bit writer, and the decoder must reproduce the
-encoder's reconstruction.   python tools/fuzz_parity.py [seconds] [seed]"""
+encoder's reconstruction.   python tests/fuzz_parity.py [seconds] [seed]"""
 import os
 import sys
 import time
@@ -9,7 +9,7 @@ import time
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))      # the oracle is used here as the checker only
 from helpers import oracle_encode_stream  # noqa: E402
 from oracle import oracle as O  # noqa: E402
 from p64_b200 import y4m  # noqa: E402
