@@ -124,6 +124,9 @@ constexpr int ME_V_FULL = 0, ME_V_SURF = 1, ME_V_TSS = 2;
 // found so far, SAD(0,0) included) none of them can win or tie, and the remaining rows are skipped.  There are two such
 // check points (after R1 and R2 rows).  Exact for any content; on content without a good match nothing is skipped and a
 // pass costs 2 (NC-1) extra row loads.
+#ifndef P64B_ME_PASS_ROWS
+#define P64B_ME_PASS_ROWS 10
+#endif
 #ifndef P64B_ME_PRUNE_R1
 #define P64B_ME_PRUNE_R1 4
 #endif
@@ -316,16 +319,17 @@ me_search_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_consta
       // winner is the minimum of a key that carries the reference's scan order).  The two-half mapping of edge columns
       // keeps the plain order (the halves would disagree about the centre; control flow must stay warp-uniform).
       constexpr bool PR = VARIANT == ME_V_FULL;
-      const int np = rpg <= 0 ? 0 : (rpg - 1) / 10 + 1;                 // passes k = 0..np-1 start at row 10k
-      const int kc = (PR && !xr) ? min(max((15 - lylo) / 10, 0), max(np - 1, 0)) : 0;
+      constexpr int PS = (PR && P64B_ME_PASS_ROWS == 5) ? 5 : 10;       // pass stride (experiments: 5-row passes prune finer)
+      const int np = rpg <= 0 ? 0 : (rpg - 1) / PS + 1;                 // passes k = 0..np-1 start at row PS*k
+      const int kc = (PR && !xr) ? min(max((15 - lylo) / PS, 0), max(np - 1, 0)) : 0;
       uint32_t bound = omv;                                             // smallest full SAD so far
       for (int v = 0; v < 2 * np; v++) {
         const int k = (PR && !xr) ? kc + ((v + 1) >> 1) * ((v & 1) ? -1 : 1) : v;
         if (k < 0 || k >= np) continue;
-        const int done = 10 * k;
+        const int done = PS * k;
         uint32_t r;
-        if (rpg - done > 5) r = sweep_pass<VARIANT, 10, PR>(colbase, c, pen, s_sad, xi, min(ystart + done, 22), xok, a.m2048, bound, units);
-        else                r = sweep_pass<VARIANT, 5, PR>(colbase, c, pen, s_sad, xi, min(ystart + done, 27), xok, a.m2048, bound, units);
+        if (PS == 10 && rpg - done > 5) r = sweep_pass<VARIANT, 10, PR>(colbase, c, pen, s_sad, xi, min(ystart + done, 22), xok, a.m2048, bound, units);
+        else                            r = sweep_pass<VARIANT, 5, PR>(colbase, c, pen, s_sad, xi, min(ystart + done, 27), xok, a.m2048, bound, units);
         best = min(best, r);
         if (PR) bound = min(bound, __reduce_min_sync(0xffffffffu, xok ? r : 0xffffffffu) >> 11);
       }
