@@ -1,12 +1,14 @@
 // sm_100a kernels of the H.261 hot path.  All arithmetic is integer except the MTYPE decision (double),
 // exactly as in the reference; citations "file:line" are into maikmerten/p64.
 //
-//   me_surface_kernel   full 31x31 SAD surface per macroblock -> three-step walk or exhaustive argmin
-//                       + the VAR/VAROR/MWOR statistics                  (me.c:187-363)
+//   me_search_kernel    block matching over the legal part of the 31x31 SAD surface: exhaustive argmin (with the exact
+//                       warp-wide early exit), the three-step walk, + the VAR/VAROR/MWOR statistics   (me.c:187-363)
 //   mb_encode_kernel    MTYPE decision, prediction (MC / half-vector chroma / loop filter), residual,
 //                       Chen DCT, quantise, zig-zag, CBP + type-4/7 fallback, inverse quantise,
 //                       Chen IDCT, reconstruct                        (p64.c:734-773, 823-913, 935-1013)
-//   overflow_patch_kernel  MBs the host overrode to "type 4, zero vector" (p64.c:776-783)
+//   overflow_patch_kernel  MBs overridden to "type 4, zero vector" on buffer overflow (p64.c:776-783)
+//   mb_decode_kernel    the decoder's inverse half                    (p64.c:971-1013, 1179-1237)
+//   plane_stats_kernel  per-plane sums and histogram for the -l statistics  (stat.c:73-130)
 #pragma once
 #include <cstdint>
 #include <cuda.h>

@@ -2,6 +2,7 @@
 host-side logic (VLC tables, bit writer, multiply-shift divider, geometry, Y4M, CLI) behaves as specified."""
 import ctypes as C
 import os
+import sys
 import re
 import subprocess
 
@@ -293,3 +294,18 @@ int main(void) {
     import torch
     if not torch.cuda.is_available():
         assert int(rc) == -2 and "no CPU fallback" in msg
+
+
+def test_integration_glue_compiles_against_the_reference_headers():
+    """INTEGRATION.md's reference-side binding (examples/p64gpu_glue.c, generated from the document's C blocks) against
+    the reference's own globals.h / prototypes.h; needs the reference tree, so it runs in the build container only"""
+    import shutil
+    import subprocess
+    ref = os.environ.get("P64_REFERENCE", "/root/reference")
+    gcc = shutil.which("gcc")
+    if not (gcc and os.path.exists(os.path.join(ref, "globals.h"))):
+        pytest.skip("reference tree not present")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run([sys.executable, os.path.join(root, "tools", "make_glue_example.py")], check=True)
+    subprocess.run([gcc, "-std=gnu99", "-fsyntax-only", "-Wall", "-Werror", "-Wno-unused", "-Wno-implicit-int", "-I", ref,
+                    "-I", os.path.join(root, "include"), os.path.join(root, "examples", "p64gpu_glue.c")], check=True)
