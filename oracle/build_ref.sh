@@ -23,6 +23,28 @@ grep -q '^\s*FastBME(x,y,pmem,x,y,fmem);' "$TMP/me_fs.c"
 gcc $CF $ALL "$TMP/me_fs.c" -lm -o "$OUT/p64_ref_fs"
 gcc $CF -fPIC -shared $REF/me.c $REF/mem.c $REF/chendct.c $REF/transform.c $REF/io.c \
     $REF/vidinput.c $REF/y4m_input.c "$(dirname "$0")/ref_shim.c" -lm -o "$OUT/libp64ref.so"
+# p64_gpu / p64_gpu_fs: the reference's own main() and stream writer with the body of p64EncodeFrame() replaced by one call
+# into ../p64_b200/libp64b200.so per frame (examples/p64gpu_dropin.c).  p64.c goes through sed into the temp dir: the
+# per-frame work is cut out and four calls are inserted; nothing of it is kept in the repository.
+HERE=$(cd "$(dirname "$0")" && pwd)
+LIBDIR=$HERE/../p64_b200
+if [ -f "$LIBDIR/libp64b200.so" ]; then
+  sed -e '/^void p64EncodeFrame()/,/^}/ s|^    GlobalMC();|    ;|' \
+      -e '/^void p64EncodeFrame()/,/^}/ s|^  WritePictureHeader();|  ;|' \
+      -e '/^void p64EncodeFrame()/,/^}/ s|^    p64EncodeGOB();|    ;|' \
+      -e '/^void p64EncodeFrame()/,/^}/ s|^  for(CurrentGOB=0;|  p64gpu_frame_bits();\n  for(CurrentGOB=0;|' \
+      -e '/^void p64EncodeSequence()/,/^}/ s|^  swopen(CImage->StreamFileName);|  swopen(CImage->StreamFileName);\n  p64gpu_init();|' \
+      -e '/^void p64EncodeSequence()/,/^}/ s|^  GQuant=MQuant=InitialQuant;|  GQuant=MQuant=InitialQuant;\n  p64gpu_init_rate();|' \
+      -e '/^void p64EncodeSequence()/,/^}/ s|^  WritePictureHeader();|  p64gpu_flush();\n  WritePictureHeader();|' \
+      "$REF/p64.c" > "$TMP/p64_gpu.c"
+  [ "$(grep -c 'p64gpu_' "$TMP/p64_gpu.c")" = 4 ]
+  REST=""; for s in $SRCS; do [ "$s" = p64 ] || REST="$REST $REF/$s.c"; done
+  for v in "" _fs; do
+    DEF=""; [ -n "$v" ] && DEF="-DP64GPU_FULL"
+    gcc $CF $DEF -I"$HERE/../include" "$TMP/p64_gpu.c" $REST $REF/me.c "$HERE/../examples/p64gpu_dropin.c" \
+        -L"$LIBDIR" -lp64b200 -Wl,-rpath,'$ORIGIN/../../p64_b200' -lm -o "$OUT/p64_gpu$v"
+  done
+fi
 cp "$REF/test.intra" "$OUT/test.intra"   # interpreter program fed on stdin for the intra-only config
 rm -rf "$TMP"
 echo "built: $(ls $OUT)"
