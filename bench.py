@@ -449,6 +449,75 @@ def rate_control_leg(L, local, S, K, pin, set_bytes, ring, me_mode, barrier):
     return out
 
 
+def main_me1024(args):
+    """BASELINE configs[3]: batched full-search +-15 SAD over 1024 synthetic CIF frame pairs resident in HBM, against the
+    measured VABSDIFF4 issue peak.  Not the default workload (that is the stream batch); one JSON line of the same shape."""
+    import torch
+    from p64_b200 import _lib, y4m
+    from p64_b200.encoder import DeviceContext
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; p64_b200 has no CPU fallback")
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    P, K, W = 1024, args.steps, args.warmup
+    w, h = y4m.DIMS[IT_CIF]
+    bank = [y4m.random_pair(IT_CIF, 50 + b, shift=((b * 5) % 29 - 14, (b * 7) % 23 - 11), noise=4) for b in range(16)]
+    ref = np.stack([bank[p % 16][0] for p in range(P)]); cur = np.stack([bank[p % 16][1] for p in range(P)])
+    ctx = DeviceContext(IT_CIF, 1)
+    stream = torch.cuda.Stream()
+    ctx.set_cuda_stream(stream.cuda_stream)
+    r, c = torch.from_numpy(ref).cuda(), torch.from_numpy(cur).cuda()
+    out = torch.zeros(P * 396 * 8, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    samples, stop = [], threading.Event()
+    with torch.cuda.stream(stream):
+        for _ in range(W):
+            ctx.motion_estimation_dev(r.data_ptr(), c.data_ptr(), P, 1, SEARCH_LIMIT, out.data_ptr())
+        torch.cuda.synchronize()
+        th = threading.Thread(target=_clocks_sampler, args=(stop, samples, 0), daemon=True)
+        th.start()
+        ctx.me_executed(reset=True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(K):
+            ctx.motion_estimation_dev(r.data_ptr(), c.data_ptr(), P, 1, SEARCH_LIMIT, out.data_ptr())
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        executed = ctx.me_executed() / K
+        extra = 0
+        while len(samples) < 5 and extra < 2000:
+            ctx.motion_estimation_dev(r.data_ptr(), c.data_ptr(), P, 1, SEARCH_LIMIT, out.data_ptr())
+            extra += 1
+            if extra % 20 == 0:
+                torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        stop.set()
+        th.join(timeout=2)
+    L = _lib.lib()
+    peak_ops, clk = C.c_double(), C.c_double()
+    _lib.check(L.p64b_measure_sad_peak(0, C.byref(peak_ops), C.byref(clk)))
+    alg = SAD_OPS_PER_CIF_FRAME * P
+    line = {"metric": "CIF frame pairs/sec, full-search ME +-15 (BASELINE configs[3])", "value": P * K / (ms * 1e-3), "unit": "frame pairs/s",
+            "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "ME microbenchmark: 1024 CIF luma pairs resident in HBM (16 distinct seeded pairs: uniform noise and a copy "
+                                   "shifted by up to +-14 with noise +-4), exhaustive search -i 31, one launch per step",
+                       "l2": f"inputs larger than L2: {2 * P * w * h >> 20} MiB of luma planes per launch"},
+            "roofline": {"kernel": "me_search_kernel", "bound": "int_issue", "achieved": alg / (ms / K * 1e-3) / 1e9, "peak": peak_ops.value / 1e9,
+                         "unit": "G packed-SAD ops/s", "frac": alg / (ms / K * 1e-3) / peak_ops.value, "traffic": None,
+                         "executed": {"packed_sad_ops_per_launch": executed, "frac_of_peak": executed / (ms / K * 1e-3) / peak_ops.value,
+                                      "share_of_algorithmic": executed / alg},
+                         "algorithmic": f"{SAD_OPS_PER_CIF_FRAME} packed SAD ops per CIF pair x {P} pairs per launch"},
+            "cpu_baseline": None, "e2e": None, "gpu_launches": K, "clocks": _summarise_clocks(samples)}
+    ctx.close()
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
+    print(json.dumps(line), flush=True)
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -457,9 +526,13 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--search", default="full", choices=["full", "tss"],
                     help="full = exhaustive FastBME -i 31 (the north-star configuration, default); tss = the stock three-step StepBME")
+    ap.add_argument("--workload", default="streams", choices=["streams", "me1024"],
+                    help="streams = the stream batch (default, BASELINE configs[4]); me1024 = the ME microbenchmark of configs[3] (1 GPU)")
     ap.add_argument("--no-rate-control", action="store_true", help="skip the extra rate-control (-r) end-to-end leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
+    if args.impl == "cuda" and args.workload == "me1024":
+        return main_me1024(args)
     return main_reference(args) if args.impl == "reference" else main_cuda(args)
 
 
