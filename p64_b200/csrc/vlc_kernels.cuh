@@ -103,9 +103,8 @@ struct BitEmitter {
 
 // One 8x8 block (EncodeDC + EncodeAC for intra types, CBPEncodeAC otherwise; codec.c:96-205, 346-355).
 // EMIT = false: returns the length in bits; EMIT = true: also writes the bits.
-template <bool EMIT>
-__device__ __forceinline__ int vlc_block(const int8_t* __restrict__ lv, bool cbp_type, const uint32_t* s_tcoef, BitEmitter* em) {
-  // non-zero mask of the 64 levels
+// non-zero mask of a block's 64 levels (bit k = level k != 0)
+__device__ __forceinline__ uint64_t vlc_nz_mask(const int8_t* __restrict__ lv) {
   uint64_t nz = 0;
   const uint4* lp = reinterpret_cast<const uint4*>(lv);
 #pragma unroll
@@ -119,6 +118,12 @@ __device__ __forceinline__ int vlc_block(const int8_t* __restrict__ lv, bool cbp
       nz |= (uint64_t)m4 << (16 * i + 4 * j);
     }
   }
+  return nz;
+}
+
+// `nz`: the block's non-zero mask (vlc_nz_mask), computed once by the caller and reused by the emitting pass
+template <bool EMIT>
+__device__ __forceinline__ int vlc_block(const int8_t* __restrict__ lv, uint64_t nz, bool cbp_type, const uint32_t* s_tcoef, BitEmitter* em) {
   int len = 0, prev = -1;
   bool first = cbp_type, any = !cbp_type;
   if (!cbp_type) {                                   // EncodeDC, codec.c:346-355
@@ -231,6 +236,7 @@ vlc_gob_kernel(const __grid_constant__ VlcArgs a) {
   uint64_t hbits = 0;
   int len = 0;
   bool coded = false;
+  uint64_t nzmask = 0;
   const int8_t* lv = a.levels + (mbi * 6 + (k ? k - 1 : 0)) * 64;
   if (is_piece) {
     if (piece == 0) {                                 // WriteGOBHeader, marker.c:182-209: GBSC, GN, GQUANT, no GSPARE
@@ -245,7 +251,7 @@ vlc_gob_kernel(const __grid_constant__ VlcArgs a) {
         if (RC) s_rec[m] = *reinterpret_cast<const uint2*>(&rec);
       } else {
         coded = vt(V_TCOEF, rec.mtype) && ((rec.cbp >> (6 - k)) & 1);      // block c = k-1: bit 5-c
-        if (coded) len = vlc_block<false>(lv, vt(V_CBP, rec.mtype), s_t.tcoef, nullptr);
+        if (coded) { nzmask = vlc_nz_mask(lv); len = vlc_block<false>(lv, nzmask, vt(V_CBP, rec.mtype), s_t.tcoef, nullptr); }
       }
     }
   }
@@ -298,7 +304,7 @@ vlc_gob_kernel(const __grid_constant__ VlcArgs a) {
       if (len > 32) { em.put((uint32_t)(hbits >> 32), len - 32); em.put((uint32_t)hbits, 32); }
       else em.put((uint32_t)hbits, len);
     } else {
-      vlc_block<true>(lv, vt(V_CBP, rec.mtype), s_t.tcoef, &em);
+      vlc_block<true>(lv, nzmask, vt(V_CBP, rec.mtype), s_t.tcoef, &em);
     }
     em.flush();
   }
