@@ -45,6 +45,7 @@ if [ -f "$LIBDIR/libp64b200.so" ]; then
         -L"$LIBDIR" -lp64b200 -Wl,-rpath,'$ORIGIN/../../p64_b200' -lm -o "$OUT/p64_gpu$v"
   done
 fi
-cp "$REF/test.intra" "$OUT/test.intra"   # interpreter program fed on stdin for the intra-only config
+cp "$REF/test.intra" "$OUT/test.intra"
+cp "$REF/short.p64" "$OUT/short.p64"      # the reference's own 1993 stream (SETUP:13-33): decoder known-answer test   # interpreter program fed on stdin for the intra-only config
 rm -rf "$TMP"
 echo "built: $(ls $OUT)"

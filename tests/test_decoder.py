@@ -208,3 +208,61 @@ def test_cli_decodes_like_the_reference(tmp_path):
     if O.have_ref():                                                   # byte-compare against the reference decoder's own file
         O.ref_decode(str(tmp_path / "s.p64"), str(tmp_path / "ref"))
         assert open(tmp_path / "ref.y4m", "rb").read() == raw
+
+
+def _short_p64():
+    import os
+    p = os.path.join(O.REF_DIR, "short.p64")
+    if not (O.have_ref() and os.path.exists(p)):
+        pytest.skip("oracle/_ref/short.p64 not present (copied there by oracle/build_ref.sh)")
+    return p
+
+
+def test_parser_reads_the_references_own_1993_stream():
+    """SURVEY 4 KAT #1, parser half: short.p64 (7 NTSC pictures written by the ORIGINAL 1993 encoder -- a foreign stream:
+    other search, MBA skips) parses into 7 pictures with consecutive temporal references, and writing the parsed records and
+    levels back with the product's bit writer reproduces the file byte for byte (a parser that dropped or misread anything
+    could not)."""
+    from p64_b200.encoder import BitWriter, Parser
+    data = open(_short_p64(), "rb").read()
+    p = Parser(data)
+    assert p.image_type == y4m.IT_NTSC
+    bw = BitWriter(y4m.IT_NTSC)
+    n, skipped = 0, 0
+    while True:
+        pic = p.next_picture()
+        if pic is None:
+            break
+        mbs, lv, tr, rep = pic
+        assert rep == 1
+        bw.picture_header(tr)
+        for gob in range(10):
+            sent = [m for m in range(33) if mbs["reserved"][gob * 33 + m] & 1]
+            if not sent:
+                continue
+            bw.gob_header(gob, int(mbs["quant"][gob * 33 + sent[0]]))
+            for m in sent:
+                bw.mb(m, mbs[gob * 33 + m], lv[gob * 33 + m])
+            skipped += 33 - len(sent)
+        n += 1
+    p.close()
+    assert n == 7
+    bw.picture_header((tr + 1) % 32)
+    bw.finish()
+    out = bw.data()
+    assert len(out) == len(data) and out == data, (len(out), len(data), skipped)
+
+
+@pytest.mark.gpu
+def test_decoder_known_answer_short_p64(tmp_path):
+    """SURVEY 4 KAT #1: the reference's own stream decoded here == decoded by the reference decoder, frame by frame"""
+    from p64_b200.encoder import Decoder
+    path = _short_p64()
+    O.ref_decode(path, str(tmp_path / "ref"))
+    w, h, want = y4m.read_y4m(str(tmp_path / "ref.y4m"))
+    dec = Decoder(open(path, "rb").read())
+    got = dec.frames()
+    dec.close()
+    assert (w, h, len(want)) == (352, 240, 7) and len(got) == 7
+    for k in range(7):
+        assert np.array_equal(got[k], want[k]), k
