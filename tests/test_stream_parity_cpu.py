@@ -59,5 +59,23 @@ def test_short_p64_intra_kat(orc, tmp_path):
     golden = open(os.path.join(ref_dir, "short.p64"), "rb").read()
     assert data[:17323] == golden[:17323]
     # frame 0 = picture header .. last MB; the trailing picture header adds 32+9 bits (NTSC PSPARE) + padding
-    from p64_b200.encoder import BitWriter
     assert len(data) * 8 >= 138588
+    # ... and the statistics block of short.trace:3-8 for that frame, through the product's bit writer counters
+    import ctypes as C
+    from helpers import levels_to_i8, recs_to_mb
+    from p64_b200._lib import FrameCounters, lib
+    from p64_b200.encoder import BitWriter
+    enc, bw = orc.Encoder(y4m.IT_NTSC), BitWriter(y4m.IT_NTSC)
+    bw.picture_header(0)
+    recs, lv = enc.encode_frame(frames[0], 8)
+    mbs, lv8 = recs_to_mb(recs), levels_to_i8(lv)
+    for gob in range(10):
+        bw.gob_header(gob, 8)
+        for m in range(33):
+            bw.mb(m, mbs[gob * 33 + m], lv8[gob * 33 + m])
+    c = FrameCounters()
+    lib().p64b_bits_counters(bw.h, C.byref(c))
+    assert bw.tell() == 138588
+    assert (c.mb_attribute_bits, c.mv_bits, c.eob_bits) == (1650, 0, 3960)
+    assert (c.y_bits, c.u_bits, c.v_bits) == (123214, 3805, 5658)
+    assert c.macro_type_freq[0] == 330 and sum(c.macro_type_freq[:]) == 330
