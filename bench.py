@@ -45,6 +45,7 @@ SAD_OPS_PER_CIF_FRAME = 343473 * 64          # legal candidates (me.c:212-213) x
 MB_BYTES_INTER = 384 + 384 + 384 + 384 + 8   # source + prediction + reconstruction + int8 levels + record
 # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full` captures of
 # this very workload (profiles/r01_ncu_me_search_kernel_v6.txt, profiles/r01_ncu_mb_encode_kernel_v5.txt), bytes
+NCU_MB_WARP_INSTR = 73_252_848     # smsp__inst_executed.sum of mb_encode_kernel v5 on this workload (profiles/r01_ncu_mb_encode_kernel_v5.txt)
 NCU_TRAFFIC = {"me_search_kernel": 51_943_168 + 1_667_328, "mb_encode_kernel": 81_309_952 + 35_024_384}
 
 
@@ -221,7 +222,7 @@ def main_cuda(args):
         ctx.encode_frames_dev(make_step(first, QUANT, ME_MODE, SEARCH_LIMIT), dev_sets.data_ptr() + ring(i) * set_bytes,
                               d_mbs.data_ptr(), d_lv.data_ptr())
 
-    NOUT = 3
+    NOUT = int(os.environ.get("P64B_BENCH_INFLIGHT", "3"))      # steps in flight (the library's pipeline depth is 3)
     pin_outs = [(L.p64b_host_alloc(S * nmb * 8), L.p64b_host_alloc(S * nmb * 384)) for _ in range(NOUT)]
     if not all(a and b for a, b in pin_outs):
         raise SystemExit("pinned allocation failed")
@@ -295,6 +296,13 @@ def main_cuda(args):
         gb = C.c_double()
         _lib.check(L.p64b_measure_h2d(local, C.c_void_p(pin), C.c_size_t(set_bytes), 10, C.byref(gb)))
         h2d_gbs = gb.value
+        # the same with every rank uploading at the same time (N > 1): what the box's host side gives all GPUs together
+        h2d_conc = h2d_gbs
+        if world > 1:
+            barrier()
+            _lib.check(L.p64b_measure_h2d(local, C.c_void_p(pin), C.c_size_t(set_bytes), 30, C.byref(gb)))
+            h2d_conc = gb.value
+            barrier()
         # ---- BASELINE configs[2]: the same streams under rate control (-r), buffer model on the device ----------
         rc_line = None
         if not args.no_rate_control:
@@ -310,7 +318,8 @@ def main_cuda(args):
         th.join(timeout=2)
 
     rc_ms = [rc_line["ms_dev"], rc_line["ms_host"]] if rc_line else [0.0, 0.0]
-    ms, ms_e2e, ms_e2e_rec, rc_ms[0], rc_ms[1] = shard.max_over_ranks([ms, ms_e2e, ms_e2e_rec] + rc_ms, dist if world > 1 else None, device="cuda")
+    ms, ms_e2e, ms_e2e_rec, rc_ms[0], rc_ms[1], neg_conc = shard.max_over_ranks([ms, ms_e2e, ms_e2e_rec] + rc_ms + [-h2d_conc], dist if world > 1 else None, device="cuda")
+    h2d_conc_min = -neg_conc          # the slowest rank's upload rate while all ranks upload
 
     frames = world * S * K
     value = frames / (ms * 1e-3)
@@ -346,6 +355,10 @@ def main_cuda(args):
         mb_roof = {"kernel": "mb_encode_kernel", "bound": "hbm", "achieved": mb_bytes / (mb_ms * 1e-3) / 1e9, "peak": hbm_peak,
                    "unit": "GB/s", "frac": (mb_bytes / (mb_ms * 1e-3) / 1e9) / hbm_peak, "traffic": NCU_TRAFFIC["mb_encode_kernel"], "avg_launch_ms": mb_ms,
                    "launches_timed": prof["mb"][1], "peak_source": peak_src,
+                   "issue": {"warp_instructions_per_launch_ncu": NCU_MB_WARP_INSTR,
+                             "frac_of_issue_peak": NCU_MB_WARP_INSTR / (mb_ms * 1e-3) / (148 * 4 * clk.value * 1e6),
+                             "note": "the bound that actually holds: warp-instructions (ncu smsp__inst_executed.sum of the committed capture) per "
+                                     "launch time vs 148 SMs x 4 schedulers x 1 instruction per clock"},
                    "note": "integer-issue bound, not HBM bound: ncu shows the ALU pipe (shifts, byte permutes, min/max, shift-adds) busy 58 % "
                            "and the FMA pipe (IMAD, IDP.4A) 32 % at 66 % issue utilisation, 3850 instructions per 8x8 block (DESIGN.md 3.2)",
                    "algorithmic": f"{MB_BYTES_INTER} B per inter macroblock (384 source + 384 prediction + 384 reconstruction + 384 int8 levels + 8 record) x {nmb * S} macroblocks per launch"}
@@ -369,6 +382,8 @@ def main_cuda(args):
                         "stream_bytes_per_step": bits_used // K, "ms_per_step": ms_e2e / K,
                         "vlc_kernels_ms_per_step": prof_bits["vlc"][0] / max(1, prof_bits["vlc"][1]),
                         "upload_alone_gbs": h2d_gbs, "upload_share_of_step": (S * fb / (h2d_gbs * 1e9)) / (ms_e2e * 1e-3 / K),
+                        "upload_all_ranks_at_once_gbs_per_gpu_min": h2d_conc_min,
+                        "upload_bound_frames_s": world * h2d_conc_min * 1e9 / fb,
                         "api": "p64b_ctx_submit_bits/p64b_ctx_wait_bits (host source frames in, finished H.261 stream bytes out; "
                                "headers + VLC on the device; pinned buffers; 3 steps in flight)"},
                 "e2e_records": {"value": frames / (ms_e2e_rec * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": S * fb,
@@ -409,7 +424,7 @@ def rate_control_leg(L, local, S, K, pin, set_bytes, ring, me_mode, barrier):
     iq = min(max(10000000 // RATE, 1), 31)
     ctx = DeviceContext(IT_CIF, S, device=local)
     ctx.set_rate_control(RATE)
-    NOUT = 3
+    NOUT = int(os.environ.get("P64B_BENCH_INFLIGHT", "3"))
 
     def run(i0, n, first):
         tickets, down, used = [], 0, 0

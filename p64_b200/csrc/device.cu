@@ -49,7 +49,10 @@ struct p64b_ctx {
   cudaStream_t own = nullptr, stream = nullptr;
   uint8_t* d_src = nullptr;       // [S][frame_bytes]   (= slot 0 of the pipelined path)
   // pipelined host path (submit / wait): NSLOT sets of device staging buffers, separate copy streams
-  static constexpr int NSLOT = 3;
+#ifndef P64B_NSLOT
+#define P64B_NSLOT 3
+#endif
+  static constexpr int NSLOT = P64B_NSLOT;    // steps in flight (4 and 5 were measured: no gain)
   uint8_t* p_src[NSLOT] = {};
   p64b_mb* p_mbs[NSLOT] = {};
   int8_t* p_levels[NSLOT] = {};
