@@ -368,8 +368,12 @@ void p64b_enc_default_params(p64b_enc_params *p);
 int p64b_enc_create(p64b_enc **out, const p64b_enc_params *p);
 void p64b_enc_destroy(p64b_enc *e);
 /* Encode the next frame of every stream: src [n_streams][frame_bytes] (host); with input_chroma set,
- * [n_streams][p64b_raw_frame_bytes()] unconverted Y4M payloads.  p64b_enc_staging() is the encoder's own pinned
- * upload buffer of that size: a reader may fill it in place and pass it as `src` (no extra copy). */
+ * [n_streams][p64b_raw_frame_bytes()] unconverted Y4M payloads.  `src` is consumed before the call returns (copied
+ * into pinned staging), so the caller may reuse it at once.  p64b_enc_staging() is the encoder's own pinned upload buffer
+ * for the NEXT frame: a reader may fill it in place and pass it as `src` (no extra copy); it changes after every encode.
+ * With the device-side coder (host_vlc = 0) frames are pipelined three deep: the call enqueues this frame and collects
+ * the one submitted three calls earlier, p64b_enc_finish() collects the rest -- p64b_enc_data() / p64b_enc_overflows() /
+ * p64b_enc_first_frame_bits() are complete after p64b_enc_finish(). */
 int p64b_enc_encode(p64b_enc *e, const uint8_t *src);
 uint8_t *p64b_enc_staging(p64b_enc *e);
 /* Trailing picture header + padding (p64.c:600-605) for every stream. Call once after the last frame. */

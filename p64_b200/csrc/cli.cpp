@@ -151,9 +151,8 @@ int main(int argc, char** argv) {
   if (loud > 0) p.host_vlc = 1;                            // the per-category bit counters live in the host bit writer
   p64b_enc* enc = nullptr;
   if (p64b_enc_create(&enc, &p)) { fprintf(stderr, "p64b: %s\n", p64b_last_error()); return 2; }
-  uint8_t* frame = p64b_enc_staging(enc);
   for (int i = start; i > 0; --i)                           // seek to StartFrame (p64.c:562-565)
-    if (p64b_y4m_read_frame(in, frame) != 1) return 3;
+    if (p64b_y4m_read_frame(in, p64b_enc_staging(enc)) != 1) return 3;
   if (p.rate && !p.initial_quant) {                        // p64.c:574-586
     int iq = 10000000 / p.rate;
     iq = iq > 31 ? 31 : (iq < 1 ? 1 : iq);
@@ -163,6 +162,7 @@ int main(int argc, char** argv) {
   printf("START>SEQUENCE\n");
   for (int cf = start; cf <= last; cf += p.frame_skip) {
     printf("START>Frame: %d\n", cf);
+    uint8_t* frame = p64b_enc_staging(enc);                  // the pinned upload buffer of THIS frame (it rotates: frames are pipelined)
     if (p64b_y4m_read_frame(in, frame) != 1) { p64b_enc_destroy(enc); return 3; }
     if (p64b_enc_encode(enc, frame)) { fprintf(stderr, "p64b: %s\n", p64b_last_error()); return 2; }
     if (loud > 0) print_frame_statistics(enc, p);

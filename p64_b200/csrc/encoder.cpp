@@ -42,7 +42,13 @@ struct p64b_enc {
   std::vector<StreamState> st;
   p64b_mb* h_mbs = nullptr;      // pinned [S][nmb]
   int8_t* h_levels = nullptr;    // pinned [S][nmb][384]
-  uint8_t* h_src = nullptr;      // pinned staging [S][frame_bytes]
+  uint8_t* h_src = nullptr;      // pinned staging [S][src_bytes] of the NEXT frame (what p64b_enc_staging returns)
+  // device path: up to three frames in flight (p64b_ctx_submit_bits), harvested in order; four staging buffers so that
+  // the one handed out for the next frame is never one a pending upload still reads
+  static constexpr int DEPTH = 3, NSTAGE = 4;
+  uint8_t* h_ring[NSTAGE] = {};
+  int64_t tickets[DEPTH] = {};
+  int harvested = 0;             // frames whose bytes have been appended to the streams
   std::vector<uint8_t> quant, overflow;
   int threads = 1;
   bool device_vlc = false;       // headers + VLC (+ rate control) run on the device (p64b_ctx_submit_bits)
@@ -75,6 +81,25 @@ inline int execute_quantization(const p64b_enc* e, const StreamState& s, int g, 
   int cur = (int)buffer_contents(e, s, g, m);
   int q = cur / e->qdfact + e->qoffs;
   return std::min(std::max(q, 1), 31);
+}
+
+// device path: collect frame k's bytes (submitted earlier) into the streams
+int harvest(p64b_enc* e, int k) {
+  p64b_bits_out o{};
+  int rc = p64b_ctx_wait_bits(e->ctx, e->tickets[k % p64b_enc::DEPTH], &o);
+  if (rc) return rc;
+  parallel_streams(e, [&](int s) {
+    StreamState& ss = e->st[s];
+    ss.dev_bytes.insert(ss.dev_bytes.end(), o.data + o.offset[s], o.data + o.offset[s] + o.nbytes[s]);
+    ss.carry = o.carry[s]; ss.carry_len = o.carry_len[s];
+    const int64_t before = ss.total_bits;
+    ss.total_bits = (int64_t)o.bit_position[s];
+    ss.last_bits = ss.total_bits - before;
+    if (k == 0) ss.first_frame_bits = ss.total_bits;
+    ss.gquant = (int)o.gquant[s]; ss.overflows = (int64_t)o.overflows[s];
+  });
+  e->harvested = k + 1;
+  return 0;
 }
 
 }  // namespace
@@ -122,13 +147,15 @@ int p64b_enc_create(p64b_enc** out, const p64b_enc_params* p) {
   for (auto& s : e->st) { s.bits = p64b_bits_create(p->image_type); s.gquant = iq; }
   e->h_mbs = (p64b_mb*)p64b_host_alloc((size_t)e->S * e->nmb * sizeof(p64b_mb));
   e->h_levels = (int8_t*)p64b_host_alloc((size_t)e->S * e->nmb * P64B_LEVELS_PER_MB);
-  e->h_src = (uint8_t*)p64b_host_alloc((size_t)e->S * e->src_bytes);
-  if (!e->h_mbs || !e->h_levels || !e->h_src) { p64b_enc_destroy(e); return P64B_ENOMEM; }
+  e->device_vlc = !p->host_vlc;
+  for (int i = 0; i < (e->device_vlc ? p64b_enc::NSTAGE : 1); i++)
+    if (!(e->h_ring[i] = (uint8_t*)p64b_host_alloc((size_t)e->S * e->src_bytes))) { p64b_enc_destroy(e); return P64B_ENOMEM; }
+  e->h_src = e->h_ring[0];
+  if (!e->h_mbs || !e->h_levels) { p64b_enc_destroy(e); return P64B_ENOMEM; }
   e->quant.assign(e->S, (uint8_t)iq);
   e->overflow.assign((size_t)e->S * e->nmb, 0);
   int hw = (int)std::thread::hardware_concurrency();
   e->threads = p->vlc_threads > 0 ? p->vlc_threads : std::max(1, std::min(hw, 64));
-  e->device_vlc = !p->host_vlc;
   if (e->device_vlc && p->rate) {                  // the buffer model runs on the device, per stream
     p64b_rate_control r{};
     r.rate = p->rate; r.frame_rate = p->frame_rate; r.frame_rate_div = p->frame_rate_div; r.frame_skip = p->frame_skip;
@@ -142,8 +169,10 @@ int p64b_enc_create(p64b_enc** out, const p64b_enc_params* p) {
 void p64b_enc_destroy(p64b_enc* e) {
   if (!e) return;
   for (auto& s : e->st) p64b_bits_destroy(s.bits);
-  p64b_host_free(e->h_mbs); p64b_host_free(e->h_levels); p64b_host_free(e->h_src);
-  p64b_ctx_destroy(e->ctx);
+  p64b_host_free(e->h_mbs); p64b_host_free(e->h_levels);
+  p64b_ctx_destroy(e->ctx);                        // (drains whatever is still in flight before the staging goes away)
+  e->ctx = nullptr;
+  for (auto* b : e->h_ring) p64b_host_free(b);
   delete e;
 }
 
@@ -156,22 +185,24 @@ int p64b_enc_encode(p64b_enc* e, const uint8_t* src) {
   step.force_intra = e->p.force_intra;
   const int tr = e->current_frame % 32;            // p64.c:637
   if (!e->device_vlc) for (auto& ss : e->st) p64b_bits_counters_reset(ss.bits);      // p64.c:640-649
-  if (src != e->h_src) memcpy(e->h_src, src, (size_t)e->S * e->src_bytes);
   int rc;
   if (e->device_vlc) {
-    // device-side entropy coding (and rate control, if any): one device step returns every stream's next whole bytes
-    step.gquant = e->st[0].gquant;
-    int64_t ticket;
-    p64b_bits_out o{};
-    if ((rc = p64b_ctx_submit_bits(e->ctx, &step, tr, e->h_src, &ticket)) || (rc = p64b_ctx_wait_bits(e->ctx, ticket, &o))) return rc;
-    parallel_streams(e, [&](int s) {
-      StreamState& ss = e->st[s];
-      ss.dev_bytes.insert(ss.dev_bytes.end(), o.data + o.offset[s], o.data + o.offset[s] + o.nbytes[s]);
-      ss.carry = o.carry[s]; ss.carry_len = o.carry_len[s];
-      ss.total_bits = (int64_t)o.bit_position[s];
-      ss.gquant = (int)o.gquant[s]; ss.overflows = (int64_t)o.overflows[s];
-    });
-  } else if (!e->p.rate) {
+    // device-side entropy coding (and rate control, if any): a device step returns every stream's next whole bytes.  Frames
+    // are pipelined: this call enqueues frame n and collects frame n-3, so uploads, kernels and downloads of neighbouring
+    // frames overlap; p64b_enc_finish() collects the rest.
+    const int n = e->frames_done;
+    if (n >= p64b_enc::DEPTH && (rc = harvest(e, n - p64b_enc::DEPTH))) return rc;
+    uint8_t* stage = e->h_ring[n % p64b_enc::NSTAGE];
+    if (src != stage) memcpy(stage, src, (size_t)e->S * e->src_bytes);
+    step.gquant = e->st[0].gquant;                  // (only the first frame's value is used under rate control)
+    if ((rc = p64b_ctx_submit_bits(e->ctx, &step, tr, stage, &e->tickets[n % p64b_enc::DEPTH]))) return rc;
+    e->h_src = e->h_ring[(n + 1) % p64b_enc::NSTAGE];     // its last user, frame n-3, has just been collected
+    e->frames_done++;
+    e->current_frame += e->p.frame_skip;
+    return 0;
+  }
+  if (src != e->h_src) memcpy(e->h_src, src, (size_t)e->S * e->src_bytes);
+  if (!e->p.rate) {
     // fixed quantiser: one device step for the whole frame of every stream, then the VLC per stream
     step.gquant = e->st[0].gquant;
     if ((rc = p64b_ctx_encode_frames(e->ctx, &step, e->h_src, e->h_mbs, e->h_levels))) return rc;
@@ -221,11 +252,11 @@ int p64b_enc_encode(p64b_enc* e, const uint8_t* src) {
   }
   for (auto& ss : e->st) {                          // p64.c:654-681
     const int64_t before = ss.total_bits;
-    if (!e->device_vlc) ss.total_bits = p64b_bits_tell(ss.bits);
+    ss.total_bits = p64b_bits_tell(ss.bits);
     ss.last_bits = ss.total_bits - before;
     if (first) ss.first_frame_bits = ss.total_bits;
-    if (e->p.rate && !e->device_vlc) ss.buffer_contents_at_end = buffer_contents(e, ss, e->ngob, 0);   // p64.c:663, before 670-680
-    if (e->p.rate && !e->device_vlc) {
+    if (e->p.rate) ss.buffer_contents_at_end = buffer_contents(e, ss, e->ngob, 0);   // p64.c:663, before 670-680
+    if (e->p.rate) {
       if (first) ss.buffer_offset = buffer_size(e) / 2 - buffer_contents(e, ss, e->ngob, 0);
       ss.buffer_offset -= (int)((int64_t)e->p.rate * e->p.frame_skip * e->p.frame_rate_div / e->p.frame_rate);
     }
@@ -238,6 +269,8 @@ int p64b_enc_encode(p64b_enc* e, const uint8_t* src) {
 int p64b_enc_finish(p64b_enc* e) {
   if (!e) return P64B_EINVAL;
   if (e->finished) return 0;
+  if (e->device_vlc)
+    for (int k = e->harvested; k < e->frames_done; k++) { int rc = harvest(e, k); if (rc) return rc; }
   // p64.c:600-605: limit file growth, trailing picture header, pad with 1-bits
   int last_plus_1 = e->p.start_frame + (e->frames_done ? (e->frames_done - 1) * e->p.frame_skip : 0) + 1;
   int cf = e->frames_done ? std::min(e->current_frame, last_plus_1) : e->current_frame;
