@@ -98,6 +98,12 @@ struct p64b_ctx {
   long long* d_buffer_offset = nullptr;     // [S] BufferOffset
   uint32_t* d_overflows = nullptr;          // [S] NumberOvfl
   bool rc_started = false;                  // the initial quantiser has been loaded
+  uint32_t* d_pic_hdr = nullptr;            // [NSLOT][2] picture header of the step in each pipeline slot
+  // The rate-control frame step is a launch-bound chain of 1 + 2 x NumberGOB + 5 small kernels: it is captured once per
+  // (pipeline slot, frame-store parity, ME queue parity, search) into a CUDA graph and replayed (one launch per frame).
+  struct RcGraph { int slot, cur, parity, me_mode, search_limit, force_intra; cudaGraphExec_t exec; int kernels; };
+  std::vector<RcGraph> rc_graphs;
+  bool use_graphs = true;
   // optional per-kernel timing with CUDA events on the launching stream (bench.py roofline)
   bool prof = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_ev[3];   // 0 = ME kernel, 1 = MB kernel, 2 = entropy-coding kernels
@@ -330,6 +336,8 @@ void p64b_ctx_destroy(p64b_ctx* c) {
   cudaFree(c->d_stats);
   cudaFree(c->d_vlc_tables); cudaFree(c->d_gob_words); cudaFree(c->d_gob_bits); cudaFree(c->d_carry); cudaFree(c->d_carry_len);
   for (int i = 0; i < p64b_ctx::NSLOT; i++) cudaFree(c->d_aux[i]);
+  for (auto& g : c->rc_graphs) cudaGraphExecDestroy(g.exec);
+  cudaFree(c->d_pic_hdr);
   cudaFree(c->d_bitpos); cudaFree(c->d_frame_bits); cudaFree(c->d_buffer_offset); cudaFree(c->d_overflows);
   for (int i = 0; i < p64b_ctx::NSLOT; i++) { cudaFree(c->d_bits_out[i]); if (c->h_bits_out[i]) cudaFreeHost(c->h_bits_out[i]); }
   if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
@@ -668,6 +676,8 @@ static int ensure_bits_buffers(p64b_ctx* c) {
   ALLOCZ(c->d_frame_bits, S * 4);
   ALLOCZ(c->d_buffer_offset, S * 8);
   ALLOCZ(c->d_overflows, S * 4);
+  ALLOCZ(c->d_pic_hdr, p64b_ctx::NSLOT * 2 * 4);
+  c->use_graphs = getenv("P64B_NO_GRAPHS") == nullptr;
   for (int i = 0; i < p64b_ctx::NSLOT; i++) { ALLOCZ(c->d_bits_out[i], c->bits_out_cap); }
   ALLOCZ(c->d_vlc_tables, sizeof(DevVlcTables));
 #undef ALLOCZ
@@ -683,6 +693,63 @@ static int ensure_host_bits(p64b_ctx* c, int slot, size_t bytes) {
   const size_t cap = std::min(c->bits_out_cap, bytes + bytes / 2);
   if (cudaHostAlloc((void**)&c->h_bits_out[slot], cap, cudaHostAllocDefault) != cudaSuccess) { set_error("cudaHostAlloc failed (bit-stream buffer)"); return P64B_ENOMEM; }
   c->h_bits_cap[slot] = cap;
+  return 0;
+}
+
+// kernel attributes and lazily resolved entry points must exist before a stream capture starts
+static int ensure_kernel_attrs(p64b_ctx* c) {
+  if (!c->me_attr_done) {
+    CU(cudaFuncSetAttribute(me_search_kernel<ME_V_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, ME_SMEM_FULL));
+    CU(cudaFuncSetAttribute(me_search_kernel<ME_V_SURF>, cudaFuncAttributeMaxDynamicSharedMemorySize, ME_SMEM_SURF));
+    CU(cudaFuncSetAttribute(me_search_kernel<ME_V_TSS>, cudaFuncAttributeMaxDynamicSharedMemorySize, ME_SMEM_FULL));
+    CU(cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, c->device));
+    c->me_attr_done = true;
+  }
+  if (!c->mb_attr_done) {
+    CU(cudaFuncSetAttribute(mb_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MB4_SMEM));
+    c->mb_attr_done = true;
+  }
+  if (!encode_tiled_fn()) { set_error("cuTensorMapEncodeTiled entry point not available"); return P64B_ECUDA; }
+  return 0;
+}
+
+// One frame step of every stream under rate control, enqueued on the context's stream (eagerly, or into a capture):
+// motion estimation once; then GOB by GOB {quantise..reconstruct with the stream's GQUANT, entropy-code, count the bits,
+// choose the next GOB's GQUANT}; macroblocks the overflow test overrode are re-reconstructed as copies at the end
+// (macroblocks of a frame do not depend on each other); SwapFS; frame assembly.
+static int enqueue_rc_frame(p64b_ctx* c, const p64b_step* st, int slot, VlcArgs a, const VlcFrameArgs& f, const RcArgs& r) {
+  int rc;
+  const uint8_t* src_dev = c->p_src[slot];
+  if (!st->first_frame) {
+    if ((rc = launch_me(c, c->d_fs[c->cur], src_dev, (size_t)c->g.frame_bytes, c->S, st->me_mode, st->search_limit, c->d_me))) return rc;
+  } else {
+    CU(cudaMemsetAsync(c->d_me, 0, (size_t)c->S * c->g.nmb * sizeof(p64b_me), c->stream));
+  }
+  CU(cudaMemsetAsync(c->d_ovf, 0, (size_t)c->S * c->g.nmb, c->stream));
+  rc_frame_begin_kernel<<<(c->S + 255) / 256, 256, 0, c->stream>>>(r, c->S, c->rc_started ? 0 : st->gquant);
+  c->rc_started = true;
+  c->launches++;
+  for (int g = 0; g < c->g.ngob; g++) {
+    if ((rc = launch_mb(c, st, src_dev, g, 1, c->d_quant, c->p_mbs[slot], c->p_levels[slot], true))) return rc;
+    a.gob_first = g; a.gob_count = 1;
+    ProfScope ps(c, 2);
+    vlc_gob_kernel<true><<<c->S, VLC_THREADS, 0, c->stream>>>(a);
+    c->launches++;
+  }
+  {
+    const int warps = c->S * c->g.nmb, threads = 256;
+    overflow_patch_kernel<<<(warps * 32 + threads - 1) / threads, threads, 0, c->stream>>>(
+        c->g, c->d_ovf, c->d_fs[c->cur], c->d_fs[c->cur ^ 1], c->d_li[c->cur], c->d_li[c->cur ^ 1], c->S);
+  }
+  swap_stores(c);
+  c->last_src = src_dev;
+  {
+    ProfScope ps(c, 2);
+    vlc_sizes_kernel<<<1, 1024, 0, c->stream>>>(f);
+    vlc_frame_kernel<<<c->S, VLC_THREADS, 0, c->stream>>>(f);
+  }
+  c->launches += 3;
+  CU(cudaGetLastError());
   return 0;
 }
 
@@ -748,7 +815,9 @@ extern "C" int p64b_ctx_submit_bits(p64b_ctx* c, const p64b_step* st, int tempor
                  ((uint64_t)(c->image_type == P64B_IT_QCIF ? 0x00 : 0x04) << 33);
     f.pic_hdr_bits = 32;
     if (c->image_type == P64B_IT_NTSC) { h |= (1ull << 32) | (0x8cull << 24); f.pic_hdr_bits = 41; }
-    f.pic_hdr[0] = (uint32_t)(h >> 32); f.pic_hdr[1] = (uint32_t)h;
+    f.pic_hdr = c->d_pic_hdr + 2 * slot;
+    set_pic_hdr_kernel<<<1, 1, 0, c->stream>>>(c->d_pic_hdr + 2 * slot, (uint32_t)(h >> 32), (uint32_t)h);
+    c->launches++;
   }
   f.gob_words = c->d_gob_words; f.gob_bits = c->d_gob_bits; f.carry = c->d_carry; f.carry_len = c->d_carry_len;
   f.bitpos = c->d_bitpos; f.out = c->d_bits_out[slot]; f.n_streams = c->S; f.ngob = c->g.ngob; f.gquant = st->gquant;
@@ -777,37 +846,37 @@ extern "C" int p64b_ctx_submit_bits(p64b_ctx* c, const p64b_step* st, int tempor
     r.bitpos = c->d_bitpos; r.frame_bits = c->d_frame_bits; r.buffer_offset = c->d_buffer_offset;
     r.quant = c->d_quant; r.ovf = c->d_ovf; r.overflows = c->d_overflows;
     a.rc = r; f.rc = r;
-    const uint8_t* src_dev = c->p_src[slot];
-    if (!st->first_frame) {
-      if ((rc = launch_me(c, c->d_fs[c->cur], src_dev, (size_t)c->g.frame_bytes, c->S, st->me_mode, st->search_limit, c->d_me))) return rc;
+    if ((rc = ensure_kernel_attrs(c))) return rc;
+    const bool graphable = c->use_graphs && !st->first_frame && c->rc_started && !c->prof;
+    if (!graphable) {
+      if ((rc = enqueue_rc_frame(c, st, slot, a, f, r))) return rc;
     } else {
-      CU(cudaMemsetAsync(c->d_me, 0, (size_t)c->S * c->g.nmb * sizeof(p64b_me), c->stream));
+      const int parity = (int)(c->me_launches & 1);
+      p64b_ctx::RcGraph* g = nullptr;
+      for (auto& e : c->rc_graphs)
+        if (e.slot == slot && e.cur == c->cur && e.parity == parity && e.me_mode == st->me_mode && e.search_limit == st->search_limit &&
+            e.force_intra == st->force_intra) { g = &e; break; }
+      if (g) {                                       // replay: the same launches with the same arguments
+        CU(cudaGraphLaunch(g->exec, c->stream));
+        c->me_launches++; c->launches += g->kernels;
+        swap_stores(c);
+        c->last_src = c->p_src[slot];
+      } else {
+        const int64_t l0 = c->launches;
+        cudaGraph_t graph = nullptr;
+        CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        rc = enqueue_rc_frame(c, st, slot, a, f, r);
+        const cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (ce != cudaSuccess || !graph) { set_error(std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce)); return P64B_ECUDA; }
+        p64b_ctx::RcGraph e{slot, c->cur ^ 1, parity, st->me_mode, st->search_limit, st->force_intra, nullptr, (int)(c->launches - l0)};
+        const cudaError_t ie = cudaGraphInstantiate(&e.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) { set_error(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie)); return P64B_ECUDA; }
+        c->rc_graphs.push_back(e);                   // (enqueue_rc_frame already flipped c->cur: the key is the state BEFORE the step)
+        CU(cudaGraphLaunch(e.exec, c->stream));
+      }
     }
-    CU(cudaMemsetAsync(c->d_ovf, 0, (size_t)c->S * c->g.nmb, c->stream));
-    rc_frame_begin_kernel<<<(c->S + 255) / 256, 256, 0, c->stream>>>(r, c->S, c->rc_started ? 0 : st->gquant);
-    c->rc_started = true;
-    c->launches++;
-    for (int g = 0; g < c->g.ngob; g++) {
-      if ((rc = launch_mb(c, st, src_dev, g, 1, c->d_quant, c->p_mbs[slot], c->p_levels[slot], true))) return rc;
-      a.gob_first = g; a.gob_count = 1;
-      ProfScope ps(c, 2);
-      vlc_gob_kernel<true><<<c->S, VLC_THREADS, 0, c->stream>>>(a);
-      c->launches++;
-    }
-    {
-      const int warps = c->S * c->g.nmb, threads = 256;
-      overflow_patch_kernel<<<(warps * 32 + threads - 1) / threads, threads, 0, c->stream>>>(
-          c->g, c->d_ovf, c->d_fs[c->cur], c->d_fs[c->cur ^ 1], c->d_li[c->cur], c->d_li[c->cur ^ 1], c->S);
-    }
-    swap_stores(c);
-    c->last_src = src_dev;
-    {
-      ProfScope ps(c, 2);
-      vlc_sizes_kernel<<<1, 1024, 0, c->stream>>>(f);
-      vlc_frame_kernel<<<c->S, VLC_THREADS, 0, c->stream>>>(f);
-    }
-    c->launches += 3;
-    CU(cudaGetLastError());
   }
   CU(cudaEventRecord(c->ev_comp[slot], c->stream));
   CU(cudaStreamWaitEvent(c->s_d2h, c->ev_comp[slot], 0));

@@ -322,6 +322,9 @@ vlc_gob_kernel(const __grid_constant__ VlcArgs a) {
   }
 }
 
+// the picture header of the step about to run (kernel parameters -> device memory; launched outside any graph)
+__global__ void set_pic_hdr_kernel(uint32_t* dst, uint32_t w0, uint32_t w1) { dst[0] = w0; dst[1] = w1; }
+
 // Start of a frame under rate control: the picture header is written before GOB 0 asks for its quantiser.
 __global__ void rc_frame_begin_kernel(RcArgs r, int n_streams, int initial_quant) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -351,7 +354,8 @@ struct VlcFrameArgs {
   unsigned long long* bitpos;  // [S]
   uint8_t* out;                // the step's output buffer (layout above)
   int n_streams, ngob;
-  uint32_t pic_hdr[2];         // picture header bits (MSB first), pic_hdr_bits long
+  const uint32_t* pic_hdr;     // [2] picture header bits (MSB first), pic_hdr_bits long -- in device memory, so that a
+                               // captured CUDA graph of the frame step can be replayed with another temporal reference
   int pic_hdr_bits;
   int gquant;                  // reported when rc.rate == 0
   RcArgs rc;
