@@ -254,6 +254,11 @@ me_search_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_consta
       issue_loads(n_next, b ^ 1);
       ticket = atomicAdd(a.queue + a.parity, 1u);
     }
+    // hint for the pass order of the exhaustive search: the vertical vector this macroblock had in the output array before
+    // this launch (in the encoder: the previous frame's vector of the same macroblock; anything else is harmless, the
+    // order of evaluation never changes the result).  Loaded early, used after the window has arrived.
+    int hint_my = 0;
+    if (VARIANT == ME_V_FULL && lane == 0) hint_my = reinterpret_cast<const volatile int*>(a.out + n)[1];
     const int r_ = n - (int)(__umulhi((uint32_t)n, a.magic_pp) >> a.shift_pp) * per_pair;
     const int by = (int)(((uint32_t)r_ * a.magic_w) >> 16), bx = r_ - by * a.mbw;
 
@@ -316,14 +321,15 @@ me_search_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_consta
     if (VARIANT != ME_V_TSS) {
       const int o = xi + 1, k = o & 3;                             // o = dx + 16
       const uint32_t* colbase = (k ? shifted + (k - 1) * ME_COPY_WORDS : win) + (o >> 2);
-      // passes of 10 (a last one of 5) dy rows.  Exhaustive search: the pass that holds dy = 0 goes first, then outwards, so
-      // that the bound of the early exit is good as soon as possible (the order of evaluation does not matter: the
+      // passes of 10 (a last one of 5) dy rows.  Exhaustive search: the pass that holds the hinted dy (the macroblock's
+      // previous vector; 0 at first) goes first, then outwards, so that the bound of the early exit is good as soon as possible (the order of evaluation does not matter: the
       // winner is the minimum of a key that carries the reference's scan order).  The two-half mapping of edge columns
       // keeps the plain order (the halves would disagree about the centre; control flow must stay warp-uniform).
       constexpr bool PR = VARIANT == ME_V_FULL;
       constexpr int PS = (PR && P64B_ME_PASS_ROWS == 5) ? 5 : 10;       // pass stride (experiments: 5-row passes prune finer)
       const int np = rpg <= 0 ? 0 : (rpg - 1) / PS + 1;                 // passes k = 0..np-1 start at row PS*k
-      const int kc = (PR && !xr) ? min(max((15 - lylo) / PS, 0), max(np - 1, 0)) : 0;
+      const int hy = min(max(__shfl_sync(0xffffffffu, hint_my, 0), -15), 15) + 15;      // hinted dy as a surface row
+      const int kc = (PR && !xr) ? min(max((hy - lylo) / PS, 0), max(np - 1, 0)) : 0;
       uint32_t bound = omv;                                             // smallest full SAD so far
       for (int v = 0; v < 2 * np; v++) {
         const int k = (PR && !xr) ? kc + ((v + 1) >> 1) * ((v & 1) ? -1 : 1) : v;

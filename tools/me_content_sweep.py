@@ -24,6 +24,9 @@ def pairs(kind):
         if kind == "bench clip (texture + noise 20, pan <= 2, temporal noise 3)":
             c = y4m.synth_clip(IT, 2, seed=1000 + s % 8, pan=((s % 5) - 2, (s % 3) - 1))
             ref[s], cur[s] = c[0, :W * H].reshape(H, W), c[1, :W * H].reshape(H, W)
+        elif kind == "camera pan (9,-7) per frame, same texture (the previous vector is the hint)":
+            c = y4m.synth_clip(IT, 2, seed=1000 + s % 8, pan=(9, -7))
+            ref[s], cur[s] = c[0, :W * H].reshape(H, W), c[1, :W * H].reshape(H, W)
         elif kind == "static scene + temporal noise 3":
             c = y4m.synth_clip(IT, 2, seed=1000 + s % 8, pan=(0, 0))
             ref[s], cur[s] = c[0, :W * H].reshape(H, W), c[1, :W * H].reshape(H, W)
@@ -38,7 +41,8 @@ ctx = DeviceContext(IT, S)
 stream = torch.cuda.Stream()
 ctx.set_cuda_stream(stream.cuda_stream)
 out = torch.zeros(S * 396 * 8, dtype=torch.int32, device="cuda")
-for kind in ["bench clip (texture + noise 20, pan <= 2, temporal noise 3)", "static scene + temporal noise 3",
+for kind in ["bench clip (texture + noise 20, pan <= 2, temporal noise 3)", "camera pan (9,-7) per frame, same texture (the previous vector is the hint)",
+             "static scene + temporal noise 3",
              "shifted copy of uniform noise, noise 4 (BASELINE configs[3])", "unrelated uniform noise (worst case: nothing can be skipped)"]:
     ref, cur = pairs(kind)
     r, c = torch.from_numpy(ref).cuda(), torch.from_numpy(cur).cuda()
