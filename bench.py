@@ -257,7 +257,8 @@ def main_cuda(args):
             step_dev(i, first=(i == 0))
         barrier()
         samples, stop = [], threading.Event()
-        th = threading.Thread(target=_clocks_sampler, args=(stop, samples, local), daemon=True)
+        # one sampler per job (rank 0's GPU): eight nvidia-smi pollers on an 8-GPU box only disturb the host side
+        th = threading.Thread(target=_clocks_sampler if rank == 0 else (lambda *a: None), args=(stop, samples, local), daemon=True)
         th.start()
         launches0 = ctx.launches
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -308,7 +309,7 @@ def main_cuda(args):
         if not args.no_rate_control:
             rc_line = rate_control_leg(L, local, S, K, pin, set_bytes, ring, ME_MODE, barrier)
         extra = 0
-        while len(samples) < 5 and extra < 400:        # short runs: keep the same load up until the sampler has rows
+        while rank == 0 and len(samples) < 5 and extra < 400:        # short runs: keep the same load up until the sampler has rows
             step_dev(W + extra)
             extra += 1
             if extra % 20 == 0:

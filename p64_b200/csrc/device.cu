@@ -915,7 +915,9 @@ extern "C" int p64b_ctx_wait_bits(p64b_ctx* c, int64_t ticket, p64b_bits_out* ou
     CU(cudaStreamSynchronize(c->s_d2h));
     c->slot_copied[slot] = doff + total;
   }
-  c->bits_budget = std::max<size_t>(total + total / 4 + 65536, 65536);
+  // next step's first copy: this frame's size + 1/8 + 32 KB (frame sizes of a batch move slowly; a frame that outgrows the
+  // budget is completed by the second copy above).  Downloads share the host link with the next step's upload.
+  c->bits_budget = std::max<size_t>(total + total / 8 + 32768, 65536);
   const uint8_t* b = c->h_bits_out[slot];
   const size_t S = (size_t)c->S;
   out->offset = reinterpret_cast<const uint32_t*>(b);
