@@ -361,7 +361,9 @@ typedef struct p64b_enc_params {
   int32_t host_vlc;        /* 1: entropy-code (and, under -r, run the rate control) on the host through the per-GOB
                               calls; default 0: both on the device (p64b_ctx_submit_bits)                       */
   int32_t input_chroma;    /* P64B_CHROMA_*: layout of the frames given to p64b_enc_encode (default 420jpeg)    */
-  int32_t reserved[1];
+  int32_t last_frame;      /* -b LastFrame + 1, or 0 = unknown (then: the last frame actually coded).  Only the trailing
+                              picture header needs it: its TR is min(CurrentFrame, LastFrame+1) % 32 (p64.c:600-602), which
+                              with -k > 1 depends on where -b stops between two coded frames                    */
 } p64b_enc_params;
 
 void p64b_enc_default_params(p64b_enc_params *p);

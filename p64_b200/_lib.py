@@ -29,7 +29,7 @@ class EncParams(C.Structure):
     """p64b_enc_params"""
     _fields_ = [(n, C.c_int32) for n in ("image_type", "n_streams", "device", "start_frame", "initial_quant", "rate",
                                          "frame_rate", "frame_rate_div", "frame_skip", "me_mode", "search_limit",
-                                         "force_intra", "vlc_threads", "host_vlc", "input_chroma")] + [("reserved", C.c_int32 * 1)]
+                                         "force_intra", "vlc_threads", "host_vlc", "input_chroma", "last_frame")]
 
 
 class Y4mInfo(C.Structure):

@@ -133,6 +133,7 @@ int main(int argc, char** argv) {
   if (file_size_bits)                                       // p64.c:572-573
     p.rate = (int)((long long)file_size_bits * p.frame_rate / p.frame_rate_div / (p.frame_skip * (last - start + 1)));
   p.start_frame = start;
+  p.last_frame = last + 1;
   if (stream_file.empty()) stream_file = prefix + ".p64";
 
   // ingest: the library's Y4M reader fills the encoder's pinned staging buffer in place; chroma types other than

@@ -272,7 +272,8 @@ int p64b_enc_finish(p64b_enc* e) {
   if (e->device_vlc)
     for (int k = e->harvested; k < e->frames_done; k++) { int rc = harvest(e, k); if (rc) return rc; }
   // p64.c:600-605: limit file growth, trailing picture header, pad with 1-bits
-  int last_plus_1 = e->p.start_frame + (e->frames_done ? (e->frames_done - 1) * e->p.frame_skip : 0) + 1;
+  int last_plus_1 = e->p.last_frame > 0 ? e->p.last_frame
+                                        : e->p.start_frame + (e->frames_done ? (e->frames_done - 1) * e->p.frame_skip : 0) + 1;
   int cf = e->frames_done ? std::min(e->current_frame, last_plus_1) : e->current_frame;
   for (auto& ss : e->st) {
     if (e->device_vlc && ss.carry_len) p64b_bits_put(ss.bits, ss.carry >> (32 - ss.carry_len), (int)ss.carry_len);   // the device's pending bits

@@ -257,7 +257,7 @@ class Encoder:
     def __init__(self, image_type: int, n_streams: int = 1, *, q: int = 0, rate: int = 0, me_mode: int = 0,
                  search_limit: int = 15, force_intra: bool = False, start_frame: int = 0, device: int = 0,
                  frame_rate=(30000, 1001), frame_skip: int = 1, vlc_threads: int = 0, host_vlc: bool = False,
-                 input_chroma="420jpeg"):
+                 input_chroma="420jpeg", last_frame=None):
         self.L = _lib.lib()
         p = default_params()
         p.image_type, p.n_streams, p.device, p.start_frame = image_type, n_streams, device, start_frame
@@ -266,6 +266,7 @@ class Encoder:
         p.vlc_threads = vlc_threads
         p.host_vlc = int(host_vlc)
         p.input_chroma = CHROMA[input_chroma] if isinstance(input_chroma, str) else int(input_chroma)
+        p.last_frame = 0 if last_frame is None else int(last_frame) + 1      # the reference's -b (p64.c:600-602)
         self.n_streams = n_streams
         self.geom = geometry(image_type)
         self.src_bytes = int(self.L.p64b_raw_frame_bytes(image_type, p.input_chroma))

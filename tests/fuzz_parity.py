@@ -54,6 +54,9 @@ while time.time() - t0 < budget:
     intra = rng.random() < 0.1
     clips = [content(it, nf, chroma) for _ in range(S)]
     kw = dict(q=q, rate=rate, me_mode=int(full), search_limit=limit, force_intra=intra)
+    if rng.random() < 0.4:                          # -f, -k, -a: they enter the buffer model and the temporal references
+        fr = [(30000, 1001), (25, 1), (15, 1), (10, 1)][int(rng.integers(0, 4))]
+        kw.update(frame_rate=fr, frame_skip=int(rng.integers(1, 4)), start_frame=int(rng.integers(0, 70)))
     enc = Encoder(it, S, input_chroma=chroma, **kw)
     for f in range(nf):
         enc.encode(np.stack([c[f] for c in clips]))
@@ -66,7 +69,8 @@ while time.time() - t0 < budget:
         ok = got[s] == want and ovf[s] == wovf
         if ok and s == 0:
             dec = Decoder(got[s]); fr = dec.frames(); dec.close()
-            ok = len(fr) == nf and np.array_equal(fr[-1], recons[-1])
+            # a picture is written once per temporal-reference step to the next one (p64.c:1047-1054): -k repeats pictures
+            ok = len(fr) == (nf - 1) * kw.get("frame_skip", 1) + 1 and np.array_equal(fr[-1], recons[-1])
         if not ok:
             fails += 1
             print("MISMATCH", dict(it=it, nf=nf, S=S, s=s, chroma=chroma, **kw), len(got[s]), len(want), ovf[s], wovf, flush=True)

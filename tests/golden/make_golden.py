@@ -40,6 +40,10 @@ CASES = [
     ("qcif4_q8_tss_444", y4m.IT_QCIF, 4, 35, dict(q=8, chroma="444")),
     ("ntsc3_q8_tss_444alpha", y4m.IT_NTSC, 3, 36, dict(q=8, chroma="444alpha")),
     ("qcif5_r64000_tss_mono", y4m.IT_QCIF, 5, 37, dict(rate=64000, chroma="mono")),
+    # -a / -k / -b: StartFrame, FrameSkip and where LastFrame falls between two coded frames (temporal references, the
+    # clamp of the trailing picture header p64.c:600-602, the per-frame deduction of the buffer model)
+    ("qcif6_q8_tss_a3_k2_b14", y4m.IT_QCIF, 6, 38, dict(q=8, start=3, frame_skip=2, last=14)),
+    ("qcif5_r64000_a30_k3_b42", y4m.IT_QCIF, 5, 39, dict(rate=64000, start=30, frame_skip=3, last=42)),
 ]
 
 
@@ -51,11 +55,15 @@ def main():
     for name, it, nf, seed, kw in CASES:
         kw = dict(kw)
         chroma = kw.pop("chroma", "420jpeg")
-        clip = y4m.synth_payloads(it, nf, seed, chroma)
+        start, skip, last = kw.pop("start", 0), kw.pop("frame_skip", 1), kw.pop("last", None)
+        clip = y4m.synth_payloads(it, nf + start, seed, chroma)
         y4m.write_y4m(f"{tmp}/c.y4m", it, clip, chroma=chroma)
-        log = O.ref_encode(f"{tmp}/c.y4m", f"{tmp}/o.p64", it, nf, **kw)
+        extra = ("-k", str(skip), "-b", str(last)) if last is not None else ()     # (a later -b overrides ref_encode's)
+        log = O.ref_encode(f"{tmp}/c.y4m", f"{tmp}/o.p64", it, nf, start=start, extra=extra, **kw)
         if chroma != "420jpeg":
             kw["chroma"] = chroma
+        if last is not None:
+            kw.update(start=start, frame_skip=skip, last=last)
         data = open(f"{tmp}/o.p64", "rb").read()
         O.ref_decode(f"{tmp}/o.p64", f"{tmp}/dec")
         _, _, dec = y4m.read_y4m(f"{tmp}/dec.y4m")

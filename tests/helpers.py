@@ -15,9 +15,9 @@ GOLDEN = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)),
 
 def golden_clip(name):
     g = GOLDEN[name]
-    clip = y4m.synth_payloads(g["image_type"], g["n_frames"], g["seed"], g["args"].get("chroma", "420jpeg"))
+    clip = y4m.synth_payloads(g["image_type"], g["n_frames"] + g["args"].get("start", 0), g["seed"], g["args"].get("chroma", "420jpeg"))
     assert hashlib.md5(clip.tobytes()).hexdigest() == g["clip_md5"], "synthetic clip generator drifted"
-    return g, clip
+    return g, clip[g["args"].get("start", 0):]      # -a with Y4M input discards StartFrame frames first (p64.c:562-565)
 
 
 def golden_kwargs(g):
@@ -25,7 +25,8 @@ def golden_kwargs(g):
     a = g["args"]
     return dict(q=a.get("q", 0), rate=a.get("rate", 0), me_mode=1 if a.get("full_search") else 0,
                 search_limit=a.get("search_limit") or 15, force_intra=bool(a.get("intra_only")),
-                **({"input_chroma": a["chroma"]} if a.get("chroma") else {}))
+                **({"input_chroma": a["chroma"]} if a.get("chroma") else {}),
+                **({"start_frame": a["start"], "frame_skip": a["frame_skip"], "last_frame": a["last"]} if a.get("frame_skip") else {}))
 
 
 def recs_to_mb(recs):
@@ -40,7 +41,7 @@ def levels_to_i8(levels):
 
 
 def oracle_encode_stream(image_type, clip, *, q=0, rate=0, me_mode=0, search_limit=15, force_intra=False,
-                         frame_rate=(30000, 1001), frame_skip=1, start_frame=0, input_chroma=None):
+                         frame_rate=(30000, 1001), frame_skip=1, start_frame=0, input_chroma=None, last_frame=None):
     """Returns (.p64 bytes, per-frame recon list, overflow count).  input_chroma: `clip` holds unconverted Y4M payloads."""
     if input_chroma:
         w, h = y4m.DIMS[image_type]
@@ -85,6 +86,8 @@ def oracle_encode_stream(image_type, clip, *, q=0, rate=0, me_mode=0, search_lim
                 boff = (rate // 4) // 2 - contents(ngob, 0)
             boff -= rate * frame_skip * frame_rate[1] // frame_rate[0]
         cur += frame_skip
-    bw.picture_header(cur % 32)
+    # p64.c:600-602: "limit file growth" -- CurrentFrame is clamped to LastFrame+1 (-b; unknown = the last frame coded)
+    last = last_frame if last_frame is not None else cur - frame_skip
+    bw.picture_header(min(cur, last + 1) % 32)
     bw.finish()
     return bw.data(), recons, ovfl

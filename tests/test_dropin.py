@@ -18,7 +18,10 @@ CASES = [n for n, g in GOLDEN.items() if not g["args"].get("intra_only") and n !
 
 def _cmd(g, prefix, out):
     a = g["args"]
-    cmd = [EXE[bool(a.get("full_search"))], "-y4m", O.FLAG[g["image_type"]], "-a", "0", "-b", str(g["n_frames"] - 1)]
+    cmd = [EXE[bool(a.get("full_search"))], "-y4m", O.FLAG[g["image_type"]], "-a", str(a.get("start", 0)),
+           "-b", str(a.get("last", g["n_frames"] - 1))]
+    if a.get("frame_skip"):
+        cmd += ["-k", str(a["frame_skip"])]
     if a.get("q"):
         cmd += ["-q", str(a["q"])]
     if a.get("rate"):
@@ -45,6 +48,8 @@ def test_reference_program_with_the_library_dropped_in_writes_the_reference_byte
         pytest.skip("oracle/_ref/p64_gpu not built (needs the reference tree at build time)")
     g, clip = golden_clip(name)
     chroma = g["args"].get("chroma", "420jpeg")
+    if g["args"].get("start"):                                        # the file holds the StartFrame frames that -a skips
+        clip = y4m.synth_payloads(g["image_type"], g["n_frames"] + g["args"]["start"], g["seed"], chroma)
     y4m.write_y4m(str(tmp_path / "c.y4m"), g["image_type"], clip, chroma=chroma)     # other chroma types: the reference's reader converts
     r = subprocess.run(_cmd(g, str(tmp_path / "c"), str(tmp_path / "o.p64")), stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
     assert r.returncode == 0, r.stdout.decode(errors="replace")[-500:]
