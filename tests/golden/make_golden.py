@@ -44,6 +44,10 @@ CASES = [
     # clamp of the trailing picture header p64.c:600-602, the per-frame deduction of the buffer model)
     ("qcif6_q8_tss_a3_k2_b14", y4m.IT_QCIF, 6, 38, dict(q=8, start=3, frame_skip=2, last=14)),
     ("qcif5_r64000_a30_k3_b42", y4m.IT_QCIF, 5, 39, dict(rate=64000, start=30, frame_skip=3, last=42)),
+    # -r 2000000 -k 3 -f 15 on CIF: (CurrentGOB*33+CurrentMDU)*Rate*FrameSkip exceeds 2^31 and WRAPS in the reference's C int
+    # arithmetic (p64.c:233-236) -- the buffer model then sees a negative deduction and overflows; part of the behaviour
+    ("cif4_r2000000_full31_a50_k3_f15", y4m.IT_CIF, 4, 77, dict(rate=2000000, full_search=True, search_limit=31, start=50,
+                                                                frame_skip=3, last=59, frame_rate=15)),
 ]
 
 
@@ -56,14 +60,18 @@ def main():
         kw = dict(kw)
         chroma = kw.pop("chroma", "420jpeg")
         start, skip, last = kw.pop("start", 0), kw.pop("frame_skip", 1), kw.pop("last", None)
+        fr = kw.pop("frame_rate", None)
         clip = y4m.synth_payloads(it, nf + start, seed, chroma)
         y4m.write_y4m(f"{tmp}/c.y4m", it, clip, chroma=chroma)
         extra = ("-k", str(skip), "-b", str(last)) if last is not None else ()     # (a later -b overrides ref_encode's)
+        extra += ("-f", str(fr)) if fr else ()
         log = O.ref_encode(f"{tmp}/c.y4m", f"{tmp}/o.p64", it, nf, start=start, extra=extra, **kw)
         if chroma != "420jpeg":
             kw["chroma"] = chroma
         if last is not None:
             kw.update(start=start, frame_skip=skip, last=last)
+        if fr:
+            kw["frame_rate"] = fr
         data = open(f"{tmp}/o.p64", "rb").read()
         O.ref_decode(f"{tmp}/o.p64", f"{tmp}/dec")
         _, _, dec = y4m.read_y4m(f"{tmp}/dec.y4m")

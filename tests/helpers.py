@@ -26,7 +26,8 @@ def golden_kwargs(g):
     return dict(q=a.get("q", 0), rate=a.get("rate", 0), me_mode=1 if a.get("full_search") else 0,
                 search_limit=a.get("search_limit") or 15, force_intra=bool(a.get("intra_only")),
                 **({"input_chroma": a["chroma"]} if a.get("chroma") else {}),
-                **({"start_frame": a["start"], "frame_skip": a["frame_skip"], "last_frame": a["last"]} if a.get("frame_skip") else {}))
+                **({"start_frame": a["start"], "frame_skip": a["frame_skip"], "last_frame": a["last"]} if a.get("frame_skip") else {}),
+                **({"frame_rate": (a["frame_rate"], 1)} if a.get("frame_rate") else {}))
 
 
 def recs_to_mb(recs):
@@ -60,8 +61,14 @@ def oracle_encode_stream(image_type, clip, *, q=0, rate=0, me_mode=0, search_lim
     gquant, boff, ovfl = iq, 0, 0
     denom = ngob * 33 * frame_rate[0] // frame_rate[1]
 
-    def contents(g, m):
-        return bw.tell() + boff - ((g * 33 + m) * rate * frame_skip) // denom
+    def c_int(v):                                   # the reference computes in C `int`: products wrap at 32 bits
+        return (v + 2 ** 31) % 2 ** 32 - 2 ** 31
+
+    def c_div(a, b):                                # C division truncates toward zero
+        return abs(a) // abs(b) * (1 if (a >= 0) == (b > 0) else -1)
+
+    def contents(g, m):                             # BufferContents(), p64.c:233-236
+        return bw.tell() + boff - c_div(c_int((g * 33 + m) * rate * frame_skip), denom)
 
     recons = []
     cur = start_frame
@@ -72,7 +79,7 @@ def oracle_encode_stream(image_type, clip, *, q=0, rate=0, me_mode=0, search_lim
         for g in range(ngob):
             if rate and not first:
                 c = contents(g, 0)
-                gquant = min(max(int(c / qdfact) + qoffs, 1), 31)      # C division truncates toward zero
+                gquant = min(max(c_div(c_int(c), qdfact) + qoffs, 1), 31)
             bw.gob_header(g, gquant)
             for m in range(33):
                 over = bool(rate) and contents(g, m) > rate // 4
@@ -84,7 +91,7 @@ def oracle_encode_stream(image_type, clip, *, q=0, rate=0, me_mode=0, search_lim
         if rate:
             if first:
                 boff = (rate // 4) // 2 - contents(ngob, 0)
-            boff -= rate * frame_skip * frame_rate[1] // frame_rate[0]
+            boff -= c_int(rate * frame_skip * frame_rate[1] // frame_rate[0])
         cur += frame_skip
     # p64.c:600-602: "limit file growth" -- CurrentFrame is clamped to LastFrame+1 (-b; unknown = the last frame coded)
     last = last_frame if last_frame is not None else cur - frame_skip

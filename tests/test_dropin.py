@@ -22,6 +22,8 @@ def _cmd(g, prefix, out):
            "-b", str(a.get("last", g["n_frames"] - 1))]
     if a.get("frame_skip"):
         cmd += ["-k", str(a["frame_skip"])]
+    if a.get("frame_rate"):
+        cmd += ["-f", str(a["frame_rate"])]
     if a.get("q"):
         cmd += ["-q", str(a["q"])]
     if a.get("rate"):

@@ -310,7 +310,8 @@ def test_cli_matches_reference_golden(tmp_path):
     from p64_b200 import build
     cli = build.build_cli()
     for name, extra in [("cif8_q8_full15", ["--me", "full"]), ("qcif12_q8_tss", []), ("qcif12_q8_intra", ["--intra-only"]),
-                        ("cif12_r128000_tss", []), ("qcif6_q8_tss_a3_k2_b14", []), ("qcif5_r64000_a30_k3_b42", [])]:
+                        ("cif12_r128000_tss", []), ("qcif6_q8_tss_a3_k2_b14", []), ("qcif5_r64000_a30_k3_b42", []),
+                        ("cif4_r2000000_full31_a50_k3_f15", ["--me", "full"])]:
         g, clip = golden_clip(name)
         a = g["args"]
         if a.get("start"):                                            # the file holds the StartFrame frames that -a skips
@@ -318,6 +319,7 @@ def test_cli_matches_reference_golden(tmp_path):
         y4m.write_y4m(str(tmp_path / "c.y4m"), g["image_type"], clip)
         cmd = [cli, "-y4m", y4m.FLAG[g["image_type"]], "-a", str(a.get("start", 0)), "-b", str(a.get("last", g["n_frames"] - 1))]
         cmd += ["-k", str(a["frame_skip"])] if a.get("frame_skip") else []
+        cmd += ["-f", str(a["frame_rate"])] if a.get("frame_rate") else []
         cmd += (["-q", str(a["q"])] if "q" in a else []) + (["-r", str(a["rate"])] if "rate" in a else [])
         cmd += (["-i", str(a["search_limit"])] if a.get("search_limit") else []) + extra
         cmd += [str(tmp_path / "c"), "-s", str(tmp_path / "o.p64")]

@@ -12,7 +12,7 @@ from p64_b200 import y4m
 
 FAST = ["cif8_q8_full15", "cif6_q3_tss", "cif6_q31_full31", "qcif12_q8_intra", "qcif12_q8_tss", "ntsc7_q8_tss",
         "ntsc7_q8_full31", "cif12_r128000_tss", "cif12_r64000_full31", "qcif20_r64000_tss",
-        "qcif6_q8_tss_a3_k2_b14", "qcif5_r64000_a30_k3_b42"]
+        "qcif6_q8_tss_a3_k2_b14", "qcif5_r64000_a30_k3_b42", "cif4_r2000000_full31_a50_k3_f15"]
 
 
 @pytest.mark.parametrize("name", FAST)
