@@ -4,6 +4,8 @@
 //   --me tss|full   the stock three-step search (me.c:352) or the exhaustive FastBME (me.c:351)   [default tss]
 //   --intra-only    stand-in for `-o < test.intra` (every macroblock intra)
 //   --device N      CUDA device
+// Several file prefixes on one command line are encoded together as one batch of independent streams (Prefix.y4m ->
+// Prefix.p64 each; same picture type and flags for all) -- the batch is what fills a GPU, one CIF stream cannot.
 // Same stdout markers as the reference (START>SEQUENCE, START>Frame: n, END>Frame: n, END>SEQUENCE, and the
 // "Bits for first frame" line, p64.c:595-611, 627, 665).
 #include <cstdio>
@@ -17,7 +19,7 @@
 static void help() {
   printf("p64b -a StartFrame -b LastFrame [-NTSC] [-CIF] [-QCIF] [-y4m]\n"
          "     [-f FrameRate[/Div]] [-i SearchLimit] [-k FrameSkip] [-q Quantization] [-r Rate] [-x FileSizeBits]\n"
-         "     [-s StreamFile] [-l 1] [-d] [--me tss|full] [--intra-only] [--device N] Y4MFilePrefix\n"
+         "     [-s StreamFile] [-l 1] [-d] [--me tss|full] [--intra-only] [--device N] Y4MFilePrefix [MorePrefixes...]\n"
          "Encodes PrefixYUV4MPEG2 file `Prefix.y4m` (or `-` for stdin) into an H.261 stream; the data-parallel hot path\n"
          "(motion estimation, DCT, quantisation, reconstruction) runs on the GPU. There is no CPU fallback.\n");
 }
@@ -84,12 +86,63 @@ static int decode_stream(const std::string& stream_file, const std::string& pref
   return 0;
 }
 
+// Several prefixes: one batch of independent streams, one frame of every stream per device step (p64b_enc_* with
+// n_streams = number of files).  Every file must have the selected picture size and the same chroma type.
+static int encode_batch(const std::vector<std::string>& prefixes, p64b_enc_params p, int start, int last) {
+  const int S = (int)prefixes.size();
+  std::vector<p64b_y4m*> in(S, nullptr);
+  p64b_y4m_info info0{};
+  for (int s = 0; s < S; s++) {
+    const std::string path = prefixes[s] + ".y4m";
+    if (p64b_y4m_open(&in[s], path.c_str())) { fprintf(stderr, "Unable to open '%s': %s\n", path.c_str(), p64b_last_error()); return -1; }
+    p64b_y4m_info info;
+    p64b_y4m_get_info(in[s], &info);
+    if (s == 0) info0 = info;
+    if (info.width != p64b_width(p.image_type) || info.height != p64b_height(p.image_type) || info.chroma != info0.chroma) {
+      fprintf(stderr, "p64b: '%s' does not match the selected image type / the first file's chroma type\n", path.c_str());
+      return 3;
+    }
+  }
+  p.input_chroma = info0.chroma;
+  p.n_streams = S;
+  p64b_enc* enc = nullptr;
+  if (p64b_enc_create(&enc, &p)) { fprintf(stderr, "p64b: %s\n", p64b_last_error()); return 2; }
+  const size_t fb = (size_t)info0.frame_bytes;
+  for (int i = start; i > 0; --i)
+    for (int s = 0; s < S; s++)
+      if (p64b_y4m_read_frame(in[s], p64b_enc_staging(enc) + s * fb) != 1) return 3;
+  printf("START>SEQUENCE\n");
+  for (int cf = start; cf <= last; cf += p.frame_skip) {
+    printf("START>Frame: %d\n", cf);
+    uint8_t* frame = p64b_enc_staging(enc);
+    for (int s = 0; s < S; s++)
+      if (p64b_y4m_read_frame(in[s], frame + s * fb) != 1) { p64b_enc_destroy(enc); return 3; }
+    if (p64b_enc_encode(enc, frame)) { fprintf(stderr, "p64b: %s\n", p64b_last_error()); return 2; }
+    printf("END>Frame: %d\n", cf);
+  }
+  p64b_enc_finish(enc);
+  for (int s = 0; s < S; s++) {
+    size_t n = 0;
+    const uint8_t* data = p64b_enc_data(enc, s, &n);
+    FILE* out = fopen((prefixes[s] + ".p64").c_str(), "wb");
+    if (!out || fwrite(data, 1, n, out) != n) { printf("Cannot Open Output File\n"); return 1; }
+    fclose(out);
+    printf("%s: Bits for first frame: %lld   Number of buffer overflows: %lld\n", prefixes[s].c_str(),
+           (long long)p64b_enc_first_frame_bits(enc, s), (long long)p64b_enc_overflows(enc, s));
+    p64b_y4m_close(in[s]);
+  }
+  printf("END>SEQUENCE\n");
+  p64b_enc_destroy(enc);
+  return 0;
+}
+
 int main(int argc, char** argv) {
   p64b_enc_params p;
   p64b_enc_default_params(&p);
   int start = 0, last = 0, file_size_bits = 0, loud = 0;
   bool decode = false;
   std::string prefix, stream_file;
+  std::vector<std::string> prefixes;
   if (argc == 1) { help(); return -1; }
   for (int i = 1; i < argc; i++) {
     std::string a = argv[i];
@@ -124,7 +177,7 @@ int main(int argc, char** argv) {
     else if (a == "-v" || a == "-c" || a == "-p") {}
     else if (a == "-") prefix = "-";
     else if (a[0] == '-') { printf("Illegal Option %s\n", a.c_str()); return 3; }
-    else prefix = a;
+    else { prefix = a; prefixes.push_back(a); }
   }
   if (prefix.empty()) { printf("A file prefix should be specified.\n"); return 3; }
   if (decode) return decode_stream(stream_file.empty() ? prefix + ".p64" : stream_file, prefix, p);
@@ -135,6 +188,7 @@ int main(int argc, char** argv) {
   p.start_frame = start;
   p.last_frame = last + 1;
   if (stream_file.empty()) stream_file = prefix + ".p64";
+  if (prefixes.size() > 1) return encode_batch(prefixes, p, start, last);
 
   // ingest: the library's Y4M reader fills the encoder's pinned staging buffer in place; chroma types other than
   // 420jpeg are converted on the device (y4m_input.c:195-545)

@@ -330,6 +330,31 @@ def test_cli_matches_reference_golden(tmp_path):
         assert f"Number of buffer overflows: {g['overflows']}" in r.stdout
 
 
+def test_cli_batch_of_files_equals_single_encodes(tmp_path):
+    """several prefixes on one p64b command line = one batch of streams; every output equals the reference's golden"""
+    import subprocess
+    from p64_b200 import build
+    cli = build.build_cli()
+    names = ["qcif12_q8_tss", "qcif20_r64000_tss"]
+    for name in names:
+        g, clip = golden_clip(name)
+        rate = g["args"].get("rate")
+        variants = []
+        for k in range(3):                                  # the golden clip and two perturbed copies
+            c = clip.copy()
+            if k:
+                c[:, ::7 * k] ^= 1
+            y4m.write_y4m(str(tmp_path / f"{name}_{k}.y4m"), g["image_type"], c)
+            variants.append(c)
+        cmd = [cli, "-y4m", "-QCIF", "-a", "0", "-b", str(g["n_frames"] - 1)] + (["-r", str(rate)] if rate else ["-q", str(g["args"]["q"])])
+        r = subprocess.run(cmd + [str(tmp_path / f"{name}_{k}") for k in range(3)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert hashlib.md5(open(tmp_path / f"{name}_0.p64", "rb").read()).hexdigest() == g["md5"]
+        for k in (1, 2):
+            want = encode_clip(g["image_type"], variants[k], **golden_kwargs(g))
+            assert open(tmp_path / f"{name}_{k}.p64", "rb").read() == want, (name, k)
+
+
 def test_pipelined_submit_wait_equals_synchronous():
     import ctypes as C
     from p64_b200 import _lib
