@@ -857,10 +857,9 @@ mb_encode_kernel(const __grid_constant__ MbArgs a) {
       for (int r = 0; r < 8; r++) {
         ld_row(tile, r, h, v[r]);
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const int l = v[r][j], sg = l >> 31, aa = abs(l);
-          const int rr = aa ? aa * q2 + qo : 0;
-          v[r][j] = (rr ^ sg) - sg;
+        for (int j = 0; j < 4; j++) {              // 4 [(2|l|+1) Q - ev] sign(l) = l * 8Q + sign(l) * 4 (Q - ev); sign(0) = 0
+          const int l = v[r][j];
+          v[r][j] = l * q2 + min(max(l, -1), 1) * qo;
         }
       }
       if (h == 0 && intra) v[0][0] = ((const int*)tile)[0] * 32;
@@ -930,10 +929,9 @@ __device__ __forceinline__ void dequant_row(int* tile, const uint32_t (&w)[16], 
   int v[8] = {level_at<8 * R + 0>(w), level_at<8 * R + 1>(w), level_at<8 * R + 2>(w), level_at<8 * R + 3>(w),
               level_at<8 * R + 4>(w), level_at<8 * R + 5>(w), level_at<8 * R + 6>(w), level_at<8 * R + 7>(w)};
 #pragma unroll
-  for (int j = 0; j < 8; j++) {                     // ICCITT[Flat]Quantize (transform.c:359-451) with the column pass's <<2 folded in
-    const int l = v[j], sg = l >> 31, aa = abs(l);
-    const int rr = aa ? aa * q2 + qo : 0;
-    v[j] = (rr ^ sg) - sg;
+  for (int j = 0; j < 8; j++) {                     // ICCITT[Flat]Quantize (transform.c:359-451) with the column pass's <<2 folded in:
+    const int l = v[j];                             // 4 [(2|l|+1) Q - ev] sign(l) = l * 8Q + sign(l) * 4 (Q - ev); sign(0) = 0
+    v[j] = l * q2 + min(max(l, -1), 1) * qo;
   }
   const int a[4] = {v[0], v[1], v[2], v[3]}, b[4] = {v[4], v[5], v[6], v[7]};
   st_row(tile, R, 0, a); st_row(tile, R, 1, b);
