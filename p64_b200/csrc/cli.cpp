@@ -183,8 +183,17 @@ int main(int argc, char** argv) {
   if (decode) return decode_stream(stream_file.empty() ? prefix + ".p64" : stream_file, prefix, p);
   if (start > last) { printf("Need positive number of frames.\n"); return 3; }
   if (p.search_limit < 1 || p.search_limit > 31 || p.initial_quant < 0 || p.initial_quant > 31) { printf("Parameter out of bounds.\n"); return 3; }
-  if (file_size_bits)                                       // p64.c:572-573
-    p.rate = (int)((long long)file_size_bits * p.frame_rate / p.frame_rate_div / (p.frame_skip * (last - start + 1)));
+  if (file_size_bits) {
+    // p64.c:572-573 in the reference's C int: FileSizeBits*FrameRate wraps at 32 bits BEFORE the divisions (at the default
+    // 30000/1001 for any FileSizeBits > 71582).  A positive wrapped rate is reproduced; a wrapped rate <= 0 (which the reference
+    // runs with a negative QDFact) is refused -- a stated departure (out of scope).
+    const int32_t prod = (int32_t)((int64_t)file_size_bits * p.frame_rate);
+    p.rate = prod / p.frame_rate_div / (p.frame_skip * (last - start + 1));
+    if (p.rate <= 0) {
+      printf("-x %d: FileSizeBits*FrameRate overflows the reference's int arithmetic (Rate: %d); use -r\n", file_size_bits, p.rate);
+      return 3;
+    }
+  }
   p.start_frame = start;
   p.last_frame = last + 1;
   if (stream_file.empty()) stream_file = prefix + ".p64";

@@ -230,6 +230,15 @@ int p64b_parser_next_picture(p64b_parser* p, p64b_mb* mbs, int8_t* levels, int* 
       // ---- DecompressMDU, p64.c:1179-1237
       last_mba += mba;
       if (last_mba >= 33) { end_frame = true; break; }      // "Apparent MDU out of range" / end of file
+      if (kMfM[mt]) {
+        // A vector that takes the 16x16 prediction outside the picture cannot come from a conforming encoder (the reference
+        // decoder would read outside its planes, io.c:200-313): the stream is corrupt from here on.
+        const int m = last_mba, W = p64b_width(p->image_type), H = p64b_height(p->image_type);
+        const int col = p->image_type == P64B_IT_QCIF ? m % 11 : (gob & 1) * 11 + m % 11;
+        const int row = p->image_type == P64B_IT_QCIF ? gob * 3 + m / 11 : (gob >> 1) * 3 + m / 11;
+        const int px = col * 16 + p->mvdh, py = row * 16 + p->mvdv;
+        if (px < 0 || py < 0 || px > W - 16 || py > H - 16) { end_frame = true; break; }
+      }
       int use_quant = p->gquant;
       if (kQuantM[mt]) { use_quant = p->mquant; p->gquant = p->mquant; }
       p64b_mb& r = mbs[gob * 33 + last_mba];

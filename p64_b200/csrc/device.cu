@@ -658,16 +658,23 @@ int p64b_ctx_profile_read(p64b_ctx* c, double* ms_total, int32_t* count) {
 // ---------------------------------------------------------------------------------------------------
 // Device-side entropy coding: the frame step that returns bytes
 // ---------------------------------------------------------------------------------------------------
+static void free_bits_buffers(p64b_ctx* c) {
+  void** ptrs[] = {(void**)&c->d_gob_words, (void**)&c->d_gob_bits, (void**)&c->d_carry, (void**)&c->d_carry_len, (void**)&c->d_bitpos,
+                   (void**)&c->d_frame_bits, (void**)&c->d_buffer_offset, (void**)&c->d_overflows, (void**)&c->d_pic_hdr, (void**)&c->d_vlc_tables};
+  for (void** p : ptrs) { cudaFree(*p); *p = nullptr; }
+  for (int i = 0; i < p64b_ctx::NSLOT; i++) { cudaFree(c->d_bits_out[i]); c->d_bits_out[i] = nullptr; }
+}
+
 static int ensure_bits_buffers(p64b_ctx* c) {
-  if (c->d_vlc_tables) return 0;
+  if (c->d_vlc_tables) return 0;          // allocated last: set only when every buffer exists (a failure below frees them all)
   const size_t S = (size_t)c->S, ng = (size_t)c->g.ngob;
   DevVlcTables t;
   fill_dev_vlc_tables(&t);
   // worst case of one frame: every block escapes every coefficient (GOB slot size) + picture header + carry
   c->bits_out_cap = vlc_data_offset(c->S) + S * (ng * VLC_GOB_WORDS * 4 + 16);
 #define ALLOCZ(p, bytes)                                                                                  \
-  if (cudaMalloc((void**)&(p), (bytes)) != cudaSuccess) { set_error("cudaMalloc failed (bit-stream buffers)"); return P64B_ENOMEM; } \
-  if (cudaMemsetAsync((p), 0, (bytes), c->stream) != cudaSuccess) { set_error("cudaMemset failed"); return P64B_ECUDA; }
+  if (cudaMalloc((void**)&(p), (bytes)) != cudaSuccess) { (p) = nullptr; free_bits_buffers(c); set_error("cudaMalloc failed (bit-stream buffers)"); return P64B_ENOMEM; } \
+  if (cudaMemsetAsync((p), 0, (bytes), c->stream) != cudaSuccess) { free_bits_buffers(c); set_error("cudaMemset failed"); return P64B_ECUDA; }
   ALLOCZ(c->d_gob_words, S * ng * VLC_GOB_WORDS * 4);
   ALLOCZ(c->d_gob_bits, S * ng * 4);
   ALLOCZ(c->d_carry, S * 4);
@@ -681,8 +688,10 @@ static int ensure_bits_buffers(p64b_ctx* c) {
   for (int i = 0; i < p64b_ctx::NSLOT; i++) { ALLOCZ(c->d_bits_out[i], c->bits_out_cap); }
   ALLOCZ(c->d_vlc_tables, sizeof(DevVlcTables));
 #undef ALLOCZ
-  CU(cudaMemcpyAsync(c->d_vlc_tables, &t, sizeof t, cudaMemcpyHostToDevice, c->stream));
-  CU(cudaStreamSynchronize(c->stream));          // `t` is on this stack frame
+  if (cudaMemcpyAsync(c->d_vlc_tables, &t, sizeof t, cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
+      cudaStreamSynchronize(c->stream) != cudaSuccess) {       // `t` is on this stack frame
+    free_bits_buffers(c); set_error("upload of the VLC tables failed"); return P64B_ECUDA;
+  }
   c->bits_budget = S * (c->image_type == P64B_IT_QCIF ? 12u : 40u) * 1024u;   // first frames are intra: generous start
   return 0;
 }
@@ -862,17 +871,26 @@ extern "C" int p64b_ctx_submit_bits(p64b_ctx* c, const p64b_step* st, int tempor
         swap_stores(c);
         c->last_src = c->p_src[slot];
       } else {
-        const int64_t l0 = c->launches;
+        const int64_t l0 = c->launches, ml0 = c->me_launches;
+        const int cur0 = c->cur;
+        const uint8_t* last0 = c->last_src;
         cudaGraph_t graph = nullptr;
         CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
         rc = enqueue_rc_frame(c, st, slot, a, f, r);
         const cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
-        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
-        if (ce != cudaSuccess || !graph) { set_error(std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce)); return P64B_ECUDA; }
+        if (rc || ce != cudaSuccess || !graph) {     // nothing was enqueued: the context's frame-store / queue state is as before
+          if (graph) cudaGraphDestroy(graph);
+          c->cur = cur0; c->me_launches = ml0; c->launches = l0; c->last_src = last0;
+          if (!rc) { set_error(std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce)); rc = P64B_ECUDA; }
+          return rc;
+        }
         p64b_ctx::RcGraph e{slot, c->cur ^ 1, parity, st->me_mode, st->search_limit, st->force_intra, nullptr, (int)(c->launches - l0)};
         const cudaError_t ie = cudaGraphInstantiate(&e.exec, graph, 0);
         cudaGraphDestroy(graph);
-        if (ie != cudaSuccess) { set_error(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie)); return P64B_ECUDA; }
+        if (ie != cudaSuccess) {
+          c->cur = cur0; c->me_launches = ml0; c->launches = l0; c->last_src = last0;
+          set_error(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie)); return P64B_ECUDA;
+        }
         c->rc_graphs.push_back(e);                   // (enqueue_rc_frame already flipped c->cur: the key is the state BEFORE the step)
         CU(cudaGraphLaunch(e.exec, c->stream));
       }

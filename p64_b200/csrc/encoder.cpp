@@ -258,7 +258,7 @@ int p64b_enc_encode(p64b_enc* e, const uint8_t* src) {
     if (e->p.rate) ss.buffer_contents_at_end = buffer_contents(e, ss, e->ngob, 0);   // p64.c:663, before 670-680
     if (e->p.rate) {
       if (first) ss.buffer_offset = buffer_size(e) / 2 - buffer_contents(e, ss, e->ngob, 0);
-      ss.buffer_offset -= (int)((int64_t)e->p.rate * e->p.frame_skip * e->p.frame_rate_div / e->p.frame_rate);
+      ss.buffer_offset -= (int32_t)((int64_t)e->p.rate * e->p.frame_skip * e->p.frame_rate_div) / e->p.frame_rate;   // the product wraps in C int BEFORE the division (p64.c:677)
     }
   }
   e->frames_done++;

@@ -977,7 +977,14 @@ mb_decode_kernel(const __grid_constant__ MbDecArgs a) {
   for (int i = 0; i < 16; i++) pk[i] = 0;
   if (!intra) {
     int dx = 0, dy = 0;
-    if (mt_is(M_MF, mt)) { dx = chroma ? mvx / 2 : mvx; dy = chroma ? mvy / 2 : mvy; }
+    if (mt_is(M_MF, mt)) {
+      dx = chroma ? mvx / 2 : mvx; dy = chroma ? mvy / 2 : mvy;
+      // records come from a bit stream (untrusted): the block is kept inside the plane.  A conforming stream never needs it
+      // (the parser rejects such vectors, decoder.cpp), so nothing the reference decodes changes.
+      const int bx = chroma ? col * 8 : col * 16 + (c & 1) * 8, by = chroma ? row * 8 : row * 16 + (c >> 1) * 8;
+      const int hh = chroma ? g.H >> 1 : g.H;
+      dx = min(max(dx, -bx), w - 8 - bx); dy = min(max(dy, -by), hh - 8 - by);
+    }
     const uint8_t* b = a.ref + fo + off + dy * w + dx;
 #pragma unroll
     for (int i = 0; i < 8; i++) { const uint2 r = fetch_row8(b + i * w); pk[2 * i] = r.x; pk[2 * i + 1] = r.y; }

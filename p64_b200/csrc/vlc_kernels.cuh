@@ -454,7 +454,7 @@ vlc_frame_kernel(const __grid_constant__ VlcFrameArgs a) {
     if (a.rc.rate) {                                   // end of frame, p64.c:670-680
       long long bo = a.rc.buffer_offset[s];
       if (a.rc.first_frame) bo = (a.rc.rate / 4) / 2 - rc_buffer_contents(a.rc, (long long)pos, bo, a.ngob, 0);
-      bo -= (int)((long long)a.rc.rate * a.rc.frame_skip * a.rc.frame_rate_div / a.rc.frame_rate);
+      bo -= (int)((long long)a.rc.rate * a.rc.frame_skip * a.rc.frame_rate_div) / a.rc.frame_rate;     // the product wraps in C int BEFORE the division (p64.c:677)
       a.rc.buffer_offset[s] = bo;
       gq = a.rc.quant[s]; novf = a.rc.overflows[s];
     }

@@ -48,6 +48,10 @@ CASES = [
     # arithmetic (p64.c:233-236) -- the buffer model then sees a negative deduction and overflows; part of the behaviour
     ("cif4_r2000000_full31_a50_k3_f15", y4m.IT_CIF, 4, 77, dict(rate=2000000, full_search=True, search_limit=31, start=50,
                                                                 frame_skip=3, last=59, frame_rate=15)),
+    # -r 1100000 -k 2 at the default 30000/1001: Rate*FrameSkip*FrameRateDiv of the per-frame deduction (p64.c:677) exceeds 2^31
+    # and wraps BEFORE the division by FrameRate (305 overflow macroblocks follow); -r 1000000 does not wrap
+    ("qcif5_r1100000_k2", y4m.IT_QCIF, 5, 40, dict(rate=1100000, start=0, frame_skip=2, last=8)),
+    ("qcif5_r1000000_k2", y4m.IT_QCIF, 5, 40, dict(rate=1000000, start=0, frame_skip=2, last=8)),
 ]
 
 

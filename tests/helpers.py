@@ -91,7 +91,7 @@ def oracle_encode_stream(image_type, clip, *, q=0, rate=0, me_mode=0, search_lim
         if rate:
             if first:
                 boff = (rate // 4) // 2 - contents(ngob, 0)
-            boff -= c_int(rate * frame_skip * frame_rate[1] // frame_rate[0])
+            boff -= c_div(c_int(rate * frame_skip * frame_rate[1]), frame_rate[0])      # the product wraps before the division (p64.c:677)
         cur += frame_skip
     # p64.c:600-602: "limit file growth" -- CurrentFrame is clamped to LastFrame+1 (-b; unknown = the last frame coded)
     last = last_frame if last_frame is not None else cur - frame_skip

@@ -91,7 +91,83 @@ def test_parser_rejects_garbage_and_survives_truncation():
         p.close()
 
 
+def _stream_with_vector(it, gob, m, mvx, mvy):
+    """one intra picture, then a picture whose only macroblock is type 4 (MC, no coefficients) with the given vector"""
+    from p64_b200.encoder import BitWriter, MB_DTYPE
+    bw = BitWriter(it)
+    lv = np.zeros((6, 64), np.int8); lv[:, 0] = 100
+    ngob = 3 if it == y4m.IT_QCIF else 12
+    bw.picture_header(0)
+    for g in range(ngob):
+        bw.gob_header(g, 8)
+        for k in range(33):
+            rec = np.zeros((), MB_DTYPE); rec["mtype"], rec["cbp"], rec["quant"] = 0, 0x3f, 8
+            bw.mb(k, rec, lv)
+    bw.picture_header(1)
+    bw.gob_header(gob, 8)
+    rec = np.zeros((), MB_DTYPE); rec["mtype"], rec["cbp"], rec["quant"], rec["mvx"], rec["mvy"] = 4, 0x3f, 8, mvx, mvy
+    bw.mb(m, rec, np.zeros((6, 64), np.int8))
+    bw.picture_header(2)
+    bw.finish()
+    return bw.data()
+
+
+@pytest.mark.parametrize("gob,m,mvx,mvy,legal", [(0, 0, -16, -16, False), (0, 0, -1, 0, False), (0, 0, 0, -1, False), (0, 0, 15, 15, True),
+                                               (2, 32, 1, 0, False), (2, 32, 0, 1, False), (2, 32, -16, -16, True), (1, 16, -16, 15, True)])
+def test_parser_rejects_vectors_that_leave_the_picture(gob, m, mvx, mvy, legal):
+    """a vector taken from the bit stream must keep the 16x16 prediction inside the picture: anything else is a corrupt
+    stream (the picture ends there), never a record that makes the device read outside the frame store"""
+    from p64_b200.encoder import Parser
+    p = Parser(_stream_with_vector(y4m.IT_QCIF, gob, m, mvx, mvy))
+    assert p.next_picture() is not None
+    pic = p.next_picture()
+    assert pic is not None
+    mbs = pic[0]
+    if legal:
+        assert mbs["reserved"][gob * 33 + m] == 1 and (int(mbs["mvx"][gob * 33 + m]), int(mbs["mvy"][gob * 33 + m])) == (mvx, mvy)
+    else:
+        assert not mbs["reserved"].any()
+    p.close()
+
+
 # ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_device_decode_clamps_hostile_vectors():
+    """records handed straight to p64b_ctx_decode_frames (no parser in front) with vectors far outside the picture, for the
+    first and the last stream of a batch: the prediction block is clamped into the plane -- no fault, deterministic output"""
+    from p64_b200.encoder import DeviceContext, MB_DTYPE
+    it, S = y4m.IT_QCIF, 3
+    w, h = y4m.DIMS[it]
+    ctx = DeviceContext(it, S)
+    nmb = ctx.geom["num_mb"]
+    rng = np.random.default_rng(3)
+    mbs = np.zeros((S, nmb), MB_DTYPE); lv = np.zeros((S, nmb, 6, 64), np.int8)
+    mbs["mtype"], mbs["cbp"], mbs["quant"], mbs["reserved"] = 0, 0x3f, 8, 1
+    lv[..., 0] = rng.integers(1, 127, (S, nmb, 6))
+    ctx.decode_frames(mbs, lv)
+    ref = [ctx.recon(s).copy() for s in range(S)]
+    for mvx, mvy in [(-16, -16), (15, 15), (-16, 15), (15, -16)]:
+        mbs["mtype"], mbs["mvx"], mbs["mvy"] = 4, mvx, mvy
+        ctx.decode_frames(mbs, np.zeros_like(lv))
+        for s in range(S):
+            got = ctx.recon(s)
+            Y, prevY = got[:w * h].reshape(h, w), ref[s][:w * h].reshape(h, w)
+            for row, col in [(0, 0), (h // 16 - 1, w // 16 - 1), (4, 5)]:
+                for c in range(4):
+                    bx, by = col * 16 + (c & 1) * 8, row * 16 + (c >> 1) * 8
+                    x, y = min(max(bx + mvx, 0), w - 8), min(max(by + mvy, 0), h - 8)
+                    assert np.array_equal(Y[by:by + 8, bx:bx + 8], prevY[y:y + 8, x:x + 8]), (mvx, mvy, s, row, col, c)
+        ctx.decode_frames(ref_records(mbs), lv)            # restore the same reference picture for the next vector
+        assert all(np.array_equal(ctx.recon(s), ref[s]) for s in range(S))
+    ctx.close()
+
+
+def ref_records(mbs):
+    out = mbs.copy()
+    out["mtype"], out["mvx"], out["mvy"] = 0, 0, 0
+    return out
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", [n for n in PLAIN if n != "qcif140_q10_tss"])
 def test_decoder_output_equals_reference_decoder(name):
