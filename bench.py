@@ -239,16 +239,18 @@ def main_cuda(args):
         for t in tickets[-NOUT:]:
             ctx.wait(t)
 
-    def run_bits_steps(i0, n):
+    def run_bits_steps(i0, n, c=None, base=None):
         """n pipelined steps through p64b_ctx_submit_bits / p64b_ctx_wait_bits: source frames up, stream bytes down.
         -> (bytes downloaded, bytes of H.261 stream produced)"""
+        c = c or ctx
+        base = base or pin
         tickets, down, used = [], 0, 0
         for j in range(n):
             if j >= NOUT:
-                o = ctx.wait_bits_raw(tickets[j - NOUT]); down += o.downloaded_bytes; used += o.total_bytes
-            tickets.append(ctx.submit_bits(make_step(False, QUANT, ME_MODE, SEARCH_LIMIT), (i0 + j) % 32, pin + ring(i0 + j) * set_bytes))
+                o = c.wait_bits_raw(tickets[j - NOUT]); down += o.downloaded_bytes; used += o.total_bytes
+            tickets.append(c.submit_bits(make_step(False, QUANT, ME_MODE, SEARCH_LIMIT), (i0 + j) % 32, base + ring(i0 + j) * set_bytes))
         for t in tickets[-NOUT:]:
-            o = ctx.wait_bits_raw(t); down += o.downloaded_bytes; used += o.total_bytes
+            o = c.wait_bits_raw(t); down += o.downloaded_bytes; used += o.total_bytes
         return down, used
 
     # ---- device-resident leg -----------------------------------------------------------------------------
@@ -304,6 +306,40 @@ def main_cuda(args):
             _lib.check(L.p64b_measure_h2d(local, C.c_void_p(pin), C.c_size_t(set_bytes), 30, C.byref(gb)))
             h2d_conc = gb.value
             barrier()
+        # ---- host link probes with every rank active at the same time (between barriers): uploads from ONE buffer (host
+        # cache friendly), uploads cycling the ring the e2e leg reads (6 x 39 MB per rank: DRAM), downloads alone, and both
+        # directions at once with the e2e leg's sizes -- what the end-to-end number is to be read against.
+        down_bytes = max(int(bits_down // max(K, 1)), 1 << 16)
+        down_buf = L.p64b_host_alloc(down_bytes)
+        ups = (C.c_void_p * n_sets)(*[pin + k * set_bytes for k in range(n_sets)])
+        link_local = []
+        for sets, mode in ((1, 1), (n_sets, 1), (n_sets, 2), (n_sets, 3)):
+            u, d = C.c_double(), C.c_double()
+            barrier()
+            _lib.check(L.p64b_measure_link(local, ups, sets, C.c_size_t(set_bytes), C.c_void_p(down_buf), C.c_size_t(down_bytes), 24, mode,
+                                           C.byref(u), C.byref(d)))
+            link_local += [u.value, d.value]
+        barrier()
+        L.p64b_host_free(down_buf)
+        # ---- attribution experiments (--experiments): the same e2e leg (a) from write-combined pinned memory, (b) with ONE
+        # process driving all GPUs from N threads while the other ranks idle
+        exp_local = [0.0, 0.0]
+        if args.experiments:
+            wc = L.p64b_host_alloc_flags(host_sets.nbytes, 1)
+            if wc:
+                C.memmove(wc, host_sets.ctypes.data, host_sets.nbytes)
+                run_bits_steps(W + 5 * K, 4, base=wc)
+                barrier()
+                t0 = time.perf_counter()
+                run_bits_steps(W + 5 * K + 4, K, base=wc)
+                barrier()
+                exp_local[0] = (time.perf_counter() - t0) * 1e3
+                L.p64b_host_free(wc)
+            if world > 1:
+                barrier()
+                if rank == 0:
+                    exp_local[1] = single_process_leg(world, S, K, W, host_sets, set_bytes, ring, ME_MODE, NOUT)
+                barrier()
         # ---- BASELINE configs[2]: the same streams under rate control (-r), buffer model on the device ----------
         rc_line = None
         if not args.no_rate_control:
@@ -319,7 +355,15 @@ def main_cuda(args):
         th.join(timeout=2)
 
     rc_ms = [rc_line["ms_dev"], rc_line["ms_host"]] if rc_line else [0.0, 0.0]
-    ms, ms_e2e, ms_e2e_rec, rc_ms[0], rc_ms[1], neg_conc = shard.max_over_ranks([ms, ms_e2e, ms_e2e_rec] + rc_ms + [-h2d_conc], dist if world > 1 else None, device="cuda")
+    red = shard.max_over_ranks([ms, ms_e2e, ms_e2e_rec] + rc_ms + [-h2d_conc] + [-x for x in link_local] + exp_local, dist if world > 1 else None, device="cuda")
+    ms, ms_e2e, ms_e2e_rec, rc_ms[0], rc_ms[1], neg_conc = red[:6]
+    link_min = [-x for x in red[6:6 + len(link_local)]]       # the slowest rank's rates
+    exp_ms = red[6 + len(link_local):]
+    link_sum = link_local
+    if world > 1:
+        t = torch.tensor(link_local, dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        link_sum = [float(x) for x in t.cpu()]
     h2d_conc_min = -neg_conc          # the slowest rank's upload rate while all ranks upload
 
     frames = world * S * K
@@ -385,12 +429,26 @@ def main_cuda(args):
                         "upload_alone_gbs": h2d_gbs, "upload_share_of_step": (S * fb / (h2d_gbs * 1e9)) / (ms_e2e * 1e-3 / K),
                         "upload_all_ranks_at_once_gbs_per_gpu_min": h2d_conc_min,
                         "upload_bound_frames_s": world * h2d_conc_min * 1e9 / fb,
+                        "link": {"note": "all ranks at once, GB/s per GPU [slowest rank, mean]; `ring` cycles the 6 source sets the e2e leg reads "
+                                         "(DRAM-sourced), `one_buffer` repeats one set (host-cache friendly); duplex = uploads and downloads "
+                                         "of the e2e leg's sizes at the same time",
+                                 "upload_one_buffer": [link_min[0], link_sum[0] / world], "upload_ring": [link_min[2], link_sum[2] / world],
+                                 "download_alone": [link_min[5], link_sum[5] / world],
+                                 "duplex_upload": [link_min[6], link_sum[6] / world], "duplex_download": [link_min[7], link_sum[7] / world],
+                                 "bound_frames_s_from_ring_upload": link_sum[2] * 1e9 / fb,
+                                 "bound_frames_s_from_duplex_upload": link_sum[6] * 1e9 / fb},
+                        "efficiency_vs_duplex_upload_bound": e2e_value / max(link_sum[6] * 1e9 / fb, 1.0),
                         "api": "p64b_ctx_submit_bits/p64b_ctx_wait_bits (host source frames in, finished H.261 stream bytes out; "
                                "headers + VLC on the device; pinned buffers; 3 steps in flight)"},
                 "e2e_records": {"value": frames / (ms_e2e_rec * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": S * fb,
                                 "d2h_bytes_per_step": S * nmb * (384 + 8), "ms_per_step": ms_e2e_rec / K,
                                 "api": "p64b_ctx_submit/p64b_ctx_wait (records + levels out, host VLC NOT included)"},
                 "gpu_launches": int(launches), "clocks": _summarise_clocks(samples)}
+        if args.experiments:
+            line["e2e_experiments"] = {
+                "write_combined_source": {"value": frames / (exp_ms[0] * 1e-3) if exp_ms[0] else None, "unit": "frames/s"},
+                "one_process_n_threads": {"value": frames / (exp_ms[1] * 1e-3) if exp_ms[1] else None, "unit": "frames/s",
+                                          "note": "rank 0 alone drives all GPUs (one thread + one p64b_ctx per GPU), the other ranks idle"}}
         if rc_line:
             line["e2e_rate_control"] = {
                 "value": world * S * K / (rc_ms[0] * 1e-3), "unit": "frames/s", "ms_per_step": rc_ms[0] / K,
@@ -413,6 +471,52 @@ def main_cuda(args):
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def single_process_leg(world, S, K, W, host_sets, set_bytes, ring, me_mode, NOUT):
+    """The e2e leg with ONE process driving every GPU of the job: a thread + a p64b_ctx per GPU (ctypes releases the GIL in
+    the calls), each with its own pinned source ring.  -> ms for K steps of all GPUs (wall clock between thread barriers)."""
+    from p64_b200 import _lib
+    from p64_b200.encoder import DeviceContext, make_step
+    L = _lib.lib()
+    ctxs, pins = [], []
+    for d in range(world):
+        ctxs.append(DeviceContext(IT_CIF, S, device=d))
+        p = L.p64b_host_alloc(host_sets.nbytes)
+        C.memmove(p, host_sets.ctypes.data, host_sets.nbytes)      # (the same content on every GPU: this leg measures the host side)
+        pins.append(p)
+    bar = threading.Barrier(world + 1)
+
+    def worker(d):
+        c, base = ctxs[d], pins[d]
+
+        def run(i0, n):
+            tickets = []
+            for j in range(n):
+                if j >= NOUT:
+                    c.wait_bits_raw(tickets[j - NOUT])
+                tickets.append(c.submit_bits(make_step(i0 + j == 0, QUANT, me_mode, SEARCH_LIMIT), (i0 + j) % 32, base + ring(i0 + j) * set_bytes))
+            for t in tickets[-NOUT:]:
+                c.wait_bits_raw(t)
+        run(0, max(W, 4))
+        bar.wait()
+        run(max(W, 4), K)
+        bar.wait()
+
+    ths = [threading.Thread(target=worker, args=(d,)) for d in range(world)]
+    for t in ths:
+        t.start()
+    bar.wait()
+    t0 = time.perf_counter()
+    bar.wait()
+    ms = (time.perf_counter() - t0) * 1e3
+    for t in ths:
+        t.join()
+    for c in ctxs:
+        c.close()
+    for p in pins:
+        L.p64b_host_free(p)
+    return ms
 
 
 RATE = 384000                 # -r of BASELINE configs[2] (SURVEY 8(d) config 3)
@@ -558,6 +662,7 @@ def main():
     ap.add_argument("--workload", default="streams", choices=["streams", "me1024"],
                     help="streams = the stream batch (default, BASELINE configs[4]); me1024 = the ME microbenchmark of configs[3] (1 GPU)")
     ap.add_argument("--no-rate-control", action="store_true", help="skip the extra rate-control (-r) end-to-end leg")
+    ap.add_argument("--experiments", action="store_true", help="extra end-to-end attribution legs (write-combined source, one process driving all GPUs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
     if args.impl == "cuda" and args.workload == "me1024":

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define P64B_VERSION 1
+#define P64B_VERSION 2
 
 /* image types: globals.h IT_NTSC/IT_CIF/IT_QCIF, selected by -NTSC/-CIF/-QCIF (p64.c:281-292) */
 #define P64B_IT_NTSC 0 /* 352x240, 10 GOBs */
@@ -258,6 +258,14 @@ int p64b_measure_sad_peak(int device, double *ops_per_s, double *sm_clock_mhz);
 /* Measured host-to-device copy rate (GB/s) of `reps` back-to-back copies of `bytes` from `host` (pinned): the ceiling of
  * the upload-bound end-to-end path. */
 int p64b_measure_h2d(int device, const void *host, size_t bytes, int reps, double *gb_per_s);
+/* Host link probe for the end-to-end attribution.  `reps` uploads of up_bytes each, taken round robin
+ * from the up_sets buffers up[0..up_sets-1] (distinct sets larger than the host's last-level cache behave like the
+ * end-to-end path; one set repeated does not), and/or `reps` downloads of down_bytes into `down`, on two copy streams.
+ * mode: 1 = uploads only, 2 = downloads only, 3 = both directions at the same time.  Rates in GB/s (0 where not run). */
+int p64b_measure_link(int device, const void *const *up, int up_sets, size_t up_bytes, void *down, size_t down_bytes, int reps,
+                      int mode, double *up_gb_per_s, double *down_gb_per_s);
+/* p64b_host_alloc with flags: 1 = write-combined (cudaHostAllocWriteCombined). */
+void *p64b_host_alloc_flags(size_t bytes, int flags);
 
 /* ---------------------------------------------------------------------------------------------
  * (2) host bit stream: headers + VLC (marker.c, codec.c, huffman.c, stream.c)
@@ -344,6 +352,7 @@ int p64b_parser_next_picture(p64b_parser *p, p64b_mb *mbs, int8_t *levels, int *
  * ------------------------------------------------------------------------------------------- */
 typedef struct p64b_enc p64b_enc;
 
+#define P64B_MAX_DEVICES 16
 typedef struct p64b_enc_params {
   int32_t image_type;
   int32_t n_streams;
@@ -364,6 +373,12 @@ typedef struct p64b_enc_params {
   int32_t last_frame;      /* -b LastFrame + 1, or 0 = unknown (then: the last frame actually coded).  Only the trailing
                               picture header needs it: its TR is min(CurrentFrame, LastFrame+1) % 32 (p64.c:600-602), which
                               with -k > 1 depends on where -b stops between two coded frames                    */
+  /* Multi-GPU: n_devices > 0 partitions the streams over devices[0..n_devices-1] in contiguous blocks whose
+   * sizes differ by at most one (the same split as p64_b200/shard.py); every device gets its own p64b_ctx and its own
+   * host worker thread, there is no exchange between them (streams are independent; one stream is sequential across
+   * frames, p64.c:661).  n_devices = 0: the single `device` above.  A device may be listed more than once. */
+  int32_t n_devices;
+  int32_t devices[P64B_MAX_DEVICES];
 } p64b_enc_params;
 
 void p64b_enc_default_params(p64b_enc_params *p);
@@ -382,7 +397,10 @@ uint8_t *p64b_enc_staging(p64b_enc *e);
 int p64b_enc_finish(p64b_enc *e);
 /* The stream's bytes so far (complete after p64b_enc_finish). */
 const uint8_t *p64b_enc_data(const p64b_enc *e, int stream, size_t *nbytes);
-p64b_ctx *p64b_enc_ctx(p64b_enc *e);
+p64b_ctx *p64b_enc_ctx(p64b_enc *e);     /* multi-device encoders: the context of the first device */
+/* Number of device partitions (1 for a single-device encoder) and the first stream / stream count of partition k. */
+int p64b_enc_partitions(const p64b_enc *e);
+int p64b_enc_partition(const p64b_enc *e, int k, int *device, int *first_stream, int *n_streams);
 /* Statistics the reference prints: buffer overflows (p64.c:779), bits of the first frame (p64.c:668). */
 int64_t p64b_enc_overflows(const p64b_enc *e, int stream);
 int64_t p64b_enc_first_frame_bits(const p64b_enc *e, int stream);

@@ -29,7 +29,8 @@ class EncParams(C.Structure):
     """p64b_enc_params"""
     _fields_ = [(n, C.c_int32) for n in ("image_type", "n_streams", "device", "start_frame", "initial_quant", "rate",
                                          "frame_rate", "frame_rate_div", "frame_skip", "me_mode", "search_limit",
-                                         "force_intra", "vlc_threads", "host_vlc", "input_chroma", "last_frame")]
+                                         "force_intra", "vlc_threads", "host_vlc", "input_chroma", "last_frame", "n_devices")] + \
+               [("devices", C.c_int32 * 16)]
 
 
 class Y4mInfo(C.Structure):
@@ -124,6 +125,8 @@ SIGNATURES = {
     "p64b_ctx_profile_read": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
     "p64b_measure_sad_peak": (_i, [_i, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "p64b_measure_h2d": (_i, [_i, _vp, _sz, _i, C.POINTER(C.c_double)]),
+    "p64b_measure_link": (_i, [_i, C.POINTER(_vp), _i, _sz, _vp, _sz, _i, _i, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "p64b_host_alloc_flags": (_vp, [_sz, _i]),
     "p64b_bits_create": (_vp, [_i]),
     "p64b_bits_destroy": (None, [_vp]),
     "p64b_bits_picture_header": (None, [_vp, _i]),
@@ -144,6 +147,8 @@ SIGNATURES = {
     "p64b_enc_finish": (_i, [_vp]),
     "p64b_enc_data": (C.POINTER(C.c_uint8), [_vp, _i, C.POINTER(_sz)]),
     "p64b_enc_ctx": (_vp, [_vp]),
+    "p64b_enc_partitions": (_i, [_vp]),
+    "p64b_enc_partition": (_i, [_vp, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "p64b_enc_overflows": (C.c_int64, [_vp, _i]),
     "p64b_enc_first_frame_bits": (C.c_int64, [_vp, _i]),
 }

@@ -359,6 +359,11 @@ void* p64b_host_alloc(size_t bytes) {
   if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { set_error("cudaHostAlloc failed"); return nullptr; }   // (write-combined: measured, no gain: 55.2 GB/s either way)
   return p;
 }
+void* p64b_host_alloc_flags(size_t bytes, int flags) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes, (flags & 1) ? cudaHostAllocWriteCombined : cudaHostAllocDefault) != cudaSuccess) { set_error("cudaHostAlloc failed"); return nullptr; }
+  return p;
+}
 void p64b_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 static void swap_stores(p64b_ctx* c) { c->cur ^= 1; }    // SwapFS(CFS,OFS), p64.c:661
@@ -973,6 +978,36 @@ int p64b_measure_h2d(int device, const void* host, size_t bytes, int reps, doubl
   }
   cudaEventDestroy(e0); cudaEventDestroy(e1); cudaStreamDestroy(st); cudaFree(d);
   *gb_per_s = (double)bytes * reps / (best * 1e-3) / 1e9;
+  return 0;
+}
+
+int p64b_measure_link(int device, const void* const* up, int up_sets, size_t up_bytes, void* down, size_t down_bytes, int reps,
+                      int mode, double* up_gb_per_s, double* down_gb_per_s) {
+  const bool do_up = mode & 1, do_down = mode & 2;
+  if (reps < 1 || (!do_up && !do_down) || (do_up && (!up || up_sets < 1 || !up_bytes)) || (do_down && (!down || !down_bytes))) return P64B_EINVAL;
+  CU(cudaSetDevice(device));
+  void *d_up = nullptr, *d_down = nullptr;
+  if (do_up) CU(cudaMalloc(&d_up, up_bytes));
+  if (do_down) { CU(cudaMalloc(&d_down, down_bytes)); CU(cudaMemset(d_down, 1, down_bytes)); }
+  cudaStream_t su, sd;
+  CU(cudaStreamCreateWithFlags(&su, cudaStreamNonBlocking)); CU(cudaStreamCreateWithFlags(&sd, cudaStreamNonBlocking));
+  cudaEvent_t u0, u1, d0, d1;
+  CU(cudaEventCreate(&u0)); CU(cudaEventCreate(&u1)); CU(cudaEventCreate(&d0)); CU(cudaEventCreate(&d1));
+  CU(cudaDeviceSynchronize());
+  if (do_up) CU(cudaEventRecord(u0, su));
+  if (do_down) CU(cudaEventRecord(d0, sd));
+  for (int i = 0; i < reps; i++) {
+    if (do_up) CU(cudaMemcpyAsync(d_up, up[i % up_sets], up_bytes, cudaMemcpyHostToDevice, su));
+    if (do_down) CU(cudaMemcpyAsync(down, d_down, down_bytes, cudaMemcpyDeviceToHost, sd));
+  }
+  if (do_up) CU(cudaEventRecord(u1, su));
+  if (do_down) CU(cudaEventRecord(d1, sd));
+  CU(cudaStreamSynchronize(su)); CU(cudaStreamSynchronize(sd));
+  float ms = 0;
+  if (up_gb_per_s) { *up_gb_per_s = 0; if (do_up) { CU(cudaEventElapsedTime(&ms, u0, u1)); *up_gb_per_s = (double)up_bytes * reps / (ms * 1e-3) / 1e9; } }
+  if (down_gb_per_s) { *down_gb_per_s = 0; if (do_down) { CU(cudaEventElapsedTime(&ms, d0, d1)); *down_gb_per_s = (double)down_bytes * reps / (ms * 1e-3) / 1e9; } }
+  cudaEventDestroy(u0); cudaEventDestroy(u1); cudaEventDestroy(d0); cudaEventDestroy(d1);
+  cudaStreamDestroy(su); cudaStreamDestroy(sd); cudaFree(d_up); cudaFree(d_down);
   return 0;
 }
 

@@ -5,8 +5,11 @@
 // the per-MB overflow test p64.c:776-783).
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
 #include <cstdint>
 #include <cstring>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -28,10 +31,28 @@ struct StreamState {
   uint32_t carry = 0, carry_len = 0;
 };
 
+// One host worker thread per device partition of a multi-device encoder: runs the partition's own p64b_enc (its own
+// p64b_ctx, pipeline and per-stream state) on request.  No data crosses partitions.
+struct Worker {
+  p64b_enc* kid = nullptr;
+  int first_stream = 0;
+  std::thread th;
+  std::mutex m;
+  std::condition_variable cv;
+  enum Task { NONE, ENCODE, FINISH, QUIT } task = NONE;
+  const uint8_t* src = nullptr;
+  bool busy = false;
+  int rc = 0;
+  std::string err;
+};
+
 }  // namespace
 
 struct p64b_enc {
   p64b_enc_params p{};
+  // multi-device parent: the partitions; everything per stream lives in the kids
+  std::vector<std::unique_ptr<Worker>> workers;
+  bool external_stage = false;   // kid of a multi-device encoder: `src` is the parent's pinned staging, used in place
   p64b_ctx* ctx = nullptr;
   int S = 0, ngob = 0, nmb = 0, frame_bytes = 0;
   int src_bytes = 0;             // bytes per stream of one input frame: frame_bytes, or the raw Y4M payload (input_chroma)
@@ -102,6 +123,53 @@ int harvest(p64b_enc* e, int k) {
   return 0;
 }
 
+void worker_main(Worker* w) {
+  for (;;) {
+    Worker::Task t;
+    const uint8_t* src;
+    {
+      std::unique_lock<std::mutex> lk(w->m);
+      w->cv.wait(lk, [&] { return w->busy; });
+      t = w->task; src = w->src;
+    }
+    int rc = 0;
+    if (t == Worker::ENCODE) rc = p64b_enc_encode(w->kid, src);
+    else if (t == Worker::FINISH) rc = p64b_enc_finish(w->kid);
+    {
+      std::lock_guard<std::mutex> lk(w->m);
+      w->rc = rc;
+      if (rc) w->err = p64b_last_error();          // the error text is per thread: hand it to the caller's
+      w->busy = false;
+    }
+    w->cv.notify_all();
+    if (t == Worker::QUIT) return;
+  }
+}
+
+// run `task` on every partition at once, wait for all; first failure wins
+int run_all(p64b_enc* e, Worker::Task task, const uint8_t* src, size_t src_bytes) {
+  for (auto& w : e->workers) {
+    std::lock_guard<std::mutex> lk(w->m);
+    w->task = task; w->src = src ? src + (size_t)w->first_stream * src_bytes : nullptr; w->busy = true;
+    w->cv.notify_all();
+  }
+  int rc = 0;
+  for (auto& w : e->workers) {
+    std::unique_lock<std::mutex> lk(w->m);
+    w->cv.wait(lk, [&] { return !w->busy; });
+    if (w->rc && !rc) { rc = w->rc; p64b::set_error(w->err); }
+  }
+  return rc;
+}
+
+// stream of a multi-device encoder -> (partition's encoder, local stream); single-device: itself
+const p64b_enc* route(const p64b_enc* e, int* stream) {
+  if (e->workers.empty()) return e;
+  for (auto it = e->workers.rbegin(); it != e->workers.rend(); ++it)
+    if (*stream >= (*it)->first_stream) { *stream -= (*it)->first_stream; return (*it)->kid; }
+  return e->workers.front()->kid;
+}
+
 }  // namespace
 
 extern "C" {
@@ -121,6 +189,39 @@ int p64b_enc_create(p64b_enc** out, const p64b_enc_params* p) {
   if (p->n_streams < 1 || p->frame_rate < 1 || p->frame_rate_div < 1 || p->frame_skip < 1 ||
       p->initial_quant < 0 || p->initial_quant > 31 || p->rate < 0 || (p->rate > 0 && p->rate < 320)) {
     p64b::set_error("bad encoder parameters"); return P64B_EINVAL;
+  }
+  if (p->n_devices < 0 || p->n_devices > P64B_MAX_DEVICES) { p64b::set_error("bad device list"); return P64B_EINVAL; }
+  if (p->n_devices > 0) {
+    // ---- multi-device: contiguous stream blocks (sizes differ by at most one), one encoder + worker thread per block
+    p64b_enc* e = new p64b_enc();
+    e->p = *p;
+    e->S = p->n_streams; e->ngob = p64b_num_gob(p->image_type); e->nmb = p64b_num_mb(p->image_type);
+    e->frame_bytes = p64b_frame_bytes(p->image_type);
+    e->src_bytes = p->input_chroma != P64B_CHROMA_420JPEG ? p64b_raw_frame_bytes(p->image_type, p->input_chroma) : e->frame_bytes;
+    if (e->ngob < 0 || e->src_bytes < 0) { delete e; p64b::set_error("unknown image or chroma type"); return P64B_EINVAL; }
+    e->current_frame = p->start_frame;
+    e->device_vlc = !p->host_vlc;
+    const int nd = p->n_devices, base = p->n_streams / nd, extra = p->n_streams % nd;
+    int first = 0, rc = 0;
+    for (int k = 0; k < nd && !rc; k++) {
+      const int n = base + (k < extra ? 1 : 0);
+      if (n == 0) continue;                          // fewer streams than devices
+      p64b_enc_params kp = *p;
+      kp.n_devices = 0; kp.device = p->devices[k]; kp.n_streams = n;
+      std::unique_ptr<Worker> w(new Worker());
+      w->first_stream = first;
+      if ((rc = p64b_enc_create(&w->kid, &kp))) break;
+      w->kid->external_stage = true;
+      e->workers.push_back(std::move(w));
+      first += n;
+    }
+    for (int i = 0; i < p64b_enc::NSTAGE && !rc; i++)
+      if (!(e->h_ring[i] = (uint8_t*)p64b_host_alloc((size_t)e->S * e->src_bytes))) rc = P64B_ENOMEM;
+    for (auto& w : e->workers) w->th = std::thread(worker_main, w.get());
+    if (rc) { p64b_enc_destroy(e); return rc; }
+    e->h_src = e->h_ring[0];
+    *out = e;
+    return 0;
   }
   p64b_enc* e = new p64b_enc();
   e->p = *p;
@@ -168,6 +269,15 @@ int p64b_enc_create(p64b_enc** out, const p64b_enc_params* p) {
 
 void p64b_enc_destroy(p64b_enc* e) {
   if (!e) return;
+  for (auto& w : e->workers) {
+    if (w->th.joinable()) {
+      { std::lock_guard<std::mutex> lk(w->m); w->task = Worker::QUIT; w->busy = true; }
+      w->cv.notify_all();
+      w->th.join();
+    }
+    p64b_enc_destroy(w->kid);                      // (drains its pipeline before the shared staging below goes away)
+  }
+  e->workers.clear();
   for (auto& s : e->st) p64b_bits_destroy(s.bits);
   p64b_host_free(e->h_mbs); p64b_host_free(e->h_levels);
   p64b_ctx_destroy(e->ctx);                        // (drains whatever is still in flight before the staging goes away)
@@ -179,6 +289,20 @@ void p64b_enc_destroy(p64b_enc* e) {
 int p64b_enc_encode(p64b_enc* e, const uint8_t* src) {
   if (!e || !src) { p64b::set_error("NULL argument"); return P64B_EINVAL; }
   if (e->finished) { p64b::set_error("encoder already finished"); return P64B_EINVAL; }
+  if (!e->workers.empty()) {
+    // multi-device: the frame goes into the parent's pinned staging ring (four deep, like a single encoder's: the buffer
+    // handed out next was last read by frame n-3, which every partition has collected when this call returns), and
+    // every partition encodes its block of streams from there, in place, on its own thread and device.
+    const int n = e->frames_done;
+    uint8_t* stage = e->h_ring[n % p64b_enc::NSTAGE];
+    if (src != stage) memcpy(stage, src, (size_t)e->S * e->src_bytes);
+    const int rc = run_all(e, Worker::ENCODE, stage, (size_t)e->src_bytes);
+    if (rc) return rc;
+    e->h_src = e->h_ring[(n + 1) % p64b_enc::NSTAGE];
+    e->frames_done++;
+    e->current_frame += e->p.frame_skip;
+    return 0;
+  }
   const bool first = e->frames_done == 0;          // CurrentFrame == StartFrame
   p64b_step step{};
   step.first_frame = first; step.me_mode = e->p.me_mode; step.search_limit = e->p.search_limit;
@@ -192,20 +316,28 @@ int p64b_enc_encode(p64b_enc* e, const uint8_t* src) {
     // frames overlap; p64b_enc_finish() collects the rest.
     const int n = e->frames_done;
     if (n >= p64b_enc::DEPTH && (rc = harvest(e, n - p64b_enc::DEPTH))) return rc;
-    uint8_t* stage = e->h_ring[n % p64b_enc::NSTAGE];
-    if (src != stage) memcpy(stage, src, (size_t)e->S * e->src_bytes);
+    const uint8_t* stage = src;                     // (partition of a multi-device encoder: the parent's staging, in place)
+    if (!e->external_stage) {
+      uint8_t* own = e->h_ring[n % p64b_enc::NSTAGE];
+      if (src != own) memcpy(own, src, (size_t)e->S * e->src_bytes);
+      stage = own;
+    }
     step.gquant = e->st[0].gquant;                  // (only the first frame's value is used under rate control)
     if ((rc = p64b_ctx_submit_bits(e->ctx, &step, tr, stage, &e->tickets[n % p64b_enc::DEPTH]))) return rc;
-    e->h_src = e->h_ring[(n + 1) % p64b_enc::NSTAGE];     // its last user, frame n-3, has just been collected
+    if (!e->external_stage) e->h_src = e->h_ring[(n + 1) % p64b_enc::NSTAGE];     // its last user, frame n-3, has just been collected
     e->frames_done++;
     e->current_frame += e->p.frame_skip;
     return 0;
   }
-  if (src != e->h_src) memcpy(e->h_src, src, (size_t)e->S * e->src_bytes);
+  const uint8_t* in = src;                          // the calls below are synchronous: a partition reads the parent's staging in place
+  if (!e->external_stage) {
+    if (src != e->h_src) memcpy(e->h_src, src, (size_t)e->S * e->src_bytes);
+    in = e->h_src;
+  }
   if (!e->p.rate) {
     // fixed quantiser: one device step for the whole frame of every stream, then the VLC per stream
     step.gquant = e->st[0].gquant;
-    if ((rc = p64b_ctx_encode_frames(e->ctx, &step, e->h_src, e->h_mbs, e->h_levels))) return rc;
+    if ((rc = p64b_ctx_encode_frames(e->ctx, &step, in, e->h_mbs, e->h_levels))) return rc;
     parallel_streams(e, [&](int s) {
       StreamState& ss = e->st[s];
       p64b_bits_picture_header(ss.bits, tr);
@@ -221,7 +353,7 @@ int p64b_enc_encode(p64b_enc* e, const uint8_t* src) {
     // per GOB (batched over streams); the overflow override is decided per MB during the VLC and patched
     // into the reconstruction at frame end.
     step.gquant = e->st[0].gquant;
-    if ((rc = p64b_ctx_frame_begin(e->ctx, &step, e->h_src))) return rc;
+    if ((rc = p64b_ctx_frame_begin(e->ctx, &step, in))) return rc;
     std::fill(e->overflow.begin(), e->overflow.end(), 0);
     parallel_streams(e, [&](int s) { p64b_bits_picture_header(e->st[s].bits, tr); });
     for (int g = 0; g < e->ngob; g++) {
@@ -269,6 +401,11 @@ int p64b_enc_encode(p64b_enc* e, const uint8_t* src) {
 int p64b_enc_finish(p64b_enc* e) {
   if (!e) return P64B_EINVAL;
   if (e->finished) return 0;
+  if (!e->workers.empty()) {
+    const int rc = run_all(e, Worker::FINISH, nullptr, 0);
+    if (!rc) e->finished = true;
+    return rc;
+  }
   if (e->device_vlc)
     for (int k = e->harvested; k < e->frames_done; k++) { int rc = harvest(e, k); if (rc) return rc; }
   // p64.c:600-605: limit file growth, trailing picture header, pad with 1-bits
@@ -291,16 +428,29 @@ int p64b_enc_finish(p64b_enc* e) {
 
 const uint8_t* p64b_enc_data(const p64b_enc* e, int stream, size_t* nbytes) {
   if (!e || stream < 0 || stream >= e->S) { if (nbytes) *nbytes = 0; return nullptr; }
+  e = route(e, &stream);
   if (e->device_vlc) { if (nbytes) *nbytes = e->st[stream].dev_bytes.size(); return e->st[stream].dev_bytes.data(); }
   return p64b_bits_data(e->st[stream].bits, nbytes);
 }
-p64b_ctx* p64b_enc_ctx(p64b_enc* e) { return e ? e->ctx : nullptr; }
+p64b_ctx* p64b_enc_ctx(p64b_enc* e) { return !e ? nullptr : (e->workers.empty() ? e->ctx : e->workers.front()->kid->ctx); }
 uint8_t* p64b_enc_staging(p64b_enc* e) { return e ? e->h_src : nullptr; }
+int p64b_enc_partitions(const p64b_enc* e) { return !e ? P64B_EINVAL : (e->workers.empty() ? 1 : (int)e->workers.size()); }
+int p64b_enc_partition(const p64b_enc* e, int k, int* device, int* first_stream, int* n_streams) {
+  if (!e || k < 0 || k >= p64b_enc_partitions(e)) { p64b::set_error("bad arguments"); return P64B_EINVAL; }
+  const p64b_enc* kid = e->workers.empty() ? e : e->workers[k]->kid;
+  if (device) *device = kid->p.device;
+  if (first_stream) *first_stream = e->workers.empty() ? 0 : e->workers[k]->first_stream;
+  if (n_streams) *n_streams = kid->S;
+  return 0;
+}
 int64_t p64b_enc_overflows(const p64b_enc* e, int stream) {
-  return (e && stream >= 0 && stream < e->S) ? e->st[stream].overflows : -1;
+  if (!e || stream < 0 || stream >= e->S) return -1;
+  e = route(e, &stream);
+  return e->st[stream].overflows;
 }
 int p64b_enc_frame_counters(const p64b_enc* e, int stream, p64b_frame_counters* out) {
   if (!e || !out || stream < 0 || stream >= e->S) { p64b::set_error("bad arguments"); return P64B_EINVAL; }
+  e = route(e, &stream);
   if (e->device_vlc) { p64b::set_error("frame counters need host_vlc = 1"); return P64B_EINVAL; }
   const StreamState& ss = e->st[stream];
   p64b_bits_counters(ss.bits, out);
@@ -309,7 +459,9 @@ int p64b_enc_frame_counters(const p64b_enc* e, int stream, p64b_frame_counters* 
   return 0;
 }
 int64_t p64b_enc_first_frame_bits(const p64b_enc* e, int stream) {
-  return (e && stream >= 0 && stream < e->S) ? e->st[stream].first_frame_bits : -1;
+  if (!e || stream < 0 || stream >= e->S) return -1;
+  e = route(e, &stream);
+  return e->st[stream].first_frame_bits;
 }
 
 }  // extern "C"

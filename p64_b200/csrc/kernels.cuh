@@ -58,8 +58,17 @@ constexpr int ME_WIN_BYTES = ME_WIN_ROWS * 48;
 constexpr int ME_BUF_WORDS = 608 + 64;                 // TMA window (564 used, padded to 128-byte multiple) + current block
 constexpr int ME_SHIFT_OFF = 2 * ME_BUF_WORDS;         // byte-shifted copies 1..3: copy k at ME_SHIFT_OFF + 8 + 584 (k-1)
 constexpr int ME_COPY_WORDS = 584;
-constexpr int ME_SAD_OFF = ME_SHIFT_OFF + 8 + 3 * ME_COPY_WORDS + 8;      // [31][31] surface (ME_V_SURF only)
-constexpr int ME_WARP_WORDS_FULL = (ME_SAD_OFF + 31) / 32 * 32;
+constexpr int ME_SAD_OFF = ME_SHIFT_OFF + 8 + 3 * ME_COPY_WORDS + 8;      // [31][31] surface (ME_V_SURF only); survivor list (ME_V_FULL)
+#ifndef P64B_ME_RA
+#define P64B_ME_RA 8
+#endif
+#ifndef P64B_ME_DENSE_T
+#define P64B_ME_DENSE_T 48
+#endif
+constexpr int ME_RA = P64B_ME_RA;               // block rows every candidate of a surviving chunk accumulates before the per-candidate elimination
+constexpr int ME_DENSE_T = P64B_ME_DENSE_T;     // more survivors than this in one chunk (of <= 320): the chunk continues densely (sliding window)
+constexpr int ME_LIST_WORDS = 160;              // survivor list: flushed when a further chunk might not fit
+constexpr int ME_WARP_WORDS_FULL = (ME_SAD_OFF + ME_LIST_WORDS + 31) / 32 * 32;
 constexpr int ME_WARP_WORDS_SURF = (ME_SAD_OFF + 31 * 31 + 31) / 32 * 32;
 constexpr int ME_CTA_WORDS = 3 * 32 /*pen tables*/ + 2 * 2 * ME_WARPS /*mbarriers*/ + 16;
 constexpr int ME_SMEM_FULL = 128 + 4 * (ME_WARPS * ME_WARP_WORDS_FULL + ME_CTA_WORDS);
@@ -111,6 +120,16 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, in
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
       ::"r"(smem_u32(dst)), "l"(tm), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
+}
+
+// next position of the work queue, by one lane.  Inline PTX: the compiler turns a plain atomicAdd into its warp-aggregated
+// form, whose result broadcast (SHFL) waits for the atomic at once -- 3 % of the kernel's warp time in the ncu source view --
+// while the value is only needed one macroblock later.
+__device__ __forceinline__ uint32_t queue_take(uint32_t* counter, int lane) {
+  uint32_t t = 0;
+  // every lane presents its own address (lane 0 the counter, the others are predicated off): nothing to aggregate
+  asm volatile("{\n.reg .pred p;\nsetp.eq.s32 p, %2, 0;\n@p atom.global.add.u32 %0, [%1], 1;\n}" : "+r"(t) : "l"(counter + lane), "r"(lane) : "memory");
+  return t;
 }
 
 constexpr int ME_V_FULL = 0, ME_V_SURF = 1, ME_V_TSS = 2;
@@ -197,6 +216,122 @@ __device__ __forceinline__ uint32_t sweep_pass(const uint32_t* __restrict__ colb
   return best + (uint32_t)yb;
 }
 
+// ---- exhaustive search: exact elimination, warp-wide first, then per candidate (ME_V_FULL) ---------------------------------
+// The reference's ComputeError leaves a candidate as soon as its partial sum reaches the best SAD so far (me.c:65, 122, 133,
+// 170); that never changes a decision because acceptance needs a strictly smaller FULL sum (me.c:220).  Here every candidate
+// whose partial sum is strictly above `bound` -- the full SAD of some candidate already evaluated, SAD(0,0) at first -- is
+// dropped: it can neither win nor tie.  Everything else is evaluated in full and enters the minimum of the key
+// SAD << 11 | scan order, so the winner is the reference's for any content and any evaluation order.
+//   chunk = 10 dy x 32 dx, accumulators in registers, sliding window:
+//     A. block rows 0..R1-1 of all candidates; the chunk is dropped when EVERY candidate is above the bound; rows R1..RA-1; again;
+//     B. (only chunks that survive -- typically the one that holds the match) the candidate with the chunk's smallest
+//        partial sum is evaluated in full by the whole warp (2 packed SADs per lane) and becomes the bound;
+//     C. survivors (partial <= bound) are found with one ballot per dy row.  More than ME_DENSE_T: the chunk continues densely
+//        (rows RA..15); else they are appended to a list in shared memory (partial | dy | dx);
+//   list: 32 survivors at a time, ONE PER LANE with two accumulator chains, finish their rows RA..15 from the byte-shifted
+//     window copies (aligned words), leaving half way when no lane is still at or below the bound.
+// What this buys depends on the content (tools/me_prune_sim.py models it): on the bench clip the search executes 0.53 of the
+// algorithmic SAD operations instead of 0.70 with the warp-wide exit alone.  Variants measured on a B200 and not kept:
+// elimination after 6 rows with every survivor finished from the list (0.48 executed, but 2400 instead of 2240 instructions
+// per macroblock: the bookkeeping of three compactions per macroblock costs what the SADs save), and a fully unrolled 30-row
+// column (code beyond the 32 KB instruction cache: 1.5x slower).
+// full SAD of the candidate at surface position (cx, cy), cooperatively: lane -> (block row lane/2, half lane%2)
+__device__ __forceinline__ uint32_t coop_sad(const uint32_t* win, const uint32_t* s_cur, int cx, int cy, int lane) {
+  const int i = lane >> 1, wc = (lane & 1) * 2, oo = cx + 1, sh = (oo & 3) * 8;
+  const uint32_t* rp = win + (cy + i) * ME_ROW_WORDS + (oo >> 2) + wc;
+  const uint32_t ra = __funnelshift_r(rp[0], rp[1], sh), rb = __funnelshift_r(rp[1], rp[2], sh);
+  const uint2 cw = *reinterpret_cast<const uint2*>(s_cur + i * 4 + wc);
+  return __reduce_add_sync(0xffffffffu, sad4(rb, cw.y, sad4(ra, cw.x, 0u)));
+}
+
+// The list's survivors, one per lane: rows RA..15 on two accumulator chains, one exit half way.
+__device__ __forceinline__ void sparse_finish(const uint32_t* win, const uint32_t* shifted, const uint32_t (&c)[16][4], const uint32_t* list,
+                                              int nlist, int lane, uint32_t m2048, uint32_t& bound, uint32_t& best, uint32_t& units) {
+  constexpr int S1 = (ME_RA + 16) / 2;
+#pragma unroll 1
+  for (int i0 = 0; i0 < nlist; i0 += 32) {
+    const bool ok = i0 + lane < nlist;
+    const uint32_t e = ok ? list[i0 + lane] : 0u;
+    uint32_t p = ok ? (e & 0xffffu) : ME_ILLEGAL, q = 0;
+    if (!__any_sync(0xffffffffu, p <= bound)) continue;              // the bound has moved since they were listed
+    const int x = (e >> 21) & 31, y = (e >> 16) & 31, o = x + 1, k = o & 3;
+    const uint32_t* b = (k ? shifted + (k - 1) * ME_COPY_WORDS : win) + (o >> 2) + y * ME_ROW_WORDS;
+#pragma unroll
+    for (int r = ME_RA; r < S1; r++) {
+      p = sad4(b[r * ME_ROW_WORDS + 0], c[r][0], p); q = sad4(b[r * ME_ROW_WORDS + 1], c[r][1], q);
+      p = sad4(b[r * ME_ROW_WORDS + 2], c[r][2], p); q = sad4(b[r * ME_ROW_WORDS + 3], c[r][3], q);
+    }
+    units += S1 - ME_RA;
+    if (!__any_sync(0xffffffffu, p + q <= bound)) continue;
+#pragma unroll
+    for (int r = S1; r < 16; r++) {
+      p = sad4(b[r * ME_ROW_WORDS + 0], c[r][0], p); q = sad4(b[r * ME_ROW_WORDS + 1], c[r][1], q);
+      p = sad4(b[r * ME_ROW_WORDS + 2], c[r][2], p); q = sad4(b[r * ME_ROW_WORDS + 3], c[r][3], q);
+    }
+    units += 16 - S1;
+    p += q;                                   // (lanes without a survivor carry ME_ILLEGAL: never the minimum)
+    best = min(best, p * m2048 + (uint32_t)(1 + x * 32 + y));
+    bound = min(bound, __reduce_min_sync(0xffffffffu, p));
+  }
+}
+
+// One chunk of 10 dy rows at surface rows yb .. yb+9 of this lane's column xi.  Returns the list length.
+__device__ __forceinline__ int full_chunk(const uint32_t* colbase, const uint32_t* win, const uint32_t* s_cur, const uint32_t (&c)[16][4],
+                                          const uint32_t* pen, uint32_t* list, int nlist, int xi, int yb, bool xok, int lane, uint32_t m2048,
+                                          uint32_t& bound, uint32_t& best, uint32_t& units, bool& dense_mode) {
+  constexpr int NC = 10, R1 = ME_PRUNE_R1;
+  const uint32_t* base = colbase + yb * ME_ROW_WORDS;
+  uint32_t a[NC];
+#pragma unroll
+  for (int j = 0; j < NC; j++) a[j] = pen[yb + j];
+  sweep_rows<NC, 0, R1>(base, c, a);
+  units += (uint32_t)(NC * R1);
+  if (sweep_hopeless<NC>(a, xok, bound)) return nlist;
+  sweep_rows<NC, R1, ME_RA>(base, c, a);
+  units += (uint32_t)(NC * (ME_RA - R1));
+  // B. the chunk's smallest partial sum; nothing at or below the bound: the chunk is done.  If promising, that candidate in full
+  int total = ME_DENSE_T + 1;
+  if (!dense_mode) {                   // (an earlier chunk of this macroblock had too many survivors: content without a sharp match)
+    uint32_t m = a[0] * 16u;
+#pragma unroll
+    for (int j = 1; j < NC; j++) m = min(m, a[j] * 16u + (uint32_t)j);
+    const uint32_t pm = __reduce_min_sync(0xffffffffu, xok ? (m >> 4) : 0xffffffffu);
+    if (pm > bound) return nlist;
+    if (2u * pm < bound) {                                             // (warp-uniform)
+      const int src = __ffs(__ballot_sync(0xffffffffu, xok && (m >> 4) == pm)) - 1;
+      const int cx = __shfl_sync(0xffffffffu, xi, src), cy = __shfl_sync(0xffffffffu, yb + (int)(m & 15u), src);
+      bound = min(bound, coop_sad(win, s_cur, cx, cy, lane));
+      units += 1;                                                     // (2 packed SADs per lane, counted as a whole candidate row)
+    }
+    // C. survivors, counted per lane first (the ballots below are only for chunks that are compacted)
+    int cnt = 0;
+#pragma unroll
+    for (int j = 0; j < NC; j++) cnt += (a[j] <= bound) ? 1 : 0;
+    total = __reduce_add_sync(0xffffffffu, xok ? cnt : 0);
+    dense_mode = total > ME_DENSE_T;
+  } else if (sweep_hopeless<NC>(a, xok, bound)) return nlist;
+  if (total > ME_DENSE_T) {
+    sweep_rows<NC, ME_RA, 16>(base, c, a);
+    units += (uint32_t)(NC * (16 - ME_RA));
+    uint32_t r = 0xffffffffu;
+#pragma unroll
+    for (int j = 0; j < NC; j++) r = min(r, a[j] * m2048 + (uint32_t)j);
+    r = xok ? r + (uint32_t)(1 + xi * 32 + yb) : 0xffffffffu;
+    best = min(best, r);
+    bound = min(bound, __reduce_min_sync(0xffffffffu, r) >> 11);
+    return nlist;
+  }
+  const uint32_t lt = (1u << lane) - 1u, tag = ((uint32_t)xi << 21) | ((uint32_t)yb << 16);
+#pragma unroll
+  for (int j = 0; j < NC; j++) {
+    const bool sv = xok && a[j] <= bound;
+    const uint32_t mk = __ballot_sync(0xffffffffu, sv);
+    if (sv) list[nlist + __popc(mk & lt)] = a[j] + tag + ((uint32_t)j << 16);
+    nlist += __popc(mk);
+  }
+  return nlist;
+}
+
 // tm_ref / tm_cur: u8 tensors {W, H, n_pairs}; boxes {48,47,1} and {16,16,1}.  grid = worker CTAs (persistent).
 // VARIANT: ME_V_FULL exhaustive argmin straight from registers; ME_V_TSS the stock three-step search evaluating only
 // the <= 33 positions it probes (8 candidates x 4 row quarters per step across the lanes, unaligned window words by
@@ -239,10 +374,8 @@ me_search_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_consta
   };
   int n = blockIdx.x * ME_WARPS + warp;           // first macroblock: static; the rest come from the queue
   uint32_t ticket = 0;                            // lane 0: queue position of the warp's NEXT macroblock
-  if (lane == 0) {
-    if (n < total) issue_loads(n, 0);
-    ticket = atomicAdd(a.queue + a.parity, 1u);
-  }
+  if (lane == 0 && n < total) issue_loads(n, 0);
+  ticket = queue_take(a.queue + a.parity, lane);
 
   uint32_t units = 0;                             // candidate rows (16 pixels each) this warp's lanes actually accumulated
   for (int it = 0; n < total; it++) {
@@ -252,9 +385,9 @@ me_search_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_consta
     if (lane == 0 && n_next < total) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the buffer's earlier generic-proxy reads are done
       issue_loads(n_next, b ^ 1);
-      ticket = atomicAdd(a.queue + a.parity, 1u);
     }
-    // hint for the pass order of the exhaustive search: the vertical vector this macroblock had in the output array before
+    if (n_next < total) ticket = queue_take(a.queue + a.parity, lane);       // (warp-uniform condition; lane 0 takes)
+    // hint for the chunk order of the exhaustive search: the vertical vector this macroblock had in the output array before
     // this launch (in the encoder: the previous frame's vector of the same macroblock; anything else is harmless, the
     // order of evaluation never changes the result).  Loaded early, used after the window has arrived.
     int hint_my = 0;
@@ -321,25 +454,43 @@ me_search_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_consta
     if (VARIANT != ME_V_TSS) {
       const int o = xi + 1, k = o & 3;                             // o = dx + 16
       const uint32_t* colbase = (k ? shifted + (k - 1) * ME_COPY_WORDS : win) + (o >> 2);
-      // passes of 10 (a last one of 5) dy rows.  Exhaustive search: the pass that holds the hinted dy (the macroblock's
-      // previous vector; 0 at first) goes first, then outwards, so that the bound of the early exit is good as soon as possible (the order of evaluation does not matter: the
-      // winner is the minimum of a key that carries the reference's scan order).  The two-half mapping of edge columns
-      // keeps the plain order (the halves would disagree about the centre; control flow must stay warp-uniform).
-      constexpr bool PR = VARIANT == ME_V_FULL;
-      constexpr int PS = (PR && P64B_ME_PASS_ROWS == 5) ? 5 : 10;       // pass stride (experiments: 5-row passes prune finer)
+      // exhaustive search: chunks of 10 dy rows (full_chunk).  Surface variant: passes of 10 (a last one of 5) dy rows.
+      constexpr int PS = 10;
       const int np = rpg <= 0 ? 0 : (rpg - 1) / PS + 1;                 // passes k = 0..np-1 start at row PS*k
-      const int hy = min(max(__shfl_sync(0xffffffffu, hint_my, 0), -15), 15) + 15;      // hinted dy as a surface row
-      const int kc = (PR && !xr) ? min(max((hy - lylo) / PS, 0), max(np - 1, 0)) : 0;
       uint32_t bound = omv;                                             // smallest full SAD so far
-      for (int v = 0; v < 2 * np; v++) {
-        const int k = (PR && !xr) ? kc + ((v + 1) >> 1) * ((v & 1) ? -1 : 1) : v;
-        if (k < 0 || k >= np) continue;
-        const int done = PS * k;
-        uint32_t r;
-        if (PS == 10 && rpg - done > 5) r = sweep_pass<VARIANT, 10, PR>(colbase, c, pen, s_sad, xi, min(ystart + done, 22), xok, a.m2048, bound, units);
-        else                            r = sweep_pass<VARIANT, 5, PR>(colbase, c, pen, s_sad, xi, min(ystart + done, 27), xok, a.m2048, bound, units);
-        best = min(best, r);
-        if (PR) bound = min(bound, __reduce_min_sync(0xffffffffu, xok ? r : 0xffffffffu) >> 11);
+      if (VARIANT == ME_V_FULL) {
+        // chunks of 10 dy rows, the one that holds the hinted dy (the macroblock's previous vector; 0 at first) first, then
+        // outwards, so that the bound is good as early as possible (the order of evaluation never changes the result).  The
+        // two-half mapping of edge columns keeps the plain order (the halves would disagree about the centre).  A last chunk of
+        // fewer than 10 rows starts earlier instead (re-evaluating a few candidates: harmless for a minimum).
+        uint32_t* list = s_sad;                                         // survivor list (the surface region of ME_V_SURF)
+        int nlist = 0;
+        bool dense_mode = false;
+        const int hy = min(max(__shfl_sync(0xffffffffu, hint_my, 0), -15), 15) + 15;      // hinted dy as a surface row
+        const int kc = !xr ? min(max((hy - lylo) / PS, 0), max(np - 1, 0)) : 0;
+#pragma unroll 1
+        for (int v = 0; v < 2 * np; v++) {
+          const int k = !xr ? kc + ((v + 1) >> 1) * ((v & 1) ? -1 : 1) : v;
+          if (k < 0 || k >= np) continue;
+          if (nlist > ME_LIST_WORDS - ME_DENSE_T) {                     // a further chunk might not fit
+            __syncwarp();
+            sparse_finish(win, shifted, c, list, nlist, lane, a.m2048, bound, best, units);
+            __syncwarp();
+            nlist = 0;
+          }
+          const int yb = min(ystart + max(min(PS * k, rpg - PS), 0), 22);
+          nlist = full_chunk(colbase, win, s_cur, c, pen, list, nlist, xi, yb, xok, lane, a.m2048, bound, best, units, dense_mode);
+        }
+        __syncwarp();
+        sparse_finish(win, shifted, c, list, nlist, lane, a.m2048, bound, best, units);
+      } else {
+        for (int v = 0; v < np; v++) {
+          const int done = PS * v;
+          uint32_t r;
+          if (rpg - done > 5) r = sweep_pass<VARIANT, 10, false>(colbase, c, pen, s_sad, xi, min(ystart + done, 22), xok, a.m2048, bound, units);
+          else                r = sweep_pass<VARIANT, 5, false>(colbase, c, pen, s_sad, xi, min(ystart + done, 27), xok, a.m2048, bound, units);
+          best = min(best, (xok && r != 0xffffffffu) ? r + (uint32_t)(1 + xi * 32) : 0xffffffffu);
+        }
       }
     }
 
@@ -358,8 +509,7 @@ me_search_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_consta
     if (full) {
       // FastBME (me.c:206-227) scans dx outer, dy inner with strict <, after probing (0,0): winner = min of
       // SAD<<11 | (1 + (dx+15)*32 + (dy+15)); (0,0) enters with order 0 so that it wins ties
-      best = (xok && best != 0xffffffffu) ? best + (uint32_t)(1 + xi * 32) : 0xffffffffu;     // (all passes may have been left early)
-      best = min(__reduce_min_sync(0xffffffffu, best), omv << 11);
+      best = min(__reduce_min_sync(0xffffffffu, best), omv << 11);       // `best` already carries the whole key
       mv = best >> 11;
       const int ord = best & 2047;
       if (ord) { mx = ((ord - 1) >> 5) - 15; my = ((ord - 1) & 31) - 15; }

@@ -257,9 +257,15 @@ class Encoder:
     def __init__(self, image_type: int, n_streams: int = 1, *, q: int = 0, rate: int = 0, me_mode: int = 0,
                  search_limit: int = 15, force_intra: bool = False, start_frame: int = 0, device: int = 0,
                  frame_rate=(30000, 1001), frame_skip: int = 1, vlc_threads: int = 0, host_vlc: bool = False,
-                 input_chroma="420jpeg", last_frame=None):
+                 input_chroma="420jpeg", last_frame=None, devices=None):
+        """devices: list of GPU indices -- the streams are partitioned over them in contiguous blocks (one context and one
+        host worker thread per GPU, no exchange); None = the single `device`."""
         self.L = _lib.lib()
         p = default_params()
+        if devices is not None:
+            p.n_devices = len(devices)
+            for k, d in enumerate(devices):
+                p.devices[k] = int(d)
         p.image_type, p.n_streams, p.device, p.start_frame = image_type, n_streams, device, start_frame
         p.initial_quant, p.rate, p.me_mode, p.search_limit = q, rate, me_mode, search_limit
         p.force_intra, p.frame_rate, p.frame_rate_div, p.frame_skip = int(force_intra), frame_rate[0], frame_rate[1], frame_skip
@@ -298,6 +304,15 @@ class Encoder:
 
     def context_handle(self):
         return C.c_void_p(self.L.p64b_enc_ctx(self.h))
+
+    def partitions(self):
+        """-> [(device, first_stream, n_streams)] of the encoder's device partitions"""
+        out = []
+        for k in range(int(self.L.p64b_enc_partitions(self.h))):
+            d, f, n = C.c_int(), C.c_int(), C.c_int()
+            check(self.L.p64b_enc_partition(self.h, k, C.byref(d), C.byref(f), C.byref(n)))
+            out.append((d.value, f.value, n.value))
+        return out
 
 
 class Y4mReader:

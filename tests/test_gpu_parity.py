@@ -512,3 +512,37 @@ def test_me_microbenchmark_size_1024_pairs():
             assert np.array_equal(got, np.tile(got[:8], (n_pairs // 8, 1, 1))), mode
     finally:
         ctx.close()
+
+
+@pytest.mark.parametrize("kw", [dict(q=8, me_mode=1, search_limit=31), dict(rate=64000), dict(q=6, host_vlc=True),
+                                dict(rate=96000, host_vlc=True, me_mode=1, search_limit=15)])
+def test_multi_device_partition_is_invisible(kw):
+    """SURVEY 8(e) inside the product: p64b_enc_params.devices partitions the streams over device contexts (one worker thread
+    and one p64b_ctx each, no exchange).  The bytes of every stream must not depend on the partition: 7 streams through one
+    context == through 3 partitions (3+2+2 streams; the test box has one GPU, so the list names it three times) == through 8
+    partitions (one of them empty)."""
+    it, S, nf = y4m.IT_QCIF, 7, 6
+    clips = [y4m.synth_clip(it, nf, seed=300 + s, pan=(s - 3, 2 - s)) for s in range(S)]
+    outs = []
+    for devices in (None, [0, 0, 0], [0] * 8):
+        enc = Encoder(it, S, devices=devices, **kw)
+        parts = enc.partitions()
+        if devices is None:
+            assert parts == [(0, 0, S)]
+        elif len(devices) == 3:
+            assert parts == [(0, 0, 3), (0, 3, 2), (0, 5, 2)]
+        else:
+            assert len(parts) == 7 and all(n == 1 for _, _, n in parts)
+        for f in range(nf):
+            enc.encode(np.stack([c[f] for c in clips]))
+        enc.finish()
+        outs.append(([enc.data(s) for s in range(S)], [enc.overflows(s) for s in range(S)], [enc.first_frame_bits(s) for s in range(S)]))
+        enc.close()
+    assert outs[0] == outs[1] == outs[2]
+    assert len(set(outs[0][0])) == S                       # the streams really differ
+
+
+def test_multi_device_errors_surface():
+    from p64_b200._lib import P64Error
+    with pytest.raises(P64Error):
+        Encoder(y4m.IT_QCIF, 2, q=8, devices=[0, 99])      # no such device: the partition's error text reaches the caller
