@@ -82,11 +82,17 @@ def _summarise_clocks(samples):
             "samples": len(samples), "power_w_max": max(float(s[2]) for s in samples)}
 
 
+_BANK = None
+
+
 def make_sources(streams, n_sets: int) -> np.ndarray:
     """uint8 [n_sets, len(streams), frame_bytes]: set t holds frame (phase_s + t) of global stream s's clip."""
     from p64_b200 import y4m
-    bank = [y4m.synth_clip(IT_CIF, n_sets + CLIP_BANK, seed=1000 + b, pan=((b % 5) - 2, (b % 3) - 1))
-            for b in range(CLIP_BANK)]
+    global _BANK
+    if _BANK is None or _BANK[0] != n_sets:
+        _BANK = (n_sets, [y4m.synth_clip(IT_CIF, n_sets + CLIP_BANK, seed=1000 + b, pan=((b % 5) - 2, (b % 3) - 1))
+                          for b in range(CLIP_BANK)])
+    bank = _BANK[1]
     out = np.empty((n_sets, len(streams), bank[0].shape[1]), np.uint8)
     for k, s in enumerate(streams):
         clip, phase = bank[s % CLIP_BANK], (s // CLIP_BANK) % CLIP_BANK
@@ -321,6 +327,10 @@ def main_cuda(args):
             link_local += [u.value, d.value]
         barrier()
         L.p64b_host_free(down_buf)
+        # ---- the headline e2e at N > 1: streams partitioned in proportion to each GPU's share of the host links
+        bal = None
+        if world > 1 and not args.equal_partition:
+            bal = balanced_e2e_leg(L, dist, world, rank, local, S, K, n_sets, ring, ME_MODE, NOUT, barrier, link_local[2])
         # ---- attribution experiments (--experiments): the same e2e leg (a) from write-combined pinned memory, (b) with ONE
         # process driving all GPUs from N threads while the other ranks idle
         exp_local = [0.0, 0.0]
@@ -355,8 +365,16 @@ def main_cuda(args):
         th.join(timeout=2)
 
     rc_ms = [rc_line["ms_dev"], rc_line["ms_host"]] if rc_line else [0.0, 0.0]
-    red = shard.max_over_ranks([ms, ms_e2e, ms_e2e_rec] + rc_ms + [-h2d_conc] + [-x for x in link_local] + exp_local, dist if world > 1 else None, device="cuda")
+    red = shard.max_over_ranks([ms, ms_e2e, ms_e2e_rec] + rc_ms + [-h2d_conc] + [-x for x in link_local] + exp_local + [bal[0] if bal else 0.0],
+                               dist if world > 1 else None, device="cuda")
     ms, ms_e2e, ms_e2e_rec, rc_ms[0], rc_ms[1], neg_conc = red[:6]
+    ms_bal = red[-1]
+    red = red[:-1]
+    bal_down = bal_used = 0
+    if bal:
+        t = torch.tensor([float(bal[2]), float(bal[3])], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        bal_down, bal_used = [int(x) for x in t.cpu()]
     link_min = [-x for x in red[6:6 + len(link_local)]]       # the slowest rank's rates
     exp_ms = red[6 + len(link_local):]
     link_sum = link_local
@@ -369,6 +387,11 @@ def main_cuda(args):
     frames = world * S * K
     value = frames / (ms * 1e-3)
     e2e_value = frames / (ms_e2e * 1e-3)
+    e2e_equal = None
+    if bal:           # headline = the balanced partition; the equal split stays in the line next to it
+        e2e_equal = {"value": e2e_value, "unit": "frames/s", "ms_per_step": ms_e2e / K, "partition": [S] * world,
+                     "note": "the same leg with 256 streams on every GPU: the job waits for the GPU whose share of the host uplinks is smallest"}
+        e2e_value = frames / (ms_bal * 1e-3)
     line = None
     if rank == 0:
         peak_ops, clk = C.c_double(), C.c_double()
@@ -423,10 +446,16 @@ def main_cuda(args):
                 "roofline": dominant, "roofline_kernels": {"me_search_kernel": me_roof, "mb_encode_kernel": mb_roof},
                 "kernel_share_of_step": {"me_search_kernel": me_ms / (me_ms + mb_ms), "mb_encode_kernel": mb_ms / (me_ms + mb_ms)},
                 "cpu_baseline": cpu,
-                "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": S * fb, "d2h_bytes_per_step": bits_down // K,
-                        "stream_bytes_per_step": bits_used // K, "ms_per_step": ms_e2e / K,
+                "e2e": {"value": e2e_value, "unit": "frames/s",
+                        "h2d_bytes_per_step": S * fb if not bal else world * S * fb, "d2h_bytes_per_step": bits_down // K if not bal else bal_down // K,
+                        "stream_bytes_per_step": bits_used // K if not bal else bal_used // K, "ms_per_step": (ms_bal if bal else ms_e2e) / K,
+                        "bytes_are": "per GPU" if not bal else "whole job (all GPUs)",
+                        "partition": [S] * world if not bal else bal[1], "partition_from_link_probe": None if not bal else bal[4],
+                        "partition_note": None if not bal else "streams per GPU, proportional to each GPU's measured share of the host links (probe, "
+                                                               "then one trial run) -- found before the timed region; stream contents and bytes do not depend on it",
+                        "equal_partition": e2e_equal,
                         "vlc_kernels_ms_per_step": prof_bits["vlc"][0] / max(1, prof_bits["vlc"][1]),
-                        "upload_alone_gbs": h2d_gbs, "upload_share_of_step": (S * fb / (h2d_gbs * 1e9)) / (ms_e2e * 1e-3 / K),
+                        "upload_alone_gbs": h2d_gbs, "upload_share_of_step_equal_partition": (S * fb / (h2d_gbs * 1e9)) / (ms_e2e * 1e-3 / K),
                         "upload_all_ranks_at_once_gbs_per_gpu_min": h2d_conc_min,
                         "upload_bound_frames_s": world * h2d_conc_min * 1e9 / fb,
                         "link": {"note": "all ranks at once, GB/s per GPU [slowest rank, mean]; `ring` cycles the 6 source sets the e2e leg reads "
@@ -438,6 +467,7 @@ def main_cuda(args):
                                  "bound_frames_s_from_ring_upload": link_sum[2] * 1e9 / fb,
                                  "bound_frames_s_from_duplex_upload": link_sum[6] * 1e9 / fb},
                         "efficiency_vs_duplex_upload_bound": e2e_value / max(link_sum[6] * 1e9 / fb, 1.0),
+                        "efficiency_vs_ring_upload_bound": e2e_value / max(link_sum[2] * 1e9 / fb, 1.0),
                         "api": "p64b_ctx_submit_bits/p64b_ctx_wait_bits (host source frames in, finished H.261 stream bytes out; "
                                "headers + VLC on the device; pinned buffers; 3 steps in flight)"},
                 "e2e_records": {"value": frames / (ms_e2e_rec * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": S * fb,
@@ -471,6 +501,74 @@ def main_cuda(args):
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def split_proportional(total, weights, floor=8):
+    """integer shares of `total` proportional to `weights` (largest remainder), each at least `floor`"""
+    w = np.maximum(np.asarray(weights, np.float64), 1e-9)
+    raw = w / w.sum() * total
+    shares = np.maximum(np.floor(raw).astype(int), floor)
+    order = np.argsort(-(raw - np.floor(raw)))
+    i = 0
+    while shares.sum() < total:
+        shares[order[i % len(order)]] += 1; i += 1
+    while shares.sum() > total:
+        k = int(np.argmax(shares)); shares[k] -= 1
+    return [int(x) for x in shares]
+
+
+def balanced_e2e_leg(L, dist, world, rank, local, S, K, n_sets, ring, me_mode, NOUT, barrier, link_rate):
+    """The end-to-end leg with the job's world*S streams partitioned over the GPUs IN PROPORTION TO WHAT EACH GPU'S HOST LINK
+    DELIVERS while all of them upload (the box's GPUs share PCIe uplinks unevenly: the equal split waits for the slowest one).
+    Streams are independent, so any partition gives the same bytes; there is still no exchange between ranks.  The split is
+    found before the timed region: from the link probe first, then corrected once from a short trial run.
+    -> (ms of K steps [max over ranks is taken by the caller], shares, bytes downloaded, stream bytes, trial shares)"""
+    import torch
+    from p64_b200.encoder import DeviceContext, make_step
+
+    def gather(x):
+        t = torch.zeros(world, dtype=torch.float64, device="cuda")
+        t[rank] = x
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [float(v) for v in t.cpu()]
+
+    def run(c, base, set_bytes, i0, n, first):
+        tickets, down, used = [], 0, 0
+        for j in range(n):
+            if j >= NOUT:
+                o = c.wait_bits_raw(tickets[j - NOUT]); down += o.downloaded_bytes; used += o.total_bytes
+            tickets.append(c.submit_bits(make_step(first and j == 0, QUANT, me_mode, SEARCH_LIMIT), (i0 + j) % 32, base + ring(i0 + j) * set_bytes))
+        for t in tickets[-NOUT:]:
+            o = c.wait_bits_raw(t); down += o.downloaded_bytes; used += o.total_bytes
+        return down, used
+
+    shares = split_proportional(world * S, gather(link_rate))
+    trial = list(shares)
+    out = None
+    for it in range(2):
+        my, start = shares[rank], sum(shares[:rank])
+        hs = make_sources(range(start, start + my), n_sets)
+        c = DeviceContext(IT_CIF, my, device=local)
+        pin = L.p64b_host_alloc(hs.nbytes)
+        C.memmove(pin, hs.ctypes.data, hs.nbytes)
+        sb = my * hs.shape[2]
+        steps = K if it else max(12, K // 3)
+        run(c, pin, sb, 0, 6, True)
+        barrier()
+        t0 = time.perf_counter()
+        down, used = run(c, pin, sb, 6, steps, False)
+        torch.cuda.synchronize()
+        mine = (time.perf_counter() - t0) * 1e3
+        barrier()
+        ms = (time.perf_counter() - t0) * 1e3
+        c.close()
+        L.p64b_host_free(pin)
+        if it == 0:       # per-stream cost of every rank in the trial -> corrected split
+            times = gather(mine)
+            shares = split_proportional(world * S, [shares[r] / max(times[r], 1e-6) for r in range(world)])
+        else:
+            out = (ms, shares, down, used, trial, my)
+    return out
 
 
 def single_process_leg(world, S, K, W, host_sets, set_bytes, ring, me_mode, NOUT):
@@ -662,6 +760,7 @@ def main():
     ap.add_argument("--workload", default="streams", choices=["streams", "me1024"],
                     help="streams = the stream batch (default, BASELINE configs[4]); me1024 = the ME microbenchmark of configs[3] (1 GPU)")
     ap.add_argument("--no-rate-control", action="store_true", help="skip the extra rate-control (-r) end-to-end leg")
+    ap.add_argument("--equal-partition", action="store_true", help="N > 1: keep 256 streams on every GPU in the end-to-end leg (default: balance by link share)")
     ap.add_argument("--experiments", action="store_true", help="extra end-to-end attribution legs (write-combined source, one process driving all GPUs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
