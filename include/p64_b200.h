@@ -264,6 +264,9 @@ int p64b_measure_h2d(int device, const void *host, size_t bytes, int reps, doubl
  * mode: 1 = uploads only, 2 = downloads only, 3 = both directions at the same time.  Rates in GB/s (0 where not run). */
 int p64b_measure_link(int device, const void *const *up, int up_sets, size_t up_bytes, void *down, size_t down_bytes, int reps,
                       int mode, double *up_gb_per_s, double *down_gb_per_s);
+/* Upload rate (GB/s) of every listed device while ALL of them upload at the same time (one host thread per device, 8 x 32 MB
+ * from pinned memory): the GPUs of a box share host uplinks, not always evenly.  p64b_enc_params.balance_links partitions by it. */
+int p64b_probe_links(const int32_t *devices, int n_devices, double *gb_per_s);
 /* p64b_host_alloc with flags: 1 = write-combined (cudaHostAllocWriteCombined). */
 void *p64b_host_alloc_flags(size_t bytes, int flags);
 
@@ -379,6 +382,10 @@ typedef struct p64b_enc_params {
    * frames, p64.c:661).  n_devices = 0: the single `device` above.  A device may be listed more than once. */
   int32_t n_devices;
   int32_t devices[P64B_MAX_DEVICES];
+  /* 1: size the blocks in proportion to the upload rate each device gets while all of them upload (p64b_probe_links,
+   * measured at creation) instead of equally -- on a box whose GPUs share host uplinks unevenly the equal split waits for
+   * the slowest link (measured at 8 GPUs: +15 % end to end).  The bytes of a stream never depend on the partition. */
+  int32_t balance_links;
 } p64b_enc_params;
 
 void p64b_enc_default_params(p64b_enc_params *p);

@@ -30,7 +30,7 @@ class EncParams(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("image_type", "n_streams", "device", "start_frame", "initial_quant", "rate",
                                          "frame_rate", "frame_rate_div", "frame_skip", "me_mode", "search_limit",
                                          "force_intra", "vlc_threads", "host_vlc", "input_chroma", "last_frame", "n_devices")] + \
-               [("devices", C.c_int32 * 16)]
+               [("devices", C.c_int32 * 16), ("balance_links", C.c_int32)]
 
 
 class Y4mInfo(C.Structure):
@@ -127,6 +127,7 @@ SIGNATURES = {
     "p64b_measure_h2d": (_i, [_i, _vp, _sz, _i, C.POINTER(C.c_double)]),
     "p64b_measure_link": (_i, [_i, C.POINTER(_vp), _i, _sz, _vp, _sz, _i, _i, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "p64b_host_alloc_flags": (_vp, [_sz, _i]),
+    "p64b_probe_links": (_i, [C.POINTER(C.c_int32), _i, C.POINTER(C.c_double)]),
     "p64b_bits_create": (_vp, [_i]),
     "p64b_bits_destroy": (None, [_vp]),
     "p64b_bits_picture_header": (None, [_vp, _i]),

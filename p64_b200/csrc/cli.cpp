@@ -19,7 +19,7 @@
 static void help() {
   printf("p64b -a StartFrame -b LastFrame [-NTSC] [-CIF] [-QCIF] [-y4m]\n"
          "     [-f FrameRate[/Div]] [-i SearchLimit] [-k FrameSkip] [-q Quantization] [-r Rate] [-x FileSizeBits]\n"
-         "     [-s StreamFile] [-l 1] [-d] [--me tss|full] [--intra-only] [--device N | --devices 0-7] Y4MFilePrefix [MorePrefixes...]\n"
+         "     [-s StreamFile] [-l 1] [-d] [--me tss|full] [--intra-only] [--device N | --devices 0-7 [--balance-links]] Y4MFilePrefix [MorePrefixes...]\n"
          "Encodes PrefixYUV4MPEG2 file `Prefix.y4m` (or `-` for stdin) into an H.261 stream; the data-parallel hot path\n"
          "(motion estimation, DCT, quantisation, reconstruction) runs on the GPU. There is no CPU fallback.\n");
 }
@@ -155,6 +155,7 @@ int main(int argc, char** argv) {
     else if (a == "--me") { std::string m = next(); p.me_mode = m == "full" ? P64B_ME_FULL : P64B_ME_TSS; }
     else if (a == "--intra-only" || a == "-o") p.force_intra = 1;
     else if (a == "--device") p.device = atoi(next());
+    else if (a == "--balance-links") p.balance_links = 1;      // with --devices: blocks in proportion to each GPU's host-link share
     else if (a == "--devices") {                           // "0-7" or "0,2,3": streams (prefixes) are partitioned over these GPUs
       p.n_devices = 0;
       for (const char* v = next(); *v;) {

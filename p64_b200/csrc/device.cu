@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -1008,6 +1009,33 @@ int p64b_measure_link(int device, const void* const* up, int up_sets, size_t up_
   if (down_gb_per_s) { *down_gb_per_s = 0; if (do_down) { CU(cudaEventElapsedTime(&ms, d0, d1)); *down_gb_per_s = (double)down_bytes * reps / (ms * 1e-3) / 1e9; } }
   cudaEventDestroy(u0); cudaEventDestroy(u1); cudaEventDestroy(d0); cudaEventDestroy(d1);
   cudaStreamDestroy(su); cudaStreamDestroy(sd); cudaFree(d_up); cudaFree(d_down);
+  return 0;
+}
+
+int p64b_probe_links(const int32_t* devices, int n_devices, double* gb_per_s) {
+  if (!devices || !gb_per_s || n_devices < 1) return P64B_EINVAL;
+  const size_t bytes = 32u << 20;
+  std::vector<void*> host(n_devices, nullptr);
+  std::vector<int> rc(n_devices, 0);
+  for (int k = 0; k < n_devices; k++) {
+    if (cudaSetDevice(devices[k]) != cudaSuccess || !(host[k] = p64b_host_alloc(bytes))) {
+      for (void* h : host) p64b_host_free(h);
+      set_error("p64b_probe_links: bad device or no pinned memory");
+      return P64B_ECUDA;
+    }
+    memset(host[k], k + 1, bytes);
+  }
+  std::vector<std::thread> th;
+  for (int k = 0; k < n_devices; k++)
+    th.emplace_back([&, k] {
+      const void* up[1] = {host[k]};
+      double d = 0;
+      p64b_measure_link(devices[k], up, 1, bytes, nullptr, 0, 2, 1, &gb_per_s[k], &d);                     // warm-up (context, first touch)
+      rc[k] = p64b_measure_link(devices[k], up, 1, bytes, nullptr, 0, 8, 1, &gb_per_s[k], &d);
+    });
+  for (auto& t : th) t.join();
+  for (void* h : host) p64b_host_free(h);
+  for (int k = 0; k < n_devices; k++) if (rc[k]) { set_error("p64b_probe_links: copy failed"); return rc[k]; }
   return 0;
 }
 

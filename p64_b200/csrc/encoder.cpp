@@ -203,8 +203,28 @@ int p64b_enc_create(p64b_enc** out, const p64b_enc_params* p) {
     e->device_vlc = !p->host_vlc;
     const int nd = p->n_devices, base = p->n_streams / nd, extra = p->n_streams % nd;
     int first = 0, rc = 0;
+    std::vector<int> share(nd);
+    for (int k = 0; k < nd; k++) share[k] = base + (k < extra ? 1 : 0);
+    if (p->balance_links && nd > 1 && p->n_streams >= 2 * nd) {
+      // blocks in proportion to what each device's host link delivers while all upload (largest remainder, at least one stream)
+      std::vector<double> gbs(nd, 0.0);
+      if ((rc = p64b_probe_links(p->devices, nd, gbs.data()))) { delete e; return rc; }
+      double sum = 0;
+      for (double g : gbs) sum += g;
+      int given = 0;
+      std::vector<std::pair<double, int>> frac;
+      for (int k = 0; k < nd; k++) {
+        const double raw = sum > 0 ? gbs[k] / sum * p->n_streams : (double)share[k];
+        share[k] = std::max(1, (int)raw);
+        given += share[k];
+        frac.emplace_back(raw - (int)raw, k);
+      }
+      std::sort(frac.rbegin(), frac.rend());
+      for (int i = 0; given < p->n_streams; i++, given++) share[frac[i % nd].second]++;
+      for (int i = 0; given > p->n_streams; i++) { int k = frac[(nd - 1 - i % nd)].second; if (share[k] > 1) { share[k]--; given--; } }
+    }
     for (int k = 0; k < nd && !rc; k++) {
-      const int n = base + (k < extra ? 1 : 0);
+      const int n = share[k];
       if (n == 0) continue;                          // fewer streams than devices
       p64b_enc_params kp = *p;
       kp.n_devices = 0; kp.device = p->devices[k]; kp.n_streams = n;

@@ -257,7 +257,7 @@ class Encoder:
     def __init__(self, image_type: int, n_streams: int = 1, *, q: int = 0, rate: int = 0, me_mode: int = 0,
                  search_limit: int = 15, force_intra: bool = False, start_frame: int = 0, device: int = 0,
                  frame_rate=(30000, 1001), frame_skip: int = 1, vlc_threads: int = 0, host_vlc: bool = False,
-                 input_chroma="420jpeg", last_frame=None, devices=None):
+                 input_chroma="420jpeg", last_frame=None, devices=None, balance_links=False):
         """devices: list of GPU indices -- the streams are partitioned over them in contiguous blocks (one context and one
         host worker thread per GPU, no exchange); None = the single `device`."""
         self.L = _lib.lib()
@@ -266,6 +266,7 @@ class Encoder:
             p.n_devices = len(devices)
             for k, d in enumerate(devices):
                 p.devices[k] = int(d)
+            p.balance_links = int(balance_links)
         p.image_type, p.n_streams, p.device, p.start_frame = image_type, n_streams, device, start_frame
         p.initial_quant, p.rate, p.me_mode, p.search_limit = q, rate, me_mode, search_limit
         p.force_intra, p.frame_rate, p.frame_rate_div, p.frame_skip = int(force_intra), frame_rate[0], frame_rate[1], frame_skip

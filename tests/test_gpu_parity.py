@@ -524,11 +524,14 @@ def test_multi_device_partition_is_invisible(kw):
     it, S, nf = y4m.IT_QCIF, 7, 6
     clips = [y4m.synth_clip(it, nf, seed=300 + s, pan=(s - 3, 2 - s)) for s in range(S)]
     outs = []
-    for devices in (None, [0, 0, 0], [0] * 8):
-        enc = Encoder(it, S, devices=devices, **kw)
+    for devices, balance in ((None, False), ([0, 0, 0], False), ([0] * 8, False), ([0, 0, 0], True)):
+        enc = Encoder(it, S, devices=devices, balance_links=balance, **kw)
         parts = enc.partitions()
         if devices is None:
             assert parts == [(0, 0, S)]
+        elif balance:      # blocks follow the measured link shares: contiguous, complete, none empty
+            assert len(parts) == 3 and parts[0][1] == 0 and all(n >= 1 for _, _, n in parts) and sum(n for _, _, n in parts) == S
+            assert all(parts[k][1] + parts[k][2] == parts[k + 1][1] for k in range(2))
         elif len(devices) == 3:
             assert parts == [(0, 0, 3), (0, 3, 2), (0, 5, 2)]
         else:
@@ -538,7 +541,7 @@ def test_multi_device_partition_is_invisible(kw):
         enc.finish()
         outs.append(([enc.data(s) for s in range(S)], [enc.overflows(s) for s in range(S)], [enc.first_frame_bits(s) for s in range(S)]))
         enc.close()
-    assert outs[0] == outs[1] == outs[2]
+    assert outs[0] == outs[1] == outs[2] == outs[3]
     assert len(set(outs[0][0])) == S                       # the streams really differ
 
 
