@@ -4,7 +4,7 @@
 #   p64_ref      stock encoder/decoder (three-step search, me.c:352)
 #   p64_ref_fs   same sources, but MotionEstimation() calls FastBME instead of StepBME: the two lines
 #                me.c:351-352 have their comment markers toggled by sed into a temp file outside the repo
-#   libp64ref.so me.c mem.c chendct.c transform.c io.c as a shared object for function-level checks
+#   libp64ref.so me.c mem.c chendct.c transform.c io.c (+ stat.c through ref_stat_shim.c) as a shared object for function-level checks
 # Flags: -O is the reference's own (makefile:6); -fcommon/-fgnu89-inline/-w only let 1993 C link under gcc 13
 # (SURVEY.md F5).  No reference source is copied into the repository.
 set -e
@@ -22,7 +22,7 @@ sed -e 's|^\(\s*\)//FastBME(x,y,pmem,x,y,fmem);|\1FastBME(x,y,pmem,x,y,fmem);|' 
 grep -q '^\s*FastBME(x,y,pmem,x,y,fmem);' "$TMP/me_fs.c"
 gcc $CF $ALL "$TMP/me_fs.c" -lm -o "$OUT/p64_ref_fs"
 gcc $CF -fPIC -shared $REF/me.c $REF/mem.c $REF/chendct.c $REF/transform.c $REF/io.c \
-    $REF/vidinput.c $REF/y4m_input.c "$(dirname "$0")/ref_shim.c" -lm -o "$OUT/libp64ref.so"
+    $REF/vidinput.c $REF/y4m_input.c "$(dirname "$0")/ref_shim.c" "$(dirname "$0")/ref_stat_shim.c" -lm -o "$OUT/libp64ref.so"
 # p64_gpu / p64_gpu_fs: the reference's own main() and stream writer with the body of p64EncodeFrame() replaced by one call
 # into ../p64_b200/libp64b200.so per frame (examples/p64gpu_dropin.c).  p64.c goes through sed into the temp dir: the
 # per-frame work is cut out and four calls are inserted; nothing of it is kept in the repository.

@@ -833,21 +833,27 @@ __device__ __forceinline__ void filter_row(const uint32_t (&pk)[16], int ra, int
   o0 = pack4_sat(o[0], o[1], o[2], o[3]); o1 = pack4_sat(o[4], o[5], o[6], o[7]);
 }
 
+// per quantiser: the multiplier M and the clamp A(Q) of fwd_row (compile-time table in constant memory: a stream's 32
+// macroblocks of a warp share the quantiser, so the access is uniform)
+struct QuantTable { uint32_t m[32], a[32]; };
+__host__ __device__ constexpr QuantTable make_quant_table() {
+  QuantTable t{};
+  for (uint32_t qq = 1; qq < 32; qq++) {
+    const uint32_t m = (1u << 18) / qq + 1u, k = ((qq & 1) ? 4u : 12u) * m, a = ((1u << 29) - 1u - k) / m;
+    t.m[qq] = m; t.a[qq] = a < 8187u ? a : 8187u;
+  }
+  return t;
+}
+__constant__ QuantTable c_quant = make_quant_table();
+
 __global__ void __launch_bounds__(MB4_THREADS, 3)
 mb_encode_kernel(const __grid_constant__ MbArgs a) {
   extern __shared__ __align__(16) uint32_t s_dyn[];
   __shared__ int s_acc[6][MB4_PER_CTA];
-  __shared__ uint32_t s_qm[32], s_qa[32];
-  __shared__ uint8_t s_mt[MB4_PER_CTA];
   const Geom& g = a.g;
   const int lane = threadIdx.x & 31, c = threadIdx.x >> 5;        // block index within the MB: p64.c:77-79
   int* tile = reinterpret_cast<int*>(s_dyn) + threadIdx.x * MB4_TILE;
   uint32_t* s_pk = reinterpret_cast<uint32_t*>(tile) + 64;        // packed prediction, 8 rows x 2 words
-  if (threadIdx.x < 32) {                                           // per quantiser: M and the clamp A(Q) of fwd_row
-    const uint32_t qq = threadIdx.x, m = qq ? (1u << 18) / qq + 1u : 0u, k = ((qq & 1) ? 4u : 12u) * m;
-    s_qm[qq] = m;
-    s_qa[qq] = qq ? min(8187u, ((1u << 29) - 1u - k) / m) : 0u;
-  }
 
   const int n_total = a.n_streams * a.gob_count * 33;
   const int n = blockIdx.x * MB4_PER_CTA + lane;
@@ -882,27 +888,24 @@ mb_encode_kernel(const __grid_constant__ MbArgs a) {
   }
   const int mvx = me0.x, mvy = me0.y;
   const int li = a.li_prev[(size_t)s * g.nmb + mbi];
-  if (c == 0) {                                     // once per macroblock; the other five warps read it after the barrier
-    int mt0 = 0;
-    if (!a.first_frame) {
-      double x = (double)me0.w / 256.0, y = (double)me0.z / 256.0;
-      int var = me1.x, varor = me1.y;
-      if (var < 64 || varor > var) {
-        if (x < 1.0 || (x < 3.0 && y > x * 0.5) || y > __ddiv_rn(x, 1.1)) mt0 = 2;
-        else if (var < 6) mt0 = 5;
-        else mt0 = 8;
-      } else mt0 = 0;
-      if (a.force_intra) mt0 = 0;
+  // (every warp takes its macroblocks' decisions itself: 40 instructions, cheaper than a CTA-wide barrier to share them)
+  int mt = 0;
+  if (!a.first_frame && !a.force_intra) {
+    const int oval = me0.w, val = me0.z, var = me1.x, varor = me1.y;
+    if (var < 64 || varor > var) {
+      // x = OVal/256.0, y = Val/256.0 (exact in double): x < 1.0 <=> OVal < 256; x < 3.0 <=> OVal < 768; y > x*0.5 <=> 2 Val > OVal
+      // (exact products); only y > x/1.1 needs the IEEE division
+      const double x = (double)oval / 256.0, y = (double)val / 256.0;
+      if (oval < 256 || (oval < 768 && 2 * val > oval) || y > __ddiv_rn(x, 1.1)) mt = 2;
+      else if (var < 6) mt = 5;
+      else mt = 8;
     }
-    if (li > 131) mt0 = 0;
-    s_mt[lane] = (uint8_t)mt0;
   }
+  if (li > 131) mt = 0;
   const int q = a.quant ? a.quant[s] : a.gquant;
-  __syncthreads();                                  // s_qm, s_qa, s_mt
-  int mt = s_mt[lane];
   const bool intra = mt_is(M_INTRA, mt);
   const uint32_t ev = (q & 1) ? 0u : 1u;
-  const int M = (int)s_qm[q], K = (int)(4u + 8u * ev) * M, A = (int)s_qa[q];
+  const int M = (int)c_quant.m[q], K = (int)(4u + 8u * ev) * M, A = (int)c_quant.a[q];
 
   // ---- prediction (SubOverlay / SubCompensate / HalfSubCompensate addressing, io.c:142-313; chroma vector = MV/2 with C
   // truncation, io.c:268-269), as packed bytes: pk[2r], pk[2r+1] = row r

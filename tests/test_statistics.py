@@ -78,6 +78,85 @@ def test_stat_from_sums_matches_stat_c_formulas():
         assert abs(st.entropy + (p[p > 0] * np.log(p[p > 0])).sum() / np.log(2.0)) < 1e-12
 
 
+def _ref_stat(src, rec, w, h):
+    """the reference's own StatisticsMem (stat.c:73-130) through oracle/_ref/libp64ref.so (ref_stat_shim.c)"""
+    import ctypes as C
+    L = C.CDLL(os.path.join(O.REF_DIR, "libp64ref.so"))
+    a, b = np.ascontiguousarray(src, np.uint8), np.ascontiguousarray(rec, np.uint8)
+    out = (C.c_double * 6)()
+    L.ref_statistics_mem(a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), C.c_int(w), C.c_int(h), out)
+    return dict(zip(("mean", "mse", "mrsnr", "snr", "psnr", "entropy"), out))
+
+
+def _have_ref_stat():
+    import ctypes as C
+    try:
+        return O.have_ref() and hasattr(C.CDLL(os.path.join(O.REF_DIR, "libp64ref.so")), "ref_statistics_mem")
+    except OSError:
+        return False
+
+
+@pytest.mark.skipif(not _have_ref_stat(), reason="oracle/_ref/libp64ref.so without the stat.c shim")
+def test_stat_from_sums_matches_the_references_stat_c():
+    """CPU: p64b_stat_from_sums fed with exact integer sums == the reference's StatisticsMem on the same planes, bit for bit
+    (same operations in the same order on exactly representable integers), incl. identical planes, a black source and a
+    constant offset"""
+    import ctypes as C
+    from p64_b200._lib import PlaneStats, Stat, lib
+    rng = np.random.default_rng(11)
+    w, h = 176, 144
+    for case in range(6):
+        src = rng.integers(0, 256, w * h).astype(np.int64)
+        rec = np.clip(src + rng.integers(-case - 1, case + 2, src.size), 0, 255)
+        if case == 1:
+            rec = src.copy()
+        if case == 2:
+            src[:] = 0
+        if case == 3:
+            src[:] = 7; rec = src + 1
+        ps = PlaneStats()
+        ps.n, ps.sum_src, ps.sum_rec = src.size, int(src.sum()), int(rec.sum())
+        ps.sum_sq_err, ps.sum_sq_src = int(((rec - src) ** 2).sum()), int((src * src).sum())
+        for v, k in zip(*np.unique(rec, return_counts=True)):
+            ps.hist[int(v)] = int(k)
+        st = Stat()
+        lib().p64b_stat_from_sums(C.byref(ps), C.byref(st))
+        want = _ref_stat(src, rec, w, h)
+        assert {k: getattr(st, k) for k in want} == want, case
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not _have_ref_stat(), reason="oracle/_ref/libp64ref.so without the stat.c shim")
+@pytest.mark.parametrize("it", [y4m.IT_QCIF, y4m.IT_CIF])
+def test_device_statistics_match_the_references_stat_c(it):
+    """GPU: plane_stats_kernel + p64b_stat_from_sums against the reference's own StatisticsMem run on the same source and
+    reconstruction planes (stat.c:73-130), every plane of every stream"""
+    import ctypes as C
+    from p64_b200._lib import Stat, lib
+    from p64_b200.encoder import DeviceContext, make_step
+    S = 2
+    w, h = y4m.DIMS[it]
+    clips = [y4m.synth_clip(it, 3, seed=70 + s, pan=(1 - s, s)) for s in range(S)]
+    ctx = DeviceContext(it, S)
+    try:
+        for f in range(3):
+            src = np.stack([c[f] for c in clips])
+            ctx.encode_frames(make_step(f == 0, 6 + 11 * f, 0, 15), src)
+            st = ctx.statistics()
+            for s in range(S):
+                rec = ctx.recon(s)
+                off = 0
+                for pl, (pw, ph) in enumerate(((w, h), (w // 2, h // 2), (w // 2, h // 2))):
+                    n = pw * ph
+                    got = Stat()
+                    lib().p64b_stat_from_sums(C.byref(st[s][pl]), C.byref(got))
+                    want = _ref_stat(src[s, off:off + n], rec[off:off + n], pw, ph)
+                    assert {k: getattr(got, k) for k in want} == want, (f, s, pl)
+                    off += n
+    finally:
+        ctx.close()
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("it", [y4m.IT_QCIF, y4m.IT_CIF, y4m.IT_NTSC])
 def test_device_sums_match_numpy(it):
