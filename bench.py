@@ -285,6 +285,22 @@ def main_cuda(args):
         prof = ctx.profile_read()
         me_executed = ctx.me_executed()        # packed SAD ops the sweeps really issued in those K launches (device counter)
         ctx.profile(False)
+        # ---- sustained: >= 3 s of the same device-resident steps back to back (does the clock hold under seconds of 80 %-ALU
+        # integer load?); the clock sampler keeps running, its rows from this window are summarised separately
+        sus = None
+        if not args.no_sustained:
+            n_sus = max(K, int(args.sustained_s * 1e3 / max(ms / K, 1e-3)))
+            s0 = len(samples)
+            barrier()
+            u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            u0.record(stream)
+            for i in range(n_sus):
+                step_dev(W + i)
+                if i % 512 == 511:
+                    stream.synchronize()            # (keeps the launch queue bounded; < 0.1 % of the window)
+            u1.record(stream)
+            barrier()
+            sus = {"ms": u0.elapsed_time(u1), "steps": n_sus, "rows": samples[s0:]}
         # ---- e2e legs: host buffers through the C-ABI calls -------------------------------------------------
         run_host_steps(W + 2 * K, 3)
         barrier()
@@ -364,6 +380,7 @@ def main_cuda(args):
         stop.set()
         th.join(timeout=2)
 
+    sus_ms = shard.max_over_ranks([sus["ms"] if sus else 0.0], dist if world > 1 else None, device="cuda")[0]
     rc_ms = [rc_line["ms_dev"], rc_line["ms_host"]] if rc_line else [0.0, 0.0]
     red = shard.max_over_ranks([ms, ms_e2e, ms_e2e_rec] + rc_ms + [-h2d_conc] + [-x for x in link_local] + exp_local + [bal[0] if bal else 0.0],
                                dist if world > 1 else None, device="cuda")
@@ -474,6 +491,14 @@ def main_cuda(args):
                                 "d2h_bytes_per_step": S * nmb * (384 + 8), "ms_per_step": ms_e2e_rec / K,
                                 "api": "p64b_ctx_submit/p64b_ctx_wait (records + levels out, host VLC NOT included)"},
                 "gpu_launches": int(launches), "clocks": _summarise_clocks(samples)}
+        if sus:
+            rows = sus["rows"]
+            mhz = sorted(int(float(r_[0])) for r_ in rows) if rows else []
+            line["sustained"] = {"value": world * S * sus["steps"] / (sus_ms * 1e-3), "unit": "frames/s", "seconds": sus_ms * 1e-3, "steps": sus["steps"],
+                                 "ms_per_step": sus_ms / sus["steps"], "vs_value": (world * S * sus["steps"] / (sus_ms * 1e-3)) / value,
+                                 "sm_mhz_median": mhz[len(mhz) // 2] if mhz else None, "sm_mhz_min": mhz[0] if mhz else None,
+                                 "power_w_max": max(float(r_[2]) for r_ in rows) if rows else None, "clock_samples": len(rows),
+                                 "note": "the device-resident leg repeated back to back for seconds (rank 0's GPU sampled every 20 ms)"}
         if args.experiments:
             line["e2e_experiments"] = {
                 "write_combined_source": {"value": frames / (exp_ms[0] * 1e-3) if exp_ms[0] else None, "unit": "frames/s"},
@@ -749,6 +774,253 @@ def main_me1024(args):
     return 0
 
 
+
+# --------------------------------------------------------------------------------------------------------------
+# BASELINE configs[1]: QCIF intra-only (DCT + quantise + IDCT path only, no ME) on 1 B200
+# --------------------------------------------------------------------------------------------------------------
+IT_QCIF = 2
+QCIF_STREAMS = 1024           # 1024 x 38 016 B = 37 MiB per source set (4 sets in the ring: larger than L2 with the outputs)
+MB_BYTES_INTRA = 384 + 384 + 384 + 8          # source + reconstruction + int8 levels + record (no prediction)
+
+
+def run_reference_intra_sample(frames_per_proc=100, cores=None):
+    """the unmodified reference, `-QCIF -o -q 8 < test.intra` (every macroblock intra), one pinned process per host core"""
+    from oracle import oracle as O
+    from p64_b200 import y4m
+    cores = cores or os.cpu_count() or 1
+    if not O.have_ref():
+        return None
+    tmp = tempfile.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        clip = y4m.synth_clip(IT_QCIF, frames_per_proc, seed=4321)
+        exe = os.path.join(O.REF_DIR, "p64_ref")
+        for c in range(cores):
+            y4m.write_y4m(f"{tmp}/c{c}.y4m", IT_QCIF, clip)
+        taskset = shutil.which("taskset")
+        t0 = time.perf_counter()
+        procs = []
+        for c in range(cores):
+            cmd = [exe, "-y4m", "-QCIF", "-a", "0", "-b", str(frames_per_proc - 1), "-q", str(QUANT), "-o", f"{tmp}/c{c}", "-s", f"{tmp}/o{c}.p64"]
+            procs.append(subprocess.Popen(([taskset, "-c", str(c)] if taskset else []) + cmd, stdin=open(os.path.join(O.REF_DIR, "test.intra"), "rb"),
+                                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL))
+        rcs = [p.wait() for p in procs]
+        dt = time.perf_counter() - t0
+        if any(rcs):
+            raise RuntimeError(f"reference encoder failed: {rcs}")
+        return {"value": cores * frames_per_proc / dt, "unit": "frames/s", "cores": cores, "kind": "reference",
+                "sample": f"{cores} pinned processes of the unmodified reference (oracle/_ref/p64_ref -QCIF -o -q {QUANT} < test.intra), each "
+                          f"encoding its own {frames_per_proc}-frame synthetic QCIF Y4M from tmpfs, incl. its VLC and file I/O"}
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def main_qcif_intra(args):
+    import torch
+    from p64_b200 import _lib, y4m
+    from p64_b200.encoder import DeviceContext, make_step
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; p64_b200 has no CPU fallback")
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    S, K, W, NSETS = QCIF_STREAMS, args.steps, args.warmup, 4
+    L = _lib.lib()
+    ctx = DeviceContext(IT_QCIF, S)
+    g = ctx.geom
+    nmb, fb = g["num_mb"], g["frame_bytes"]
+    stream = torch.cuda.Stream()
+    ctx.set_cuda_stream(stream.cuda_stream)
+    bank = [y4m.synth_clip(IT_QCIF, NSETS + 8, seed=4321 + b, pan=((b % 5) - 2, (b % 3) - 1)) for b in range(8)]
+    host_sets = np.empty((NSETS, S, fb), np.uint8)
+    for s_ in range(S):
+        host_sets[:, s_] = bank[s_ % 8][(s_ // 8) % 8:(s_ // 8) % 8 + NSETS]
+    pin = L.p64b_host_alloc(host_sets.nbytes)
+    C.memmove(pin, host_sets.ctypes.data, host_sets.nbytes)
+    dev_sets = torch.from_numpy(host_sets).cuda()
+    d_mbs = torch.zeros(S * nmb * 8, dtype=torch.uint8, device="cuda")
+    d_lv = torch.zeros(S * nmb * 384, dtype=torch.int8, device="cuda")
+    set_bytes = S * fb
+    step = make_step(False, QUANT, 0, 15, force_intra=True)
+    samples, stop = [], threading.Event()
+    with torch.cuda.stream(stream):
+        for i in range(W):
+            ctx.encode_frames_dev(make_step(i == 0, QUANT, 0, 15, force_intra=True), dev_sets.data_ptr() + (i % NSETS) * set_bytes, d_mbs.data_ptr(), d_lv.data_ptr())
+        torch.cuda.synchronize()
+        th = threading.Thread(target=_clocks_sampler, args=(stop, samples, 0), daemon=True)
+        th.start()
+        l0 = ctx.launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(K):
+            ctx.encode_frames_dev(step, dev_sets.data_ptr() + ((W + i) % NSETS) * set_bytes, d_mbs.data_ptr(), d_lv.data_ptr())
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        launches = ctx.launches - l0
+        ctx.profile(True)
+        for i in range(K):
+            ctx.encode_frames_dev(step, dev_sets.data_ptr() + ((W + i) % NSETS) * set_bytes, d_mbs.data_ptr(), d_lv.data_ptr())
+        prof = ctx.profile_read()
+        ctx.profile(False)
+        # e2e: host frames in, stream bytes out
+        def run_bits(i0, n):
+            tickets, down, used = [], 0, 0
+            for j in range(n):
+                if j >= 3:
+                    o = ctx.wait_bits_raw(tickets[j - 3]); down += o.downloaded_bytes; used += o.total_bytes
+                tickets.append(ctx.submit_bits(step, (i0 + j) % 32, pin + ((i0 + j) % NSETS) * set_bytes))
+            for t in tickets[-3:]:
+                o = ctx.wait_bits_raw(t); down += o.downloaded_bytes; used += o.total_bytes
+            return down, used
+        run_bits(0, 4)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        down, used = run_bits(4, K)
+        torch.cuda.synchronize()
+        ms_e2e = (time.perf_counter() - t0) * 1e3
+        extra = 0
+        while len(samples) < 5 and extra < 3000:
+            ctx.encode_frames_dev(step, dev_sets.data_ptr(), d_mbs.data_ptr(), d_lv.data_ptr()); extra += 1
+            if extra % 50 == 0:
+                torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        stop.set(); th.join(timeout=2)
+    mb_ms = prof["mb"][0] / max(1, prof["mb"][1])
+    hbm_peak, peak_src = 6650.0, "fallback"
+    try:
+        hbm_peak, peak_src = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        pass
+    mb_bytes = MB_BYTES_INTRA * nmb * S
+    line = {"metric": "QCIF frames/sec encoded intra-only (DCT+Q+IDCT path, BASELINE configs[1])", "value": S * K / (ms * 1e-3), "unit": "frames/s", "n_gpus": 1,
+            "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": f"{S} independent synthetic QCIF 176x144 4:2:0 streams, every macroblock intra (`-o < test.intra`), fixed quantiser {QUANT}, no ME; "
+                                   "one step = one frame of every stream", "streams_per_gpu": S, "frames_per_step": S,
+                       "l2": f"inputs larger than L2: ring of {NSETS} source sets ({NSETS * set_bytes >> 20} MiB) + frame stores + outputs = {(NSETS + 3) * set_bytes >> 20} MiB"},
+            "roofline": {"kernel": "mb_encode_kernel", "bound": "hbm", "achieved": mb_bytes / (mb_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": mb_bytes / (mb_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None, "avg_launch_ms": mb_ms, "launches_timed": prof["mb"][1], "peak_source": peak_src,
+                         "note": "integer-issue bound like the inter case (DESIGN.md 3.2); intra macroblocks skip the prediction fetch and the loop filter",
+                         "algorithmic": f"{MB_BYTES_INTRA} B per intra macroblock (384 source + 384 reconstruction + 384 int8 levels + 8 record) x {nmb * S} macroblocks per launch"},
+            "cpu_baseline": run_reference_intra_sample(),
+            "e2e": {"value": S * K / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": S * fb, "d2h_bytes_per_step": down // K,
+                    "stream_bytes_per_step": used // K, "ms_per_step": ms_e2e / K,
+                    "api": "p64b_ctx_submit_bits/p64b_ctx_wait_bits (host source frames in, finished H.261 stream bytes out; pinned buffers; 3 steps in flight)"},
+            "gpu_launches": int(launches), "clocks": _summarise_clocks(samples)}
+    ctx.close()
+    L.p64b_host_free(pin)
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# --------------------------------------------------------------------------------------------------------------
+# BASELINE configs[4] at full length: 256 streams per GPU x 300 frames through the sequence encoder, every stream hashed
+# --------------------------------------------------------------------------------------------------------------
+def main_config5(args):
+    """300 CIF frames of 256 streams per GPU (2048 on 8 GPUs) through the public sequence encoder (p64b_enc_*: host frames in,
+    .p64 bytes out, device-side VLC), fixed quantiser 8, exhaustive search -i 31.  Crosses the forced-intra refresh
+    (LastIntra > 131, p64.c:772-773) and nine temporal-reference wraps inside a batch.  Every stream is md5'd; streams that play
+    the same clip at the same phase must be byte-identical; one stream per distinct (clip, phase) pair up to `--sample` is
+    byte-compared with the unmodified reference encoder (oracle/_ref/p64_ref_fs) run on that stream's frames."""
+    import hashlib
+    import torch
+    import torch.distributed as dist
+    from oracle import oracle as O
+    from p64_b200 import shard, y4m
+    from p64_b200.encoder import Encoder
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; p64_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    S, NF = STREAMS_PER_GPU, args.frames
+    streams = list(shard.stream_range(S * world, world, rank))
+    bank = [y4m.synth_clip(IT_CIF, NF + CLIP_BANK, seed=1000 + b, pan=((b % 5) - 2, (b % 3) - 1)) for b in range(CLIP_BANK)]
+    keys = [(s_ % CLIP_BANK, (s_ // CLIP_BANK) % CLIP_BANK) for s_ in streams]
+    enc = Encoder(IT_CIF, S, q=QUANT, me_mode=1, search_limit=SEARCH_LIMIT, device=local)
+    fb = bank[0].shape[1]
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t_enc = 0.0
+    t_all = time.perf_counter()
+    for f in range(NF):
+        frame = enc.staging()                   # the reader's role: the next frame of every stream goes straight into the encoder's pinned staging
+        for k, (b, ph) in enumerate(keys):
+            frame[k] = bank[b][ph + f]
+        t0 = time.perf_counter()
+        enc.encode(frame)                       # host frames in, 3 frames in flight
+        t_enc += time.perf_counter() - t0
+    t0 = time.perf_counter()
+    enc.finish()
+    t_enc += time.perf_counter() - t0
+    wall = time.perf_counter() - t_all
+    data = [enc.data(k) for k in range(S)]
+    enc.close()
+    md5s = [hashlib.md5(d).hexdigest() for d in data]
+    by_key = {}
+    consistent = True
+    for k, key in enumerate(keys):
+        consistent &= by_key.setdefault(key, md5s[k]) == md5s[k]
+    # byte-compare a sample with the unmodified reference (one stream per distinct (clip, phase) pair, this rank's first ones)
+    compared, equal = [], True
+    if O.have_ref() and args.sample > 0:
+        todo = list(by_key)[:args.sample]
+        tmp = tempfile.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        try:
+            procs = []
+            for i, (b, ph) in enumerate(todo):
+                y4m.write_y4m(f"{tmp}/c{i}.y4m", IT_CIF, bank[b][ph:ph + NF])
+                cmd = [os.path.join(O.REF_DIR, "p64_ref_fs"), "-y4m", "-CIF", "-a", "0", "-b", str(NF - 1), "-q", str(QUANT), "-i", str(SEARCH_LIMIT), f"{tmp}/c{i}", "-s", f"{tmp}/o{i}.p64"]
+                procs.append(subprocess.Popen(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL))
+            for i, (key, pr) in enumerate(zip(todo, procs)):
+                pr.wait()
+                ref = open(f"{tmp}/o{i}.p64", "rb").read()
+                k = keys.index(key)
+                ok = ref == data[k]
+                equal &= ok
+                compared.append({"stream": streams[k], "clip": key[0], "phase": key[1], "bytes": len(ref), "md5": hashlib.md5(ref).hexdigest(), "equal": bool(ok)})
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+    t_enc_max, wall_max = shard.max_over_ranks([t_enc, wall], dist if world > 1 else None, device="cuda")
+    all_md5 = [md5s]
+    flags = [bool(consistent), bool(equal)]
+    all_cmp = [compared]
+    if world > 1:
+        all_md5 = [None] * world; dist.all_gather_object(all_md5, md5s)
+        fl = [None] * world; dist.all_gather_object(fl, flags); flags = [all(x[0] for x in fl), all(x[1] for x in fl)]
+        all_cmp = [None] * world; dist.all_gather_object(all_cmp, compared)
+    if rank == 0:
+        flat = [m for r_ in all_md5 for m in r_]
+        frames = world * S * NF
+        line = {"metric": "CIF frames/sec encoded (ME+DCT+Q+recon)", "value": frames / t_enc_max, "unit": "frames/s", "n_gpus": world, "steps": NF, "warmup": 0,
+                "ms_per_step": t_enc_max * 1e3 / NF, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": {"workload": f"BASELINE configs[4] at full length: {world * S} independent synthetic CIF streams ({S} per GPU) x {NF} frames through the sequence "
+                                       f"encoder p64b_enc_* (host frames in, .p64 bytes out; device-side headers + VLC), fixed quantiser {QUANT}, full-search ME +-15 (-i {SEARCH_LIMIT}); "
+                                       "first frame intra, forced-intra refresh after 132 inter frames, TR wraps every 32 frames",
+                           "streams_per_gpu": S, "frames_per_stream": NF, "parallelism": f"streams partitioned over {world} GPU(s), no collective"},
+                "value_is": "end to end: seconds inside p64b_enc_encode/p64b_enc_finish (max over ranks); the frames are assembled in the encoder's pinned staging buffer (p64b_enc_staging, as the p64b command's Y4M reader does) -> upload -> kernels -> bytes",
+                "wall_s_including_input_assembly": wall_max,
+                "streams": len(flat), "md5_of_all_stream_md5s": hashlib.md5("".join(flat).encode()).hexdigest(),
+                "same_input_same_bytes": flags[0],
+                "byte_compared_with_reference": {"all_equal": flags[1], "streams": [c for r_ in all_cmp for c in r_],
+                                                 "reference": "oracle/_ref/p64_ref_fs -y4m -CIF -q 8 -i 31 on the stream's own frames"},
+                "e2e": {"value": frames / t_enc_max, "unit": "frames/s", "h2d_bytes_per_step": S * fb, "d2h_bytes_per_step": sum(len(d) for d in data) // NF},
+                "cpu_baseline": None, "gpu_launches": None}
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0 if (flags[0] and flags[1]) else 1
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -757,15 +1029,25 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--search", default="full", choices=["full", "tss"],
                     help="full = exhaustive FastBME -i 31 (the north-star configuration, default); tss = the stock three-step StepBME")
-    ap.add_argument("--workload", default="streams", choices=["streams", "me1024"],
-                    help="streams = the stream batch (default, BASELINE configs[4]); me1024 = the ME microbenchmark of configs[3] (1 GPU)")
+    ap.add_argument("--workload", default="streams", choices=["streams", "me1024", "qcif_intra", "config5"],
+                    help="streams = the stream batch (default, BASELINE configs[4] per-GPU share); me1024 = the ME microbenchmark of configs[3] (1 GPU); "
+                         "qcif_intra = configs[1] (QCIF intra-only, 1 GPU); config5 = configs[4] at full length (300 frames per stream, every stream hashed, "
+                         "a sample byte-compared with the reference encoder)")
+    ap.add_argument("--frames", type=int, default=300, help="config5: frames per stream")
+    ap.add_argument("--sample", type=int, default=8, help="config5: streams per rank byte-compared with the reference encoder")
     ap.add_argument("--no-rate-control", action="store_true", help="skip the extra rate-control (-r) end-to-end leg")
+    ap.add_argument("--no-sustained", action="store_true", help="skip the multi-second sustained leg")
+    ap.add_argument("--sustained-s", type=float, default=3.0, help="length of the sustained leg in seconds")
     ap.add_argument("--equal-partition", action="store_true", help="N > 1: keep 256 streams on every GPU in the end-to-end leg (default: balance by link share)")
     ap.add_argument("--experiments", action="store_true", help="extra end-to-end attribution legs (write-combined source, one process driving all GPUs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
     if args.impl == "cuda" and args.workload == "me1024":
         return main_me1024(args)
+    if args.impl == "cuda" and args.workload == "qcif_intra":
+        return main_qcif_intra(args)
+    if args.impl == "cuda" and args.workload == "config5":
+        return main_config5(args)
     return main_reference(args) if args.impl == "reference" else main_cuda(args)
 
 

@@ -292,6 +292,13 @@ class Encoder:
         frames = np.ascontiguousarray(frames, np.uint8).reshape(self.n_streams, self.src_bytes)
         check(self.L.p64b_enc_encode(self.h, _ptr(frames)))
 
+    def staging(self) -> np.ndarray:
+        """the encoder's own pinned upload buffer for the NEXT frame, uint8 [n_streams, src_bytes]: fill it in place and pass it
+        to encode() -- no staging copy then.  It changes after every encode()."""
+        p = self.L.p64b_enc_staging(self.h)
+        buf = (C.c_uint8 * (self.n_streams * self.src_bytes)).from_address(p)
+        return np.frombuffer(buf, np.uint8).reshape(self.n_streams, self.src_bytes)
+
     def finish(self):
         check(self.L.p64b_enc_finish(self.h))
 
