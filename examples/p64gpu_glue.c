@@ -8,35 +8,52 @@
 #include "globals.h"
 #include "p64_b200.h"
 
-extern IMAGE *CImage; extern FRAME *CFrame; extern FSTORE *CFS;
+extern IMAGE *CImage; extern FRAME *CFrame; extern FSTORE *CFS, *OFS;
 extern int ImageType, CurrentFrame, StartFrame, CurrentGOB, CurrentMDU, NumberGOB, NumberMDU;
 extern int MType, CBP, MVDH, MVDV, GQuant, UseQuant, SearchLimit, Oracle, Rate;
 extern int MeX[], MeY[], MeVal[], MeOVal[], MeVAR[], MeVAROR[], MeMWOR[];
+extern unsigned char **LastIntra;
+extern int IntraMType[];
 
 static p64b_ctx *ctx; static p64b_mb *mbs; static int8_t *levels; static uint8_t *src, *ovf; static uint8_t q1[1];
-static p64b_step step;
+static p64b_me *me; static p64b_step step; static int img_t;
+int p64gpu_ovf;                                /* set by the MAIN LOOP's overflow branch (p64.c:776-783) for the macroblock at hand */
 
 static void die(void) { BEGIN("p64gpu"); WHEREAMI(); printf("p64gpu: %s\n", p64b_last_error()); exit(ERROR_MEMORY); }
 
 void p64gpu_init(void) {                       /* call once from p64EncodeSequence after ClearFS (p64.c:535) */
-  int t = ImageType == IT_CIF ? P64B_IT_CIF : ImageType == IT_QCIF ? P64B_IT_QCIF : P64B_IT_NTSC;
+  int t = img_t = ImageType == IT_CIF ? P64B_IT_CIF : ImageType == IT_QCIF ? P64B_IT_QCIF : P64B_IT_NTSC;
   if (p64b_ctx_create(&ctx, 0, t, 1)) die();
   src    = p64b_host_alloc(p64b_frame_bytes(t));
   mbs    = p64b_host_alloc(p64b_num_mb(t) * sizeof(p64b_mb));
   levels = p64b_host_alloc(p64b_num_mb(t) * P64B_LEVELS_PER_MB);
   ovf    = calloc(p64b_num_mb(t), 1);
+  me     = calloc(p64b_num_mb(t), sizeof(p64b_me));
 }
 
 void p64gpu_frame_begin(void) {                /* replaces `if (CurrentFrame!=StartFrame) GlobalMC();` p64.c:635-636 */
-  int i; unsigned char *d = src;
-  for (i = 0; i < 3; i++) {                    /* ReadIob() already ran: copy out of the Y4M reader's buffer (io.c:635-644) */
-    memcpy(d, CFrame->Iob[i]->mem->data, CFrame->Iob[i]->mem->len); d += CFrame->Iob[i]->mem->len;
+  int i, n; unsigned char *d = src;
+  const int wh = p64b_width(img_t) * p64b_height(img_t);
+  for (i = 0; i < 3; i++) {                    /* ReadIob() already ran: the planes as ReadBlock walks them (io.c:636-645, 793-803) */
+    n = i ? wh / 4 : wh;
+    memcpy(d, CFrame->Iob[i]->mem->data, n); d += n;
   }
   step.first_frame = CurrentFrame == StartFrame;
-  step.me_mode = P64B_ME_TSS;                  /* P64B_ME_FULL to get the FastBME build (me.c:351) */
+#ifdef P64GPU_FULL
+  step.me_mode = P64B_ME_FULL;                 /* the FastBME build (me.c:351) */
+#else
+  step.me_mode = P64B_ME_TSS;
+#endif
   step.search_limit = SearchLimit; step.force_intra = 0; step.gquant = GQuant;
   if (p64b_ctx_frame_begin(ctx, &step, src)) die();
-  if (Oracle) { /* fill MeX.. for CallOracle */ }
+  if (!step.first_frame) {                     /* the reference's result arrays (me.c:49-59): the decision code and CallOracle read them */
+    if (p64b_ctx_me_records(ctx, 0, me)) die();
+    n = (wh / 256);
+    for (i = 0; i < n; i++) {
+      MeX[i] = me[i].mx; MeY[i] = me[i].my; MeVal[i] = me[i].val; MeOVal[i] = me[i].oval;
+      MeVAR[i] = me[i].var; MeVAROR[i] = me[i].varor; MeMWOR[i] = me[i].mwor;
+    }
+  }
   memset(ovf, 0, NumberGOB * NumberMDU);
 }
 
@@ -45,18 +62,21 @@ void p64gpu_gob(void) {                        /* call in p64EncodeGOB right aft
   if (p64b_ctx_encode_gob(ctx, &step, CurrentGOB, q1, mbs, levels)) die();
 }
 
-/* replaces the decision + ReadCompressMDU + the inverse half of WriteMDU + DecodeSaveMDU for one MB:
-   sets the globals WriteMBHeader()/Encode*() read and fills inputbuf[c][k] with the zig-zag levels */
+/* replaces ReadCompressMDU + the inverse half of WriteMDU + DecodeSaveMDU for one MB: sets the globals
+   WriteMBHeader()/Encode*() read and fills inputbuf[c][k] with the zig-zag levels; keeps LastIntra (p64.c:909-910) and the
+   installed Iob (what Bpos() of the next macroblock's decision code relies on, p64.c:1007-1010) as the reference leaves them */
 void p64gpu_mb(int overflow, int inputbuf[10][64]) {
   const p64b_mb *r = &mbs[CurrentMDU]; const int8_t *l = levels + CurrentMDU * P64B_LEVELS_PER_MB; int c, k;
   if (overflow) { MType = 4; CBP = 0x3f; MVDH = MVDV = 0; ovf[CurrentGOB * NumberMDU + CurrentMDU] = 1; }
   else { MType = r->mtype; CBP = r->cbp; MVDH = r->mvx; MVDV = r->mvy; }
   UseQuant = GQuant;
   for (c = 0; c < 6; c++) for (k = 0; k < 64; k++)
-    inputbuf[c][k] = (k == 0 && MType < 2) ? (uint8_t)l[64 * c] : l[64 * c + k];   /* intra DC is unsigned */
+    inputbuf[c][k] = overflow ? 0 : (k == 0 && MType < 2) ? (uint8_t)l[64 * c] : l[64 * c + k];   /* intra DC is unsigned */
+  if (IntraMType[MType]) LastIntra[CurrentGOB][CurrentMDU] = 0; else LastIntra[CurrentGOB][CurrentMDU]++;
+  InstallFS(2, OFS);
 }
 
-void p64gpu_frame_end(void) { if (p64b_ctx_frame_end(ctx, Rate ? ovf : 0)) die(); }   /* replaces SwapFS p64.c:661 */
+void p64gpu_frame_end(void) { if (p64b_ctx_frame_end(ctx, Rate ? ovf : 0)) die(); }   /* with SwapFS p64.c:661 */
 
 /* ---- 3b: the device writes the bits too (fixed quantiser) ---- */
 static unsigned int pending, pending_len;

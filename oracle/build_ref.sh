@@ -45,6 +45,31 @@ if [ -f "$LIBDIR/libp64b200.so" ]; then
         -L"$LIBDIR" -lp64b200 -Wl,-rpath,'$ORIGIN/../../p64_b200' -lm -o "$OUT/p64_gpu$v"
   done
 fi
+# p64_gpu_hv / p64_gpu_hv_fs: the reference-shaped binding of INTEGRATION.md section 3 (examples/p64gpu_glue.c), executed: the
+# reference keeps its own headers, VLC (WriteMBHeader, EncodeDC/AC, CBPEncodeAC), rate control (ExecuteQuantization, the
+# overflow branch) and stream writer; GlobalMC, ReadCompressMDU and DecodeSaveMDU are replaced by the per-frame / per-GOB /
+# per-macroblock calls into the library.  Again p64.c only passes through sed into the temp dir.
+if [ -f "$LIBDIR/libp64b200.so" ]; then
+  TMP2=$(mktemp -d)
+  sed -e '1i extern int p64gpu_ovf;' \
+      -e '/^void p64EncodeSequence()/,/^}/ s|^  swopen(CImage->StreamFileName);|  swopen(CImage->StreamFileName);\n  p64gpu_init();|' \
+      -e '/^void p64EncodeFrame()/,/^}/ s|^  InstallFS(0,CFS);|  InstallFS(0,CFS);\n  p64gpu_frame_begin();|' \
+      -e '/^void p64EncodeFrame()/,/^}/ s|^    GlobalMC();|    ;|' \
+      -e '/^void p64EncodeFrame()/,/^}/ s|^  SwapFS(CFS,OFS);|  SwapFS(CFS,OFS);\n  p64gpu_frame_end();|' \
+      -e '/^void p64EncodeGOB()/,/^}/ s|^  switch (ImageType)|  p64gpu_gob();\n  switch (ImageType)|' \
+      -e '/^void p64EncodeGOB()/,/^}/ s|^      LastMType=MType;|      LastMType=MType; p64gpu_ovf=0;|' \
+      -e '/^void p64EncodeGOB()/,/^}/ s|^[ \t]*MType=4;     /\* No coefficient transmission \*/|	  MType=4; p64gpu_ovf=1;|' \
+      -e '/^static void p64EncodeMDU()/,/^}/ s|^  ReadCompressMDU();|  p64gpu_mb(p64gpu_ovf, inputbuf);|' \
+      -e '/^static void p64EncodeMDU()/,/^}/ s|^  DecodeSaveMDU();|  ;|' \
+      "$REF/p64.c" > "$TMP2/p64_gpu_hv.c"
+  [ "$(grep -c 'p64gpu_' "$TMP2/p64_gpu_hv.c")" = 8 ]
+  for v in "" _fs; do
+    DEF=""; [ -n "$v" ] && DEF="-DP64GPU_FULL"
+    gcc $CF $DEF -I"$HERE/../include" "$TMP2/p64_gpu_hv.c" $REST $REF/me.c "$HERE/../examples/p64gpu_glue.c" \
+        -L"$LIBDIR" -lp64b200 -Wl,-rpath,'$ORIGIN/../../p64_b200' -lm -o "$OUT/p64_gpu_hv$v"
+  done
+  rm -rf "$TMP2"
+fi
 cp "$REF/test.intra" "$OUT/test.intra"
 cp "$REF/short.p64" "$OUT/short.p64"      # the reference's own 1993 stream (SETUP:13-33): decoder known-answer test   # interpreter program fed on stdin for the intra-only config
 rm -rf "$TMP"
