@@ -267,6 +267,10 @@ int p64b_measure_link(int device, const void *const *up, int up_sets, size_t up_
 /* Upload rate (GB/s) of every listed device while ALL of them upload at the same time (one host thread per device, 8 x 32 MB
  * from pinned memory): the GPUs of a box share host uplinks, not always evenly.  p64b_enc_params.balance_links partitions by it. */
 int p64b_probe_links(const int32_t *devices, int n_devices, double *gb_per_s);
+/* Debug builds (-DP64B_BOUNDS_CHECK) check every shared-memory access of the motion-estimation and macroblock kernels against
+ * the region its thread may touch (compute-sanitizer is not available on every pool).  Returns 1 and the number of violations
+ * on `device` since the library was loaded (+ the kernels.cuh line of the last one) from such a build, 0 from the product build. */
+int p64b_debug_oob(int device, uint32_t *violations, uint32_t *last_line);
 /* p64b_host_alloc with flags: 1 = write-combined (cudaHostAllocWriteCombined). */
 void *p64b_host_alloc_flags(size_t bytes, int flags);
 

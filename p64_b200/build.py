@@ -48,6 +48,15 @@ def build_lib(force: bool = False, verbose: bool = False, out: str = LIB, define
     return out
 
 
+BOUNDS_LIB = os.path.join(HERE, "libp64b200_bounds.so")
+
+
+def build_bounds_lib(force: bool = False) -> str:
+    """the -DP64B_BOUNDS_CHECK debug build (every shared-memory access of the ME / macroblock kernels checked), next to the
+    product library so that it travels with a snapshot; used by tests/test_bounds_check.py through P64B_LIB"""
+    return build_lib(force, out=BOUNDS_LIB, defines=["P64B_BOUNDS_CHECK"])
+
+
 def build_cli(force: bool = False) -> str:
     src = os.path.join(CSRC, "cli.cpp")
     build_lib(force)

@@ -1012,6 +1012,19 @@ int p64b_measure_link(int device, const void* const* up, int up_sets, size_t up_
   return 0;
 }
 
+int p64b_debug_oob(int device, uint32_t* violations, uint32_t* last_line) {
+  unsigned int v[2] = {0, 0};
+  if (cudaSetDevice(device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess ||
+      cudaMemcpyFromSymbol(v, g_oob, sizeof v) != cudaSuccess) { set_error("p64b_debug_oob: device not usable"); return P64B_ECUDA; }
+  if (violations) *violations = v[0];
+  if (last_line) *last_line = v[1];
+#ifdef P64B_BOUNDS_CHECK
+  return 1;
+#else
+  return 0;
+#endif
+}
+
 int p64b_probe_links(const int32_t* devices, int n_devices, double* gb_per_s) {
   if (!devices || !gb_per_s || n_devices < 1) return P64B_EINVAL;
   const size_t bytes = 32u << 20;

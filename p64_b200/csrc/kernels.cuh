@@ -97,6 +97,30 @@ __device__ __forceinline__ uint32_t sad4(uint32_t a, uint32_t b, uint32_t c) {
   return d;
 }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- debug build (-DP64B_BOUNDS_CHECK): every shared-memory access of me_search_kernel and mb_encode_kernel is checked against the
+// region its thread may touch (the warp's slice + the CTA tables; the thread's tile + the CTA exchange array).  compute-sanitizer
+// is closed on this pool, so this is how the hand-computed offsets of the warp-synchronous kernels are validated
+// (tests/test_bounds_check.py runs edge / corner macroblocks and ragged stream counts through such a build).  Violations are
+// counted in g_oob[0] (g_oob[1] = source line of the last one) and the access is redirected to the region's first word.
+__device__ unsigned int g_oob[2];
+#ifdef P64B_BOUNDS_CHECK
+__device__ __forceinline__ uint32_t smck_fix(uint32_t ad, uint32_t bytes, uint32_t lo, uint32_t hi, uint32_t lo2, uint32_t hi2, int line) {
+  if ((ad >= lo && ad + bytes <= hi) || (ad >= lo2 && ad + bytes <= hi2)) return ad;
+  atomicAdd(&g_oob[0], 1u);
+  g_oob[1] = (unsigned)line;
+  return lo;
+}
+#define P64B_SM_T(T, p, lim) (*reinterpret_cast<T*>(__cvta_shared_to_generic(smck_fix(smem_u32(p), (uint32_t)sizeof(T), (lim).lo, (lim).hi, (lim).lo2, (lim).hi2, __LINE__))))
+#else
+#define P64B_SM_T(T, p, lim) (*reinterpret_cast<T*>(p))
+#endif
+struct SmLim { uint32_t lo, hi, lo2, hi2; };        // two [lo, hi) windows of shared-memory addresses (unused in the product build)
+#define SMR(p) P64B_SM_T(const uint32_t, (p), lim)
+#define SMR2(p) P64B_SM_T(const uint2, (p), lim)
+#define SMR4(p) P64B_SM_T(const uint4, (p), lim)
+#define SMW(p) P64B_SM_T(uint32_t, (p), lim)
+#define SMW4(p) P64B_SM_T(uint4, (p), lim)
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -158,11 +182,11 @@ constexpr int ME_PRUNE_R1 = P64B_ME_PRUNE_R1, ME_PRUNE_R2 = P64B_ME_PRUNE_R2;   
 
 // block rows [R0, R1) of all NC candidates: window rows R0 .. R1-1+NC-1
 template <int NC, int R0, int R1>
-__device__ __forceinline__ void sweep_rows(const uint32_t* __restrict__ base, const uint32_t (&c)[16][4], uint32_t (&a)[NC]) {
+__device__ __forceinline__ void sweep_rows(const uint32_t* __restrict__ base, const uint32_t (&c)[16][4], uint32_t (&a)[NC], const SmLim& lim) {
 #pragma unroll
   for (int t = R0; t < R1 - 1 + NC; t++) {
-    const uint32_t r0 = base[t * ME_ROW_WORDS + 0], r1 = base[t * ME_ROW_WORDS + 1];
-    const uint32_t r2 = base[t * ME_ROW_WORDS + 2], r3 = base[t * ME_ROW_WORDS + 3];
+    const uint32_t r0 = SMR(base + t * ME_ROW_WORDS + 0), r1 = SMR(base + t * ME_ROW_WORDS + 1);
+    const uint32_t r2 = SMR(base + t * ME_ROW_WORDS + 2), r3 = SMR(base + t * ME_ROW_WORDS + 3);
 #pragma unroll
     for (int j = 0; j < NC; j++) {
       const int i = t - j;
@@ -184,31 +208,31 @@ __device__ __forceinline__ bool sweep_hopeless(const uint32_t (&a)[NC], bool xok
 template <int VARIANT, int NC, bool PRUNE>
 __device__ __forceinline__ uint32_t sweep_pass(const uint32_t* __restrict__ colbase, const uint32_t (&c)[16][4],
                                                const uint32_t* pen, uint32_t* s_sad, int xi, int yb, bool xok,
-                                               uint32_t m2048, uint32_t bound, uint32_t& units) {
+                                               uint32_t m2048, uint32_t bound, uint32_t& units, const SmLim& lim) {
   const uint32_t* base = colbase + yb * ME_ROW_WORDS;
   uint32_t a[NC];
 #pragma unroll
-  for (int j = 0; j < NC; j++) a[j] = pen[yb + j];
+  for (int j = 0; j < NC; j++) a[j] = SMR(pen + yb + j);
   if (PRUNE) {
     constexpr int R1 = ME_PRUNE_R1, R2 = ME_PRUNE_R2;
-    sweep_rows<NC, 0, R1>(base, c, a);
+    sweep_rows<NC, 0, R1>(base, c, a, lim);
     units += (uint32_t)(NC * R1);
     if (sweep_hopeless<NC>(a, xok, bound)) return 0xffffffffu;
     if (R2 > R1) {
-      sweep_rows<NC, R1, R2>(base, c, a);
+      sweep_rows<NC, R1, R2>(base, c, a, lim);
       units += (uint32_t)(NC * (R2 - R1));
       if (sweep_hopeless<NC>(a, xok, bound)) return 0xffffffffu;
     }
-    sweep_rows<NC, R2, 16>(base, c, a);
+    sweep_rows<NC, R2, 16>(base, c, a, lim);
     units += (uint32_t)(NC * (16 - R2));
   } else {
-    sweep_rows<NC, 0, 16>(base, c, a);
+    sweep_rows<NC, 0, 16>(base, c, a, lim);
     units += (uint32_t)(NC * 16);
   }
   if (VARIANT == ME_V_SURF) {
 #pragma unroll
     for (int j = 0; j < NC; j++)
-      if (xok && a[j] < ME_ILLEGAL) s_sad[(yb + j) * 31 + xi] = a[j];     // the rest keeps the 0xffffffff prefill
+      if (xok && a[j] < ME_ILLEGAL) SMW(s_sad + (yb + j) * 31 + xi) = a[j];     // the rest keeps the 0xffffffff prefill
   }
   uint32_t best = 0xffffffffu;
 #pragma unroll
@@ -236,37 +260,38 @@ __device__ __forceinline__ uint32_t sweep_pass(const uint32_t* __restrict__ colb
 // per macroblock: the bookkeeping of three compactions per macroblock costs what the SADs save), and a fully unrolled 30-row
 // column (code beyond the 32 KB instruction cache: 1.5x slower).
 // full SAD of the candidate at surface position (cx, cy), cooperatively: lane -> (block row lane/2, half lane%2)
-__device__ __forceinline__ uint32_t coop_sad(const uint32_t* win, const uint32_t* s_cur, int cx, int cy, int lane) {
+__device__ __forceinline__ uint32_t coop_sad(const uint32_t* win, const uint32_t* s_cur, int cx, int cy, int lane, const SmLim& lim) {
   const int i = lane >> 1, wc = (lane & 1) * 2, oo = cx + 1, sh = (oo & 3) * 8;
   const uint32_t* rp = win + (cy + i) * ME_ROW_WORDS + (oo >> 2) + wc;
-  const uint32_t ra = __funnelshift_r(rp[0], rp[1], sh), rb = __funnelshift_r(rp[1], rp[2], sh);
-  const uint2 cw = *reinterpret_cast<const uint2*>(s_cur + i * 4 + wc);
+  const uint32_t w0 = SMR(rp), w1 = SMR(rp + 1), w2 = SMR(rp + 2);
+  const uint32_t ra = __funnelshift_r(w0, w1, sh), rb = __funnelshift_r(w1, w2, sh);
+  const uint2 cw = SMR2(s_cur + i * 4 + wc);
   return __reduce_add_sync(0xffffffffu, sad4(rb, cw.y, sad4(ra, cw.x, 0u)));
 }
 
 // The list's survivors, one per lane: rows RA..15 on two accumulator chains, one exit half way.
 __device__ __forceinline__ void sparse_finish(const uint32_t* win, const uint32_t* shifted, const uint32_t (&c)[16][4], const uint32_t* list,
-                                              int nlist, int lane, uint32_t m2048, uint32_t& bound, uint32_t& best, uint32_t& units) {
+                                              int nlist, int lane, uint32_t m2048, uint32_t& bound, uint32_t& best, uint32_t& units, const SmLim& lim) {
   constexpr int S1 = (ME_RA + 16) / 2;
 #pragma unroll 1
   for (int i0 = 0; i0 < nlist; i0 += 32) {
     const bool ok = i0 + lane < nlist;
-    const uint32_t e = ok ? list[i0 + lane] : 0u;
+    const uint32_t e = ok ? SMR(list + i0 + lane) : 0u;
     uint32_t p = ok ? (e & 0xffffu) : ME_ILLEGAL, q = 0;
     if (!__any_sync(0xffffffffu, p <= bound)) continue;              // the bound has moved since they were listed
     const int x = (e >> 21) & 31, y = (e >> 16) & 31, o = x + 1, k = o & 3;
     const uint32_t* b = (k ? shifted + (k - 1) * ME_COPY_WORDS : win) + (o >> 2) + y * ME_ROW_WORDS;
 #pragma unroll
     for (int r = ME_RA; r < S1; r++) {
-      p = sad4(b[r * ME_ROW_WORDS + 0], c[r][0], p); q = sad4(b[r * ME_ROW_WORDS + 1], c[r][1], q);
-      p = sad4(b[r * ME_ROW_WORDS + 2], c[r][2], p); q = sad4(b[r * ME_ROW_WORDS + 3], c[r][3], q);
+      p = sad4(SMR(b + r * ME_ROW_WORDS + 0), c[r][0], p); q = sad4(SMR(b + r * ME_ROW_WORDS + 1), c[r][1], q);
+      p = sad4(SMR(b + r * ME_ROW_WORDS + 2), c[r][2], p); q = sad4(SMR(b + r * ME_ROW_WORDS + 3), c[r][3], q);
     }
     units += S1 - ME_RA;
     if (!__any_sync(0xffffffffu, p + q <= bound)) continue;
 #pragma unroll
     for (int r = S1; r < 16; r++) {
-      p = sad4(b[r * ME_ROW_WORDS + 0], c[r][0], p); q = sad4(b[r * ME_ROW_WORDS + 1], c[r][1], q);
-      p = sad4(b[r * ME_ROW_WORDS + 2], c[r][2], p); q = sad4(b[r * ME_ROW_WORDS + 3], c[r][3], q);
+      p = sad4(SMR(b + r * ME_ROW_WORDS + 0), c[r][0], p); q = sad4(SMR(b + r * ME_ROW_WORDS + 1), c[r][1], q);
+      p = sad4(SMR(b + r * ME_ROW_WORDS + 2), c[r][2], p); q = sad4(SMR(b + r * ME_ROW_WORDS + 3), c[r][3], q);
     }
     units += 16 - S1;
     p += q;                                   // (lanes without a survivor carry ME_ILLEGAL: never the minimum)
@@ -278,16 +303,16 @@ __device__ __forceinline__ void sparse_finish(const uint32_t* win, const uint32_
 // One chunk of 10 dy rows at surface rows yb .. yb+9 of this lane's column xi.  Returns the list length.
 __device__ __forceinline__ int full_chunk(const uint32_t* colbase, const uint32_t* win, const uint32_t* s_cur, const uint32_t (&c)[16][4],
                                           const uint32_t* pen, uint32_t* list, int nlist, int xi, int yb, bool xok, int lane, uint32_t m2048,
-                                          uint32_t& bound, uint32_t& best, uint32_t& units, bool& dense_mode) {
+                                          uint32_t& bound, uint32_t& best, uint32_t& units, bool& dense_mode, const SmLim& lim) {
   constexpr int NC = 10, R1 = ME_PRUNE_R1;
   const uint32_t* base = colbase + yb * ME_ROW_WORDS;
   uint32_t a[NC];
 #pragma unroll
-  for (int j = 0; j < NC; j++) a[j] = pen[yb + j];
-  sweep_rows<NC, 0, R1>(base, c, a);
+  for (int j = 0; j < NC; j++) a[j] = SMR(pen + yb + j);
+  sweep_rows<NC, 0, R1>(base, c, a, lim);
   units += (uint32_t)(NC * R1);
   if (sweep_hopeless<NC>(a, xok, bound)) return nlist;
-  sweep_rows<NC, R1, ME_RA>(base, c, a);
+  sweep_rows<NC, R1, ME_RA>(base, c, a, lim);
   units += (uint32_t)(NC * (ME_RA - R1));
   // B. the chunk's smallest partial sum; nothing at or below the bound: the chunk is done.  If promising, that candidate in full
   int total = ME_DENSE_T + 1;
@@ -300,7 +325,7 @@ __device__ __forceinline__ int full_chunk(const uint32_t* colbase, const uint32_
     if (2u * pm < bound) {                                             // (warp-uniform)
       const int src = __ffs(__ballot_sync(0xffffffffu, xok && (m >> 4) == pm)) - 1;
       const int cx = __shfl_sync(0xffffffffu, xi, src), cy = __shfl_sync(0xffffffffu, yb + (int)(m & 15u), src);
-      bound = min(bound, coop_sad(win, s_cur, cx, cy, lane));
+      bound = min(bound, coop_sad(win, s_cur, cx, cy, lane, lim));
       units += 1;                                                     // (2 packed SADs per lane, counted as a whole candidate row)
     }
     // C. survivors, counted per lane first (the ballots below are only for chunks that are compacted)
@@ -311,7 +336,7 @@ __device__ __forceinline__ int full_chunk(const uint32_t* colbase, const uint32_
     dense_mode = total > ME_DENSE_T;
   } else if (sweep_hopeless<NC>(a, xok, bound)) return nlist;
   if (total > ME_DENSE_T) {
-    sweep_rows<NC, ME_RA, 16>(base, c, a);
+    sweep_rows<NC, ME_RA, 16>(base, c, a, lim);
     units += (uint32_t)(NC * (16 - ME_RA));
     uint32_t r = 0xffffffffu;
 #pragma unroll
@@ -326,7 +351,7 @@ __device__ __forceinline__ int full_chunk(const uint32_t* colbase, const uint32_
   for (int j = 0; j < NC; j++) {
     const bool sv = xok && a[j] <= bound;
     const uint32_t mk = __ballot_sync(0xffffffffu, sv);
-    if (sv) list[nlist + __popc(mk & lt)] = a[j] + tag + ((uint32_t)j << 16);
+    if (sv) SMW(list + nlist + __popc(mk & lt)) = a[j] + tag + ((uint32_t)j << 16);
     nlist += __popc(mk);
   }
   return nlist;
@@ -350,11 +375,14 @@ me_search_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_consta
   uint32_t* s_pen = sm + ME_WARPS * WARP_WORDS;                          // [3][32] per row class: 0 or ME_ILLEGAL
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_pen + 96) + 2 * warp;   // one mbarrier per buffer
   uint32_t* s_sad = wsm + ME_SAD_OFF;
+  // (debug build) what this thread may touch: its warp's slice, and the CTA's tables + mbarriers
+  const SmLim lim = {smem_u32(wsm), smem_u32(wsm + WARP_WORDS), smem_u32(s_pen), smem_u32(s_pen + ME_CTA_WORDS)};
+  (void)lim;
 
   if (threadIdx.x < 96) {
     const int cls = threadIdx.x >> 5, r = threadIdx.x & 31;
     const int lo = (a.rg.ylo >> (8 * cls)) & 0xff, hi = (int)((a.rg.yhi >> (8 * cls)) & 0xff) - 1;
-    s_pen[threadIdx.x] = (r >= lo && r <= hi) ? 0u : ME_ILLEGAL;
+    SMW(s_pen + threadIdx.x) = (r >= lo && r <= hi) ? 0u : ME_ILLEGAL;
   }
   if (lane == 0) { mbar_init(bars, 1); mbar_init(bars + 1, 1); }
   __syncthreads();
@@ -411,15 +439,15 @@ me_search_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_consta
     const uint32_t* s_cur = win + 608;                                // [16][4]
     uint32_t* shifted = wsm + ME_SHIFT_OFF + 8;                       // copy k at shifted + 584 (k-1)
     if (VARIANT == ME_V_SURF)
-      for (int i = lane; i < 31 * 31; i += 32) s_sad[i] = 0xffffffffu;
+      for (int i = lane; i < 31 * 31; i += 32) SMW(s_sad + i) = 0xffffffffu;
 
     mbar_wait(bars + b, (it >> 1) & 1);
     // byte-shifted copies 1..3: each 16-byte quad + the following word yields the three shifted quads
 #pragma unroll 1
     for (int u = lane; VARIANT != ME_V_TSS && u < ME_WIN_ROWS * 3; u += 32) {
       const int idx = 4 * u;                          // row (u/3) * 12 + 4 * (u%3)
-      const uint4 v = *reinterpret_cast<const uint4*>(win + idx);
-      const uint32_t nx = win[idx + 4];
+      const uint4 v = SMR4(win + idx);
+      const uint32_t nx = SMR(win + idx + 4);
       // funnel shift right by 8k as hi32(lo * 2^(32-8k)) + hi * 2^(32-8k): IMAD.HI + IMAD on the otherwise idle FMA pipe
       // (SHF would compete with VABSDIFF4 for the ALU pipe); the multipliers come in registers so they stay multiplies
 #pragma unroll
@@ -428,14 +456,14 @@ me_search_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_consta
         uint4 o;
         o.x = __umulhi(v.x, m) + v.y * m; o.y = __umulhi(v.y, m) + v.z * m;
         o.z = __umulhi(v.z, m) + v.w * m; o.w = __umulhi(v.w, m) + nx * m;
-        *reinterpret_cast<uint4*>(shifted + (k - 1) * ME_COPY_WORDS + idx) = o;
+        SMW4(shifted + (k - 1) * ME_COPY_WORDS + idx) = o;
       }
     }
     uint32_t c[16][4];
     if (VARIANT != ME_V_TSS) {
 #pragma unroll
       for (int i = 0; i < 16; i++) {
-        const uint4 v = reinterpret_cast<const uint4*>(s_cur)[i];
+        const uint4 v = SMR4(s_cur + 4 * i);
         c[i][0] = v.x; c[i][1] = v.y; c[i][2] = v.z; c[i][3] = v.w;
       }
     }
@@ -443,8 +471,8 @@ me_search_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_consta
     uint32_t omv;
     {
       const int i = lane >> 1, wc = (lane & 1) * 2;
-      const uint2 r = *reinterpret_cast<const uint2*>(win + (15 + i) * ME_ROW_WORDS + 4 + wc);
-      const uint2 cw = *reinterpret_cast<const uint2*>(s_cur + i * 4 + wc);
+      const uint2 r = SMR2(win + (15 + i) * ME_ROW_WORDS + 4 + wc);
+      const uint2 cw = SMR2(s_cur + i * 4 + wc);
       omv = __reduce_add_sync(0xffffffffu, sad4(r.y, cw.y, sad4(r.x, cw.x, 0u)));
     }
     __syncwarp();
@@ -474,21 +502,21 @@ me_search_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_consta
           if (k < 0 || k >= np) continue;
           if (nlist > ME_LIST_WORDS - ME_DENSE_T) {                     // a further chunk might not fit
             __syncwarp();
-            sparse_finish(win, shifted, c, list, nlist, lane, a.m2048, bound, best, units);
+            sparse_finish(win, shifted, c, list, nlist, lane, a.m2048, bound, best, units, lim);
             __syncwarp();
             nlist = 0;
           }
           const int yb = min(ystart + max(min(PS * k, rpg - PS), 0), 22);
-          nlist = full_chunk(colbase, win, s_cur, c, pen, list, nlist, xi, yb, xok, lane, a.m2048, bound, best, units, dense_mode);
+          nlist = full_chunk(colbase, win, s_cur, c, pen, list, nlist, xi, yb, xok, lane, a.m2048, bound, best, units, dense_mode, lim);
         }
         __syncwarp();
-        sparse_finish(win, shifted, c, list, nlist, lane, a.m2048, bound, best, units);
+        sparse_finish(win, shifted, c, list, nlist, lane, a.m2048, bound, best, units, lim);
       } else {
         for (int v = 0; v < np; v++) {
           const int done = PS * v;
           uint32_t r;
-          if (rpg - done > 5) r = sweep_pass<VARIANT, 10, false>(colbase, c, pen, s_sad, xi, min(ystart + done, 22), xok, a.m2048, bound, units);
-          else                r = sweep_pass<VARIANT, 5, false>(colbase, c, pen, s_sad, xi, min(ystart + done, 27), xok, a.m2048, bound, units);
+          if (rpg - done > 5) r = sweep_pass<VARIANT, 10, false>(colbase, c, pen, s_sad, xi, min(ystart + done, 22), xok, a.m2048, bound, units, lim);
+          else                r = sweep_pass<VARIANT, 5, false>(colbase, c, pen, s_sad, xi, min(ystart + done, 27), xok, a.m2048, bound, units, lim);
           best = min(best, (xok && r != 0xffffffffu) ? r + (uint32_t)(1 + xi * 32) : 0xffffffffu);
         }
       }
@@ -497,10 +525,10 @@ me_search_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_consta
     const size_t mb_index = (size_t)n;
     if (VARIANT == ME_V_SURF) {
       __syncwarp();
-      if (lane == 0) s_sad[15 * 31 + 15] = omv;     // (0,0) is in the surface even where a later probe of it would be illegal
+      if (lane == 0) SMW(s_sad + 15 * 31 + 15) = omv;     // (0,0) is in the surface even where a later probe of it would be illegal
       __syncwarp();
       if (a.surface)   // test hook: the whole surface, [dy+15][dx+15], 0xffffffff = illegal position
-        for (int i = lane; i < 31 * 31; i += 32) a.surface[mb_index * 961 + i] = s_sad[i];
+        for (int i = lane; i < 31 * 31; i += 32) a.surface[mb_index * 961 + i] = SMR(s_sad + i);
     }
 
     // ---- search result
@@ -521,7 +549,7 @@ me_search_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_consta
       uint32_t cq[4][4];
 #pragma unroll
       for (int i = 0; i < 4; i++) {
-        const uint4 v = reinterpret_cast<const uint4*>(s_cur)[4 * qr + i];
+        const uint4 v = SMR4(s_cur + 4 * (4 * qr + i));
         cq[i][0] = v.x; cq[i][1] = v.y; cq[i][2] = v.z; cq[i][3] = v.w;
       }
       for (int step = 8; step >= 1; step >>= 1) {
@@ -533,8 +561,8 @@ me_search_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_consta
           const uint32_t* p = win + (dyi + 4 * qr) * ME_ROW_WORDS + (o >> 2);
 #pragma unroll
           for (int i = 0; i < 4; i++) {
-            const uint32_t w0 = p[i * ME_ROW_WORDS], w1 = p[i * ME_ROW_WORDS + 1], w2 = p[i * ME_ROW_WORDS + 2],
-                           w3 = p[i * ME_ROW_WORDS + 3], w4 = p[i * ME_ROW_WORDS + 4];
+            const uint32_t w0 = SMR(p + i * ME_ROW_WORDS), w1 = SMR(p + i * ME_ROW_WORDS + 1), w2 = SMR(p + i * ME_ROW_WORDS + 2),
+                           w3 = SMR(p + i * ME_ROW_WORDS + 3), w4 = SMR(p + i * ME_ROW_WORDS + 4);
             sad = sad4(__funnelshift_r(w0, w1, sh), cq[i][0], sad);
             sad = sad4(__funnelshift_r(w1, w2, sh), cq[i][1], sad);
             sad = sad4(__funnelshift_r(w2, w3, sh), cq[i][2], sad);
@@ -561,7 +589,7 @@ me_search_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_consta
           int nn = lane < 4 ? lane : lane + 1;        // skip the centre (index 4)
           int dx = mx + (nn % 3 - 1) * step, dy = my + (nn / 3 - 1) * step;
           if (dx >= -15 && dx <= 15 && dy >= -15 && dy <= 15) {
-            uint32_t sv = s_sad[(dy + 15) * 31 + dx + 15];
+            uint32_t sv = SMR(s_sad + (dy + 15) * 31 + dx + 15);
             if (sv != 0xffffffffu) key = min(key, (sv << 4) | (uint32_t)(lane + 1));
           }
         }
@@ -580,8 +608,9 @@ me_search_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_consta
     {
       const int i = lane >> 1, wc = (lane & 1) * 2, oo = mx + 16, sh = (oo & 3) * 8;
       const uint32_t* rp = win + (my + 15 + i) * ME_ROW_WORDS + (oo >> 2) + wc;      // unaligned: three words, two funnel shifts
-      const uint32_t ra = __funnelshift_r(rp[0], rp[1], sh), rb = __funnelshift_r(rp[1], rp[2], sh);
-      const uint2 cw = *reinterpret_cast<const uint2*>(s_cur + i * 4 + wc);
+      const uint32_t w0 = SMR(rp), w1 = SMR(rp + 1), w2 = SMR(rp + 2);
+      const uint32_t ra = __funnelshift_r(w0, w1, sh), rb = __funnelshift_r(w1, w2, sh);
+      const uint2 cw = SMR2(s_cur + i * 4 + wc);
       uint32_t smm = sad4(rb, 0u, sad4(ra, 0u, 0u));
       uint32_t so = __dp4a(rb, rb, __dp4a(ra, ra, 0u));
       uint32_t sv = so + __dp4a(cw.y, cw.y, __dp4a(cw.x, cw.x, 0u)) - 2u * __dp4a(rb, cw.y, __dp4a(ra, cw.x, 0u));
@@ -757,11 +786,23 @@ __device__ __forceinline__ uint32_t put_byte(uint32_t w, int v) {
 template <int K>
 __device__ __forceinline__ void zig_insert(uint32_t (&out)[16], int v) { out[K >> 2] = put_byte<K & 3>(out[K >> 2], v); }
 
+// (debug build) the calling thread's own tile in the dynamic shared memory of mb_encode_kernel / mb_decode_kernel
+__device__ __forceinline__ SmLim mb_tile_lim() {
+#ifdef P64B_BOUNDS_CHECK
+  extern __shared__ __align__(16) uint32_t dbg_dyn[];
+  const uint32_t lo = smem_u32(dbg_dyn) + threadIdx.x * MB4_TILE * 4u;
+  return SmLim{lo, lo + MB4_TILE * 4u, lo, lo + MB4_TILE * 4u};
+#else
+  return SmLim{0, 0, 0, 0};
+#endif
+}
 __device__ __forceinline__ void st_row(int* tile, int r, int h, const int (&v)[4]) {
-  *reinterpret_cast<int4*>(tile + 8 * r + 4 * h) = make_int4(v[0], v[1], v[2], v[3]);
+  const SmLim lim = mb_tile_lim(); (void)lim;
+  P64B_SM_T(int4, tile + 8 * r + 4 * h, lim) = make_int4(v[0], v[1], v[2], v[3]);
 }
 __device__ __forceinline__ void ld_row(const int* tile, int r, int h, int (&v)[4]) {
-  const int4 q = *reinterpret_cast<const int4*>(tile + 8 * r + 4 * h);
+  const SmLim lim = mb_tile_lim(); (void)lim;
+  const int4 q = P64B_SM_T(const int4, tile + 8 * r + 4 * h, lim);
   v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
 }
 
@@ -854,6 +895,9 @@ mb_encode_kernel(const __grid_constant__ MbArgs a) {
   const int lane = threadIdx.x & 31, c = threadIdx.x >> 5;        // block index within the MB: p64.c:77-79
   int* tile = reinterpret_cast<int*>(s_dyn) + threadIdx.x * MB4_TILE;
   uint32_t* s_pk = reinterpret_cast<uint32_t*>(tile) + 64;        // packed prediction, 8 rows x 2 words
+  SmLim lim = mb_tile_lim();                                      // (debug build) + the CTA's exchange array
+  lim.lo2 = smem_u32(&s_acc[0][0]); lim.hi2 = lim.lo2 + (uint32_t)sizeof(s_acc);
+  (void)lim;
 
   const int n_total = a.n_streams * a.gob_count * 33;
   const int n = blockIdx.x * MB4_PER_CTA + lane;
@@ -952,7 +996,7 @@ mb_encode_kernel(const __grid_constant__ MbArgs a) {
   }
   // the prediction moves to shared memory: it is needed again only row by row in the reconstruction
 #pragma unroll
-  for (int i = 0; i < 4; i++) reinterpret_cast<uint4*>(s_pk)[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+  for (int i = 0; i < 4; i++) SMW4(s_pk + 4 * i) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
 
   // ---- row pass, bound, quantise, zig-zag (transform.c:561-568): byte k of the output = level at raster izig(k)
   uint32_t out[16];
@@ -971,14 +1015,14 @@ mb_encode_kernel(const __grid_constant__ MbArgs a) {
   }
 
   // ---- CBP and the type-4 / type-7 fallback (p64.c:887-908)
-  s_acc[c][lane] = acc;
+  P64B_SM_T(int, &s_acc[c][lane], lim) = acc;
   __syncthreads();
   int cbp = 0x3f, nz = 0;
   {
     int pm = 0, cb = 0;
 #pragma unroll
     for (int k = 0; k < 6; k++) {
-      const int ak = s_acc[k][lane];
+      const int ak = P64B_SM_T(const int, &s_acc[k][lane], lim);
       if (ak && !pm) pm = 1 << (5 - k);
       if (ak > 1) cb |= 1 << (5 - k);
       if (ak) nz |= 1 << (5 - k);
@@ -996,7 +1040,7 @@ mb_encode_kernel(const __grid_constant__ MbArgs a) {
   if (!intra && mt_final == 4 && (mvx | mvy)) {
     fetch_pred(true);
 #pragma unroll
-    for (int i = 0; i < 4; i++) reinterpret_cast<uint4*>(s_pk)[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+    for (int i = 0; i < 4; i++) SMW4(s_pk + 4 * i) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
   }
   uint2* op = reinterpret_cast<uint2*>(a.out + fo + off);
   if (coded) {
@@ -1032,7 +1076,7 @@ mb_encode_kernel(const __grid_constant__ MbArgs a) {
         x[0] = p0[0]; x[1] = p0[1]; x[2] = p0[2]; x[3] = p0[3]; x[4] = p1[0]; x[5] = p1[1]; x[6] = p1[2]; x[7] = p1[3];
       }
       idct8<0>(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);
-      const uint2 pw = *reinterpret_cast<const uint2*>(s_pk + 2 * r);
+      const uint2 pw = SMR2(s_pk + 2 * r);
       int o[8];
 #pragma unroll
       for (int j = 0; j < 4; j++) {              // + prediction byte j by a byte dot product (FMA pipe); the clamp is in the pack
@@ -1043,7 +1087,7 @@ mb_encode_kernel(const __grid_constant__ MbArgs a) {
     }
   } else if (active) {
 #pragma unroll
-    for (int r = 0; r < 8; r++) op[r * wq] = *reinterpret_cast<const uint2*>(s_pk + 2 * r);   // reconstruction = prediction
+    for (int r = 0; r < 8; r++) op[r * wq] = SMR2(s_pk + 2 * r);   // reconstruction = prediction
   }
   if (active && c == 0) {
     const bool mf = mt_is(M_MF, mt_final);
