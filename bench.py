@@ -43,10 +43,13 @@ IT_CIF = 1
 # algorithmic work per unit (DESIGN.md "Measurement")
 SAD_OPS_PER_CIF_FRAME = 343473 * 64          # legal candidates (me.c:212-213) x 64 packed 4-byte SADs each
 MB_BYTES_INTER = 384 + 384 + 384 + 384 + 8   # source + prediction + reconstruction + int8 levels + record
-# DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full` captures of
-# this very workload (profiles/r01_ncu_me_search_kernel_v6.txt, profiles/r01_ncu_mb_encode_kernel_v5.txt), bytes
-NCU_MB_WARP_INSTR = 73_252_848     # smsp__inst_executed.sum of mb_encode_kernel v5 on this workload (profiles/r01_ncu_mb_encode_kernel_v5.txt)
-NCU_TRAFFIC = {"me_search_kernel": 51_943_168 + 1_667_328, "mb_encode_kernel": 81_309_952 + 35_024_384}
+# DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) and warp-instruction counts from the committed `ncu --set full`
+# captures of this very workload and of the code as committed (profiles/r02_ncu_me_search_kernel_v7.txt,
+# profiles/r02_ncu_mb_encode_kernel_v6.txt), bytes / instructions per launch
+NCU_CAPTURE = "profiles/r02_ncu_me_search_kernel_v7.txt, profiles/r02_ncu_mb_encode_kernel_v6.txt (round 2, code as committed)"
+NCU_MB_WARP_INSTR = 69_068_928     # smsp__inst_executed.sum of mb_encode_kernel v6
+NCU_ME_WARP_INSTR = 229_705_424    # smsp__inst_executed.sum of me_search_kernel v7
+NCU_TRAFFIC = {"me_search_kernel": 55_187_968 + 1_454_592, "mb_encode_kernel": 81_264_640 + 33_761_024}
 
 
 def _clocks_sampler(stop, out, gpu_index):
@@ -425,27 +428,29 @@ def main_cuda(args):
             pass
         me_roof = {"kernel": "me_search_kernel", "bound": "int_issue", "achieved": me_ops / (me_ms * 1e-3) / 1e9,
                    "peak": peak_ops.value / 1e9, "unit": "G packed-SAD ops/s", "frac": (me_ops / (me_ms * 1e-3)) / peak_ops.value,
-                   "traffic": NCU_TRAFFIC["me_search_kernel"], "avg_launch_ms": me_ms, "launches_timed": prof["me"][1],
+                   "traffic": NCU_TRAFFIC["me_search_kernel"], "traffic_source": NCU_CAPTURE, "avg_launch_ms": me_ms, "launches_timed": prof["me"][1],
+                   "issue": {"warp_instructions_per_launch_ncu": NCU_ME_WARP_INSTR, "frac_of_issue_peak": NCU_ME_WARP_INSTR / (me_ms * 1e-3) / (148 * 4 * clk.value * 1e6)},
                    "peak_source": "measured live: VABSDIFF4.U8.ACC issue-rate probe (p64b_measure_sad_peak)",
                    "executed": {"packed_sad_ops_per_launch": me_executed / max(1, prof["me"][1]),
                                 "rate_g_ops_s": me_executed / max(1, prof["me"][1]) / (me_ms * 1e-3) / 1e9,
                                 "frac_of_peak": me_executed / max(1, prof["me"][1]) / (me_ms * 1e-3) / peak_ops.value,
                                 "share_of_algorithmic": me_executed / max(1, prof["me"][1]) / me_ops,
-                                "note": "exact warp-wide early exit (ComputeError's `error >= MV` exit, me.c:122-170): a pass whose candidates are all "
-                                        "strictly above the best full SAD after 4 of 16 rows is dropped; `achieved`/`frac` count the ALGORITHMIC ops "
-                                        "(every legal candidate in full) per the bench contract and can exceed 1 on matchable content; "
-                                        "`executed` is what the ALU pipe really issued (device counter, includes masked surplus lanes)"},
+                                "note": "exact elimination (ComputeError's `error >= MV` exit, me.c:122-170): a chunk of 10 x 32 candidates is dropped when all are "
+                                        "strictly above the best full SAD after 4 or 8 of 16 rows; of a chunk that survives only the candidates still at or below "
+                                        "it are finished (one per lane, from a list in shared memory).  `achieved`/`frac` count the ALGORITHMIC ops (every legal "
+                                        "candidate in full) per the bench contract and can exceed 1 on matchable content; `executed` is what the ALU pipe really "
+                                        "issued (device counter, includes masked surplus lanes)"},
                    "algorithmic": (f"{SAD_OPS_PER_CIF_FRAME} packed SAD ops per CIF frame (343473 legal candidates x 64) x {S} frames per launch" if ME_MODE
                                    else f"three-step search: at most 33 probes x 64 packed SAD ops per macroblock (upper bound) x {396 * S} macroblocks per launch")}
         mb_roof = {"kernel": "mb_encode_kernel", "bound": "hbm", "achieved": mb_bytes / (mb_ms * 1e-3) / 1e9, "peak": hbm_peak,
                    "unit": "GB/s", "frac": (mb_bytes / (mb_ms * 1e-3) / 1e9) / hbm_peak, "traffic": NCU_TRAFFIC["mb_encode_kernel"], "avg_launch_ms": mb_ms,
                    "launches_timed": prof["mb"][1], "peak_source": peak_src,
-                   "issue": {"warp_instructions_per_launch_ncu": NCU_MB_WARP_INSTR,
+                   "issue": {"warp_instructions_per_launch_ncu": NCU_MB_WARP_INSTR, "ncu_capture": NCU_CAPTURE,
                              "frac_of_issue_peak": NCU_MB_WARP_INSTR / (mb_ms * 1e-3) / (148 * 4 * clk.value * 1e6),
                              "note": "the bound that actually holds: warp-instructions (ncu smsp__inst_executed.sum of the committed capture) per "
                                      "launch time vs 148 SMs x 4 schedulers x 1 instruction per clock"},
                    "note": "integer-issue bound, not HBM bound: ncu shows the ALU pipe (shifts, byte permutes, min/max, shift-adds) busy 58 % "
-                           "and the FMA pipe (IMAD, IDP.4A) 32 % at 66 % issue utilisation, 3850 instructions per 8x8 block (DESIGN.md 3.2)",
+                           "and the FMA pipe (IMAD, IDP.4A) 33 % at 68 % issue utilisation, 3630 instructions per 8x8 block (DESIGN.md 3.2)",
                    "algorithmic": f"{MB_BYTES_INTER} B per inter macroblock (384 source + 384 prediction + 384 reconstruction + 384 int8 levels + 8 record) x {nmb * S} macroblocks per launch"}
         dominant = me_roof if me_ms >= mb_ms else mb_roof
         cpu = None

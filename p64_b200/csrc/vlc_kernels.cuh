@@ -5,13 +5,17 @@
 //   EncodeDC / EncodeAC / CBPEncodeAC  codec.c:96-205, 346-355      WritePictureHeader  marker.c:103-137
 //   mputv  stream.c:193-205 (MSB first)
 //
-//   vlc_gob_kernel    one CTA per (stream, GOB), one warp per macroblock (lane = header or a quarter of a block): the
-//                     macroblocks are measured, a warp scan places them, and a second walk writes the bits into a
+//   vlc_gob_kernel    one CTA per (stream, GOB): one thread per piece (GOB header, 33 x {MB header, 6 blocks});
+//                     pass 1 measures every piece, a CTA-wide scan places them, pass 2 writes the bits into a
 //                     shared-memory image of the GOB, which is then stored unshifted into the GOB's scratch slot.
 //   vlc_frame_kernel  one CTA per stream: carry bits of the previous frame + picture header + the GOB strings are
 //                     gathered word by word (funnel shifts) into the frame's byte chunk; the < 8 trailing bits stay
 //                     on the device as the next frame's carry, so the host only ever appends whole bytes.
 // Bit strings are MSB first: bit i of a string is bit (31 - i % 32) of word i / 32.
+// Tried in round 2 and not kept (measured on a B200, 256 CIF streams): one WARP per macroblock with lane = header or a quarter of a
+// block (16 consecutive coefficients), the block's non-zero mask exchanged by shuffles.  The zig-zag order puts nearly all
+// non-zero levels into the first quarter, so the quarter-0 lanes do the work while 28 lanes wait: 121 M warp-instructions and
+// 0.149 ms per launch instead of 71 M and 0.116 ms for the thread-per-piece form below.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -21,6 +25,7 @@
 
 namespace p64b {
 
+constexpr int VLC_PIECES = 1 + 33 * 7;                  // GOB header + 33 x (MB header + 6 blocks)
 constexpr int VLC_THREADS = 256;
 constexpr int VLC_BLOCK_MAX_BITS = 8 + 63 * 20 + 2;     // intra DC + 63 escapes + EOB
 constexpr int VLC_MBHDR_MAX_BITS = 1 + 10 + 5 + 11 + 11 + 9;
@@ -100,6 +105,66 @@ struct BitEmitter {
   }
 };
 
+// One 8x8 block (EncodeDC + EncodeAC for intra types, CBPEncodeAC otherwise; codec.c:96-205, 346-355).
+// EMIT = false: returns the length in bits; EMIT = true: also writes the bits.
+// non-zero mask of a block's 64 levels (bit k = level k != 0)
+__device__ __forceinline__ uint64_t vlc_nz_mask(const int8_t* __restrict__ lv) {
+  uint64_t nz = 0;
+  const uint4* lp = reinterpret_cast<const uint4*>(lv);
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const uint4 q = __ldg(lp + i);
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const uint32_t hi = (w[j] | ((w[j] & 0x7f7f7f7fu) + 0x7f7f7f7fu)) & 0x80808080u;     // bit 7 of every non-zero byte
+      const uint32_t m4 = (((hi >> 7) * 0x01020408u) >> 24) & 0xfu;
+      nz |= (uint64_t)m4 << (16 * i + 4 * j);
+    }
+  }
+  return nz;
+}
+
+// `nz`: the block's non-zero mask (vlc_nz_mask), computed once by the caller and reused by the emitting pass
+template <bool EMIT>
+__device__ __forceinline__ int vlc_block(const int8_t* __restrict__ lv, uint64_t nz, bool cbp_type, const uint32_t* s_tcoef, BitEmitter* em) {
+  int len = 0, prev = -1;
+  bool first = cbp_type, any = !cbp_type;
+  if (!cbp_type) {                                   // EncodeDC, codec.c:346-355
+    int dc = (uint8_t)lv[0];
+    dc = min(max(dc, 1), 254);
+    if (dc == 128) dc = 255;
+    if (EMIT) em->put((uint32_t)dc, 8);
+    len = 8; prev = 0; nz &= ~1ull;
+  }
+  while (nz) {
+    const int p = __ffsll((long long)nz) - 1;
+    nz &= nz - 1;
+    const int run = p - prev - 1, v = lv[p], a = abs(v);
+    prev = p;
+    if (first && run == 0 && a == 1) {               // "1s" for the first coefficient of a CBP-coded block
+      if (EMIT) em->put(2u | (uint32_t)(v < 0), 2);
+      len += 2;
+    } else {
+      const uint32_t e = (run < 32 && a < 16) ? s_tcoef[run * 16 + a] : 0u;
+      if (e) {
+        const int n = (int)(e >> 16) + 1;
+        if (EMIT) em->put(((e & 0xffffu) << 1) | (uint32_t)(v < 0), n);
+        len += n;
+      } else {                                       // escape: 000001 + 6-bit run + 8-bit level (codec.c:113-115)
+        if (EMIT) em->put((1u << 14) | ((uint32_t)run << 8) | (uint32_t)(v & 0xff), 20);
+        len += 20;
+      }
+    }
+    first = false; any = true;
+  }
+  if (any) {                                         // EOB "10"; an all-zero CBP block gets none (codec.c:169-174)
+    if (EMIT) em->put(2u, 2);
+    len += 2;
+  }
+  return len;
+}
+
 // Macroblock header (WriteMBHeader, marker.c:288-354): MBA (always 1: this encoder never skips a macroblock,
 // p64.c:928-930), MTYPE, [MQUANT], [MVD pair], [CBP].  Returns the bits right-aligned, *n = length (<= 47).
 __device__ __forceinline__ uint64_t vlc_mb_header(const p64b_mb& r, const p64b_mb& prev, int m, const DevVlcTables* t, int* n) {
@@ -124,165 +189,84 @@ __device__ __forceinline__ uint64_t vlc_mb_header(const p64b_mb& r, const p64b_m
   return b;
 }
 
-// ---- one macroblock by one warp -------------------------------------------------------------------------------------------
-// lane 0 = the macroblock header; lane 1 + 4 b + q = quarter q (16 coefficients in transmission order) of block b.  A lane walks
-// the non-zero levels of its quarter: the run to the previous non-zero level comes from the block's 64-bit non-zero mask (the
-// four quarter masks exchanged by shuffles), the code from the table in shared memory (codec.c:96-205: escapes as in 113-115,
-// the two-bit code for a leading +-1 of a CBP-coded block, EOB after the last quarter; EncodeDC codec.c:346-355 on quarter 0 of
-// intra blocks).  EMIT = false returns the lane's length in bits, EMIT = true writes the bits at bit offset `at` of `buf`.
-struct MbLane {
-  uint4 lv;           // the quarter's 16 levels (zero when the block is not coded)
-  uint32_t nz16;      // non-zero mask of the quarter (bit 0 of quarter 0 cleared for intra blocks: the DC goes separately)
-  int prevpos;        // position of the last non-zero level before this quarter (-1: none; 0 for intra blocks: the DC)
-  bool coded, cbp_type, eob;
-};
-__device__ __forceinline__ MbLane vlc_mb_lane(const p64b_mb& rec, const int8_t* __restrict__ lv_mb, int lane) {
-  MbLane L;
-  const int b = (lane - 1) >> 2, q = (lane - 1) & 3;
-  const bool blk = lane >= 1 && lane <= 24;
-  const int mt = rec.mtype;
-  L.cbp_type = vt(V_CBP, mt);
-  L.coded = blk && vt(V_TCOEF, mt) && ((rec.cbp >> (5 - b)) & 1);
-  L.lv = make_uint4(0, 0, 0, 0);
-  if (L.coded) L.lv = __ldg(reinterpret_cast<const uint4*>(lv_mb + b * 64 + q * 16));
-  const uint32_t w[4] = {L.lv.x, L.lv.y, L.lv.z, L.lv.w};
-  uint32_t nz = 0;
+// exclusive scan of one value per thread over the CTA; *total = sum.  Two barriers.
+__device__ __forceinline__ uint32_t vlc_cta_scan(uint32_t len, uint32_t* s_wsum, uint32_t* s_total, uint32_t* total) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t x = len;
 #pragma unroll
-  for (int j = 0; j < 4; j++) {
-    const uint32_t hi = (w[j] | ((w[j] & 0x7f7f7f7fu) + 0x7f7f7f7fu)) & 0x80808080u;     // bit 7 of every non-zero byte
-    nz |= ((((hi >> 7) * 0x01020408u) >> 24) & 0xfu) << (4 * j);
-  }
-  if (q == 0 && !L.cbp_type) nz &= ~1u;
-  L.nz16 = nz;
-  // masks of the lower quarters of the same block (lanes base .. base+3): every lane takes part in the shuffles
-  const int base = 1 + 4 * b;
-  const uint32_t m0 = __shfl_sync(0xffffffffu, nz, base & 31), m1 = __shfl_sync(0xffffffffu, nz, (base + 1) & 31),
-                 m2 = __shfl_sync(0xffffffffu, nz, (base + 2) & 31), m3 = __shfl_sync(0xffffffffu, nz, (base + 3) & 31);
-  const uint64_t all = (uint64_t)(m0 | (m1 << 16)) | ((uint64_t)(m2 | (m3 << 16)) << 32);
-  const uint64_t below = q ? (all & ((1ull << (16 * q)) - 1ull)) : 0ull;
-  L.prevpos = below ? 63 - __clzll((long long)below) : (L.cbp_type ? -1 : 0);
-  L.eob = L.coded && q == 3 && (!L.cbp_type || all != 0ull);            // an all-zero CBP block gets no EOB (codec.c:169-174)
-  return L;
-}
-template <bool EMIT>
-__device__ __forceinline__ int vlc_lane_bits(const MbLane& L, int lane, const uint32_t* s_tcoef, uint32_t* buf, uint32_t at) {
-  if (!L.coded) return 0;
-  BitEmitter em(buf, at);
-  const int q = (lane - 1) & 3;
-  int len = 0, prev = L.prevpos;
-  const uint32_t w[4] = {L.lv.x, L.lv.y, L.lv.z, L.lv.w};
-  if (q == 0 && !L.cbp_type) {                       // EncodeDC, codec.c:346-355
-    int dc = (int)(w[0] & 0xffu);
-    dc = min(max(dc, 1), 254);
-    if (dc == 128) dc = 255;
-    if (EMIT) em.put((uint32_t)dc, 8);
-    len = 8;
-  }
-  uint32_t nz = L.nz16;
-  while (nz) {
-    const int pl = __ffs((int)nz) - 1;
-    nz &= nz - 1;
-    const int p = 16 * q + pl, run = p - prev - 1;
-    const int v = (int)(int8_t)(w[pl >> 2] >> (8 * (pl & 3))), a = abs(v);
-    prev = p;
-    if (L.cbp_type && p == 0 && a == 1) {            // "1s": a leading +-1 of a CBP-coded block (first && run == 0)
-      if (EMIT) em.put(2u | (uint32_t)(v < 0), 2);
-      len += 2;
-    } else {
-      const uint32_t e = (run < 32 && a < 16) ? s_tcoef[run * 16 + a] : 0u;
-      if (e) {
-        const int n = (int)(e >> 16) + 1;
-        if (EMIT) em.put(((e & 0xffffu) << 1) | (uint32_t)(v < 0), n);
-        len += n;
-      } else {                                       // escape: 000001 + 6-bit run + 8-bit level (codec.c:113-115)
-        if (EMIT) em.put((1u << 14) | ((uint32_t)run << 8) | (uint32_t)(v & 0xff), 20);
-        len += 20;
-      }
-    }
-  }
-  if (L.eob) { if (EMIT) em.put(2u, 2); len += 2; }  // EOB "10"
-  if (EMIT) em.flush();
-  return len;
+  for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+  __syncthreads();                                     // s_wsum / s_total of an earlier scan have been read
+  if (lane == 31) s_wsum[warp] = x;
+  __syncthreads();
+  uint32_t base = 0;
+  for (int w = 0; w < warp; w++) base += s_wsum[w];
+  if (tid == VLC_THREADS - 1) *s_total = base + x;
+  __syncthreads();
+  *total = *s_total;
+  return base + x - len;
 }
 
-// One CTA per (stream, GOB), ONE WARP PER MACROBLOCK (8 warps take the 33 macroblocks in 5 rounds).
-//   measure  every warp sizes its macroblocks' 25 pieces (header + 24 block quarters), a warp scan places them inside the
-//            macroblock (kept in shared memory relative to the end of the header);
-//   place    warp 0 scans the 33 macroblock sizes behind the 26-bit GOB header;
-//   emit     the warps walk their macroblocks again and write the bits into a zeroed shared-memory image of the GOB (words
-//            wholly inside a piece are plain stores, the partial first and last words atomic ORs), stored unshifted into the
-//            GOB's scratch slot.
-// RC = true: one GOB of every stream under rate control.  The macroblocks are first sized as if none were overridden; the bit
-// position of every macroblock header then gives the overflow test (p64.c:776) of all 33 macroblocks at once, exact up to
-// and including the first one that fires.  Only when one fires does thread 0 walk the GOB in order (an overridden macroblock
-// is MType 4 with a zero vector and no coefficients, which also changes the MVD predictor of its successor, marker.c:310-338),
-// after which the macroblocks are re-placed.  The CTA then publishes the GOB's length and the next GOB's GQUANT
-// (ExecuteQuantization, p64.c:458-481).
-constexpr int VLC_WARPS = VLC_THREADS / 32;
-constexpr int VLC_ROUNDS = (33 + VLC_WARPS - 1) / VLC_WARPS;
+// RC = true: one GOB of every stream under rate control.  Pieces are first measured as if no macroblock were
+// overridden; the bit position of every macroblock header then gives the overflow test (p64.c:776) of all 33 macroblocks at
+// once, exact up to and including the first one that fires.  Only when one fires does thread 0 walk the GOB in order
+// (an overridden macroblock is MType 4 with a zero vector and no coefficients, which also changes the MVD predictor of
+// its successor, marker.c:310-338), after which the pieces are re-placed.  The CTA then publishes the GOB's length and
+// the next GOB's GQUANT (ExecuteQuantization, p64.c:458-481).
 template <bool RC>
 __global__ void __launch_bounds__(VLC_THREADS)
 vlc_gob_kernel(const __grid_constant__ VlcArgs a) {
   __shared__ uint32_t s_buf[VLC_GOB_WORDS];
   __shared__ DevVlcTables s_t;
   __shared__ uint32_t s_total;
-  __shared__ uint32_t s_mb_off[34];                  // bit offset of every macroblock in the GOB string; [33] = total
-  __shared__ uint16_t s_hdr_len[33], s_coef_bits[33];
-  __shared__ uint16_t s_lane_off[33][32];            // lane's offset inside the macroblock, from the end of the header
+  __shared__ uint32_t s_wsum[VLC_THREADS / 32];
+  __shared__ uint32_t s_len[RC ? VLC_THREADS : 1];
   __shared__ uint2 s_rec[RC ? 33 : 1];
   __shared__ unsigned long long s_hb[RC ? 33 : 1];
   __shared__ uint8_t s_hl[RC ? 33 : 1], s_ovf[RC ? 33 : 1];
-  __shared__ int s_fired;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x;
   const int s = blockIdx.x / a.gob_count, gob = a.gob_first + blockIdx.x % a.gob_count;
   for (int i = tid; i < DEV_VLC_WORDS; i += VLC_THREADS) reinterpret_cast<uint32_t*>(&s_t)[i] = reinterpret_cast<const uint32_t*>(a.tables)[i];
   const int gquant = RC ? (int)a.rc.quant[s] : a.gquant;
   long long tell0 = 0, boff = 0;                      // mwtell() before this GOB's header; BufferOffset
   if (RC) { tell0 = (long long)a.rc.bitpos[s] + a.rc.frame_bits[s]; boff = a.rc.buffer_offset[s]; }
-  if (tid == 0) s_fired = 0;
-  __syncthreads();
-  const size_t mb0 = (size_t)s * a.nmb + gob * 33;
-
-  // ---- measure
-#pragma unroll 1
-  for (int r = 0; r < VLC_ROUNDS; r++) {
-    const int m = r * VLC_WARPS + warp;
-    if (m >= 33) break;                               // (warp-uniform)
-    const p64b_mb rec = a.mbs[mb0 + m];
-    const p64b_mb prev = m ? a.mbs[mb0 + m - 1] : p64b_mb{};
-    int hl;
-    (void)vlc_mb_header(rec, prev, m, &s_t, &hl);
-    const MbLane L = vlc_mb_lane(rec, a.levels + (mb0 + m) * P64B_LEVELS_PER_MB, lane);
-    const int len = vlc_lane_bits<false>(L, lane, s_t.tcoef, nullptr, 0);
-    int x = len;                                      // inclusive scan over lanes 1..24 (lane 0 carries 0)
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
-    s_lane_off[m][lane] = (uint16_t)(x - len);
-    if (lane == 31) { s_hdr_len[m] = (uint16_t)hl; s_coef_bits[m] = (uint16_t)x; }
-    if (RC && lane == 0) s_rec[m] = *reinterpret_cast<const uint2*>(&rec);
-  }
   __syncthreads();
 
-  // ---- place: macroblock offsets behind the GOB header (26 bits), by warp 0
-  auto place = [&](bool fired) {
-    if (warp == 0) {
-      auto size_of = [&](int i) -> uint32_t {
-        if (RC && fired) return (uint32_t)s_hl[i] + (s_ovf[i] ? 0u : (uint32_t)s_coef_bits[i]);
-        return (uint32_t)s_hdr_len[i] + (uint32_t)s_coef_bits[i];
-      };
-      const uint32_t mine = size_of(lane), last = size_of(32);
-      uint32_t x = mine;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
-      s_mb_off[lane] = 26u + x - mine;
-      if (lane == 31) { s_mb_off[32] = 26u + x; s_mb_off[33] = 26u + x + last; s_total = 26u + x + last; }
+  // ---- this thread's piece
+  const int piece = tid;                              // 0: GOB header; 1 + 7m: header of MB m; 1 + 7m + 1 + c: block c
+  const bool is_piece = piece < VLC_PIECES;
+  const int m = piece ? (piece - 1) / 7 : 0, k = piece ? (piece - 1) % 7 : 0;
+  const size_t mbi = (size_t)s * a.nmb + gob * 33 + m;
+  p64b_mb rec{}, prev{};
+  uint64_t hbits = 0;
+  int len = 0;
+  bool coded = false;
+  uint64_t nzmask = 0;
+  const int8_t* lv = a.levels + (mbi * 6 + (k ? k - 1 : 0)) * 64;
+  if (is_piece) {
+    if (piece == 0) {                                 // WriteGOBHeader, marker.c:182-209: GBSC, GN, GQUANT, no GSPARE
+      const int gn = (a.qcif ? (gob << 1) : gob) + 1;
+      hbits = (1ull << 10) | ((uint64_t)gn << 6) | ((uint64_t)gquant << 1);
+      len = 26;
+    } else {
+      rec = a.mbs[mbi];
+      if (k == 0) {
+        if (m) prev = a.mbs[mbi - 1];
+        hbits = vlc_mb_header(rec, prev, m, &s_t, &len);
+        if (RC) s_rec[m] = *reinterpret_cast<const uint2*>(&rec);
+      } else {
+        coded = vt(V_TCOEF, rec.mtype) && ((rec.cbp >> (6 - k)) & 1);      // block c = k-1: bit 5-c
+        if (coded) { nzmask = vlc_nz_mask(lv); len = vlc_block<false>(lv, nzmask, vt(V_CBP, rec.mtype), s_t.tcoef, nullptr); }
+      }
     }
-    __syncthreads();
-  };
-  place(false);
+  }
+
+  // ---- placement: exclusive scan of the piece lengths
+  uint32_t total;
+  uint32_t off = vlc_cta_scan((uint32_t)len, s_wsum, &s_total, &total);
   if (RC) {
     const int bsize = a.rc.rate / 4;                   // BufferSize(), p64.c:237
-    const bool fires = tid < 33 && rc_buffer_contents(a.rc, tell0 + s_mb_off[tid], boff, gob, tid) > bsize;
+    s_len[tid] = (uint32_t)len;
+    const bool fires = is_piece && piece && k == 0 && rc_buffer_contents(a.rc, tell0 + off, boff, gob, m) > bsize;
     if (__syncthreads_or(fires)) {
       if (tid == 0) {
         uint32_t bits = 26;
@@ -295,14 +279,16 @@ vlc_gob_kernel(const __grid_constant__ VlcArgs a) {
           s_hb[i] = vlc_mb_header(r, pe, i, &s_t, &n);
           s_hl[i] = (uint8_t)n; s_ovf[i] = o;
           bits += (uint32_t)n;
-          if (!o) bits += s_coef_bits[i];
+          if (!o) for (int c = 0; c < 6; c++) bits += s_len[1 + 7 * i + 1 + c];
           pe = r;
         }
-        s_fired = 1;
       }
       __syncthreads();
-      if (tid < 33) a.rc.ovf[mb0 + tid] = s_ovf[tid];
-      place(true);
+      if (is_piece && piece) {
+        if (k == 0) { hbits = s_hb[m]; len = s_hl[m]; a.rc.ovf[mbi] = s_ovf[m]; }
+        else if (s_ovf[m]) len = 0;
+      }
+      off = vlc_cta_scan((uint32_t)len, s_wsum, &s_total, &total);
       if (tid < 32) {                                  // NumberOvfl
         uint32_t n = (uint32_t)s_ovf[tid] + (tid == 0 ? (uint32_t)s_ovf[32] : 0u);
 #pragma unroll
@@ -311,39 +297,20 @@ vlc_gob_kernel(const __grid_constant__ VlcArgs a) {
       }
     }
   }
-  const uint32_t total = s_total;
   const uint32_t nwords = (total + 31) >> 5;
   for (uint32_t i = tid; i < nwords + 1; i += VLC_THREADS) s_buf[i] = 0;
   __syncthreads();
 
-  // ---- emit
-  const bool fired = RC && s_fired;
-  if (tid == 0) {                                     // WriteGOBHeader, marker.c:182-209: GBSC, GN, GQUANT, no GSPARE
-    const int gn = (a.qcif ? (gob << 1) : gob) + 1;
-    BitEmitter em(s_buf, 0);
-    em.put((1u << 10) | ((uint32_t)gn << 6) | ((uint32_t)gquant << 1), 26);
-    em.flush();
-  }
-#pragma unroll 1
-  for (int r = 0; r < VLC_ROUNDS; r++) {
-    const int m = r * VLC_WARPS + warp;
-    if (m >= 33) break;
-    const p64b_mb rec = a.mbs[mb0 + m];
-    const bool ovf = RC && fired && s_ovf[m];
-    const MbLane L = vlc_mb_lane(rec, a.levels + (mb0 + m) * P64B_LEVELS_PER_MB, lane);
-    int hl;
-    uint64_t hb;
-    if (RC && fired) { hb = s_hb[m]; hl = s_hl[m]; }
-    else { const p64b_mb prev = m ? a.mbs[mb0 + m - 1] : p64b_mb{}; hb = vlc_mb_header(rec, prev, m, &s_t, &hl); }
-    const uint32_t at = s_mb_off[m];
-    if (lane == 0) {
-      BitEmitter em(s_buf, at);
-      if (hl > 32) { em.put((uint32_t)(hb >> 32), hl - 32); em.put((uint32_t)hb, 32); }
-      else em.put((uint32_t)hb, hl);
-      em.flush();
-    } else if (!ovf) {
-      vlc_lane_bits<true>(L, lane, s_t.tcoef, s_buf, at + (uint32_t)hl + s_lane_off[m][lane]);
+  // ---- pass 2: the bits
+  if (len) {
+    BitEmitter em(s_buf, off);
+    if (k == 0) {
+      if (len > 32) { em.put((uint32_t)(hbits >> 32), len - 32); em.put((uint32_t)hbits, 32); }
+      else em.put((uint32_t)hbits, len);
+    } else {
+      vlc_block<true>(lv, nzmask, vt(V_CBP, rec.mtype), s_t.tcoef, &em);
     }
+    em.flush();
   }
   __syncthreads();
   uint32_t* dst = a.gob_words + ((size_t)s * a.ngob + gob) * VLC_GOB_WORDS;
