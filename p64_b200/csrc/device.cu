@@ -904,7 +904,9 @@ extern "C" int p64b_ctx_submit_bits(p64b_ctx* c, const p64b_step* st, int tempor
   }
   CU(cudaEventRecord(c->ev_comp[slot], c->stream));
   CU(cudaStreamWaitEvent(c->s_d2h, c->ev_comp[slot], 0));
-  const size_t copy = std::min(c->bits_out_cap, vlc_data_offset(c->S) + c->bits_budget);
+  // (attribution experiments only, DESIGN.md section 6: P64B_BITS_D2H=header downloads the per-stream table without the stream bytes)
+  static const bool header_only = getenv("P64B_BITS_D2H") && !strcmp(getenv("P64B_BITS_D2H"), "header");
+  const size_t copy = header_only ? vlc_data_offset(c->S) : std::min(c->bits_out_cap, vlc_data_offset(c->S) + c->bits_budget);
   if ((rc = ensure_host_bits(c, slot, copy))) return rc;
   CU(cudaMemcpyAsync(c->h_bits_out[slot], c->d_bits_out[slot], copy, cudaMemcpyDeviceToHost, c->s_d2h));
   CU(cudaEventRecord(c->ev_d2h[slot], c->s_d2h));
@@ -924,7 +926,8 @@ extern "C" int p64b_ctx_wait_bits(p64b_ctx* c, int64_t ticket, p64b_bits_out* ou
   CU(cudaEventSynchronize(c->ev_d2h[slot]));
   const size_t doff = vlc_data_offset(c->S);
   size_t total = reinterpret_cast<const uint32_t*>(c->h_bits_out[slot])[c->S];
-  if (doff + total > c->slot_copied[slot]) {
+  static const bool header_only = getenv("P64B_BITS_D2H") && !strcmp(getenv("P64B_BITS_D2H"), "header");
+  if (doff + total > c->slot_copied[slot] && !header_only) {
     // the frame was larger than the download budget: fetch the rest (rare; the budget follows the frame sizes)
     const size_t have = c->slot_copied[slot];
     if (c->h_bits_cap[slot] < doff + total) {
@@ -939,9 +942,10 @@ extern "C" int p64b_ctx_wait_bits(p64b_ctx* c, int64_t ticket, p64b_bits_out* ou
     CU(cudaStreamSynchronize(c->s_d2h));
     c->slot_copied[slot] = doff + total;
   }
-  // next step's first copy: this frame's size + 1/8 + 32 KB (frame sizes of a batch move slowly; a frame that outgrows the
-  // budget is completed by the second copy above).  Downloads share the host link with the next step's upload.
-  c->bits_budget = std::max<size_t>(total + total / 8 + 32768, 65536);
+  // next step's first copy: this frame's size + 1/32 + 16 KB (the size of a whole batch's frame moves slowly; a frame that
+  // outgrows the budget is completed by the second copy above).  Downloads share the host link with the uploads, and on a box
+  // whose GPUs share uplinks every downloaded byte costs upload time: no generous slack.
+  c->bits_budget = std::max<size_t>(total + total / 32 + 16384, 65536);
   const uint8_t* b = c->h_bits_out[slot];
   const size_t S = (size_t)c->S;
   out->offset = reinterpret_cast<const uint32_t*>(b);
