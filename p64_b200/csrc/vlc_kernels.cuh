@@ -15,7 +15,11 @@
 // Tried in round 2 and not kept (measured on a B200, 256 CIF streams): one WARP per macroblock with lane = header or a quarter of a
 // block (16 consecutive coefficients), the block's non-zero mask exchanged by shuffles.  The zig-zag order puts nearly all
 // non-zero levels into the first quarter, so the quarter-0 lanes do the work while 28 lanes wait: 121 M warp-instructions and
-// 0.149 ms per launch instead of 71 M and 0.116 ms for the thread-per-piece form below.
+// 0.149 ms per launch instead of 71 M and 0.116 ms for the thread-per-piece form below.  Also tried: one ITEM (intra DC, non-zero
+// level, EOB) per lane from a list in stream order, coded once and kept in registers until the macroblocks are placed (one walk
+// instead of two): bit-exact, ALU pipe 51 % instead of 72 %, but again 70 M warp-instructions and 0.116 ms -- with 11 warps
+// taking 33 macroblocks in 3 rounds between five CTA barriers, the barrier stalls (3.9 per issue) eat what the single walk saves
+// (profiles/r02_ncu_vlc_gob_kernel_item_per_lane_rejected.txt).
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
