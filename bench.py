@@ -288,6 +288,17 @@ def main_cuda(args):
         prof = ctx.profile_read()
         me_executed = ctx.me_executed()        # packed SAD ops the sweeps really issued in those K launches (device counter)
         ctx.profile(False)
+        # ---- the same resident step INCLUDING the device-side headers + VLC (what the reference arm's number includes too)
+        for i in range(3):
+            ctx.encode_bits_dev(make_step(False, QUANT, ME_MODE, SEARCH_LIMIT), (W + i) % 32, dev_sets.data_ptr() + ring(W + i) * set_bytes)
+        barrier()
+        v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        v0.record(stream)
+        for i in range(K):
+            ctx.encode_bits_dev(make_step(False, QUANT, ME_MODE, SEARCH_LIMIT), (W + 3 + i) % 32, dev_sets.data_ptr() + ring(W + 3 + i) * set_bytes)
+        v1.record(stream)
+        barrier()
+        ms_vlc_resident = v0.elapsed_time(v1)
         # ---- sustained: >= 3 s of the same device-resident steps back to back (does the clock hold under seconds of 80 %-ALU
         # integer load?); the clock sampler keeps running, its rows from this window are summarised separately
         sus = None
@@ -383,7 +394,7 @@ def main_cuda(args):
         stop.set()
         th.join(timeout=2)
 
-    sus_ms = shard.max_over_ranks([sus["ms"] if sus else 0.0], dist if world > 1 else None, device="cuda")[0]
+    sus_ms, ms_vlc_resident = shard.max_over_ranks([sus["ms"] if sus else 0.0, ms_vlc_resident], dist if world > 1 else None, device="cuda")
     rc_ms = [rc_line["ms_dev"], rc_line["ms_host"]] if rc_line else [0.0, 0.0]
     red = shard.max_over_ranks([ms, ms_e2e, ms_e2e_rec] + rc_ms + [-h2d_conc] + [-x for x in link_local] + exp_local + [bal[0] if bal else 0.0],
                                dist if world > 1 else None, device="cuda")
@@ -468,6 +479,9 @@ def main_cuda(args):
                 "roofline": dominant, "roofline_kernels": {"me_search_kernel": me_roof, "mb_encode_kernel": mb_roof},
                 "kernel_share_of_step": {"me_search_kernel": me_ms / (me_ms + mb_ms), "mb_encode_kernel": mb_ms / (me_ms + mb_ms)},
                 "cpu_baseline": cpu,
+                "value_with_vlc": {"value": frames / (ms_vlc_resident * 1e-3), "unit": "frames/s", "ms_per_step": ms_vlc_resident / K,
+                                   "note": "device-resident like `value`, but the step also writes the headers and the VLC on the device (p64b_ctx_encode_bits_dev): "
+                                           "like for like with the reference arm, whose number includes its VLC"},
                 "e2e": {"value": e2e_value, "unit": "frames/s",
                         "h2d_bytes_per_step": S * fb if not bal else world * S * fb, "d2h_bytes_per_step": bits_down // K if not bal else bal_down // K,
                         "stream_bytes_per_step": bits_used // K if not bal else bal_used // K, "ms_per_step": (ms_bal if bal else ms_e2e) / K,

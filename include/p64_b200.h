@@ -168,6 +168,11 @@ typedef struct p64b_bits_out {
 int p64b_ctx_submit_bits(p64b_ctx *ctx, const p64b_step *step, int temporal_reference, const uint8_t *src,
                          int64_t *ticket);
 int p64b_ctx_wait_bits(p64b_ctx *ctx, int64_t ticket, p64b_bits_out *out);
+/* The frame step of p64b_ctx_submit_bits with the source frames already on the device and the output left there (fixed
+ * quantiser only): motion estimation, macroblock kernel and the headers + VLC kernels, nothing copied.  For measurements
+ * that include the entropy coding but not the host link (bench.py `value_with_vlc`); asynchronous on the context's stream.
+ * Not to be mixed with steps still in flight from p64b_ctx_submit_bits (it uses pipeline slot 0's buffers). */
+int p64b_ctx_encode_bits_dev(p64b_ctx *ctx, const p64b_step *step, int temporal_reference, const uint8_t *src_dev);
 
 /* Rate control on the device (-r).  Once configured (before the first frame), p64b_ctx_submit_bits()
  * runs the reference's buffer model per stream ON THE DEVICE: motion estimation once per frame, then GOB by GOB

@@ -90,6 +90,7 @@ SIGNATURES = {
     "p64b_ctx_encode_frames_dev": (_i, [_vp, C.POINTER(Step), _vp, _vp, _vp]),
     "p64b_ctx_submit_bits": (_i, [_vp, C.POINTER(Step), _i, _vp, C.POINTER(C.c_int64)]),
     "p64b_ctx_wait_bits": (_i, [_vp, C.c_int64, C.POINTER(BitsOut)]),
+    "p64b_ctx_encode_bits_dev": (_i, [_vp, C.POINTER(Step), _i, _vp]),
     "p64b_ctx_set_rate_control": (_i, [_vp, C.POINTER(RateControl)]),
     "p64b_raw_frame_bytes": (_i, [_i, _i]),
     "p64b_ctx_set_input_chroma": (_i, [_vp, _i]),

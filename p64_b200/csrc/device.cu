@@ -917,6 +917,35 @@ extern "C" int p64b_ctx_submit_bits(p64b_ctx* c, const p64b_step* st, int tempor
   return 0;
 }
 
+extern "C" int p64b_ctx_encode_bits_dev(p64b_ctx* c, const p64b_step* st, int temporal_reference, const uint8_t* src_dev) {
+  if (!c || !src_dev) { set_error("NULL argument"); return P64B_EINVAL; }
+  if (c->frame_src) { set_error("p64b_ctx_encode_bits_dev inside frame_begin/frame_end"); return P64B_EINVAL; }
+  if (c->rate.rate) { set_error("p64b_ctx_encode_bits_dev: fixed quantiser only"); return P64B_EINVAL; }
+  int rc;
+  if ((rc = check_step(st)) || (rc = check_quant(st->gquant)) || (rc = use_device(c)) || (rc = ensure_bits_buffers(c))) return rc;
+  VlcFrameArgs f{};
+  uint64_t h = (0x10ull << 44) | ((uint64_t)(temporal_reference & 31) << 39) | ((uint64_t)(c->image_type == P64B_IT_QCIF ? 0x00 : 0x04) << 33);
+  f.pic_hdr_bits = 32;
+  if (c->image_type == P64B_IT_NTSC) { h |= (1ull << 32) | (0x8cull << 24); f.pic_hdr_bits = 41; }
+  f.pic_hdr = c->d_pic_hdr;
+  set_pic_hdr_kernel<<<1, 1, 0, c->stream>>>(c->d_pic_hdr, (uint32_t)(h >> 32), (uint32_t)h);
+  f.gob_words = c->d_gob_words; f.gob_bits = c->d_gob_bits; f.carry = c->d_carry; f.carry_len = c->d_carry_len;
+  f.bitpos = c->d_bitpos; f.out = c->d_bits_out[0]; f.n_streams = c->S; f.ngob = c->g.ngob; f.gquant = st->gquant;
+  VlcArgs a{};
+  a.tables = c->d_vlc_tables; a.mbs = c->p_mbs[0]; a.levels = c->p_levels[0];
+  a.gob_words = c->d_gob_words; a.gob_bits = c->d_gob_bits;
+  a.n_streams = c->S; a.ngob = c->g.ngob; a.nmb = c->g.nmb; a.qcif = c->g.qcif; a.gquant = st->gquant;
+  a.gob_first = 0; a.gob_count = c->g.ngob;
+  if ((rc = p64b_ctx_encode_frames_dev(c, st, src_dev, c->p_mbs[0], c->p_levels[0]))) return rc;
+  ProfScope ps(c, 2);
+  vlc_gob_kernel<false><<<c->S * c->g.ngob, VLC_THREADS, 0, c->stream>>>(a);
+  vlc_sizes_kernel<<<1, 1024, 0, c->stream>>>(f);
+  vlc_frame_kernel<<<c->S, VLC_THREADS, 0, c->stream>>>(f);
+  c->launches += 4;
+  CU(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int p64b_ctx_wait_bits(p64b_ctx* c, int64_t ticket, p64b_bits_out* out) {
   if (!c || !out || ticket < 0 || ticket >= c->submitted || ticket + p64b_ctx::NSLOT < c->submitted) { set_error("bad ticket"); return P64B_EINVAL; }
   int rc;

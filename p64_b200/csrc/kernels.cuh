@@ -37,9 +37,10 @@ struct Geom {
 //     the current one is processed, so the TMA latency is never exposed;
 //   * the window is replicated shifted by 1..3 bytes (TMA needs a 16-byte aligned innermost start), so that every
 //     packed-SAD operand in the hot loop is an aligned 32-bit shared-memory word (no PRMT/funnel shift in the loop);
-//   * lane = dx position; the warp sweeps the legal dy positions in passes of 10 (or 5) candidates per thread: a
-//     thread keeps the whole current block in 64 registers and slides down 15+NC window rows (4 LDS.32 per row),
-//     feeding NC independent VABSDIFF4.U8.ACC chains.
+//   * lane = dx position; the warp sweeps the legal dy positions in chunks of 10 candidates per thread: a
+//     thread keeps the whole current block in 64 registers and slides down the window rows (4 LDS.32 per row),
+//     feeding 10 independent VABSDIFF4.U8.ACC chains; the exhaustive search eliminates candidates exactly, warp-wide
+//     first and then one by one (see full_chunk below).
 // Only the part of the 31x31 surface that the reference can ever look at is evaluated: the legal positions
 // (me.c:212-213, 292-293) inside the search range -- 30x30 for FastBME -i 31 inside the frame ([-15,14],
 // me.c:206-208), 31x31 for StepBME, 15 or 16 wide/high for macroblocks on a frame edge.  With <= 16 legal dx the
@@ -158,27 +159,10 @@ __device__ __forceinline__ uint32_t queue_take(uint32_t* counter, int lane) {
 
 constexpr int ME_V_FULL = 0, ME_V_SURF = 1, ME_V_TSS = 2;
 
-// One pass: this thread's NC candidates at dy positions yb .. yb+NC-1 (accumulators start at 0 or ME_ILLEGAL from the
-// row table).  Returns min_j (SAD_j << 11 | yb + j): the dy part of the exhaustive-search key.  ME_V_SURF also
-// stores the legal entries into the surface.
-//
-// PRUNE (exhaustive search only): the reference's ComputeError leaves a candidate as soon as its partial sum reaches the
-// best SAD so far (me.c:65, 122, 133, 170) -- which never changes a decision, because acceptance needs a strictly smaller
-// FULL sum (me.c:220).  The warp-wide form of that early exit: the pass first accumulates block rows 0..R1-1 of all its
-// candidates, and if every legal candidate of every lane is already strictly above `bound` (the smallest full SAD
-// found so far, SAD(0,0) included) none of them can win or tie, and the remaining rows are skipped.  There are two such
-// check points (after R1 and R2 rows).  Exact for any content; on content without a good match nothing is skipped and a
-// pass costs 2 (NC-1) extra row loads.
-#ifndef P64B_ME_PASS_ROWS
-#define P64B_ME_PASS_ROWS 10
-#endif
 #ifndef P64B_ME_PRUNE_R1
 #define P64B_ME_PRUNE_R1 4
 #endif
-#ifndef P64B_ME_PRUNE_R2
-#define P64B_ME_PRUNE_R2 8
-#endif
-constexpr int ME_PRUNE_R1 = P64B_ME_PRUNE_R1, ME_PRUNE_R2 = P64B_ME_PRUNE_R2;   // check points (block rows done); R2 == R1: one check
+constexpr int ME_PRUNE_R1 = P64B_ME_PRUNE_R1;   // first warp-wide check point of a chunk (block rows done); the second is ME_RA
 
 // block rows [R0, R1) of all NC candidates: window rows R0 .. R1-1+NC-1
 template <int NC, int R0, int R1>
@@ -205,30 +189,18 @@ __device__ __forceinline__ bool sweep_hopeless(const uint32_t (&a)[NC], bool xok
   return __reduce_min_sync(0xffffffffu, xok ? m : 0xffffffffu) > bound;
 }
 
-template <int VARIANT, int NC, bool PRUNE>
+// Surface variant (test hook): one pass of NC candidates per thread at dy positions yb .. yb+NC-1 in full (accumulators start at
+// 0 or ME_ILLEGAL from the row table); the legal entries go into the surface in shared memory.
+template <int VARIANT, int NC>
 __device__ __forceinline__ uint32_t sweep_pass(const uint32_t* __restrict__ colbase, const uint32_t (&c)[16][4],
                                                const uint32_t* pen, uint32_t* s_sad, int xi, int yb, bool xok,
-                                               uint32_t m2048, uint32_t bound, uint32_t& units, const SmLim& lim) {
+                                               uint32_t m2048, uint32_t& units, const SmLim& lim) {
   const uint32_t* base = colbase + yb * ME_ROW_WORDS;
   uint32_t a[NC];
 #pragma unroll
   for (int j = 0; j < NC; j++) a[j] = SMR(pen + yb + j);
-  if (PRUNE) {
-    constexpr int R1 = ME_PRUNE_R1, R2 = ME_PRUNE_R2;
-    sweep_rows<NC, 0, R1>(base, c, a, lim);
-    units += (uint32_t)(NC * R1);
-    if (sweep_hopeless<NC>(a, xok, bound)) return 0xffffffffu;
-    if (R2 > R1) {
-      sweep_rows<NC, R1, R2>(base, c, a, lim);
-      units += (uint32_t)(NC * (R2 - R1));
-      if (sweep_hopeless<NC>(a, xok, bound)) return 0xffffffffu;
-    }
-    sweep_rows<NC, R2, 16>(base, c, a, lim);
-    units += (uint32_t)(NC * (16 - R2));
-  } else {
-    sweep_rows<NC, 0, 16>(base, c, a, lim);
-    units += (uint32_t)(NC * 16);
-  }
+  sweep_rows<NC, 0, 16>(base, c, a, lim);
+  units += (uint32_t)(NC * 16);
   if (VARIANT == ME_V_SURF) {
 #pragma unroll
     for (int j = 0; j < NC; j++)
@@ -515,8 +487,8 @@ me_search_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_consta
         for (int v = 0; v < np; v++) {
           const int done = PS * v;
           uint32_t r;
-          if (rpg - done > 5) r = sweep_pass<VARIANT, 10, false>(colbase, c, pen, s_sad, xi, min(ystart + done, 22), xok, a.m2048, bound, units, lim);
-          else                r = sweep_pass<VARIANT, 5, false>(colbase, c, pen, s_sad, xi, min(ystart + done, 27), xok, a.m2048, bound, units, lim);
+          if (rpg - done > 5) r = sweep_pass<VARIANT, 10>(colbase, c, pen, s_sad, xi, min(ystart + done, 22), xok, a.m2048, units, lim);
+          else                r = sweep_pass<VARIANT, 5>(colbase, c, pen, s_sad, xi, min(ystart + done, 27), xok, a.m2048, units, lim);
           best = min(best, (xok && r != 0xffffffffu) ? r + (uint32_t)(1 + xi * 32) : 0xffffffffu);
         }
       }

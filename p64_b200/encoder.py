@@ -103,6 +103,10 @@ class DeviceContext:
         check(self.L.p64b_ctx_submit_bits(self.h, C.byref(step), int(temporal_reference), C.c_void_p(src_ptr), C.byref(t)))
         return t.value
 
+    def encode_bits_dev(self, step: Step, temporal_reference: int, src_dev: int):
+        """the bits step with device-resident source frames, output left on the device (measurements only)"""
+        check(self.L.p64b_ctx_encode_bits_dev(self.h, C.byref(step), int(temporal_reference), _ptr(src_dev)))
+
     def wait_bits(self, ticket: int):
         """-> (chunks: list of bytes per stream, carry, carry_len, bit_position) of that step"""
         o = BitsOut()

@@ -549,3 +549,32 @@ def test_multi_device_errors_surface():
     from p64_b200._lib import P64Error
     with pytest.raises(P64Error):
         Encoder(y4m.IT_QCIF, 2, q=8, devices=[0, 99])      # no such device: the partition's error text reaches the caller
+
+
+def test_resident_bits_step_is_the_same_step():
+    """p64b_ctx_encode_bits_dev (source already on the device, output left there: bench.py's `value_with_vlc`) runs the same
+    kernels as p64b_ctx_submit_bits: after it, the stream state (carry bits, bit position, reconstruction, LastIntra) is what
+    the host-buffer call leaves, so the following frames' bytes are identical."""
+    import torch
+    it, S = y4m.IT_QCIF, 3
+    clips = [y4m.synth_clip(it, 3, seed=610 + s, pan=(s, -s)) for s in range(S)]
+    frames = [np.stack([c[f] for c in clips]).copy() for f in range(3)]
+    outs = []
+    for resident_first in (False, True):
+        ctx = DeviceContext(it, S)
+        try:
+            chunks = []
+            for f in range(3):
+                step = make_step(f == 0, 7, 1, 31)
+                if resident_first and f == 0:
+                    d = torch.from_numpy(frames[0]).cuda()
+                    ctx.encode_bits_dev(step, 0, d.data_ptr())
+                    torch.cuda.synchronize()
+                    continue
+                t = ctx.submit_bits(step, f % 32, frames[f].ctypes.data)
+                c, carry, clen, pos = ctx.wait_bits(t)
+                chunks.append((c, list(carry), list(clen), list(pos)))
+            outs.append((chunks[-2:], [ctx.recon(s).tobytes() for s in range(S)], [ctx.last_intra(s).tobytes() for s in range(S)]))
+        finally:
+            ctx.close()
+    assert outs[0] == outs[1]
