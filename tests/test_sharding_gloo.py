@@ -59,3 +59,24 @@ def test_world_size_2_gloo():
             assert not (set(d) & set(merged))
             merged.update(d)
         assert sorted(merged) == list(range(11))
+
+
+def test_link_proportional_split_is_a_partition():
+    """bench.py's link-balanced end-to-end partition (and encoder.cpp's balance_links): integer shares proportional to the
+    measured link rates, summing to the job's stream count, none below the floor"""
+    import importlib.util
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    sys.modules["bench_mod"] = bench
+    spec.loader.exec_module(bench)
+    sp = bench.split_proportional
+    assert sp(2048, [23.5] * 4 + [36.0] * 4) == [202, 202, 202, 202, 310, 310, 310, 310]
+    assert sp(512, [55.2, 55.2]) == [256, 256]
+    for total, w in [(2048, [1, 2, 3, 4, 5, 6, 7, 8]), (1024, [29.0, 29.1, 28.9, 29.0]), (300, [0.0, 10.0, 10.0]), (64, [1e-9, 1.0])]:
+        s = sp(total, w)
+        assert sum(s) == total and min(s) >= 8 and len(s) == len(w)
+        big = [i for i, x in enumerate(w) if x > 1e-6]
+        for i in big:                                   # proportional to within rounding and the floor of the starved ranks
+            assert abs(s[i] - total * w[i] / sum(w)) <= 8 * len(w)
