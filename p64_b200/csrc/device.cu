@@ -844,7 +844,7 @@ extern "C" int p64b_ctx_submit_bits(p64b_ctx* c, const p64b_step* st, int tempor
     if ((rc = p64b_ctx_encode_frames_dev(c, st, c->p_src[slot], c->p_mbs[slot], c->p_levels[slot]))) return rc;
     a.gob_first = 0; a.gob_count = c->g.ngob;
     ProfScope ps(c, 2);
-    vlc_gob_kernel<false><<<c->S * c->g.ngob, VLC_THREADS, 0, c->stream>>>(a);
+    vlc_gob_seq_kernel<<<(c->S * c->g.ngob + VLC_SEQ_WARPS - 1) / VLC_SEQ_WARPS, VLC_SEQ_THREADS, 0, c->stream>>>(a);
     vlc_sizes_kernel<<<1, 1024, 0, c->stream>>>(f);
     vlc_frame_kernel<<<c->S, VLC_THREADS, 0, c->stream>>>(f);
     c->launches += 3;
@@ -938,7 +938,7 @@ extern "C" int p64b_ctx_encode_bits_dev(p64b_ctx* c, const p64b_step* st, int te
   a.gob_first = 0; a.gob_count = c->g.ngob;
   if ((rc = p64b_ctx_encode_frames_dev(c, st, src_dev, c->p_mbs[0], c->p_levels[0]))) return rc;
   ProfScope ps(c, 2);
-  vlc_gob_kernel<false><<<c->S * c->g.ngob, VLC_THREADS, 0, c->stream>>>(a);
+  vlc_gob_seq_kernel<<<(c->S * c->g.ngob + VLC_SEQ_WARPS - 1) / VLC_SEQ_WARPS, VLC_SEQ_THREADS, 0, c->stream>>>(a);
   vlc_sizes_kernel<<<1, 1024, 0, c->stream>>>(f);
   vlc_frame_kernel<<<c->S, VLC_THREADS, 0, c->stream>>>(f);
   c->launches += 4;

@@ -5,21 +5,15 @@
 //   EncodeDC / EncodeAC / CBPEncodeAC  codec.c:96-205, 346-355      WritePictureHeader  marker.c:103-137
 //   mputv  stream.c:193-205 (MSB first)
 //
-//   vlc_gob_kernel    one CTA per (stream, GOB): one thread per piece (GOB header, 33 x {MB header, 6 blocks});
+//   vlc_gob_seq_kernel  fixed quantiser: one WARP per (stream, GOB), macroblock after macroblock, one item (intra DC, level,
+//                     EOB) per lane, the words streamed out through a small ring in shared memory -- no measuring pass.
+//   vlc_gob_kernel    rate control: one CTA per (stream, GOB): one thread per piece (GOB header, 33 x {MB header, 6 blocks});
 //                     pass 1 measures every piece, a CTA-wide scan places them, pass 2 writes the bits into a
 //                     shared-memory image of the GOB, which is then stored unshifted into the GOB's scratch slot.
 //   vlc_frame_kernel  one CTA per stream: carry bits of the previous frame + picture header + the GOB strings are
 //                     gathered word by word (funnel shifts) into the frame's byte chunk; the < 8 trailing bits stay
 //                     on the device as the next frame's carry, so the host only ever appends whole bytes.
 // Bit strings are MSB first: bit i of a string is bit (31 - i % 32) of word i / 32.
-// Tried in round 2 and not kept (measured on a B200, 256 CIF streams): one WARP per macroblock with lane = header or a quarter of a
-// block (16 consecutive coefficients), the block's non-zero mask exchanged by shuffles.  The zig-zag order puts nearly all
-// non-zero levels into the first quarter, so the quarter-0 lanes do the work while 28 lanes wait: 121 M warp-instructions and
-// 0.149 ms per launch instead of 71 M and 0.116 ms for the thread-per-piece form below.  Also tried: one ITEM (intra DC, non-zero
-// level, EOB) per lane from a list in stream order, coded once and kept in registers until the macroblocks are placed (one walk
-// instead of two): bit-exact, ALU pipe 51 % instead of 72 %, but again 70 M warp-instructions and 0.116 ms -- with 11 warps
-// taking 33 macroblocks in 3 rounds between five CTA barriers, the barrier stalls (3.9 per issue) eat what the single walk saves
-// (profiles/r02_ncu_vlc_gob_kernel_item_per_lane_rejected.txt).
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -191,6 +185,188 @@ __device__ __forceinline__ uint64_t vlc_mb_header(const p64b_mb& r, const p64b_m
   if (vt(V_CBP, mt)) put(t->cbp[r.cbp]);
   *n = len;
   return b;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Fixed quantiser (round 2): ONE WARP PER GOB, macroblock after macroblock, one ITEM per lane.
+// A macroblock's bit string is a header followed by items in a fixed order: per coded block [intra DC], the non-zero levels in
+// transmission order, [EOB].  The warp that owns a GOB knows the bit position it has reached, so nothing has to be measured
+// first and placed later: per macroblock
+//   list   lanes 1..24 (block b, quarter q) stage their 16 levels in shared memory and write the descriptors of their items
+//          (block | kind | position) into the warp's list at positions given by a warp scan of the counts: stream order;
+//   code   lane k takes item k, 32 at a time: the run comes from the previous descriptor, the code from the table in shared
+//          memory (codec.c:96-205: escapes as in 113-115, the two-bit code for a leading +-1 of a CBP-coded block; EncodeDC
+//          codec.c:346-355); a warp scan of the lengths places the items behind the header;
+//   emit   every lane ORs its item into a 64-word ring in shared memory; the words the position has passed are stored to the
+//          GOB's scratch slot and zeroed.
+// The next macroblock's record and levels are loaded while the current one is coded.  No CTA-wide barrier after the table
+// load, no image of the GOB in shared memory (1.9 KB per warp instead of 34 KB per CTA), every level is looked at once.
+// Measured on 256 CIF frames: 57.9 M warp-instructions, 0.108 ms (profiles/r02_ncu_vlc_gob_seq_kernel.txt).
+// The thread-per-piece kernel below (round 1) measures every piece, scans, and walks the levels again to write them, waiting
+// for the busiest block of every warp in both walks and at five CTA barriers: 71 M warp-instructions per 256 CIF frames,
+// 0.116 ms.  It remains the rate-control kernel (one GOB per stream per launch: 256 GOBs cannot feed 148 SMs with one warp
+// each).  Two CTA-per-GOB re-mappings tried on the way were no faster than it (a lane per block quarter: the zig-zag order
+// puts the non-zero levels into the first quarter, 121 M / 0.149 ms; an item per lane with the codes kept in registers between
+// a measuring and an emitting phase: 70 M / 0.116 ms, 3.9 barrier stalls per issue) -- profiles/r02_ncu_vlc_gob_kernel_*.
+constexpr int VLC_SEQ_WARPS = 4;
+constexpr int VLC_SEQ_THREADS = 32 * VLC_SEQ_WARPS;
+constexpr int VLC_ITEMS_MAX = 6 * 66;                   // per macroblock: 6 x (DC or position 0, 63 levels, EOB) at most
+constexpr int VLC_RING = 64;                            // words; one sub-round adds at most 47 + 32 x 20 bits = 22 words
+
+// list: stages the macroblock's levels and writes its item descriptors in stream order; returns the number of items
+__device__ __forceinline__ int vlc_list_items(const p64b_mb& rec, uint4 v, int lane, uint8_t* stage, uint16_t* items) {
+  const int mt = rec.mtype;
+  const bool cbp_type = vt(V_CBP, mt);
+  const int b = (lane - 1) >> 2, q = (lane - 1) & 3;
+  const bool blk = lane >= 1 && lane <= 24;
+  const bool coded = blk && vt(V_TCOEF, mt) && ((rec.cbp >> (5 - b)) & 1);
+  if (!coded) v = make_uint4(0, 0, 0, 0);               // (the levels were loaded before the record was known)
+  if (blk) *reinterpret_cast<uint4*>(stage + (lane - 1) * 16) = v;
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  uint32_t nz = 0;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const uint32_t hi = (w[j] | ((w[j] & 0x7f7f7f7fu) + 0x7f7f7f7fu)) & 0x80808080u;     // bit 7 of every non-zero byte
+    nz |= ((((hi >> 7) * 0x01020408u) >> 24) & 0xfu) << (4 * j);
+  }
+  if (q == 0 && !cbp_type) nz &= ~1u;                      // the intra DC is its own item
+  const uint32_t anym = __ballot_sync(0xffffffffu, coded && nz != 0);
+  const bool dc = coded && q == 0 && !cbp_type;
+  const bool eob = coded && q == 3 && (!cbp_type || ((anym >> (1 + 4 * b)) & 0xfu));       // an all-zero CBP block gets no EOB (codec.c:169-174)
+  const int cnt = __popc(nz) + (dc ? 1 : 0) + (eob ? 1 : 0);
+  int x = cnt;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+  const int total = __shfl_sync(0xffffffffu, x, 31);
+  int idx = x - cnt;
+  const uint32_t base = (uint32_t)b << 8;
+  if (dc) items[idx++] = (uint16_t)(base | (1u << 6));
+  while (nz) {
+    const int pl = __ffs((int)nz) - 1;
+    nz &= nz - 1;
+    items[idx++] = (uint16_t)(base | (uint32_t)(16 * q + pl));
+  }
+  if (eob) items[idx++] = (uint16_t)(base | (2u << 6) | 63u);
+  __syncwarp();
+  return total;
+}
+
+// code: item k of the list -> (code bits, length)
+__device__ __forceinline__ void vlc_code_item(int k, int total, const uint16_t* items, const uint8_t* stage, const uint32_t* s_tcoef,
+                                              uint32_t& code, int& len) {
+  code = 0; len = 0;
+  if (k >= total) return;
+  const uint32_t d = items[k];
+  const int b = (int)(d >> 8), kind = (int)((d >> 6) & 3u), p = (int)(d & 63u);
+  if (kind == 1) {                                     // EncodeDC, codec.c:346-355
+    int dc = stage[b * 64];
+    dc = min(max(dc, 1), 254);
+    if (dc == 128) dc = 255;
+    code = (uint32_t)dc; len = 8;
+  } else if (kind == 2) {                              // EOB "10"
+    code = 2u; len = 2;
+  } else {
+    const int v = (int)(int8_t)stage[b * 64 + p], a = abs(v);
+    int prevp = -1;                                    // the previous item of the same block is its DC (position 0) or a level
+    if (k > 0) { const uint32_t pd = items[k - 1]; if ((int)(pd >> 8) == b) prevp = (int)(pd & 63u); }
+    const int run = p - prevp - 1;
+    if (p == 0 && a == 1) {                            // "1s": a leading +-1 of a CBP-coded block (only those list position 0)
+      code = 2u | (uint32_t)(v < 0); len = 2;
+    } else {
+      const uint32_t e = (run < 32 && a < 16) ? s_tcoef[run * 16 + a] : 0u;
+      if (e) { len = (int)(e >> 16) + 1; code = ((e & 0xffffu) << 1) | (uint32_t)(v < 0); }
+      else { code = (1u << 14) | ((uint32_t)run << 8) | (uint32_t)(v & 0xff); len = 20; }     // escape (codec.c:113-115)
+    }
+  }
+}
+
+
+// OR `n` bits (n <= 32, v < 2^n) into the ring of VLC_RING zeroed words that holds the MSB-first GOB string around the ABSOLUTE
+// bit offset `o`
+__device__ __forceinline__ void vlc_or_ring(uint32_t* ring, uint32_t o, uint32_t v, int n) {
+  if (!n) return;
+  const uint32_t w = o >> 5;
+  const int sh = (int)(o & 31), over = sh + n - 32;
+  if (over <= 0) atomicOr(ring + (w & (VLC_RING - 1)), v << (-over));
+  else { atomicOr(ring + (w & (VLC_RING - 1)), v >> over); atomicOr(ring + ((w + 1) & (VLC_RING - 1)), v << (32 - over)); }
+}
+
+__global__ void __launch_bounds__(VLC_SEQ_THREADS)
+vlc_gob_seq_kernel(const __grid_constant__ VlcArgs a) {
+  __shared__ DevVlcTables s_t;
+  __shared__ __align__(16) uint8_t s_stage[VLC_SEQ_WARPS][384];
+  __shared__ uint16_t s_items[VLC_SEQ_WARPS][VLC_ITEMS_MAX + 4];
+  __shared__ uint32_t s_ring[VLC_SEQ_WARPS][VLC_RING];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < DEV_VLC_WORDS; i += VLC_SEQ_THREADS) reinterpret_cast<uint32_t*>(&s_t)[i] = reinterpret_cast<const uint32_t*>(a.tables)[i];
+  for (int i = lane; i < VLC_RING; i += 32) s_ring[warp][i] = 0;
+  __syncthreads();
+  const int task = blockIdx.x * VLC_SEQ_WARPS + warp;
+  if (task >= a.n_streams * a.gob_count) return;        // (no barrier below)
+  const int s = task / a.gob_count, gob = a.gob_first + task % a.gob_count;
+  const size_t mb0 = (size_t)s * a.nmb + gob * 33;
+  uint8_t* stage = s_stage[warp];
+  uint16_t* items = s_items[warp];
+  uint32_t* ring = s_ring[warp];
+  uint32_t* dst = a.gob_words + ((size_t)s * a.ngob + gob) * VLC_GOB_WORDS;
+  const int8_t* lv0 = a.levels + mb0 * P64B_LEVELS_PER_MB;
+  const bool blk = lane >= 1 && lane <= 24;
+
+  uint32_t pos = 26, wbase = 0;                        // bits written so far; first word of the GOB string still in the ring
+  if (lane == 0) {                                     // WriteGOBHeader, marker.c:182-209: GBSC, GN, GQUANT, no GSPARE
+    const int gn = (a.qcif ? (gob << 1) : gob) + 1;
+    vlc_or_ring(ring, 0, (1u << 10) | ((uint32_t)gn << 6) | ((uint32_t)a.gquant << 1), 26);
+  }
+  // the words [wbase, pos / 32) are final: store them and hand their ring slots back
+  auto flush = [&]() {
+    __syncwarp();
+    const uint32_t n = (pos >> 5) - wbase;              // <= 23 < 32
+    if ((uint32_t)lane < n) { const uint32_t w = wbase + (uint32_t)lane; dst[w] = ring[w & (VLC_RING - 1)]; ring[w & (VLC_RING - 1)] = 0; }
+    wbase += n;
+    __syncwarp();
+  };
+  p64b_mb prev{};
+  uint2 rec_next = __ldg(reinterpret_cast<const uint2*>(a.mbs + mb0));
+  uint4 lv_next = make_uint4(0, 0, 0, 0);
+  if (blk) lv_next = __ldg(reinterpret_cast<const uint4*>(lv0 + (lane - 1) * 16));
+#pragma unroll 1
+  for (int m = 0; m < 33; m++) {
+    const uint2 rw = rec_next;
+    const uint4 lv = lv_next;
+    if (m + 1 < 33) {                                   // the next macroblock's record and levels: in flight while this one is coded
+      rec_next = __ldg(reinterpret_cast<const uint2*>(a.mbs + mb0 + m + 1));
+      if (blk) lv_next = __ldg(reinterpret_cast<const uint4*>(lv0 + (size_t)(m + 1) * P64B_LEVELS_PER_MB + (lane - 1) * 16));
+    }
+    const p64b_mb rec = *reinterpret_cast<const p64b_mb*>(&rw);
+    int hl;
+    const uint64_t hb = vlc_mb_header(rec, prev, m, &s_t, &hl);
+    prev = rec;
+    if (lane == 0) {
+      if (hl > 32) { vlc_or_ring(ring, pos, (uint32_t)(hb >> 32), hl - 32); vlc_or_ring(ring, pos + (uint32_t)(hl - 32), (uint32_t)hb, 32); }
+      else vlc_or_ring(ring, pos, (uint32_t)hb, hl);
+    }
+    pos += (uint32_t)hl;
+    const int total = vlc_list_items(rec, lv, lane, stage, items);
+    if (total == 0) flush();
+#pragma unroll 1
+    for (int k0 = 0; k0 < total; k0 += 32) {
+      uint32_t code; int len;
+      vlc_code_item(k0 + lane, total, items, stage, s_t.tcoef, code, len);
+      int x = len;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+      vlc_or_ring(ring, pos + (uint32_t)(x - len), code, len);
+      pos += (uint32_t)__shfl_sync(0xffffffffu, x, 31);
+      flush();
+    }
+  }
+  __syncwarp();
+  const uint32_t nwords = (pos + 31) >> 5;               // the partial last word, + one zero word for the gather's look-ahead
+  if (lane == 0) {
+    if (pos & 31) dst[pos >> 5] = ring[(pos >> 5) & (VLC_RING - 1)];
+    dst[nwords] = 0;
+    a.gob_bits[(size_t)s * a.ngob + gob] = pos;
+  }
 }
 
 // exclusive scan of one value per thread over the CTA; *total = sum.  Two barriers.
