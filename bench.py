@@ -596,7 +596,7 @@ def balanced_e2e_leg(L, dist, world, rank, local, S, K, n_sets, ring, me_mode, N
         pin = L.p64b_host_alloc(hs.nbytes)
         C.memmove(pin, hs.ctypes.data, hs.nbytes)
         sb = my * hs.shape[2]
-        steps = K if it else max(12, K // 3)
+        steps = K if it else max(16, K // 2)
         run(c, pin, sb, 0, 6, True)
         barrier()
         t0 = time.perf_counter()
