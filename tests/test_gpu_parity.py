@@ -330,12 +330,16 @@ def test_cli_matches_reference_golden(tmp_path):
         assert f"Number of buffer overflows: {g['overflows']}" in r.stdout
 
 
-def test_cli_batch_of_files_equals_single_encodes(tmp_path):
-    """several prefixes on one p64b command line = one batch of streams; every output equals the reference's golden"""
+@pytest.mark.parametrize("devices", [None, "0,0", "0-0", "0,0,0,0,0"])
+def test_cli_batch_of_files_equals_single_encodes(tmp_path, devices):
+    """several prefixes on one p64b command line = one batch of streams; every output equals the reference's golden -- also
+    with the batch partitioned over a device list (--devices; the test box has one GPU, so the list repeats it; five entries
+    for three streams leave two partitions empty) and --balance-links"""
     import subprocess
     from p64_b200 import build
     cli = build.build_cli()
     names = ["qcif12_q8_tss", "qcif20_r64000_tss"]
+    extra = (["--devices", devices] + (["--balance-links"] if devices == "0,0" else [])) if devices else []
     for name in names:
         g, clip = golden_clip(name)
         rate = g["args"].get("rate")
@@ -347,7 +351,7 @@ def test_cli_batch_of_files_equals_single_encodes(tmp_path):
             y4m.write_y4m(str(tmp_path / f"{name}_{k}.y4m"), g["image_type"], c)
             variants.append(c)
         cmd = [cli, "-y4m", "-QCIF", "-a", "0", "-b", str(g["n_frames"] - 1)] + (["-r", str(rate)] if rate else ["-q", str(g["args"]["q"])])
-        r = subprocess.run(cmd + [str(tmp_path / f"{name}_{k}") for k in range(3)], capture_output=True, text=True)
+        r = subprocess.run(cmd + extra + [str(tmp_path / f"{name}_{k}") for k in range(3)], capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
         assert hashlib.md5(open(tmp_path / f"{name}_0.p64", "rb").read()).hexdigest() == g["md5"]
         for k in (1, 2):
