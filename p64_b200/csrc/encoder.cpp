@@ -248,7 +248,9 @@ int p64b_enc_create(p64b_enc** out, const p64b_enc_params* p) {
       std::unique_ptr<Worker> w(new Worker());
       w->first_stream = first;
       if ((rc = p64b_enc_create(&w->kid, &kp))) break;
-      w->kid->external_stage = true;
+      w->kid->external_stage = true;                  // the partition reads the parent's staging in place: its own ring is not needed
+      for (auto*& b : w->kid->h_ring) { p64b_host_free(b); b = nullptr; }
+      w->kid->h_src = nullptr;
       e->workers.push_back(std::move(w));
       first += n;
     }

@@ -57,7 +57,8 @@ while time.time() - t0 < budget:
     if rng.random() < 0.4:                          # -f, -k, -a: they enter the buffer model and the temporal references
         fr = [(30000, 1001), (25, 1), (15, 1), (10, 1)][int(rng.integers(0, 4))]
         kw.update(frame_rate=fr, frame_skip=int(rng.integers(1, 4)), start_frame=int(rng.integers(0, 70)))
-    enc = Encoder(it, S, input_chroma=chroma, **kw)
+    devs = None if rng.random() < 0.6 else [0] * int(rng.integers(1, 5))         # the batch partitioned over device contexts (one GPU, listed k times)
+    enc = Encoder(it, S, input_chroma=chroma, devices=devs, balance_links=bool(devs) and rng.random() < 0.3, **kw)
     for f in range(nf):
         enc.encode(np.stack([c[f] for c in clips]))
     enc.finish()
@@ -73,7 +74,7 @@ while time.time() - t0 < budget:
             ok = len(fr) == (nf - 1) * kw.get("frame_skip", 1) + 1 and np.array_equal(fr[-1], recons[-1])
         if not ok:
             fails += 1
-            print("MISMATCH", dict(it=it, nf=nf, S=S, s=s, chroma=chroma, **kw), len(got[s]), len(want), ovf[s], wovf, flush=True)
+            print("MISMATCH", dict(it=it, nf=nf, S=S, s=s, chroma=chroma, devs=devs, **kw), len(got[s]), len(want), ovf[s], wovf, flush=True)
     cases += 1
 print(f"fuzz: {cases} cases, {fails} mismatches, {time.time() - t0:.0f} s")
 sys.exit(1 if fails else 0)
