@@ -299,7 +299,8 @@ int p64b_ctx_create(p64b_ctx** out, int device, int image_type, int n_streams) {
   ALLOC(c->d_levels, nm * P64B_LEVELS_PER_MB);
   ALLOC(c->d_quant, (size_t)n_streams);
   ALLOC(c->d_ovf, nm);
-  ALLOC(c->d_me_queue, 4 * sizeof(uint32_t));   // two work counters + the 64-bit executed-work counter
+  ALLOC(c->d_me_queue, 64 * sizeof(uint32_t));  // two work counters + the 64-bit executed-work counter (+ room: the kernel forms one
+                                                // address per lane for its predicated queue atomic, only lane 0's is ever used)
   c->p_src[0] = c->d_src; c->p_mbs[0] = c->d_mbs; c->p_levels[0] = c->d_levels;
   for (int i = 1; i < p64b_ctx::NSLOT; i++) {
     ALLOC(c->p_src[i], fb + slack);
