@@ -326,9 +326,11 @@ def main_cuda(args):
         barrier()
         ctx.profile(True)
         t0 = time.perf_counter()
+        sc0 = int(L.p64b_ctx_second_copies(ctx.h))
         bits_down, bits_used = run_bits_steps(W + 3 * K + 7, K)
         barrier()
         ms_e2e = (time.perf_counter() - t0) * 1e3
+        second_copies = int(L.p64b_ctx_second_copies(ctx.h)) - sc0
         prof_bits = ctx.profile_read()
         ctx.profile(False)
         # ---- what the PCIe link gives: the step's upload alone, back to back, pinned -> HBM (the e2e legs are upload-bound)
@@ -486,6 +488,7 @@ def main_cuda(args):
                         "h2d_bytes_per_step": S * fb if not bal else world * S * fb, "d2h_bytes_per_step": bits_down // K if not bal else bal_down // K,
                         "stream_bytes_per_step": bits_used // K if not bal else bal_used // K, "ms_per_step": (ms_bal if bal else ms_e2e) / K,
                         "bytes_are": "per GPU" if not bal else "whole job (all GPUs)",
+                        "second_copies_equal_partition_leg_rank0": second_copies,
                         "partition": [S] * world if not bal else bal[1], "partition_from_link_probe": None if not bal else bal[4],
                         "partition_note": None if not bal else "streams per GPU, proportional to each GPU's measured share of the host links (probe, "
                                                                "then one trial run) -- found before the timed region; stream contents and bytes do not depend on it",

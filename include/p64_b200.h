@@ -246,6 +246,8 @@ void p64b_stat_from_sums(const p64b_plane_stats *sums, p64b_stat *out);
 int p64b_ctx_last_intra(p64b_ctx *ctx, int stream, uint8_t *out);
 /* number of kernel launches issued by this context so far */
 int64_t p64b_ctx_launches(const p64b_ctx *ctx);
+/* Steps of p64b_ctx_wait_bits whose frame was larger than the download budget (completed by a second copy). */
+int64_t p64b_ctx_second_copies(const p64b_ctx *ctx);
 /* Packed 4-byte SAD operations (VABSDIFF4.U8.ACC lane-instructions) the motion-estimation kernel has EXECUTED so far in
  * its search sweeps, counted on the device; reset != 0 zeroes the counter.  The exhaustive search leaves a pass early when
  * no candidate of the pass can still win (the warp-wide form of ComputeError's early exit, me.c:122-170), so this is what

@@ -121,6 +121,7 @@ SIGNATURES = {
     "p64b_ctx_statistics": (_i, [_vp, _vp]),
     "p64b_stat_from_sums": (None, [C.POINTER(PlaneStats), C.POINTER(Stat)]),
     "p64b_ctx_launches": (C.c_int64, [_vp]),
+    "p64b_ctx_second_copies": (C.c_int64, [_vp]),
     "p64b_ctx_me_executed": (_i, [_vp, C.POINTER(C.c_uint64), _i]),
     "p64b_ctx_profile": (_i, [_vp, _i]),
     "p64b_ctx_profile_read": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int32)]),

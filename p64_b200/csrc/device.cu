@@ -60,7 +60,7 @@ struct p64b_ctx {
   cudaEvent_t ev_h2d[NSLOT] = {}, ev_comp[NSLOT] = {}, ev_d2h[NSLOT] = {};
   bool slot_used[NSLOT] = {};
   bool slot_bits[NSLOT] = {};      // the slot's last step came from p64b_ctx_submit_bits
-  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_fix = nullptr;   // s_fix: the rare second download of a frame that outgrew its budget
   int64_t submitted = 0;
   uint8_t* d_fs[2] = {nullptr, nullptr};   // frame stores; d_fs[cur] = CFS (reference), d_fs[cur^1] = OFS
   uint8_t* d_li[2] = {nullptr, nullptr};   // LastIntra, same double buffering
@@ -88,7 +88,9 @@ struct p64b_ctx {
   uint8_t* d_bits_out[NSLOT] = {};
   uint8_t* h_bits_out[NSLOT] = {};          // pinned; grown on demand
   size_t h_bits_cap[NSLOT] = {}, slot_copied[NSLOT] = {};
-  size_t bits_budget = 0;                   // data bytes downloaded with the first copy (adapts to the last frame's size)
+  size_t bits_budget = 0;                   // data bytes downloaded with the first copy (adapts to the last frames' sizes)
+  size_t bits_recent[4] = {};               // totals of the last four steps collected
+  int64_t second_copies = 0;                // steps whose frame outgrew the budget (completed by a second, synchronous copy)
   // ingest (p64b_ctx_set_input_chroma): host sources are unconverted Y4M payloads; chroma converted on the device
   int chroma = P64B_CHROMA_420JPEG;
   size_t raw_bytes = 0, aux_bytes = 0;      // per frame: whole payload; the part of its chroma the conversion reads
@@ -313,7 +315,8 @@ int p64b_ctx_create(p64b_ctx** out, int device, int image_type, int n_streams) {
         cudaEventCreateWithFlags(&c->ev_d2h[i], cudaEventDisableTiming) != cudaSuccess) { set_error("event create failed"); return fail(P64B_ECUDA); }
   if (cudaStreamCreateWithFlags(&c->own, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream create failed"); return fail(P64B_ECUDA); }
+      cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->s_fix, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream create failed"); return fail(P64B_ECUDA); }
   c->stream = c->own;
 #undef ALLOC
   if (cudaDeviceSynchronize() != cudaSuccess) { set_error("sync failed"); return fail(P64B_ECUDA); }
@@ -344,6 +347,7 @@ void p64b_ctx_destroy(p64b_ctx* c) {
   for (int i = 0; i < p64b_ctx::NSLOT; i++) { cudaFree(c->d_bits_out[i]); if (c->h_bits_out[i]) cudaFreeHost(c->h_bits_out[i]); }
   if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
   if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
+  if (c->s_fix) cudaStreamDestroy(c->s_fix);
   if (c->own) cudaStreamDestroy(c->own);
   delete c;
 }
@@ -626,6 +630,7 @@ int p64b_ctx_last_intra(p64b_ctx* c, int stream, uint8_t* out) {
 }
 
 int64_t p64b_ctx_launches(const p64b_ctx* c) { return c ? c->launches : 0; }
+int64_t p64b_ctx_second_copies(const p64b_ctx* c) { return c ? c->second_copies : 0; }
 
 int p64b_ctx_me_executed(p64b_ctx* c, uint64_t* packed_sad_ops, int reset) {
   if (!c || !packed_sad_ops) { set_error("NULL argument"); return P64B_EINVAL; }
@@ -968,14 +973,19 @@ extern "C" int p64b_ctx_wait_bits(p64b_ctx* c, int64_t ticket, p64b_bits_out* ou
       CU(cudaFreeHost(c->h_bits_out[slot]));
       c->h_bits_out[slot] = nb; c->h_bits_cap[slot] = cap;
     }
-    CU(cudaMemcpyAsync(c->h_bits_out[slot] + have, c->d_bits_out[slot] + have, doff + total - have, cudaMemcpyDeviceToHost, c->s_d2h));
-    CU(cudaStreamSynchronize(c->s_d2h));
+    // (on the copy-back stream this copy would queue behind the downloads of the steps already submitted, i.e. behind their
+    // kernels: the context's upload stream is idle-waiting far less often and keeps the pipeline depth)
+    CU(cudaMemcpyAsync(c->h_bits_out[slot] + have, c->d_bits_out[slot] + have, doff + total - have, cudaMemcpyDeviceToHost, c->s_fix));
+    CU(cudaStreamSynchronize(c->s_fix));
     c->slot_copied[slot] = doff + total;
+    c->second_copies++;
   }
-  // next step's first copy: this frame's size + 1/32 + 16 KB (the size of a whole batch's frame moves slowly; a frame that
-  // outgrows the budget is completed by the second copy above).  Downloads share the host link with the uploads, and on a box
+  // next step's first copy: the largest of the last four frames + 1/32 + 16 KB (the size of a whole batch's frame moves slowly;
+  // a frame that outgrows the budget is completed by the second copy above, which stalls the host for a copy's latency).  Downloads share the host link with the uploads, and on a box
   // whose GPUs share uplinks every downloaded byte costs upload time: no generous slack.
-  c->bits_budget = std::max<size_t>(total + total / 32 + 16384, 65536);
+  c->bits_recent[ticket & 3] = total;
+  const size_t recent = std::max(std::max(c->bits_recent[0], c->bits_recent[1]), std::max(c->bits_recent[2], c->bits_recent[3]));
+  c->bits_budget = std::max<size_t>(recent + recent / 32 + 16384, 65536);
   const uint8_t* b = c->h_bits_out[slot];
   const size_t S = (size_t)c->S;
   out->offset = reinterpret_cast<const uint32_t*>(b);
