@@ -91,6 +91,7 @@ struct p64b_ctx {
   size_t bits_budget = 0;                   // data bytes downloaded with the first copy (adapts to the last frames' sizes)
   size_t bits_recent[4] = {};               // totals of the last four steps collected
   int64_t second_copies = 0;                // steps whose frame outgrew the budget (completed by a second, synchronous copy)
+  int pending_d2h = -1;                     // slot whose download waits for the next step's upload to finish (see p64b_ctx_submit_bits)
   // ingest (p64b_ctx_set_input_chroma): host sources are unconverted Y4M payloads; chroma converted on the device
   int chroma = P64B_CHROMA_420JPEG;
   size_t raw_bytes = 0, aux_bytes = 0;      // per frame: whole payload; the part of its chroma the conversion reads
@@ -815,6 +816,18 @@ extern "C" int p64b_ctx_set_rate_control(p64b_ctx* c, const p64b_rate_control* r
   return 0;
 }
 
+// the download of a bits step: the per-stream table + the stream bytes up to the budget, on the copy-back stream
+static int issue_bits_download(p64b_ctx* c, int slot) {
+  static const bool header_only = getenv("P64B_BITS_D2H") && !strcmp(getenv("P64B_BITS_D2H"), "header");    // attribution experiments only
+  const size_t copy = header_only ? vlc_data_offset(c->S) : std::min(c->bits_out_cap, vlc_data_offset(c->S) + c->bits_budget);
+  int rc;
+  if ((rc = ensure_host_bits(c, slot, copy))) return rc;
+  CU(cudaMemcpyAsync(c->h_bits_out[slot], c->d_bits_out[slot], copy, cudaMemcpyDeviceToHost, c->s_d2h));
+  CU(cudaEventRecord(c->ev_d2h[slot], c->s_d2h));
+  c->slot_copied[slot] = copy;
+  return 0;
+}
+
 extern "C" int p64b_ctx_submit_bits(p64b_ctx* c, const p64b_step* st, int temporal_reference, const uint8_t* src, int64_t* ticket) {
   if (!c || !src || !ticket) { set_error("NULL argument"); return P64B_EINVAL; }
   if (c->frame_src) { set_error("p64b_ctx_submit_bits inside frame_begin/frame_end"); return P64B_EINVAL; }
@@ -828,6 +841,11 @@ extern "C" int p64b_ctx_submit_bits(p64b_ctx* c, const p64b_step* st, int tempor
   if ((rc = upload_source(c, slot, c->p_src[slot], src, c->s_h2d))) return rc;
   CU(cudaEventRecord(c->ev_h2d[slot], c->s_h2d));
   CU(cudaStreamWaitEvent(c->stream, c->ev_h2d[slot], 0));
+  if (c->pending_d2h >= 0) {                 // the previous step's download starts when this upload has finished
+    CU(cudaStreamWaitEvent(c->s_d2h, c->ev_h2d[slot], 0));
+    if ((rc = issue_bits_download(c, c->pending_d2h))) return rc;
+    c->pending_d2h = -1;
+  }
   if ((rc = ingest_source(c, slot, c->p_src[slot]))) return rc;
   // WritePictureHeader, marker.c:103-137: PSC(20) TR(5) PTYPE(6) [PEI=1 PSPARE(8) for NTSC, p64.c:408-423] PEI=0
   VlcFrameArgs f{};
@@ -910,13 +928,13 @@ extern "C" int p64b_ctx_submit_bits(p64b_ctx* c, const p64b_step* st, int tempor
   }
   CU(cudaEventRecord(c->ev_comp[slot], c->stream));
   CU(cudaStreamWaitEvent(c->s_d2h, c->ev_comp[slot], 0));
-  // (attribution experiments only, DESIGN.md section 6: P64B_BITS_D2H=header downloads the per-stream table without the stream bytes)
-  static const bool header_only = getenv("P64B_BITS_D2H") && !strcmp(getenv("P64B_BITS_D2H"), "header");
-  const size_t copy = header_only ? vlc_data_offset(c->S) : std::min(c->bits_out_cap, vlc_data_offset(c->S) + c->bits_budget);
-  if ((rc = ensure_host_bits(c, slot, copy))) return rc;
-  CU(cudaMemcpyAsync(c->h_bits_out[slot], c->d_bits_out[slot], copy, cudaMemcpyDeviceToHost, c->s_d2h));
-  CU(cudaEventRecord(c->ev_d2h[slot], c->s_d2h));
-  c->slot_copied[slot] = copy;
+  // The download of this step is not started now but when the NEXT step's upload has finished (or at p64b_ctx_wait_bits, if no
+  // further step was submitted): a download that falls into the last part of an upload slows that upload down (measured on
+  // one B200: 340 k -> 357 k frames/s end to end, 0.94 -> 0.985 of the upload bound), one that starts
+  // together with an upload does not.  P64B_D2H_IMMEDIATE=1 restores the immediate download (attribution only).
+  static const bool defer = getenv("P64B_D2H_IMMEDIATE") == nullptr;
+  if (defer) c->pending_d2h = slot;
+  else if ((rc = issue_bits_download(c, slot))) return rc;
   c->slot_used[slot] = true;
   c->slot_bits[slot] = true;
   *ticket = c->submitted++;
@@ -957,7 +975,12 @@ extern "C" int p64b_ctx_wait_bits(p64b_ctx* c, int64_t ticket, p64b_bits_out* ou
   int rc;
   if ((rc = use_device(c))) return rc;
   const int slot = (int)(ticket % p64b_ctx::NSLOT);
-  if (!c->slot_bits[slot] || !c->h_bits_out[slot]) { set_error("ticket was not issued by p64b_ctx_submit_bits"); return P64B_EINVAL; }
+  if (!c->slot_bits[slot]) { set_error("ticket was not issued by p64b_ctx_submit_bits"); return P64B_EINVAL; }
+  if (c->pending_d2h == slot) {              // nobody submitted a further step: download now
+    if ((rc = issue_bits_download(c, slot))) return rc;
+    c->pending_d2h = -1;
+  }
+  if (!c->h_bits_out[slot]) { set_error("ticket was not issued by p64b_ctx_submit_bits"); return P64B_EINVAL; }
   CU(cudaEventSynchronize(c->ev_d2h[slot]));
   const size_t doff = vlc_data_offset(c->S);
   size_t total = reinterpret_cast<const uint32_t*>(c->h_bits_out[slot])[c->S];
