@@ -77,7 +77,8 @@ struct p64b_ctx {
   bool me_attr_done = false, mb_attr_done = false, dec_attr_done = false;   // per context: function attributes are per device
   int n_sm = 0;
   uint32_t* d_me_queue = nullptr;   // [2] work counters of the persistent ME kernel (alternating per launch)
-  int64_t me_launches = 0;
+  int64_t me_launches = 0, vlc_launches = 0;
+  int vlc_ctas_per_sm = 0;
   // device-side entropy coding (p64b_ctx_submit_bits / p64b_ctx_wait_bits), allocated on first use
   DevVlcTables* d_vlc_tables = nullptr;
   uint32_t* d_gob_words = nullptr;          // [S][ngob][VLC_GOB_WORDS] GOB bit strings
@@ -678,6 +679,20 @@ static void free_bits_buffers(p64b_ctx* c) {
   for (int i = 0; i < p64b_ctx::NSLOT; i++) { cudaFree(c->d_bits_out[i]); c->d_bits_out[i] = nullptr; }
 }
 
+// Launch shape of the fixed-quantiser entropy kernel: as many CTAs as are resident at once (the warps take pieces from a queue),
+// and this launch's queue counter (the kernel zeroes the other one for the next launch, like the motion search's).
+static int vlc_seq_grid(p64b_ctx* c, VlcArgs* a, int* grid) {
+  if (!c->vlc_ctas_per_sm) {
+    if (!c->n_sm) CU(cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, c->device));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->vlc_ctas_per_sm, vlc_gob_seq_kernel, VLC_SEQ_THREADS, 0));
+    if (c->vlc_ctas_per_sm < 1) c->vlc_ctas_per_sm = 1;
+  }
+  const int tasks = c->S * c->g.ngob * VLC_PPG;
+  *grid = std::min((tasks + VLC_SEQ_WARPS - 1) / VLC_SEQ_WARPS, c->n_sm * c->vlc_ctas_per_sm);
+  a->queue = c->d_me_queue + 8; a->parity = (int)(c->vlc_launches++ & 1);
+  return 0;
+}
+
 static int ensure_bits_buffers(p64b_ctx* c) {
   if (c->d_vlc_tables) return 0;          // allocated last: set only when every buffer exists (a failure below frees them all)
   const size_t S = (size_t)c->S, ng = (size_t)c->g.ngob;
@@ -689,7 +704,7 @@ static int ensure_bits_buffers(p64b_ctx* c) {
   if (cudaMalloc((void**)&(p), (bytes)) != cudaSuccess) { (p) = nullptr; free_bits_buffers(c); set_error("cudaMalloc failed (bit-stream buffers)"); return P64B_ENOMEM; } \
   if (cudaMemsetAsync((p), 0, (bytes), c->stream) != cudaSuccess) { free_bits_buffers(c); set_error("cudaMemset failed"); return P64B_ECUDA; }
   ALLOCZ(c->d_gob_words, S * ng * VLC_GOB_WORDS * 4);
-  ALLOCZ(c->d_gob_bits, S * ng * 4);
+  ALLOCZ(c->d_gob_bits, S * ng * VLC_PPG * 4);
   ALLOCZ(c->d_carry, S * 4);
   ALLOCZ(c->d_carry_len, S * 4);
   ALLOCZ(c->d_bitpos, S * 8);
@@ -768,7 +783,7 @@ static int enqueue_rc_frame(p64b_ctx* c, const p64b_step* st, int slot, VlcArgs 
   {
     ProfScope ps(c, 2);
     vlc_sizes_kernel<<<1, 1024, 0, c->stream>>>(f);
-    vlc_frame_kernel<<<c->S, VLC_THREADS, 0, c->stream>>>(f);
+    vlc_frame_kernel<<<c->S, VLC_FRAME_THREADS, 0, c->stream>>>(f);
   }
   c->launches += 3;
   CU(cudaGetLastError());
@@ -854,9 +869,13 @@ extern "C" int p64b_ctx_submit_bits(p64b_ctx* c, const p64b_step* st, int tempor
                  ((uint64_t)(c->image_type == P64B_IT_QCIF ? 0x00 : 0x04) << 33);
     f.pic_hdr_bits = 32;
     if (c->image_type == P64B_IT_NTSC) { h |= (1ull << 32) | (0x8cull << 24); f.pic_hdr_bits = 41; }
-    f.pic_hdr = c->d_pic_hdr + 2 * slot;
-    set_pic_hdr_kernel<<<1, 1, 0, c->stream>>>(c->d_pic_hdr + 2 * slot, (uint32_t)(h >> 32), (uint32_t)h);
-    c->launches++;
+    if (c->rate.rate) {
+      f.pic_hdr = c->d_pic_hdr + 2 * slot;
+      set_pic_hdr_kernel<<<1, 1, 0, c->stream>>>(c->d_pic_hdr + 2 * slot, (uint32_t)(h >> 32), (uint32_t)h);
+      c->launches++;
+    } else {
+      f.pic_hdr = nullptr; f.pic_hdr_imm[0] = (uint32_t)(h >> 32); f.pic_hdr_imm[1] = (uint32_t)h;
+    }
   }
   f.gob_words = c->d_gob_words; f.gob_bits = c->d_gob_bits; f.carry = c->d_carry; f.carry_len = c->d_carry_len;
   f.bitpos = c->d_bitpos; f.out = c->d_bits_out[slot]; f.n_streams = c->S; f.ngob = c->g.ngob; f.gquant = st->gquant;
@@ -867,10 +886,13 @@ extern "C" int p64b_ctx_submit_bits(p64b_ctx* c, const p64b_step* st, int tempor
   if (!c->rate.rate) {
     if ((rc = p64b_ctx_encode_frames_dev(c, st, c->p_src[slot], c->p_mbs[slot], c->p_levels[slot]))) return rc;
     a.gob_first = 0; a.gob_count = c->g.ngob;
+    f.ppg = VLC_PPG;
+    int grid;
+    if ((rc = vlc_seq_grid(c, &a, &grid))) return rc;
     ProfScope ps(c, 2);
-    vlc_gob_seq_kernel<<<(c->S * c->g.ngob + VLC_SEQ_WARPS - 1) / VLC_SEQ_WARPS, VLC_SEQ_THREADS, 0, c->stream>>>(a);
+    vlc_gob_seq_kernel<<<grid, VLC_SEQ_THREADS, 0, c->stream>>>(a);
     vlc_sizes_kernel<<<1, 1024, 0, c->stream>>>(f);
-    vlc_frame_kernel<<<c->S, VLC_THREADS, 0, c->stream>>>(f);
+    vlc_frame_kernel<<<c->S, VLC_FRAME_THREADS, 0, c->stream>>>(f);
     c->launches += 3;
     CU(cudaGetLastError());
   } else {
@@ -951,8 +973,7 @@ extern "C" int p64b_ctx_encode_bits_dev(p64b_ctx* c, const p64b_step* st, int te
   uint64_t h = (0x10ull << 44) | ((uint64_t)(temporal_reference & 31) << 39) | ((uint64_t)(c->image_type == P64B_IT_QCIF ? 0x00 : 0x04) << 33);
   f.pic_hdr_bits = 32;
   if (c->image_type == P64B_IT_NTSC) { h |= (1ull << 32) | (0x8cull << 24); f.pic_hdr_bits = 41; }
-  f.pic_hdr = c->d_pic_hdr;
-  set_pic_hdr_kernel<<<1, 1, 0, c->stream>>>(c->d_pic_hdr, (uint32_t)(h >> 32), (uint32_t)h);
+  f.pic_hdr = nullptr; f.pic_hdr_imm[0] = (uint32_t)(h >> 32); f.pic_hdr_imm[1] = (uint32_t)h;
   f.gob_words = c->d_gob_words; f.gob_bits = c->d_gob_bits; f.carry = c->d_carry; f.carry_len = c->d_carry_len;
   f.bitpos = c->d_bitpos; f.out = c->d_bits_out[0]; f.n_streams = c->S; f.ngob = c->g.ngob; f.gquant = st->gquant;
   VlcArgs a{};
@@ -961,11 +982,14 @@ extern "C" int p64b_ctx_encode_bits_dev(p64b_ctx* c, const p64b_step* st, int te
   a.n_streams = c->S; a.ngob = c->g.ngob; a.nmb = c->g.nmb; a.qcif = c->g.qcif; a.gquant = st->gquant;
   a.gob_first = 0; a.gob_count = c->g.ngob;
   if ((rc = p64b_ctx_encode_frames_dev(c, st, src_dev, c->p_mbs[0], c->p_levels[0]))) return rc;
+  f.ppg = VLC_PPG;
+  int grid;
+  if ((rc = vlc_seq_grid(c, &a, &grid))) return rc;
   ProfScope ps(c, 2);
-  vlc_gob_seq_kernel<<<(c->S * c->g.ngob + VLC_SEQ_WARPS - 1) / VLC_SEQ_WARPS, VLC_SEQ_THREADS, 0, c->stream>>>(a);
+  vlc_gob_seq_kernel<<<grid, VLC_SEQ_THREADS, 0, c->stream>>>(a);
   vlc_sizes_kernel<<<1, 1024, 0, c->stream>>>(f);
-  vlc_frame_kernel<<<c->S, VLC_THREADS, 0, c->stream>>>(f);
-  c->launches += 4;
+  vlc_frame_kernel<<<c->S, VLC_FRAME_THREADS, 0, c->stream>>>(f);
+  c->launches += 3;
   CU(cudaGetLastError());
   return 0;
 }

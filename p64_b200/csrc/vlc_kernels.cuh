@@ -27,7 +27,16 @@ constexpr int VLC_PIECES = 1 + 33 * 7;                  // GOB header + 33 x (MB
 constexpr int VLC_THREADS = 256;
 constexpr int VLC_BLOCK_MAX_BITS = 8 + 63 * 20 + 2;     // intra DC + 63 escapes + EOB
 constexpr int VLC_MBHDR_MAX_BITS = 1 + 10 + 5 + 11 + 11 + 9;
-constexpr int VLC_GOB_WORDS = (26 + 33 * (VLC_MBHDR_MAX_BITS + 6 * VLC_BLOCK_MAX_BITS) + 31) / 32 + 8;   // slot size, words
+// The fixed-quantiser kernel writes a GOB as VLC_PPG independent pieces of 4, 4 and 3 macroblocks per macroblock row; the frame
+// kernel concatenates pieces exactly as it concatenates whole GOBs (rate control: one piece per GOB).  Piece `pc` starts at
+// macroblock vlc_piece_m0(pc) of the GOB and at word m0 * VLC_MB_WORDS of the GOB's slot.
+constexpr int VLC_PPG = 9;
+__host__ __device__ constexpr int vlc_piece_m0(int pc) { return 11 * (pc / 3) + 4 * (pc % 3); }
+__host__ __device__ constexpr int vlc_piece_n(int pc) { return pc % 3 == 2 ? 3 : 4; }
+constexpr int VLC_MB_WORDS = (VLC_MBHDR_MAX_BITS + 6 * VLC_BLOCK_MAX_BITS) / 32 + 4;   // n >= 1 macroblocks + the GOB header + a partial and a look-ahead word fit n of these
+static_assert((26 + (VLC_MBHDR_MAX_BITS + 6 * VLC_BLOCK_MAX_BITS) + 31) / 32 + 1 <= VLC_MB_WORDS, "a piece fits its part of the slot");
+constexpr int VLC_GOB_WORDS_1 = (26 + 33 * (VLC_MBHDR_MAX_BITS + 6 * VLC_BLOCK_MAX_BITS) + 31) / 32 + 8;
+constexpr int VLC_GOB_WORDS = VLC_GOB_WORDS_1 > 33 * VLC_MB_WORDS ? VLC_GOB_WORDS_1 : 33 * VLC_MB_WORDS;   // slot size, words
 constexpr int VLC_PIC_HDR_MAX_BITS = 41;
 
 // Rate control on the device ("exact per-MB bit counts on device let GQUANT selection and the overflow
@@ -66,8 +75,10 @@ struct VlcArgs {
   const DevVlcTables* tables;
   const p64b_mb* mbs;        // [S][nmb] GOB-major
   const int8_t* levels;      // [S][nmb][6][64] transmission order
-  uint32_t* gob_words;       // [S][ngob][VLC_GOB_WORDS] scratch
-  uint32_t* gob_bits;        // [S][ngob]
+  uint32_t* gob_words;       // [S][ngob][VLC_GOB_WORDS] scratch; the fixed-quantiser kernel puts piece pc at vlc_piece_m0(pc) * VLC_MB_WORDS of the slot
+  uint32_t* gob_bits;        // [S][ngob] (rate control) or [S][ngob][VLC_PPG]
+  uint32_t* queue;           // [2] piece counters of the fixed-quantiser kernel: this launch takes from queue[parity], zeroes the other
+  int parity;
   int n_streams, ngob, nmb;
   int qcif;                  // GOB numbers 1,3,5 (p64.c:709-711)
   int gquant;                // GQUANT of every stream when rc.rate == 0
@@ -188,40 +199,33 @@ __device__ __forceinline__ uint64_t vlc_mb_header(const p64b_mb& r, const p64b_m
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
-// Fixed quantiser (round 2): ONE WARP PER GOB, macroblock after macroblock, one ITEM per lane.
-// A macroblock's bit string is a header followed by items in a fixed order: per coded block [intra DC], the non-zero levels in
-// transmission order, [EOB].  The warp that owns a GOB knows the bit position it has reached, so nothing has to be measured
-// first and placed later: per macroblock
-//   list   lanes 1..24 (block b, quarter q) stage their 16 levels in shared memory and write the descriptors of their items
-//          (block | kind | position) into the warp's list at positions given by a warp scan of the counts: stream order;
+// Fixed quantiser (round 2): a GOB is written as VLC_PPG independent PIECES of 4, 4 and 3 macroblocks per macroblock row
+// (a macroblock's bits depend on nothing but its own record and its left neighbour's vector: MBA is always 1, the
+// quantiser is fixed); ONE WARP codes a piece in ONE pass, one ITEM per lane.
+// A piece's bit string is, per macroblock, the header followed by items in a fixed order: per coded block [intra DC], the
+// non-zero levels in transmission order, [EOB].  The header counts as two more items (its bits above and below bit 32).
+//   list   lane 6j+b (macroblock j of the piece, block b) holds the block's 64 levels: it stages them in shared memory
+//          and writes the descriptors of its items (lane | kind | position) into the warp's list at the position a warp
+//          scan of the counts gives: stream order; lanes 24+j build the headers (WriteMBHeader, marker.c:288-354);
 //   code   lane k takes item k, 32 at a time: the run comes from the previous descriptor, the code from the table in shared
 //          memory (codec.c:96-205: escapes as in 113-115, the two-bit code for a leading +-1 of a CBP-coded block; EncodeDC
-//          codec.c:346-355); a warp scan of the lengths places the items behind the header;
+//          codec.c:346-355); a warp scan of the lengths places the items;
 //   emit   every lane ORs its item into a 64-word ring in shared memory; the words the position has passed are stored to the
-//          GOB's scratch slot and zeroed.
-// The next macroblock's record and levels are loaded while the current one is coded.  No CTA-wide barrier after the table
-// load, no image of the GOB in shared memory (1.9 KB per warp instead of 34 KB per CTA), every level is looked at once.
-// Measured on 256 CIF frames: 57.9 M warp-instructions, 0.108 ms (profiles/r02_ncu_vlc_gob_seq_kernel.txt).
-// The thread-per-piece kernel below (round 1) measures every piece, scans, and walks the levels again to write them, waiting
-// for the busiest block of every warp in both walks and at five CTA barriers: 71 M warp-instructions per 256 CIF frames,
-// 0.116 ms.  It remains the rate-control kernel (one GOB per stream per launch: 256 GOBs cannot feed 148 SMs with one warp
-// each).  Two CTA-per-GOB re-mappings tried on the way were no faster than it (a lane per block quarter: the zig-zag order
-// puts the non-zero levels into the first quarter, 121 M / 0.149 ms; an item per lane with the codes kept in registers between
-// a measuring and an emitting phase: 70 M / 0.116 ms, 3.9 barrier stalls per issue) -- profiles/r02_ncu_vlc_gob_kernel_*.
+//          piece's scratch slot and zeroed.
+// The warps of a resident grid take pieces from a queue.  Every level is looked at once, nothing is measured first and
+// placed later, no CTA-wide barrier after the table load.
+// History (256 CIF frames per launch): thread per (GOB header | MB header | block), measure / scan / write: 71 M
+// warp-instructions, 0.116 ms (round 1; still the rate-control kernel, one GOB per stream per launch).  One warp per GOB,
+// macroblock after macroblock, lane per block quarter for the list: 57.9 M, 0.108 ms at 21 warps per SM (3 072 GOBs).  The same
+// per piece of 3 macroblocks from a queue: 61 M, 0.090 ms.  This kernel: the list, the headers and the scans are shared by
+// 4 macroblocks, the item rounds are full (profiles/r02_ncu_vlc_gob_seq_kernel*.txt).
 constexpr int VLC_SEQ_WARPS = 4;
 constexpr int VLC_SEQ_THREADS = 32 * VLC_SEQ_WARPS;
-constexpr int VLC_ITEMS_MAX = 6 * 66;                   // per macroblock: 6 x (DC or position 0, 63 levels, EOB) at most
-constexpr int VLC_RING = 64;                            // words; one sub-round adds at most 47 + 32 x 20 bits = 22 words
+constexpr int VLC_PASS_MBS = 4;
+constexpr int VLC_ITEMS_MAX = VLC_PASS_MBS * (6 * 65 + 2);   // per block: DC or position 0, 63 levels, EOB; + the header halves
+constexpr int VLC_RING = 64;                            // words; one round adds at most 4 x 47 + 32 x 20 bits = 26 words
 
-// list: stages the macroblock's levels and writes its item descriptors in stream order; returns the number of items
-__device__ __forceinline__ int vlc_list_items(const p64b_mb& rec, uint4 v, int lane, uint8_t* stage, uint16_t* items) {
-  const int mt = rec.mtype;
-  const bool cbp_type = vt(V_CBP, mt);
-  const int b = (lane - 1) >> 2, q = (lane - 1) & 3;
-  const bool blk = lane >= 1 && lane <= 24;
-  const bool coded = blk && vt(V_TCOEF, mt) && ((rec.cbp >> (5 - b)) & 1);
-  if (!coded) v = make_uint4(0, 0, 0, 0);               // (the levels were loaded before the record was known)
-  if (blk) *reinterpret_cast<uint4*>(stage + (lane - 1) * 16) = v;
+__device__ __forceinline__ uint32_t vlc_nz16(uint4 v) {      // bit k = byte k of the 16 is non-zero
   const uint32_t w[4] = {v.x, v.y, v.z, v.w};
   uint32_t nz = 0;
 #pragma unroll
@@ -229,143 +233,178 @@ __device__ __forceinline__ int vlc_list_items(const p64b_mb& rec, uint4 v, int l
     const uint32_t hi = (w[j] | ((w[j] & 0x7f7f7f7fu) + 0x7f7f7f7fu)) & 0x80808080u;     // bit 7 of every non-zero byte
     nz |= ((((hi >> 7) * 0x01020408u) >> 24) & 0xfu) << (4 * j);
   }
-  if (q == 0 && !cbp_type) nz &= ~1u;                      // the intra DC is its own item
-  const uint32_t anym = __ballot_sync(0xffffffffu, coded && nz != 0);
-  const bool dc = coded && q == 0 && !cbp_type;
-  const bool eob = coded && q == 3 && (!cbp_type || ((anym >> (1 + 4 * b)) & 0xfu));       // an all-zero CBP block gets no EOB (codec.c:169-174)
-  const int cnt = __popc(nz) + (dc ? 1 : 0) + (eob ? 1 : 0);
-  int x = cnt;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
-  const int total = __shfl_sync(0xffffffffu, x, 31);
-  int idx = x - cnt;
-  const uint32_t base = (uint32_t)b << 8;
-  if (dc) items[idx++] = (uint16_t)(base | (1u << 6));
-  while (nz) {
-    const int pl = __ffs((int)nz) - 1;
-    nz &= nz - 1;
-    items[idx++] = (uint16_t)(base | (uint32_t)(16 * q + pl));
-  }
-  if (eob) items[idx++] = (uint16_t)(base | (2u << 6) | 63u);
-  __syncwarp();
-  return total;
+  return nz;
 }
-
-// code: item k of the list -> (code bits, length)
-__device__ __forceinline__ void vlc_code_item(int k, int total, const uint16_t* items, const uint8_t* stage, const uint32_t* s_tcoef,
-                                              uint32_t& code, int& len) {
-  code = 0; len = 0;
-  if (k >= total) return;
-  const uint32_t d = items[k];
-  const int b = (int)(d >> 8), kind = (int)((d >> 6) & 3u), p = (int)(d & 63u);
-  if (kind == 1) {                                     // EncodeDC, codec.c:346-355
-    int dc = stage[b * 64];
-    dc = min(max(dc, 1), 254);
-    if (dc == 128) dc = 255;
-    code = (uint32_t)dc; len = 8;
-  } else if (kind == 2) {                              // EOB "10"
-    code = 2u; len = 2;
-  } else {
-    const int v = (int)(int8_t)stage[b * 64 + p], a = abs(v);
-    int prevp = -1;                                    // the previous item of the same block is its DC (position 0) or a level
-    if (k > 0) { const uint32_t pd = items[k - 1]; if ((int)(pd >> 8) == b) prevp = (int)(pd & 63u); }
-    const int run = p - prevp - 1;
-    if (p == 0 && a == 1) {                            // "1s": a leading +-1 of a CBP-coded block (only those list position 0)
-      code = 2u | (uint32_t)(v < 0); len = 2;
-    } else {
-      const uint32_t e = (run < 32 && a < 16) ? s_tcoef[run * 16 + a] : 0u;
-      if (e) { len = (int)(e >> 16) + 1; code = ((e & 0xffffu) << 1) | (uint32_t)(v < 0); }
-      else { code = (1u << 14) | ((uint32_t)run << 8) | (uint32_t)(v & 0xff); len = 20; }     // escape (codec.c:113-115)
-    }
-  }
-}
-
-
-// OR `n` bits (n <= 32, v < 2^n) into the ring of VLC_RING zeroed words that holds the MSB-first GOB string around the ABSOLUTE
+// OR `n` bits (n <= 32, v < 2^n) into the ring of VLC_RING zeroed words that holds the MSB-first string around the ABSOLUTE
 // bit offset `o`
 __device__ __forceinline__ void vlc_or_ring(uint32_t* ring, uint32_t o, uint32_t v, int n) {
-  if (!n) return;
   const uint32_t w = o >> 5;
-  const int sh = (int)(o & 31), over = sh + n - 32;
-  if (over <= 0) atomicOr(ring + (w & (VLC_RING - 1)), v << (-over));
-  else { atomicOr(ring + (w & (VLC_RING - 1)), v >> over); atomicOr(ring + ((w + 1) & (VLC_RING - 1)), v << (32 - over)); }
+  const uint64_t win = (uint64_t)v << ((64 - (int)(o & 31) - n) & 63);     // the bits in the 64-bit window that starts at word w (n = 0: v = 0)
+  const uint32_t hi = (uint32_t)(win >> 32), lo = (uint32_t)win;
+  if (hi) atomicOr(ring + (w & (VLC_RING - 1)), hi);
+  if (lo) atomicOr(ring + ((w + 1) & (VLC_RING - 1)), lo);
 }
 
-__global__ void __launch_bounds__(VLC_SEQ_THREADS)
+// next piece of the launch's queue, taken by lane 0 (the same predicated per-lane-address atomic as the motion search's queue:
+// a plain atomicAdd is warp-aggregated and its result broadcast waits for the atomic at once)
+__device__ __forceinline__ uint32_t vlc_queue_take(uint32_t* counter, int lane) {
+  uint32_t t = 0;
+  asm volatile("{\n.reg .pred p;\nsetp.eq.s32 p, %2, 0;\n@p atom.global.add.u32 %0, [%1], 1;\n}" : "+r"(t) : "l"(counter + lane), "r"(lane) : "memory");
+  return t;
+}
+
+#ifndef P64B_VLC_MIN_CTAS
+#define P64B_VLC_MIN_CTAS 1
+#endif
+__global__ void __launch_bounds__(VLC_SEQ_THREADS, P64B_VLC_MIN_CTAS)
 vlc_gob_seq_kernel(const __grid_constant__ VlcArgs a) {
   __shared__ DevVlcTables s_t;
-  __shared__ __align__(16) uint8_t s_stage[VLC_SEQ_WARPS][384];
-  __shared__ uint16_t s_items[VLC_SEQ_WARPS][VLC_ITEMS_MAX + 4];
+  __shared__ __align__(16) uint8_t s_stage[VLC_SEQ_WARPS][24 * 64];
+  __shared__ uint16_t s_items[VLC_SEQ_WARPS][VLC_ITEMS_MAX + 8];
   __shared__ uint32_t s_ring[VLC_SEQ_WARPS][VLC_RING];
+  __shared__ uint2 s_lit[VLC_SEQ_WARPS][24 * 4];      // (bits, length) of the items that are not levels: per block-lane DC, header above bit 32, header low 32 bits, EOB
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (blockIdx.x == 0 && tid == 0) a.queue[a.parity ^ 1] = 0;     // the next launch's counter
   for (int i = tid; i < DEV_VLC_WORDS; i += VLC_SEQ_THREADS) reinterpret_cast<uint32_t*>(&s_t)[i] = reinterpret_cast<const uint32_t*>(a.tables)[i];
   for (int i = lane; i < VLC_RING; i += 32) s_ring[warp][i] = 0;
-  __syncthreads();
-  const int task = blockIdx.x * VLC_SEQ_WARPS + warp;
-  if (task >= a.n_streams * a.gob_count) return;        // (no barrier below)
-  const int s = task / a.gob_count, gob = a.gob_first + task % a.gob_count;
-  const size_t mb0 = (size_t)s * a.nmb + gob * 33;
+  __syncthreads();                                      // (no barrier below)
+  const int n_tasks = a.n_streams * a.gob_count * VLC_PPG, n_workers = (int)gridDim.x * VLC_SEQ_WARPS;
   uint8_t* stage = s_stage[warp];
   uint16_t* items = s_items[warp];
   uint32_t* ring = s_ring[warp];
-  uint32_t* dst = a.gob_words + ((size_t)s * a.ngob + gob) * VLC_GOB_WORDS;
-  const int8_t* lv0 = a.levels + mb0 * P64B_LEVELS_PER_MB;
-  const bool blk = lane >= 1 && lane <= 24;
-
-  uint32_t pos = 26, wbase = 0;                        // bits written so far; first word of the GOB string still in the ring
-  if (lane == 0) {                                     // WriteGOBHeader, marker.c:182-209: GBSC, GN, GQUANT, no GSPARE
-    const int gn = (a.qcif ? (gob << 1) : gob) + 1;
-    vlc_or_ring(ring, 0, (1u << 10) | ((uint32_t)gn << 6) | ((uint32_t)a.gquant << 1), 26);
-  }
-  // the words [wbase, pos / 32) are final: store them and hand their ring slots back
-  auto flush = [&]() {
-    __syncwarp();
-    const uint32_t n = (pos >> 5) - wbase;              // <= 23 < 32
-    if ((uint32_t)lane < n) { const uint32_t w = wbase + (uint32_t)lane; dst[w] = ring[w & (VLC_RING - 1)]; ring[w & (VLC_RING - 1)] = 0; }
-    wbase += n;
-    __syncwarp();
-  };
-  p64b_mb prev{};
-  uint2 rec_next = __ldg(reinterpret_cast<const uint2*>(a.mbs + mb0));
-  uint4 lv_next = make_uint4(0, 0, 0, 0);
-  if (blk) lv_next = __ldg(reinterpret_cast<const uint4*>(lv0 + (lane - 1) * 16));
+  uint2* lit = s_lit[warp];
+  const int j = lane < 24 ? lane / 6 : lane - 24, b = lane - 6 * j;       // lanes 0..23: block b of macroblock j; 24..27: header of j
+  int task = blockIdx.x * VLC_SEQ_WARPS + warp;         // first piece: static; the rest come from the queue
+  uint32_t ticket = vlc_queue_take(a.queue + a.parity, lane);
 #pragma unroll 1
-  for (int m = 0; m < 33; m++) {
-    const uint2 rw = rec_next;
-    const uint4 lv = lv_next;
-    if (m + 1 < 33) {                                   // the next macroblock's record and levels: in flight while this one is coded
-      rec_next = __ldg(reinterpret_cast<const uint2*>(a.mbs + mb0 + m + 1));
-      if (blk) lv_next = __ldg(reinterpret_cast<const uint4*>(lv0 + (size_t)(m + 1) * P64B_LEVELS_PER_MB + (lane - 1) * 16));
+  while (task < n_tasks) {
+    const int task_next = n_workers + (int)__shfl_sync(0xffffffffu, ticket, 0);
+    if (task_next < n_tasks) ticket = vlc_queue_take(a.queue + a.parity, lane);
+    const int pc = task % VLC_PPG, sg = task / VLC_PPG;
+    const int s = sg / a.gob_count, gob = a.gob_first + sg % a.gob_count;
+    const int m0 = vlc_piece_m0(pc), nm = vlc_piece_n(pc);
+    const size_t mb0 = (size_t)s * a.nmb + gob * 33 + m0;
+    uint32_t* dst = a.gob_words + ((size_t)s * a.ngob + gob) * VLC_GOB_WORDS + m0 * VLC_MB_WORDS;
+
+    // ---- loads: the macroblock's record; lanes 0..23 their block's levels; lanes 24..27 the left neighbour's record
+    const bool mine = j < nm;
+    p64b_mb rec{}, prev{};
+    uint4 lv[4] = {};
+    if (mine) {
+      const uint2 rw = __ldg(reinterpret_cast<const uint2*>(a.mbs + mb0 + j));
+      rec = *reinterpret_cast<const p64b_mb*>(&rw);
+      if (lane >= 24) {
+        if (m0 + j) { const uint2 pw = __ldg(reinterpret_cast<const uint2*>(a.mbs + mb0 + j - 1)); prev = *reinterpret_cast<const p64b_mb*>(&pw); }
+      } else {
+        const uint4* lp = reinterpret_cast<const uint4*>(a.levels + (mb0 + j) * P64B_LEVELS_PER_MB + b * 64);
+#pragma unroll
+        for (int i = 0; i < 4; i++) lv[i] = __ldg(lp + i);
+      }
     }
-    const p64b_mb rec = *reinterpret_cast<const p64b_mb*>(&rw);
-    int hl;
-    const uint64_t hb = vlc_mb_header(rec, prev, m, &s_t, &hl);
-    prev = rec;
-    if (lane == 0) {
-      if (hl > 32) { vlc_or_ring(ring, pos, (uint32_t)(hb >> 32), hl - 32); vlc_or_ring(ring, pos + (uint32_t)(hl - 32), (uint32_t)hb, 32); }
-      else vlc_or_ring(ring, pos, (uint32_t)hb, hl);
+    uint32_t pos = 0, wbase = 0;                         // bits written so far; first word of the piece's string still in the ring
+    if (m0 == 0) {                                       // WriteGOBHeader, marker.c:182-209: GBSC, GN, GQUANT, no GSPARE
+      const int gn = (a.qcif ? (gob << 1) : gob) + 1;
+      if (lane == 0) vlc_or_ring(ring, 0, (1u << 10) | ((uint32_t)gn << 6) | ((uint32_t)a.gquant << 1), 26);
+      pos = 26;
     }
-    pos += (uint32_t)hl;
-    const int total = vlc_list_items(rec, lv, lane, stage, items);
-    if (total == 0) flush();
+    // the words [wbase, pos / 32) are final: store them and hand their ring slots back
+    auto flush = [&]() {
+      __syncwarp();
+      const uint32_t n = (pos >> 5) - wbase;              // <= 32
+      if ((uint32_t)lane < n) { const uint32_t w = wbase + (uint32_t)lane; dst[w] = ring[w & (VLC_RING - 1)]; ring[w & (VLC_RING - 1)] = 0; }
+      wbase += n;
+      __syncwarp();
+    };
+    // ---- list
+    const int mt = rec.mtype;
+    const bool cbp_type = vt(V_CBP, mt);
+    const bool coded = mine && lane < 24 && vt(V_TCOEF, mt) && ((rec.cbp >> (5 - b)) & 1);
+    uint32_t nzl = 0, nzh = 0;
+    if (lane >= 24) {
+      if (mine) {
+        int hl;
+        const uint64_t hb = vlc_mb_header(rec, prev, m0 + j, &s_t, &hl);
+        lit[24 * j + 1] = make_uint2((uint32_t)(hb >> 32), (uint32_t)max(hl - 32, 0));
+        lit[24 * j + 2] = make_uint2((uint32_t)hb, (uint32_t)min(hl, 32));
+      }
+    } else {
+      if (!coded) { lv[0] = lv[1] = lv[2] = lv[3] = make_uint4(0, 0, 0, 0); }      // (the levels were loaded before the record was known)
+#pragma unroll
+      for (int i = 0; i < 4; i++) *reinterpret_cast<uint4*>(stage + lane * 64 + i * 16) = lv[i];
+      nzl = vlc_nz16(lv[0]) | (vlc_nz16(lv[1]) << 16);
+      nzh = vlc_nz16(lv[2]) | (vlc_nz16(lv[3]) << 16);
+    }
+    const bool dc = coded && !cbp_type;
+    if (dc) {                                              // the intra DC is its own item: EncodeDC, codec.c:346-355
+      nzl &= ~1u;
+      int v = (int)(lv[0].x & 0xffu);
+      v = min(max(v, 1), 254);
+      if (v == 128) v = 255;
+      lit[4 * lane] = make_uint2((uint32_t)v, 8u);
+    }
+    const bool eob = coded && (!cbp_type || (nzl | nzh));  // an all-zero CBP block gets no EOB (codec.c:169-174)
+    if (eob) lit[4 * lane + 3] = make_uint2(2u, 2u);       // "10"
+    const bool head = mine && lane < 24 && b == 0;         // the macroblock's header goes in front of its first block
+    const int cnt = __popc(nzl) + __popc(nzh) + (dc ? 1 : 0) + (eob ? 1 : 0) + (head ? 2 : 0);
+    int x = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+    const int total = __shfl_sync(0xffffffffu, x, 31);
+    {
+      int idx = x - cnt;
+      const uint32_t base = (uint32_t)lane << 8;
+      if (head) { items[idx++] = (uint16_t)(base | 0xc0u); items[idx++] = (uint16_t)(base | 0xc1u); }
+      if (dc) items[idx++] = (uint16_t)(base | 0x80u);
+      while (nzl) { const int pl = __ffs((int)nzl) - 1; nzl &= nzl - 1; items[idx++] = (uint16_t)(base | (uint32_t)pl); }
+      while (nzh) { const int pl = __ffs((int)nzh) - 1; nzh &= nzh - 1; items[idx++] = (uint16_t)(base | 32u | (uint32_t)pl); }
+      if (eob) items[idx++] = (uint16_t)(base | 0xc2u);
+    }
+    __syncwarp();
+    // ---- code + emit, 32 items at a time
 #pragma unroll 1
     for (int k0 = 0; k0 < total; k0 += 32) {
-      uint32_t code; int len;
-      vlc_code_item(k0 + lane, total, items, stage, s_t.tcoef, code, len);
-      int x = len;
+      const int k = k0 + lane;
+      uint32_t code = 0; int len = 0;
+      if (k < total) {
+        // descriptors: a level = lane << 8 | position; the others have bit 7 set: DC 0x80 (as a predecessor it reads as
+        // position 0), header halves 0xc0 / 0xc1, EOB 0xc2 -- their bits come from `lit`
+        const uint32_t d = items[k];
+        const int L = (int)(d >> 8);
+        if (d & 0x80u) {
+          const uint2 t = lit[4 * L + (int)(d & 3u) + (int)((d >> 6) & 1u)];
+          code = t.x; len = (int)t.y;
+        } else {
+          const int p = (int)(d & 63u);
+          const int v = (int)(int8_t)stage[L * 64 + p], av = abs(v);
+          const uint32_t pd = items[k - 1];                // (item 0 is a header half: k > 0 here)
+          const int prevp = ((int)(pd >> 8) == L && !(pd & 0x40u)) ? (int)(pd & 63u) : -1;     // the block's DC or previous level
+          const int run = p - prevp - 1;
+          if (p == 0 && av == 1) {                         // "1s": a leading +-1 of a CBP-coded block (only those list position 0)
+            code = 2u | (uint32_t)(v < 0); len = 2;
+          } else {
+            const uint32_t e = (run < 32 && av < 16) ? s_t.tcoef[run * 16 + av] : 0u;
+            if (e) { len = (int)(e >> 16) + 1; code = ((e & 0xffffu) << 1) | (uint32_t)(v < 0); }
+            else { code = (1u << 14) | ((uint32_t)run << 8) | (uint32_t)(v & 0xff); len = 20; }     // escape (codec.c:113-115)
+          }
+        }
+      }
+      int y = len;
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
-      vlc_or_ring(ring, pos + (uint32_t)(x - len), code, len);
-      pos += (uint32_t)__shfl_sync(0xffffffffu, x, 31);
-      flush();
+      for (int d = 1; d < 32; d <<= 1) { const int z = __shfl_up_sync(0xffffffffu, y, d); if (lane >= d) y += z; }
+      vlc_or_ring(ring, pos + (uint32_t)(y - len), code, len);
+      pos += (uint32_t)__shfl_sync(0xffffffffu, y, 31);
+      if ((pos >> 5) - wbase >= 7) flush();               // (a round adds at most 26 words: never more than 32 to store, 59 in the ring)
     }
-  }
-  __syncwarp();
-  const uint32_t nwords = (pos + 31) >> 5;               // the partial last word, + one zero word for the gather's look-ahead
-  if (lane == 0) {
-    if (pos & 31) dst[pos >> 5] = ring[(pos >> 5) & (VLC_RING - 1)];
-    dst[nwords] = 0;
-    a.gob_bits[(size_t)s * a.ngob + gob] = pos;
+    flush();
+    const uint32_t nwords = (pos + 31) >> 5;               // the partial last word, + one zero word for the gather's look-ahead
+    if (lane == 0) {
+      const uint32_t w = (pos >> 5) & (VLC_RING - 1);
+      if (pos & 31) { dst[pos >> 5] = ring[w]; ring[w] = 0; }    // (the ring is all zero again for the warp's next piece)
+      dst[nwords] = 0;
+      a.gob_bits[((size_t)s * a.ngob + gob) * VLC_PPG + pc] = pos;
+    }
+    __syncwarp();
+    task = task_next;
   }
 }
 
@@ -538,8 +577,10 @@ struct VlcFrameArgs {
   unsigned long long* bitpos;  // [S]
   uint8_t* out;                // the step's output buffer (layout above)
   int n_streams, ngob;
+  int ppg = 1;                 // pieces per GOB: 1 with rate control, VLC_PPG without (at vlc_piece_m0() * VLC_MB_WORDS of the slot)
   const uint32_t* pic_hdr;     // [2] picture header bits (MSB first), pic_hdr_bits long -- in device memory, so that a
-                               // captured CUDA graph of the frame step can be replayed with another temporal reference
+                               // captured CUDA graph of the frame step can be replayed with another temporal reference;
+  uint32_t pic_hdr_imm[2];     // NULL: the bits are these (fixed quantiser: nothing is captured)
   int pic_hdr_bits;
   int gquant;                  // reported when rc.rate == 0
   RcArgs rc;
@@ -552,7 +593,8 @@ __device__ __forceinline__ uint32_t* vlc_out_rc(uint8_t* out, int S, int field) 
   return reinterpret_cast<uint32_t*>(out + vlc_bitpos_offset(S) + (size_t)S * 8) + field * S;
 }
 
-// chunk sizes and their packed offsets: one CTA, streams in blocks of blockDim.x with a running base
+// chunk sizes and their packed offsets: one CTA; four threads sum a stream's piece lengths (independent loads), then a scan
+// over the streams, in blocks of blockDim.x / 4 streams with a running base
 __global__ void __launch_bounds__(1024)
 vlc_sizes_kernel(const __grid_constant__ VlcFrameArgs a) {
   __shared__ uint32_t s_w[32];
@@ -560,18 +602,25 @@ vlc_sizes_kernel(const __grid_constant__ VlcFrameArgs a) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint32_t* off = vlc_out_u32(a.out, a.n_streams, 0);
   uint32_t* nb = vlc_out_u32(a.out, a.n_streams, 1);
+  const int np = a.ngob * a.ppg, per = blockDim.x >> 2;
   if (tid == 0) s_base = 0;
   __syncthreads();
-  for (int s0 = 0; s0 < a.n_streams; s0 += blockDim.x) {
-    const int s = s0 + tid;
-    uint32_t bytes = 0;
+  for (int s0 = 0; s0 < a.n_streams; s0 += per) {
+    const int s = s0 + (tid >> 2), q = tid & 3;
+    uint32_t bits = 0;
     if (s < a.n_streams) {
-      uint32_t bits = a.carry_len[s] + (uint32_t)a.pic_hdr_bits;
-      for (int g = 0; g < a.ngob; g++) bits += a.gob_bits[(size_t)s * a.ngob + g];
-      bytes = bits >> 3;
-      nb[s] = bytes;
+      const uint32_t* gb = a.gob_bits + (size_t)s * np;
+#pragma unroll
+      for (int i = 0; i < (12 * VLC_PPG + 3) / 4; i++) if (q + 4 * i < np) bits += gb[q + 4 * i];     // (all in flight at once)
     }
-    uint32_t x = (bytes + 3u) & ~3u;
+    bits += __shfl_xor_sync(0xffffffffu, bits, 1);
+    bits += __shfl_xor_sync(0xffffffffu, bits, 2);
+    uint32_t x = 0;
+    if (s < a.n_streams && q == 0) {
+      const uint32_t bytes = (bits + a.carry_len[s] + (uint32_t)a.pic_hdr_bits) >> 3;
+      nb[s] = bytes;
+      x = (bytes + 3u) & ~3u;
+    }
     const uint32_t mine = x;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
@@ -579,7 +628,7 @@ vlc_sizes_kernel(const __grid_constant__ VlcFrameArgs a) {
     __syncthreads();
     uint32_t base = s_base;
     for (int w = 0; w < warp; w++) base += s_w[w];
-    if (s < a.n_streams) off[s] = base + x - mine;
+    if (s < a.n_streams && q == 0) off[s] = base + x - mine;
     __syncthreads();
     if (tid == blockDim.x - 1) s_base = base + x;
     __syncthreads();
@@ -587,27 +636,53 @@ vlc_sizes_kernel(const __grid_constant__ VlcFrameArgs a) {
   if (tid == 0) off[a.n_streams] = s_base;
 }
 
-__global__ void __launch_bounds__(VLC_THREADS)
+// One CTA per stream: the carry bits of the previous frame, the picture header and the pieces are concatenated into the
+// frame's byte chunk.  An output word that lies inside one piece is a funnel shift of two adjacent words of that piece
+// with a shift that is the same for the whole piece: the warps take pieces in turn and stream them (coalesced loads and
+// stores, no search).  The words that hold a piece boundary -- at most one per piece -- are assembled bit by bit.
+constexpr int VLC_FRAME_THREADS = 1024;              // 32 warps: a warp's pieces are a chain of dependent round trips to L2
+__global__ void __launch_bounds__(VLC_FRAME_THREADS)
 vlc_frame_kernel(const __grid_constant__ VlcFrameArgs a) {
-  constexpr int MAXP = 2 + 12;
+  constexpr int MAXP = 2 + 12 * VLC_PPG;
+  static_assert(MAXP <= 128, "the offsets are scanned by four warps");
   __shared__ uint32_t s_off[MAXP + 1];
   __shared__ uint32_t s_small[2][3];                  // piece 0 (carry) and 1 (picture header) as word arrays
-  const int s = blockIdx.x, tid = threadIdx.x, np = 2 + a.ngob;
-  if (tid == 0) {
-    uint32_t o = 0;
-    s_off[0] = 0; o += a.carry_len[s];
-    s_off[1] = o; o += (uint32_t)a.pic_hdr_bits;
-    for (int g = 0; g < a.ngob; g++) { s_off[2 + g] = o; o += a.gob_bits[(size_t)s * a.ngob + g]; }
-    s_off[np] = o;
-    s_small[0][0] = a.carry[s]; s_small[0][1] = 0; s_small[0][2] = 0;
-    s_small[1][0] = a.pic_hdr[0]; s_small[1][1] = a.pic_hdr[1]; s_small[1][2] = 0;
+  __shared__ uint32_t s_wsum[4];
+  const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, ng = a.ngob * a.ppg, np = 2 + ng;
+  {
+    uint32_t len = 0;
+    if (tid == 0) len = a.carry_len[s];
+    else if (tid == 1) len = (uint32_t)a.pic_hdr_bits;
+    else if (tid < np) len = a.gob_bits[(size_t)s * ng + (tid - 2)];
+    uint32_t x = len;
+    if (warp < 4) {
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+      if (lane == 31) s_wsum[warp] = x;
+    }
+    if (tid == 0) {
+      s_small[0][0] = a.carry[s]; s_small[0][1] = 0; s_small[0][2] = 0;
+      s_small[1][0] = a.pic_hdr ? a.pic_hdr[0] : a.pic_hdr_imm[0]; s_small[1][1] = a.pic_hdr ? a.pic_hdr[1] : a.pic_hdr_imm[1]; s_small[1][2] = 0;
+    }
+    __syncthreads();
+    if (warp < 4) {
+      uint32_t base = 0;
+      for (int w = 0; w < warp; w++) base += s_wsum[w];
+      if (tid < np) s_off[tid] = base + x - len;
+      if (tid == 127) s_off[np] = base + x;
+    }
   }
   __syncthreads();
   const uint32_t total = s_off[np];
+  const uint32_t* slot0 = a.gob_words + (size_t)s * a.ngob * VLC_GOB_WORDS;
+  auto piece_words = [&](int p) -> const uint32_t* {
+    const int q = p - 2;
+    return p < 2 ? s_small[p] : slot0 + (size_t)(q / a.ppg) * VLC_GOB_WORDS + (a.ppg > 1 ? vlc_piece_m0(q % a.ppg) * VLC_MB_WORDS : 0);
+  };
   // 32 bits of the concatenation starting at bit o (zeros beyond the end)
   auto get32 = [&](uint32_t o) -> uint32_t {
-    int p = 0;
-    while (p < np - 1 && s_off[p + 1] <= o) p++;
+    int p = 0, hi = np;                                // the last piece that starts at or before o
+    while (hi - p > 1) { const int mid = (p + hi) >> 1; if (s_off[mid] <= o) p = mid; else hi = mid; }
     uint32_t res = 0;
     int filled = 0;
     while (filled < 32 && p < np) {
@@ -615,7 +690,7 @@ vlc_frame_kernel(const __grid_constant__ VlcFrameArgs a) {
       if (avail <= 0) { p++; continue; }
       const int take = min(32 - filled, avail);
       const uint32_t local = o - s_off[p];
-      const uint32_t* src = p < 2 ? s_small[p] : a.gob_words + ((size_t)s * a.ngob + (p - 2)) * VLC_GOB_WORDS;
+      const uint32_t* src = piece_words(p);
       uint32_t v = __funnelshift_l(src[(local >> 5) + 1], src[local >> 5], local & 31);
       if (take < 32) v &= ~(0xffffffffu >> take);
       res |= v >> filled;
@@ -625,7 +700,20 @@ vlc_frame_kernel(const __grid_constant__ VlcFrameArgs a) {
   };
   const uint32_t nbytes = total >> 3, nwords = (nbytes + 3) >> 2;
   uint32_t* out = reinterpret_cast<uint32_t*>(a.out + vlc_data_offset(a.n_streams) + vlc_out_u32(a.out, a.n_streams, 0)[s]);
-  for (uint32_t w = tid; w < nwords; w += VLC_THREADS) out[w] = __byte_perm(get32(32 * w), 0, 0x0123);   // stream order = big endian
+  // (stream order = big endian)
+  for (int p = warp; p < np; p += VLC_FRAME_THREADS / 32) {    // words inside one piece
+    const uint32_t o = s_off[p], e = s_off[p + 1];
+    const uint32_t w0 = (o + 31) >> 5, w1 = min(e >> 5, nwords);
+    if (w1 <= w0) continue;
+    const uint32_t* src = piece_words(p);                      // output word w0 + i starts in word i of the piece, at bit `sh`
+    const uint32_t sh = (0u - o) & 31, n = w1 - w0;
+#pragma unroll 4
+    for (uint32_t i = lane; i < n; i += 32) out[w0 + i] = __byte_perm(__funnelshift_l(src[i + 1], src[i], sh), 0, 0x0123);
+  }
+  if (tid < np) {                                              // the word in which piece `tid` ends, if it ends inside a word
+    const uint32_t o = s_off[tid], e = s_off[tid + 1];
+    if (e > o && (e & 31) && (e >> 5) < nwords) out[e >> 5] = __byte_perm(get32(e & ~31u), 0, 0x0123);
+  }
   if (tid == 0) {
     const uint32_t rem = total & 7;
     const uint32_t cbits = rem ? (get32(8 * nbytes) & ~(0xffffffffu >> rem)) : 0u;
