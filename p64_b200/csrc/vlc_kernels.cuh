@@ -5,14 +5,18 @@
 //   EncodeDC / EncodeAC / CBPEncodeAC  codec.c:96-205, 346-355      WritePictureHeader  marker.c:103-137
 //   mputv  stream.c:193-205 (MSB first)
 //
-//   vlc_gob_seq_kernel  fixed quantiser: one WARP per (stream, GOB), macroblock after macroblock, one item (intra DC, level,
+//   vlc_gob_seq_kernel  fixed quantiser: a GOB is nine independent pieces of 4, 4 and 3 macroblocks; the warps of a resident
+//                     grid take pieces from a queue and code one in one pass: one item (header half, intra DC, level,
 //                     EOB) per lane, the words streamed out through a small ring in shared memory -- no measuring pass.
 //   vlc_gob_kernel    rate control: one CTA per (stream, GOB): one thread per piece (GOB header, 33 x {MB header, 6 blocks});
 //                     pass 1 measures every piece, a CTA-wide scan places them, pass 2 writes the bits into a
 //                     shared-memory image of the GOB, which is then stored unshifted into the GOB's scratch slot.
-//   vlc_frame_kernel  one CTA per stream: carry bits of the previous frame + picture header + the GOB strings are
-//                     gathered word by word (funnel shifts) into the frame's byte chunk; the < 8 trailing bits stay
-//                     on the device as the next frame's carry, so the host only ever appends whole bytes.
+//   vlc_sizes_kernel  whole bytes of every stream's chunk and their packed offsets.
+//   vlc_frame_kernel  one CTA per stream: carry bits of the previous frame + picture header + the pieces (or whole GOBs)
+//                     are concatenated into the frame's byte chunk: a word inside one piece is a funnel shift with the
+//                     piece's own shift (streamed by a warp), a word that holds a piece boundary is assembled bit by
+//                     bit; the < 8 trailing bits stay on the device as the next frame's carry, so the host only ever
+//                     appends whole bytes.
 // Bit strings are MSB first: bit i of a string is bit (31 - i % 32) of word i / 32.
 #pragma once
 #include <cstdint>
@@ -218,7 +222,7 @@ __device__ __forceinline__ uint64_t vlc_mb_header(const p64b_mb& r, const p64b_m
 // warp-instructions, 0.116 ms (round 1; still the rate-control kernel, one GOB per stream per launch).  One warp per GOB,
 // macroblock after macroblock, lane per block quarter for the list: 57.9 M, 0.108 ms at 21 warps per SM (3 072 GOBs).  The same
 // per piece of 3 macroblocks from a queue: 61 M, 0.090 ms.  This kernel: the list, the headers and the scans are shared by
-// 4 macroblocks, the item rounds are full (profiles/r02_ncu_vlc_gob_seq_kernel*.txt).
+// 4 macroblocks, the item rounds are full: 42 M, 0.073 ms (profiles/r02_ncu_vlc_pieces_final.txt).
 constexpr int VLC_SEQ_WARPS = 4;
 constexpr int VLC_SEQ_THREADS = 32 * VLC_SEQ_WARPS;
 constexpr int VLC_PASS_MBS = 4;
