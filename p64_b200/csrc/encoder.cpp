@@ -8,6 +8,7 @@
 #include <condition_variable>
 #include <cstdint>
 #include <cstring>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -48,6 +49,52 @@ struct Worker {
 
 }  // namespace
 
+// A few host threads that stay alive for the encoder's lifetime: the per-frame host work (appending every stream's bytes,
+// the host VLC, the staging copy) is a parallel loop of well under a millisecond, and starting threads for each one costs
+// more than the loop (300 frames x 256 streams: 0.9 -> 2.7 ms per step from run to run with per-call threads).
+struct Pool {
+  std::mutex m;
+  std::condition_variable cv_work, cv_done;
+  std::vector<std::thread> th;
+  const std::function<void(int)>* fn = nullptr;
+  int n = 0;
+  std::atomic<int> next{0};
+  int running = 0;                 // workers that have not yet left the current loop
+  uint64_t gen = 0;
+  bool quit = false;
+  explicit Pool(int workers) {
+    for (int i = 0; i < workers; i++) th.emplace_back([this] { loop(); });
+  }
+  ~Pool() {
+    { std::lock_guard<std::mutex> lk(m); quit = true; }
+    cv_work.notify_all();
+    for (auto& t : th) t.join();
+  }
+  void loop() {
+    uint64_t seen = 0;
+    std::unique_lock<std::mutex> lk(m);
+    for (;;) {
+      cv_work.wait(lk, [&] { return quit || gen != seen; });
+      if (quit) return;
+      seen = gen;
+      const std::function<void(int)>* f = fn;
+      const int cnt = n;
+      lk.unlock();
+      for (int i; (i = next.fetch_add(1)) < cnt;) (*f)(i);
+      lk.lock();
+      if (--running == 0) cv_done.notify_one();
+    }
+  }
+  // f(0) .. f(cnt-1), each once, on the workers and the caller; returns when all are done
+  void run(int cnt, const std::function<void(int)>& f) {
+    { std::lock_guard<std::mutex> lk(m); fn = &f; n = cnt; next.store(0); running = (int)th.size(); gen++; }
+    cv_work.notify_all();
+    for (int i; (i = next.fetch_add(1)) < cnt;) f(i);
+    std::unique_lock<std::mutex> lk(m);
+    cv_done.wait(lk, [&] { return running == 0; });
+  }
+};
+
 struct p64b_enc {
   p64b_enc_params p{};
   // multi-device parent: the partitions; everything per stream lives in the kids
@@ -72,21 +119,25 @@ struct p64b_enc {
   int harvested = 0;             // frames whose bytes have been appended to the streams
   std::vector<uint8_t> quant, overflow;
   int threads = 1;
+  std::unique_ptr<Pool> pool;    // created at the first parallel loop
   bool device_vlc = false;       // headers + VLC (+ rate control) run on the device (p64b_ctx_submit_bits)
 };
 
 namespace {
 
+Pool* pool_of(p64b_enc* e) {
+  // the device path's host work is memory-bound (a few MB per frame): eight threads; the host VLC takes what it is given
+  if (!e->pool) e->pool.reset(new Pool(std::max(1, e->device_vlc ? std::min(e->threads, 8) : e->threads) - 1));
+  return e->pool.get();
+}
+
 template <class F>
 void parallel_streams(p64b_enc* e, F f) {
   const int T = std::min(e->threads, e->S);
   if (T <= 1) { for (int s = 0; s < e->S; s++) f(s); return; }
-  std::atomic<int> next{0};
-  std::vector<std::thread> th;
-  th.reserve(T);
-  for (int t = 0; t < T; t++)
-    th.emplace_back([&] { for (int s; (s = next.fetch_add(1)) < e->S;) f(s); });
-  for (auto& x : th) x.join();
+  const int per = e->device_vlc ? 8 : 1;               // streams per work item
+  const std::function<void(int)> job = [&](int i) { for (int s = i * per; s < std::min(e->S, (i + 1) * per); s++) f(s); };
+  pool_of(e)->run((e->S + per - 1) / per, job);
 }
 
 // the caller's frame set into pinned staging: 39 MB per step at 256 CIF streams -- one core copies that in 3 ms, which would
@@ -94,15 +145,9 @@ void parallel_streams(p64b_enc* e, F f) {
 void copy_frames(p64b_enc* e, uint8_t* dst, const uint8_t* src, size_t bytes) {
   const int T = (int)std::min<size_t>(std::min(e->threads, 8), bytes >> 20);
   if (T <= 1) { memcpy(dst, src, bytes); return; }
-  std::vector<std::thread> th;
-  th.reserve(T);
-  const size_t chunk = ((bytes + T - 1) / T + 4095) & ~(size_t)4095;
-  for (int t = 0; t < T; t++) {
-    const size_t o = (size_t)t * chunk;
-    if (o >= bytes) break;
-    th.emplace_back([=] { memcpy(dst + o, src + o, std::min(chunk, bytes - o)); });
-  }
-  for (auto& x : th) x.join();
+  const size_t chunk = (size_t)1 << 20;
+  const std::function<void(int)> job = [&](int i) { const size_t o = (size_t)i * chunk; memcpy(dst + o, src + o, std::min(chunk, bytes - o)); };
+  pool_of(e)->run((int)((bytes + chunk - 1) / chunk), job);
 }
 
 // BufferContents(), p64.c:233-237, with CurrentGOB=g, CurrentMDU=m. int arithmetic as in the reference.
