@@ -272,7 +272,7 @@ vlc_gob_seq_kernel(const __grid_constant__ VlcArgs a) {
   for (int i = tid; i < DEV_VLC_WORDS; i += VLC_SEQ_THREADS) reinterpret_cast<uint32_t*>(&s_t)[i] = reinterpret_cast<const uint32_t*>(a.tables)[i];
   for (int i = lane; i < VLC_RING; i += 32) s_ring[warp][i] = 0;
   __syncthreads();                                      // (no barrier below)
-  const int n_tasks = a.n_streams * a.gob_count * VLC_PPG, n_workers = (int)gridDim.x * VLC_SEQ_WARPS;
+  const int n_tasks = a.n_streams * a.ngob * VLC_PPG, n_workers = (int)gridDim.x * VLC_SEQ_WARPS;
   uint8_t* stage = s_stage[warp];
   uint16_t* items = s_items[warp];
   uint32_t* ring = s_ring[warp];
@@ -284,11 +284,11 @@ vlc_gob_seq_kernel(const __grid_constant__ VlcArgs a) {
   while (task < n_tasks) {
     const int task_next = n_workers + (int)__shfl_sync(0xffffffffu, ticket, 0);
     if (task_next < n_tasks) ticket = vlc_queue_take(a.queue + a.parity, lane);
+    // task = (stream * ngob + gob) * VLC_PPG + piece (this kernel always codes whole frames: nmb = 33 ngob)
     const int pc = task % VLC_PPG, sg = task / VLC_PPG;
-    const int s = sg / a.gob_count, gob = a.gob_first + sg % a.gob_count;
     const int m0 = vlc_piece_m0(pc), nm = vlc_piece_n(pc);
-    const size_t mb0 = (size_t)s * a.nmb + gob * 33 + m0;
-    uint32_t* dst = a.gob_words + ((size_t)s * a.ngob + gob) * VLC_GOB_WORDS + m0 * VLC_MB_WORDS;
+    const size_t mb0 = (size_t)sg * 33 + m0;
+    uint32_t* dst = a.gob_words + (size_t)sg * VLC_GOB_WORDS + m0 * VLC_MB_WORDS;
 
     // ---- loads: the macroblock's record; lanes 0..23 their block's levels; lanes 24..27 the left neighbour's record
     const bool mine = j < nm;
@@ -307,6 +307,7 @@ vlc_gob_seq_kernel(const __grid_constant__ VlcArgs a) {
     }
     uint32_t pos = 0, wbase = 0;                         // bits written so far; first word of the piece's string still in the ring
     if (m0 == 0) {                                       // WriteGOBHeader, marker.c:182-209: GBSC, GN, GQUANT, no GSPARE
+      const int gob = sg % a.ngob;
       const int gn = (a.qcif ? (gob << 1) : gob) + 1;
       if (lane == 0) vlc_or_ring(ring, 0, (1u << 10) | ((uint32_t)gn << 6) | ((uint32_t)a.gquant << 1), 26);
       pos = 26;
@@ -359,8 +360,9 @@ vlc_gob_seq_kernel(const __grid_constant__ VlcArgs a) {
       const uint32_t base = (uint32_t)lane << 8;
       if (head) { items[idx++] = (uint16_t)(base | 0xc0u); items[idx++] = (uint16_t)(base | 0xc1u); }
       if (dc) items[idx++] = (uint16_t)(base | 0x80u);
-      while (nzl) { const int pl = __ffs((int)nzl) - 1; nzl &= nzl - 1; items[idx++] = (uint16_t)(base | (uint32_t)pl); }
-      while (nzh) { const int pl = __ffs((int)nzh) - 1; nzh &= nzh - 1; items[idx++] = (uint16_t)(base | 32u | (uint32_t)pl); }
+      // (bit-reversed masks: the next position is a count of leading zeros, one instruction)
+      for (uint32_t r = __brev(nzl); r;) { const int pl = __clz((int)r); r &= ~(0x80000000u >> pl); items[idx++] = (uint16_t)(base | (uint32_t)pl); }
+      for (uint32_t r = __brev(nzh); r;) { const int pl = __clz((int)r); r &= ~(0x80000000u >> pl); items[idx++] = (uint16_t)(base | 32u | (uint32_t)pl); }
       if (eob) items[idx++] = (uint16_t)(base | 0xc2u);
     }
     __syncwarp();
@@ -405,7 +407,7 @@ vlc_gob_seq_kernel(const __grid_constant__ VlcArgs a) {
       const uint32_t w = (pos >> 5) & (VLC_RING - 1);
       if (pos & 31) { dst[pos >> 5] = ring[w]; ring[w] = 0; }    // (the ring is all zero again for the warp's next piece)
       dst[nwords] = 0;
-      a.gob_bits[((size_t)s * a.ngob + gob) * VLC_PPG + pc] = pos;
+      a.gob_bits[task] = pos;
     }
     __syncwarp();
     task = task_next;
