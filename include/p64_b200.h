@@ -278,6 +278,9 @@ int p64b_probe_links(const int32_t *devices, int n_devices, double *gb_per_s);
  * the region its thread may touch (compute-sanitizer is not available on every pool).  Returns 1 and the number of violations
  * on `device` since the library was loaded (+ the kernels.cuh line of the last one) from such a build, 0 from the product build. */
 int p64b_debug_oob(int device, uint32_t *violations, uint32_t *last_line);
+/* Self-test of the sequence encoder's host thread pool (no GPU needed): `rounds` parallel loops of `items` items on `workers`
+ * threads + the caller; 0 if every item ran exactly once in every round. */
+int p64b_debug_pool_selftest(int workers, int items, int rounds);
 /* p64b_host_alloc with flags: 1 = write-combined (cudaHostAllocWriteCombined). */
 void *p64b_host_alloc_flags(size_t bytes, int flags);
 

@@ -130,6 +130,7 @@ SIGNATURES = {
     "p64b_measure_link": (_i, [_i, C.POINTER(_vp), _i, _sz, _vp, _sz, _i, _i, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "p64b_host_alloc_flags": (_vp, [_sz, _i]),
     "p64b_debug_oob": (_i, [_i, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "p64b_debug_pool_selftest": (_i, [_i, _i, _i]),
     "p64b_probe_links": (_i, [C.POINTER(C.c_int32), _i, C.POINTER(C.c_double)]),
     "p64b_bits_create": (_vp, [_i]),
     "p64b_bits_destroy": (None, [_vp]),

@@ -351,6 +351,20 @@ int p64b_enc_create(p64b_enc** out, const p64b_enc_params* p) {
   return 0;
 }
 
+int p64b_debug_pool_selftest(int workers, int items, int rounds) {
+  if (workers < 0 || workers > 256 || items < 0 || rounds < 0) { p64b::set_error("bad argument"); return P64B_EINVAL; }
+  Pool pool(workers);
+  std::vector<std::atomic<int>> hits(items);
+  for (auto& h : hits) h.store(0);
+  for (int r = 0; r < rounds; r++) {
+    const std::function<void(int)> job = [&](int i) { hits[i].fetch_add(1); };
+    pool.run(items, job);
+    for (int i = 0; i < items; i++)
+      if (hits[i].load() != r + 1) { p64b::set_error("thread pool: an item did not run exactly once"); return P64B_EINVAL; }
+  }
+  return 0;
+}
+
 void p64b_enc_destroy(p64b_enc* e) {
   if (!e) return;
   for (auto& w : e->workers) {

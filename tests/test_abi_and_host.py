@@ -309,3 +309,10 @@ def test_integration_glue_compiles_against_the_reference_headers():
     subprocess.run([sys.executable, os.path.join(root, "tools", "make_glue_example.py")], check=True)
     subprocess.run([gcc, "-std=gnu99", "-fsyntax-only", "-Wall", "-Werror", "-Wno-unused", "-Wno-implicit-int", "-I", ref,
                     "-I", os.path.join(root, "include"), os.path.join(root, "examples", "p64gpu_glue.c")], check=True)
+
+
+@pytest.mark.parametrize("workers,items,rounds", [(0, 5, 3), (1, 1, 50), (3, 256, 400), (7, 32, 2000), (15, 1000, 50), (63, 7, 300)])
+def test_encoder_thread_pool_runs_every_item_exactly_once(L, workers, items, rounds):
+    """The sequence encoder's per-frame host loops (appending the streams' bytes, the staging copy, the host VLC) run on a
+    persistent pool; many short rounds back to back are its worst case (a worker that wakes late must not miss or repeat one)."""
+    assert L.p64b_debug_pool_selftest(workers, items, rounds) == 0
